@@ -1,0 +1,266 @@
+"""Stages A-C have no reference fixture (parity unpinned), so the C++ oracle is cross-checked
+against an independent pure-Python transcription of the same Java sources (oracle/pyref.py) on small inputs,
+and against brute-force properties."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyref
+from oracle_ffi import FMT_FASTA, FMT_FASTQ, FMT_FASTQ33, FMT_FASTQ64, OracleError
+
+
+def rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def make_fastq(rng, n_reads, max_len=60, p_n=0.03, p_bang=0.03, crlf=False, blanks=False, lower=False, offset=33):
+    nl = "\r\n" if crlf else "\n"
+    out = []
+    for i in range(n_reads):
+        L = rng.randint(0, max_len)
+        seq = "".join(("N" if rng.random() < p_n else rng.choice("ACGTacgt" if lower else "ACGT")) for _ in range(L))
+        if rng.random() < 0.1 and L:
+            p = rng.randrange(L)
+            seq = seq[:p] + rng.choice(".n") + seq[p + 1:]
+        zero = chr(offset)
+        qual = "".join((zero if rng.random() < p_bang else chr(rng.randint(offset + 1, min(126, offset + 41)))) for _ in range(L))
+        if blanks and rng.random() < 0.2:
+            out.append("")
+        out.append(f"@r{i} some comment")
+        out.append(seq)
+        if blanks and rng.random() < 0.2:
+            out.append("")
+        out.append("+" + (f"r{i}" if rng.random() < 0.3 else ""))
+        out.append(qual)
+    text = nl.join(out) + (nl if rng.random() < 0.8 else "")
+    return text.encode()
+
+
+def table_dict(t):
+    k, c = t.dump()
+    return dict(zip(k.tolist(), c.tolist()))
+
+
+@pytest.mark.parametrize("k", [3, 5, 11, 21, 31])
+@pytest.mark.parametrize("variant", ["plain", "crlf", "blanks", "lower"])
+def test_fastq_count_matches_pyref(oracle, k, variant):
+    rng = random.Random(1000 * k + len(variant))
+    data = make_fastq(rng, 120, max_len=90, crlf=variant == "crlf", blanks=variant == "blanks", lower=variant == "lower")
+    t = oracle.table(k, threads=1).count_bytes(data, FMT_FASTQ33)
+    want = pyref.count_runs(pyref.fastq_runs(data, 33), k)
+    assert table_dict(t) == want
+    assert t.size() == len(want)
+
+
+def test_fastq_sniffing(oracle):
+    rng = random.Random(7)
+    # all quality chars >= 64 -> sniffed as Phred+64: '@' (64) becomes the split char, 'A'.. are fine
+    data = make_fastq(rng, 50, offset=64)
+    assert pyref.sniff_offset(data) == 64
+    a = table_dict(oracle.table(7).count_bytes(data, FMT_FASTQ))
+    assert a == pyref.count_runs(pyref.fastq_runs(data, 64), 7)
+    assert a == table_dict(oracle.table(7).count_bytes(data, FMT_FASTQ64))
+    # one low char in the first 1000 records -> Phred+33
+    data33 = make_fastq(rng, 50, offset=33)
+    assert pyref.sniff_offset(data33) == 33
+    assert table_dict(oracle.table(7).count_bytes(data33, FMT_FASTQ)) == pyref.count_runs(pyref.fastq_runs(data33, 33), 7)
+
+
+def test_fastq_phred_wraps_at_64(oracle):
+    """Stored phred is 6 bits (DnaQ.java:147-150): Sanger char 97 ('a', phred 64) wraps to 0 and splits the read."""
+    seq = "ACGTACGTAC"
+    qual = "IIIIaIIIII"
+    data = f"@r\n{seq}\n+\n{qual}\n".encode()
+    got = table_dict(oracle.table(3).count_bytes(data, FMT_FASTQ33))
+    want = pyref.count_runs([[pyref.CODE[c] for c in "ACGT"], [pyref.CODE[c] for c in "CGTAC"]], 3)
+    assert got == want
+
+
+def test_fastq_errors(oracle):
+    def bad(data, fmt=FMT_FASTQ33):
+        with pytest.raises(OracleError):
+            oracle.table(5).count_bytes(data, fmt)
+    bad(b"@r\nACGT\n+\nIII\n")            # length mismatch (FastqReader.java:67-70)
+    bad(b"@r\nACGT\n+\n")                 # unexpected EOF (:105-108)
+    bad(b"@r\nACGT\n")                    # sequence without quality (:61-64)
+    bad(b"r\nACGT\n+\nIIII\n")            # header must start with @ or + (:99-103)
+    bad(b"@r\nACXT\n+\nIIII\n")           # illegal nucleotide (DnaTools.java:61-62)
+    bad(b"@r\nACRT\n+\nIIII\n")           # IUPAC: random in the reference, rejected here
+    bad(b"@r\nACGT\n+\nII\x1fI\n")        # quality char < 33 (Sanger.java:7-12)
+    bad(b"@r\nACGT\n+\nII!I\n", FMT_FASTQ64)   # forced Phred+64 with a low char (Illumina.java:7-12)
+    # N positions skip the quality check (FastqReader.java:75-76)
+    oracle.table(5).count_bytes(b"@r\nACNT\n+\nII\x1fI\n", FMT_FASTQ33)
+    # empty input and blank-only input are fine
+    assert oracle.table(5).count_bytes(b"", FMT_FASTQ33).size() == 0
+    assert oracle.table(5).count_bytes(b"\n\n\n", FMT_FASTQ33).size() == 0
+
+
+@pytest.mark.parametrize("k", [4, 15, 31])
+def test_fasta_count_matches_pyref(oracle, k):
+    rng = random.Random(k)
+    lines = []
+    for i in range(80):
+        if rng.random() < 0.9:
+            lines.append((">" if rng.random() < 0.8 else ";") + f"r{i}")
+        if rng.random() < 0.05:
+            lines.append(">double header")
+        for _ in range(rng.randint(0, 3)):
+            L = rng.randint(0, 70)
+            s = rand_seq(rng, L, "ACGTacgt")
+            if rng.random() < 0.08 and L:
+                p = rng.randrange(L)
+                s = s[:p] + rng.choice("Nn") + s[p + 1:]
+            lines.append(s)
+            if rng.random() < 0.1:
+                lines.append("")
+    data = ("\n".join(lines) + "\n").encode()
+    got = table_dict(oracle.table(k).count_bytes(data, FMT_FASTA))
+    assert got == pyref.count_runs(pyref.fasta_runs(data), k)
+    with pytest.raises(OracleError):
+        oracle.table(k).count_bytes(b">r\nAC.T\n", FMT_FASTA)   # '.' is not tolerated by new Dna(s)
+
+
+def test_saturation_and_absent(oracle):
+    t = oracle.table(3)
+    data = (">r\n" + "A" * 40000 + "\n").encode()
+    t.count_bytes(data, FMT_FASTA)
+    assert t.get(0) == 32767          # AAA saturates (NumUtils.java:21-26); key 0 is the FREE-key side slot
+    assert t.get(5) == -1             # absent -> -1 (Long2ShortHashMap.java:171-174)
+    assert t.size() == 1
+
+
+def test_threads_do_not_change_the_table(oracle):
+    rng = random.Random(3)
+    data = make_fastq(rng, 3000, max_len=100)
+    a = oracle.table(9, threads=1).count_bytes(data, FMT_FASTQ33)
+    b = oracle.table(9, threads=8).count_bytes(data, FMT_FASTQ33)
+    ka, ca = a.dump()
+    kb, cb = b.dump()
+    assert np.array_equal(ka, kb) and np.array_equal(ca, cb)
+    assert a.stats() == b.stats()
+
+
+@pytest.mark.parametrize("k", range(1, 32))
+def test_bit_revcomp_equals_string_revcomp(oracle, k):
+    rng = random.Random(k)
+    for _ in range(50):
+        s = rand_seq(rng, k)
+        code = oracle.encode(s)
+        assert code == pyref.encode(s)
+        assert oracle.decode(code, k) == s
+        assert oracle.decode(oracle.revcomp(code, k), k) == pyref.rc_str(s)
+        assert oracle.canonical(code, k) == min(code, pyref.revcomp_code(code, k))
+
+
+def small_graph(rng, k, genome_len=400, n_reads=300, read_len=40):
+    genome = rand_seq(rng, genome_len)
+    # a repeat so the graph branches
+    genome = genome[:150] + genome[20:60] + genome[150:]
+    reads = []
+    for i in range(n_reads):
+        s = rng.randrange(0, len(genome) - read_len)
+        r = genome[s:s + read_len]
+        if rng.random() < 0.5:
+            r = pyref.rc_str(r)
+        if rng.random() < 0.2:
+            p = rng.randrange(read_len)
+            r = r[:p] + rng.choice("ACGT") + r[p + 1:]
+        reads.append(f">r{i}\n{r}\n")
+    return genome, "".join(reads).encode()
+
+
+@pytest.mark.parametrize("k", [5, 7, 12, 31])
+@pytest.mark.parametrize("direction", [-1, 0, 1])
+@pytest.mark.parametrize("limits", [(None, 3), (10, None), (40, 6), (100000, None), (1, None), (None, 0)])
+def test_bfs_matches_pyref(oracle, k, direction, limits):
+    rng = random.Random(k * 100 + direction)
+    genome, data = small_graph(rng, k)
+    t = oracle.table(k).count_bytes(data, FMT_FASTA)
+    table = table_dict(t)
+    target = genome[100:100 + max(k + 5, 30)]
+    target = target + target[:k]   # duplicate seed k-mers
+    max_kmers, max_radius = limits
+    for min_cov in (1, 2):
+        want = pyref.bfs(table, target, k, min_cov, max_kmers, max_radius, direction)
+        got = t.bfs(target, min_cov, max_kmers, max_radius, direction)
+        if want is None:
+            assert got is None
+            continue
+        order, dist = got
+        assert order == list(want.keys())          # same set AND same discovery order
+        assert dist.tolist() == list(want.values())
+
+
+@pytest.mark.parametrize("both", [False, True])
+def test_environment_matches_pyref(oracle, both, tmp_path):
+    k = 9
+    rng = random.Random(99)
+    genome, data = small_graph(rng, k, genome_len=900, n_reads=900)
+    t = oracle.table(k).count_bytes(data, FMT_FASTA)
+    target = genome[300:360]
+    fa = tmp_path / "seq.fasta"
+    fa.write_text(f">gene one\n{target[:30]}\n{target[30:]}\n")
+    n = t.env_find(str(fa), 2, 150, None, both, 1, str(tmp_path / "out"))
+    assert n == 1
+    want = pyref.environment(table_dict(t), target, k, 2, 150, None, both)
+    lines = (tmp_path / "out" / "gene one" / "graph.txt").read_text().splitlines()
+    assert lines == [f"{kmer} {c}" for kmer, c in want]
+    assert (tmp_path / "out" / "gene one" / "env.txt").read_text().splitlines() == lines
+    for f in ("graph.gfa", "seqs.fasta", "tsvs/nodes.tsv", "tsvs/edges.tsv"):
+        assert (tmp_path / "out" / "gene one" / f).exists()
+
+
+def test_level_synchronous_rule_equals_fifo_rule():
+    """ordering a batch's candidates by (parent queue index, neighbour slot) and keeping the first
+    occurrence gives the same set and discovery order as the sequential FIFO loop, also when --maxkmers is hit.
+    This is the rule the GPU BFS implements; here it is simulated in Python against pyref.bfs."""
+    def batched(table, seq, k, min_cov, max_kmers, max_radius, direction, batch):
+        def occ(kmer):
+            c = pyref.encode(kmer)
+            return table.get(min(c, pyref.revcomp_code(c, k)), -1)
+        queue, dist = [], {}
+        for i in range(len(seq) - k + 1):
+            kmer = seq[i:i + k]
+            if occ(kmer) >= min_cov and kmer not in dist:
+                queue.append(kmer)
+                dist[kmer] = 0
+        if not queue:
+            return None
+        head, stopped = 0, False
+        while head < len(queue) and not stopped:
+            parents = queue[head:head + batch]
+            head += len(parents)
+            cands = []
+            for p in parents:
+                left = [n + p[:-1] for n in pyref.NUC]
+                right = [p[1:] + n for n in pyref.NUC]
+                nbs = left if direction == -1 else right if direction == 1 else [x for pr in zip(left, right) for x in pr]
+                for nb in nbs:
+                    if occ(nb) >= min_cov and (max_radius is None or dist[p] + 1 <= max_radius):
+                        cands.append((nb, dist[p] + 1))
+            seen = set()
+            for nb, d in cands:                       # first occurrence in candidate order
+                if nb in dist or nb in seen:
+                    continue
+                seen.add(nb)
+                if max_kmers is not None and len(dist) >= max_kmers:
+                    stopped = True                    # budget exhausted: nothing can ever be added again
+                    break
+                queue.append(nb)
+                dist[nb] = d
+        return dist
+    rng = random.Random(5)
+    for trial in range(60):
+        k = 7
+        genome, data = small_graph(rng, k, genome_len=300, n_reads=200, read_len=30)
+        table = pyref.count_runs(pyref.fasta_runs(data), k)
+        target = genome[50:90] + genome[50:60]
+        for direction in (-1, 0, 1):
+            for mk, mr in ((None, 4), (25, None), (60, 8)):
+                for batch in (1, 3, 64):
+                    a = pyref.bfs(table, target, k, 1, mk, mr, direction)
+                    b = batched(table, target, k, 1, mk, mr, direction, batch)
+                    assert (a is None) == (b is None)
+                    if a is not None:
+                        assert list(a.items()) == list(b.items())
