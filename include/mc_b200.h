@@ -1,0 +1,164 @@
+/* libmcgpu — B200-native (sm_100a) drop-in for MetaCherchant's environment-finder hot path.
+ *
+ * C ABI: plain pointers and sizes, opaque handles, no torch/C++ types.  Every entry point names
+ * the reference interface it replaces (file:line; src/ = /root/reference/src/, ITMO!/ = inside
+ * lib/itmo-assembler-src.jar ru/ifmo/genetics/).  The Java side binds these through the JNI shim
+ * in jni/mc_jni.cpp.
+ *
+ * Conventions
+ *   - every function returns MC_OK (0) or a negative mc_status; mc_last_error() gives the message
+ *     of the last failure on the calling thread (text follows the reference's exception messages).
+ *   - k-mers are 2-bit packed, first base most significant, A=0 G=1 C=2 T=3
+ *     (ITMO!/dna/DnaTools.java:31,123-129); table keys are min(fw, rc) (ITMO!/utils/KmerUtils.java:58-60).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with MC_ERR_CUDA.
+ */
+#ifndef MC_B200_H
+#define MC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mc_status {
+    MC_OK = 0,
+    MC_ERR_CUDA = -1,        /* no device / CUDA runtime failure */
+    MC_ERR_ARG = -2,         /* bad argument (k outside 1..31, null pointer, ...) */
+    MC_ERR_IO = -3,          /* "Failed to read from file <path>" (src/io/IOUtils.java:292) */
+    MC_ERR_FORMAT = -4,      /* malformed FASTA/FASTQ: the reference throws from its reader threads */
+    MC_ERR_NOMEM = -5,       /* table does not fit in device memory */
+    MC_ERR_UNSUPPORTED = -6, /* reference feature outside the GPU path (gz/bz2/binq input, k > 31, ...) */
+    MC_ERR_CAPACITY = -7     /* caller-provided output buffer too small */
+} mc_status;
+
+/* input formats: ITMO!/io/ReadersUtils.java:27-54 (by file suffix) and :63-77 (quality-offset sniffing) */
+enum { MC_FMT_FASTA = 0, MC_FMT_FASTQ = 1 /* sniff offset on the first 1000 records */, MC_FMT_FASTQ33 = 33, MC_FMT_FASTQ64 = 64 };
+
+typedef struct mc_ctx mc_ctx;       /* one per GPU: device, streams, staging buffers */
+typedef struct mc_table mc_table;   /* the k-mer count map, resident in HBM */
+
+const char* mc_last_error(void);
+const char* mc_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------- */
+int mc_ctx_create(int device, mc_ctx** out);
+void mc_ctx_destroy(mc_ctx* ctx);
+/* chunk size (bytes of reads per device batch, default 256 MiB) — the analogue of READS_WORK_RANGE_SIZE (src/io/IOUtils.java:25) */
+int mc_ctx_set_chunk_bytes(mc_ctx* ctx, size_t bytes);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+uint64_t mc_ctx_launches(const mc_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam 1 — counting.  Replaces
+ *   BigLong2ShortHashMap IOUtils.loadReads(File[] files, int k, int minSeqLen=0, int P, Logger)   src/io/IOUtils.java:217-248
+ *   (readers ITMO!/io/readers/{FastqReader,FastaReader,FastaReaderFromXQSourceTrunc}.java, k-mers
+ *    ITMO!/dna/kmers/ShortKmer.java:104-149, map ITMO!/structures/map/BigLong2ShortHashMap.java:40-77).
+ * ---------------------------------------------------------------------------------------------- */
+/* new BigLong2ShortHashMap(...) (src/io/IOUtils.java:220-221).  capacity_hint = expected distinct k-mers (0 = grow on demand).
+ * shard_bits/shard_id: this table owns the keys whose hash has its top shard_bits bits == shard_id (multi-GPU, 0/0 = everything). */
+int mc_table_create(mc_ctx* ctx, int k, uint64_t capacity_hint, int shard_bits, int shard_id, mc_table** out);
+void mc_table_free(mc_table* t);
+/* loadReads over files: format by suffix, FASTQ offset sniffed per file; counts into a fresh table */
+int mc_count_files(mc_ctx* ctx, const char* const* paths, int n_paths, int k, mc_table** out);
+/* streaming form: `buf` is HOST memory holding whole records (a file, or a record-aligned slice of one) */
+int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt, mc_table* t);
+/* same, `dbuf` already resident in device memory (bench `value` leg; also the multi-GPU pipeline) */
+int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fmt, mc_table* t);
+/* BigLong2ShortHashMap.size() — "Hashtable size: N kmers" (src/tools/EnvironmentFinderMain.java:137) */
+uint64_t mc_table_size(const mc_table* t);
+/* reader statistics: sequences seen / runs after N- and quality-splitting / bases in runs / k-mer instances
+ * ("N reads added", good/total statistics, src/io/IOUtils.java:239-245,313) */
+int mc_table_stats(const mc_table* t, uint64_t* reads, uint64_t* runs, uint64_t* bases, uint64_t* kmers);
+/* addAndBound(key, freq) for (key,count) pairs — Kmers2HMWorker (src/io/IOUtils.java:71-92) */
+int mc_table_add_pairs(mc_table* t, const uint64_t* keys, const int16_t* counts, size_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam 2 — lookups.  Replaces short BigLong2ShortHashMap.get(long) (-1 = absent,
+ * ITMO!/structures/map/Long2ShortHashMap.java:159-175) and entryIterator() (src/io/IOUtils.java:47).
+ * ---------------------------------------------------------------------------------------------- */
+int mc_table_get(const mc_table* t, const uint64_t* keys, size_t n, int16_t* out);
+/* entries with count >= min_count, sorted by key.  Pass cap = 0 to query *n only. */
+int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, int16_t* counts, size_t cap, size_t* n);
+/* coverage-threshold compaction (B2/K4): a new, densely sized table holding only count >= min_count */
+int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc_table** solid);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam 3 — environments.  Replaces, batched over all targets,
+ *   new OneSequenceCalculator(seq, k, minOcc, outPrefix, workPrefix, hasher=null, reads, logger,
+ *                             bothDirs, chunkLength, termMode, trim=false).run()
+ *   (src/tools/EnvironmentFinderMain.java:218-225, src/algo/OneSequenceCalculator.java:98-114).
+ * max_kmers / max_radius: -1 = unset (at least one must be set, EnvironmentFinderMain.java:171-175).
+ * Writes <out_dir>/<names[i]>/{graph.txt, env.txt, seqs.fasta, graph.gfa, tsvs/nodes.tsv, tsvs/edges.tsv}.
+ * found[i] (optional) = 1 if target i had at least one seed k-mer, else 0 (the reference logs
+ * "Could not find any k-mers of the target gene in the input, halting." and writes nothing).
+ * ---------------------------------------------------------------------------------------------- */
+int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets, int k,
+                int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs, int chunk_len, const char* out_dir,
+                int* found);
+/* one BFS pass (runBfs, OneSequenceCalculator.java:154-220): oriented k-mers in discovery order.
+ * dir: -1 left, +1 right, 0 both.  Returns in *n the number visited (0 = no seeds). */
+int mc_bfs(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int dir,
+           uint64_t* kmers, int32_t* dist, int16_t* counts, size_t cap, size_t* n);
+/* the environment of one target as (ASCII-canonical k-mer packed 2-bit, count), in graph.txt order */
+int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
+                 int both_dirs, uint64_t* kmers, int32_t* counts, size_t cap, size_t* n);
+/* FASTA target loader (src/io/RichFastaReader.java:38-76 + DnaQ(str,0).toString()): returns a handle to iterate */
+typedef struct mc_targets mc_targets;
+int mc_targets_load(const char* fasta_path, mc_targets** out);
+int mc_targets_count(const mc_targets* t);
+const char* mc_targets_seq(const mc_targets* t, int i);
+const char* mc_targets_name(const mc_targets* t, int i);   /* header minus first char = output sub-directory */
+void mc_targets_free(mc_targets* t);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam 4 — environment-finder-multi.  Replaces
+ *   new MultiSequenceCalculator(seq, k, outPrefix, logger, graphs).run() + printGene + printProbability
+ *   (src/tools/EnvironmentFinderMultiMain.java:81-168).
+ * ---------------------------------------------------------------------------------------------- */
+int mc_env_multi(mc_ctx* ctx, const char* const* env_paths, int n_envs, const char* seq_fasta, int gene_id, const char* out_dir);
+
+/* ------------------------------------------------------------------------------------------------
+ * "next" row f-1 — kmer-counter's on-disk table (src/io/IOUtils.java:39-65,94-126): big-endian
+ * (int64 key, int16 count) records with count > threshold.
+ * ---------------------------------------------------------------------------------------------- */
+int mc_table_print_kmers(const mc_table* t, int threshold, const char* out_file, const char* stat_file, uint64_t* good);
+int mc_table_load_kmers(mc_table* t, const char* path, int freq_threshold);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU building blocks: one process per GPU; keys are exchanged by the host
+ * layer (torch.distributed all_to_all over NCCL/NVLink) between these two calls.
+ * ---------------------------------------------------------------------------------------------- */
+/* parse + extract the canonical k-mers of a device-resident chunk, hashed and partitioned by owner
+ * (top shard_bits bits of the hash): d_keys receives the hashed keys grouped by owner, counts[o] the
+ * number for owner o.  d_keys must hold at least mc_max_kmers(len, fmt, k) entries. */
+int mc_extract_partition_device(mc_ctx* ctx, const void* dbuf, size_t len, int fmt, int k, int shard_bits,
+                                uint64_t* d_keys, uint64_t* counts /* host, 1<<shard_bits entries */, mc_table* stats_sink);
+uint64_t mc_max_kmers(size_t len, int fmt, int k);
+/* insert hashed keys (as produced above) that this table owns; device pointer */
+int mc_table_insert_hashed_device(mc_table* t, const uint64_t* d_hkeys, size_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bench/test utility (NOT reference API): synthetic metagenome reads generated on the device
+ * (include/mc_synth.h).  `params` is a mc_synth_params blob built by mc_synth_init.
+ * ---------------------------------------------------------------------------------------------- */
+int mc_synth_generate_device(mc_ctx* ctx, const void* params, size_t params_size, uint64_t first, uint64_t count, void* d_out);
+/* plain device-memory helpers for hosts without their own allocator (the JNI shim, the CLI) */
+int mc_device_alloc(mc_ctx* ctx, size_t bytes, void** d_ptr);
+int mc_device_free(mc_ctx* ctx, void* d_ptr);
+int mc_memcpy_d2h(mc_ctx* ctx, void* dst, const void* d_src, size_t bytes);
+int mc_memcpy_h2d(mc_ctx* ctx, void* d_dst, const void* src, size_t bytes);
+int mc_ctx_sync(mc_ctx* ctx);
+/* CUDA-event timing on the context's stream (bench.py times kernels on the stream they are launched on) */
+int mc_event_record(mc_ctx* ctx, int slot /*0..15*/);
+int mc_event_elapsed_ms(mc_ctx* ctx, int slot_a, int slot_b, float* ms);
+/* per-stage device times of the last mc_count_* call, milliseconds: [0]=parse [1]=extract+count [2]=grow/rehash */
+int mc_ctx_stage_ms(mc_ctx* ctx, float* ms3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MC_B200_H */

@@ -1,0 +1,176 @@
+// Context, device-memory helpers, CUDA-event timing and the synthetic workload generator kernel.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mc_synth.h"
+#include "mc_common.cuh"
+
+extern "C" int mc_ctx_create(int device, mc_ctx** out) {
+    try {
+        if (!out) mc_throw(MC_ERR_ARG, "null argument");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            mc_throw(MC_ERR_CUDA, "no CUDA device available (%s): libmcgpu has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        }
+        if (device < 0 || device >= n) mc_throw(MC_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+        MC_CUDA(cudaSetDevice(device));
+        mc_ctx* c = new mc_ctx();
+        c->device = device;
+        cudaDeviceProp prop;
+        MC_CUDA(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            delete c;
+            mc_throw(MC_ERR_CUDA, "device %d is sm_%d%d; libmcgpu is built for sm_100a only", device, prop.major, prop.minor);
+        }
+        MC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        MC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : c->ev) MC_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : c->stage_ev) MC_CUDA(cudaEventCreate(&ev));
+        MC_CUDA(cudaMallocHost(&c->h_pinned_small, 4096));
+        *out = c;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" void mc_ctx_destroy(mc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_chunk[i]);
+        cudaFreeHost(c->h_stage[i]);
+    }
+    for (int i = 0; i < 4; i++) cudaFree(c->d_scratch[i]);
+    cudaFreeHost(c->h_pinned_small);
+    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    for (auto& ev : c->stage_ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+extern "C" int mc_ctx_set_chunk_bytes(mc_ctx* c, size_t bytes) {
+    if (!c || bytes < 4096 || bytes > ((size_t)3 << 30)) {
+        mc_set_error("chunk size must be in [4 KiB, 3 GiB]");
+        return MC_ERR_ARG;
+    }
+    c->chunk_bytes = bytes;
+    return MC_OK;
+}
+extern "C" uint64_t mc_ctx_launches(const mc_ctx* c) { return c ? c->launches : 0; }
+
+void* mc_scratch(mc_ctx* ctx, int slot, size_t bytes) {
+    if (bytes > ctx->d_scratch_cap[slot]) {
+        MC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_scratch[slot]);
+        ctx->d_scratch[slot] = nullptr;
+        ctx->d_scratch_cap[slot] = 0;
+        size_t cap = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&ctx->d_scratch[slot], cap);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            mc_throw(MC_ERR_NOMEM, "cannot allocate %.1f MiB of device scratch", (double)cap / (1 << 20));
+        }
+        ctx->d_scratch_cap[slot] = cap;
+    }
+    return ctx->d_scratch[slot];
+}
+
+#define MC_API_TRY try {
+#define MC_API_END                  \
+    return MC_OK;                   \
+    }                               \
+    catch (const McError& e) {      \
+        mc_set_error(e.what());     \
+        return e.code;              \
+    }
+
+extern "C" int mc_device_alloc(mc_ctx* c, size_t bytes, void** p) {
+    MC_API_TRY
+    if (!c || !p) mc_throw(MC_ERR_ARG, "null argument");
+    MC_CUDA(cudaSetDevice(c->device));
+    MC_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+    MC_API_END
+}
+extern "C" int mc_device_free(mc_ctx* c, void* p) {
+    MC_API_TRY
+    if (!c) mc_throw(MC_ERR_ARG, "null argument");
+    MC_CUDA(cudaSetDevice(c->device));
+    MC_CUDA(cudaStreamSynchronize(c->stream));
+    MC_CUDA(cudaFree(p));
+    MC_API_END
+}
+extern "C" int mc_memcpy_d2h(mc_ctx* c, void* dst, const void* src, size_t bytes) {
+    MC_API_TRY
+    MC_CUDA(cudaSetDevice(c->device));
+    MC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MC_CUDA(cudaStreamSynchronize(c->stream));
+    MC_API_END
+}
+extern "C" int mc_memcpy_h2d(mc_ctx* c, void* dst, const void* src, size_t bytes) {
+    MC_API_TRY
+    MC_CUDA(cudaSetDevice(c->device));
+    MC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    MC_CUDA(cudaStreamSynchronize(c->stream));
+    MC_API_END
+}
+extern "C" int mc_ctx_sync(mc_ctx* c) {
+    MC_API_TRY
+    MC_CUDA(cudaSetDevice(c->device));
+    MC_CUDA(cudaStreamSynchronize(c->stream));
+    MC_CUDA(cudaStreamSynchronize(c->copy_stream));
+    MC_API_END
+}
+extern "C" int mc_event_record(mc_ctx* c, int slot) {
+    MC_API_TRY
+    if (slot < 0 || slot >= 16) mc_throw(MC_ERR_ARG, "event slot out of range");
+    MC_CUDA(cudaEventRecord(c->ev[slot], c->stream));
+    MC_API_END
+}
+extern "C" int mc_event_elapsed_ms(mc_ctx* c, int a, int b, float* ms) {
+    MC_API_TRY
+    if (a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) mc_throw(MC_ERR_ARG, "bad event slot");
+    MC_CUDA(cudaEventSynchronize(c->ev[b]));
+    MC_CUDA(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+    MC_API_END
+}
+extern "C" int mc_ctx_stage_ms(mc_ctx* c, float* ms3) {
+    MC_API_TRY
+    if (!c || !ms3) mc_throw(MC_ERR_ARG, "null argument");
+    for (int i = 0; i < 3; i++) ms3[i] = c->stage_ms[i];
+    MC_API_END
+}
+
+// --------------------------------------------------------------------------------------------
+// synthetic reads on the device (bench/test utility; twin of oracle/mc_synth_cpu.cpp)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_synth(const mc_synth_params* __restrict__ p, uint64_t first, uint64_t count, uint8_t* out) {
+    const uint32_t rb = mc_synth_record_bytes(p);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        mc_synth_write_record(p, first + i, out + i * rb);
+}
+
+extern "C" int mc_synth_generate_device(mc_ctx* c, const void* params, size_t params_size, uint64_t first, uint64_t count, void* d_out) {
+    MC_API_TRY
+    if (!c || !params || !d_out) mc_throw(MC_ERR_ARG, "null argument");
+    if (params_size != sizeof(mc_synth_params)) mc_throw(MC_ERR_ARG, "mc_synth_params size mismatch (%zu vs %zu)", params_size, sizeof(mc_synth_params));
+    MC_CUDA(cudaSetDevice(c->device));
+    mc_synth_params* d_p;
+    MC_CUDA(cudaMalloc(&d_p, sizeof(mc_synth_params)));
+    MC_CUDA(cudaMemcpyAsync(d_p, params, sizeof(mc_synth_params), cudaMemcpyHostToDevice, c->stream));
+    uint64_t blocks = (count + 127) / 128;
+    if (blocks > (uint64_t)c->sm_count * 32) blocks = (uint64_t)c->sm_count * 32;
+    if (blocks < 1) blocks = 1;
+    k_synth<<<(int)blocks, 128, 0, c->stream>>>(d_p, first, count, (uint8_t*)d_out);
+    MC_CUDA(cudaGetLastError());
+    MC_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_p);
+    MC_API_END
+}

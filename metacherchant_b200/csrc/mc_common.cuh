@@ -1,0 +1,251 @@
+// Shared device/host definitions of libmcgpu (sm_100a).  See include/mc_b200.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/mc_b200.h"
+
+// --------------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------------
+struct McError : std::runtime_error {
+    int code;
+    McError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] void mc_throw(int code, const char* fmt, ...);
+void mc_set_error(const std::string& msg);
+
+#define MC_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            mc_throw(_e == cudaErrorMemoryAllocation ? MC_ERR_NOMEM : MC_ERR_CUDA, "CUDA error %s at %s:%d: %s", \
+                     cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e));                 \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------
+// k-mer arithmetic (2-bit, A0 G1 C2 T3, first base most significant)
+// --------------------------------------------------------------------------------------------
+// ITMO!/utils/KmerUtils.java:12-22 restated: reverse the 2-bit groups, complement, align.
+__host__ __device__ __forceinline__ uint64_t mc_revcomp(uint64_t x, int k) {
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);                                                                       // reverse all 64 bits
+    x = ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);           // un-reverse inside each pair
+#else
+    x = ((x & 0x3333333333333333ULL) << 2) | ((x & 0xccccccccccccccccULL) >> 2);
+    x = ((x & 0x0f0f0f0f0f0f0f0fULL) << 4) | ((x & 0xf0f0f0f0f0f0f0f0ULL) >> 4);
+    x = ((x & 0x00ff00ff00ff00ffULL) << 8) | ((x & 0xff00ff00ff00ff00ULL) >> 8);
+    x = ((x & 0x0000ffff0000ffffULL) << 16) | ((x & 0xffff0000ffff0000ULL) >> 16);
+    x = (x << 32) | (x >> 32);
+#endif
+    return (~x) >> (64 - 2 * k);
+}
+__host__ __device__ __forceinline__ uint64_t mc_canonical(uint64_t fw, int k) {
+    uint64_t rc = mc_revcomp(fw, k);
+    return fw < rc ? fw : rc;   // 2k <= 62 bits: unsigned == Java's signed Math.min
+}
+
+// nucleotide code of an input byte: 0..3, 4 = N/n (and '.' in FASTQ mode, decided by the caller), 5 = invalid
+__host__ __device__ __forceinline__ int mc_nuc_code(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'G': case 'g': return 1;
+        case 'C': case 'c': return 2;
+        case 'T': case 't': return 3;
+        case 'N': case 'n': return 4;
+        default: return 5;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// The count table (replaces BigLong2ShortHashMap).
+//
+// key -> h = mix62(key), a BIJECTION on 62-bit values, so (bucket, tag) identifies the key and the key
+// itself is never stored (quotienting).  Layout in HBM: nb = 2^q buckets of 4 x u64 (one 32-byte sector).
+//   h (62 bits) = [ shard : shard_bits | bucket : q | tag : tag_bits ]
+//   slot word   = [ tag : <=41 | disp : 3 | count : 20 ]      0 = empty (count >= 1 for live slots)
+// disp = how many buckets past its home bucket the entry sits (linear probing over <= 8 buckets); the
+// rare entry that finds 8 full buckets goes to a small full-key stash.  count saturates at 32767
+// (NumUtils.addAndBound, ITMO!/utils/NumUtils.java:21-26): an update reads the word, and only adds
+// while count < 32767; concurrent adders can overshoot by at most the number of resident threads
+// (< 2^19), which 20 bits absorb; readers clamp to 32767.
+// --------------------------------------------------------------------------------------------
+#define MC_COUNT_BITS 20
+#define MC_DISP_BITS 3
+#define MC_MAX_DISP 8
+#define MC_COUNT_MASK ((1ULL << MC_COUNT_BITS) - 1)
+#define MC_TAG_SHIFT (MC_COUNT_BITS + MC_DISP_BITS)
+#define MC_MAX_TAG_BITS (64 - MC_TAG_SHIFT)   // 41
+#define MC_SAT 32767u
+#define MC_M62 ((1ULL << 62) - 1)
+#define MC_HASH_SENTINEL 0xFFFFFFFFFFFFFFFFULL   // never a valid 62-bit hash
+
+#define MC_MIX_C1 0x1E3779B97F4A7C15ULL   // odd, < 2^62
+#define MC_MIX_C2 0x3F58476D1CE4E5B9ULL   // odd, < 2^62
+
+__host__ __device__ __forceinline__ uint64_t mc_mix62(uint64_t x) {
+    x ^= x >> 31;
+    x = (x * MC_MIX_C1) & MC_M62;
+    x ^= x >> 29;
+    x = (x * MC_MIX_C2) & MC_M62;
+    x ^= x >> 32;
+    return x;
+}
+uint64_t mc_unmix62(uint64_t h);   // host + device versions in mc_table.cu
+__device__ uint64_t mc_unmix62_dev(uint64_t h);
+
+struct McTableDev {
+    uint64_t* slots;          // nb * 4 words
+    uint64_t nb_mask;         // nb - 1
+    int q;                    // log2(nb)
+    int tag_bits;             // 62 - shard_bits - q  (<= 41)
+    int shard_bits;
+    uint64_t tag_mask;
+    uint64_t* stash_keys;     // hashed key + 1 (0 = empty), stash_mask + 1 entries
+    uint32_t* stash_counts;
+    uint32_t stash_mask;
+    unsigned long long* counters;   // [0] distinct keys, [1] stash entries, [2] reads, [3] runs, [4] bases, [5] kmers
+    unsigned int* flags;            // bit 0: stash full (table overflow)
+};
+enum { MC_CNT_KEYS = 0, MC_CNT_STASH = 1, MC_CNT_READS = 2, MC_CNT_RUNS = 3, MC_CNT_BASES = 4, MC_CNT_KMERS = 5, MC_CNT_N = 8 };
+#define MC_FLAG_OVERFLOW 1u
+
+__device__ __forceinline__ void mc_load_bucket(const uint64_t* p, uint64_t w[4]) {
+    // one 32-byte sector, straight from L2 (atomics live there): LDG.E.256
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+}
+
+__device__ __forceinline__ bool mc_stash_add(const McTableDev& t, uint64_t h, uint32_t inc) {
+    uint64_t want = h + 1;
+    uint32_t pos = (uint32_t)(h * 0x9E3779B97F4A7C15ULL >> 40) & t.stash_mask;
+    for (uint32_t probe = 0; probe <= t.stash_mask; probe++, pos = (pos + 1) & t.stash_mask) {
+        uint64_t cur = atomicCAS((unsigned long long*)&t.stash_keys[pos], 0ULL, (unsigned long long)want);
+        if (cur == 0 || cur == want) {
+            if (cur == 0) atomicAdd(&t.counters[MC_CNT_STASH], 1ULL);
+            uint32_t old = atomicAdd(&t.stash_counts[pos], inc);
+            if (old > 0x7FFFFFFFu - inc) atomicSub(&t.stash_counts[pos], inc);   // keep far away from wrap
+            return cur == 0;
+        }
+    }
+    atomicOr(t.flags, MC_FLAG_OVERFLOW);
+    return false;
+}
+__device__ __forceinline__ int mc_stash_get(const McTableDev& t, uint64_t h) {
+    uint64_t want = h + 1;
+    uint32_t pos = (uint32_t)(h * 0x9E3779B97F4A7C15ULL >> 40) & t.stash_mask;
+    for (uint32_t probe = 0; probe <= t.stash_mask; probe++, pos = (pos + 1) & t.stash_mask) {
+        uint64_t cur = __ldcg(&t.stash_keys[pos]);
+        if (cur == 0) return -1;
+        if (cur == want) {
+            uint32_t c = __ldcg(&t.stash_counts[pos]);
+            return c > MC_SAT ? (int)MC_SAT : (int)c;
+        }
+    }
+    return -1;
+}
+
+// Adds `inc` (1 on the hot path) to the count of hashed key h (shard bits already stripped by the caller's
+// mask inside).  Returns true when the key was new.  Lock-free: slots only ever go empty -> occupied and the
+// tag|disp part is immutable, so probing in a fixed order and resolving stale "empty" reads through
+// atomicCAS never creates a duplicate.
+__device__ __forceinline__ bool mc_table_add(const McTableDev& t, uint64_t h, uint32_t inc) {
+    const uint64_t hl = h & ((1ULL << (62 - t.shard_bits)) - 1);
+    const uint64_t tag = hl & t.tag_mask;
+    const uint64_t b0 = hl >> t.tag_bits;
+#pragma unroll 1
+    for (uint32_t d = 0; d < MC_MAX_DISP; d++) {
+        const uint64_t b = (b0 + d) & t.nb_mask;
+        uint64_t* bucket = t.slots + b * 4;
+        uint64_t w[4];
+        mc_load_bucket(bucket, w);
+        const uint64_t want = (tag << MC_TAG_SHIFT) | ((uint64_t)d << MC_COUNT_BITS);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            uint64_t cur = w[s];
+            if (cur == 0) {
+                cur = atomicCAS((unsigned long long*)&bucket[s], 0ULL, (unsigned long long)(want | inc));
+                if (cur == 0) return true;   // claimed: new key
+            }
+            if ((cur >> MC_COUNT_BITS) == (want >> MC_COUNT_BITS)) {
+                if (inc == 1) {
+                    if ((cur & MC_COUNT_MASK) < MC_SAT) atomicAdd((unsigned long long*)&bucket[s], 1ULL);
+                } else {
+                    // rare path (add_pairs, rehash): saturating CAS loop
+                    while ((cur & MC_COUNT_MASK) < MC_SAT) {
+                        uint64_t c = (cur & MC_COUNT_MASK) + inc;
+                        if (c > MC_SAT) c = MC_SAT;
+                        uint64_t nv = (cur & ~MC_COUNT_MASK) | c;
+                        uint64_t seen = atomicCAS((unsigned long long*)&bucket[s], (unsigned long long)cur, (unsigned long long)nv);
+                        if (seen == cur) break;
+                        cur = seen;
+                    }
+                }
+                return false;
+            }
+        }
+    }
+    return mc_stash_add(t, hl, inc);
+}
+
+// count of hashed key h clamped to 32767, or -1 when absent (Long2ShortHashMap.get)
+__device__ __forceinline__ int mc_table_lookup(const McTableDev& t, uint64_t h) {
+    const uint64_t hl = h & ((1ULL << (62 - t.shard_bits)) - 1);
+    const uint64_t tag = hl & t.tag_mask;
+    const uint64_t b0 = hl >> t.tag_bits;
+#pragma unroll 1
+    for (uint32_t d = 0; d < MC_MAX_DISP; d++) {
+        const uint64_t b = (b0 + d) & t.nb_mask;
+        uint64_t w[4];
+        mc_load_bucket(t.slots + b * 4, w);
+        const uint64_t want = ((tag << MC_TAG_SHIFT) | ((uint64_t)d << MC_COUNT_BITS)) >> MC_COUNT_BITS;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (w[s] == 0) return -1;   // an empty slot ends the probe sequence (no deletions)
+            if ((w[s] >> MC_COUNT_BITS) == want) {
+                uint32_t c = (uint32_t)(w[s] & MC_COUNT_MASK);
+                return c > MC_SAT ? (int)MC_SAT : (int)c;
+            }
+        }
+    }
+    return mc_stash_get(t, hl);
+}
+
+// --------------------------------------------------------------------------------------------
+// host-side objects behind the opaque handles
+// --------------------------------------------------------------------------------------------
+struct mc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    cudaEvent_t stage_ev[8] = {};
+    size_t chunk_bytes = (size_t)256 << 20;
+    uint64_t launches = 0;
+    float stage_ms[3] = {0, 0, 0};
+    int sm_count = 148;
+    // reusable device scratch for the parser (grown on demand)
+    void* d_chunk[2] = {nullptr, nullptr};
+    size_t d_chunk_cap[2] = {0, 0};
+    void* h_stage[2] = {nullptr, nullptr};
+    size_t h_stage_cap[2] = {0, 0};
+    void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // slot 0: parser arrays, 1: tile counts + header, 2: extract keys, 3: misc
+    size_t d_scratch_cap[4] = {0, 0, 0, 0};
+    void* h_pinned_small = nullptr;   // 4 KiB pinned for small read-backs
+};
+
+struct mc_table {
+    mc_ctx* ctx = nullptr;
+    int k = 0;
+    uint32_t shard_id = 0;   // this table owns hashes whose top dev.shard_bits bits equal shard_id
+    McTableDev dev{};
+    uint64_t nb = 0;
+    uint64_t capacity_slots() const { return nb * 4; }
+};
+
+// kernels / host helpers shared across translation units
+void mc_table_reserve(mc_table* t, uint64_t additional_keys_upper_bound);   // grow (rehash) until it fits
+uint64_t mc_table_keys(const mc_table* t);                                  // synchronising read of the key counter
+void* mc_scratch(mc_ctx* ctx, int slot, size_t bytes);                      // grows ctx->d_scratch[slot]; contents are lost on growth
+#define MC_LAUNCH(ctx) ((ctx)->launches++)
