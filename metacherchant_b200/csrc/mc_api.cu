@@ -1,5 +1,6 @@
 // Context, device-memory helpers, CUDA-event timing and the synthetic workload generator kernel.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mc_synth.h"
@@ -24,6 +25,15 @@ extern "C" int mc_ctx_create(int device, mc_ctx** out) {
         if (prop.major < 10) {
             delete c;
             mc_throw(MC_ERR_CUDA, "device %d is sm_%d%d; libmcgpu is built for sm_100a only", device, prop.major, prop.minor);
+        }
+        // The count table is probed one 32-byte sector at a time at random addresses.  With the default L2 fetch
+        // granularity every miss pulls a whole 128-byte line from HBM (measured: 4 DRAM sectors per probe, ncu
+        // profiles/r1a); ask for sector-sized fills instead.  MC_L2_FETCH=32|64|128 overrides (for experiments).
+        {
+            size_t gran = 32;
+            if (const char* e = getenv("MC_L2_FETCH")) gran = (size_t)atoi(e);
+            if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+            cudaGetLastError();
         }
         MC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         MC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
