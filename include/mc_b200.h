@@ -106,6 +106,9 @@ int mc_bfs(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, 
 /* the environment of one target as (ASCII-canonical k-mer packed 2-bit, count), in graph.txt order */
 int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
                  int both_dirs, uint64_t* kmers, int32_t* counts, size_t cap, size_t* n);
+/* stage D alone (createPicture, OneSequenceCalculator.java:326-339) from an environment file with "KMER COUNT" lines
+ * (DeBruijnGraphUtils.loadGraph): writes the same six files under out_dir.  target_seq may be "" (no gene node). */
+int mc_env_from_graph_txt(mc_ctx* ctx, const char* graph_txt, const char* target_seq, int k, int chunk_len, const char* out_dir);
 /* FASTA target loader (src/io/RichFastaReader.java:38-76 + DnaQ(str,0).toString()): returns a handle to iterate */
 typedef struct mc_targets mc_targets;
 int mc_targets_load(const char* fasta_path, mc_targets** out);

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mc_env_find": (i32, [vp, vp, C.POINTER(cp), C.POINTER(cp), i32, i32, i32, i64, i64, i32, i32, cp, C.POINTER(i32)]),
     "mc_bfs": (i32, [vp, vp, cp, i32, i32, i64, i64, i32, vp, vp, vp, sz, C.POINTER(sz)]),
     "mc_env_kmers": (i32, [vp, vp, cp, i32, i32, i64, i64, i32, vp, vp, sz, C.POINTER(sz)]),
+    "mc_env_from_graph_txt": (i32, [vp, cp, cp, i32, i32, cp]),
     "mc_targets_load": (i32, [cp, C.POINTER(vp)]),
     "mc_targets_count": (i32, [vp]),
     "mc_targets_seq": (cp, [vp, i32]),

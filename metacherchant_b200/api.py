@@ -112,6 +112,25 @@ class Context:
                                    -1 if max_radius is None else max_radius, int(both_dirs), chunk_len, os.fspath(out_dir).encode(), found))
         return [bool(x) for x in found]
 
+    def env_from_graph_txt(self, graph_txt, target_seq, k, chunk_len, out_dir):
+        check(self.lib.mc_env_from_graph_txt(self.h, os.fspath(graph_txt).encode(), target_seq.encode(), k, chunk_len, os.fspath(out_dir).encode()))
+
+    def load_targets(self, fasta_path):
+        """RichFastaReader: [(name, sequence)] of a target FASTA."""
+        h = C.c_void_p()
+        check(self.lib.mc_targets_load(os.fspath(fasta_path).encode(), C.byref(h)))
+        try:
+            n = self.lib.mc_targets_count(h)
+            out = []
+            for i in range(n):
+                name = self.lib.mc_targets_name(h, i)
+                if name is None:
+                    raise McError(-4, f"target {i} has no header entry (IndexOutOfBoundsException in the reference)")
+                out.append((name.decode(), self.lib.mc_targets_seq(h, i).decode()))
+            return out
+        finally:
+            self.lib.mc_targets_free(h)
+
     def multi_environment(self, env_paths, seq_fasta, gene_id, out_dir):
         arr = (C.c_char_p * len(env_paths))(*[os.fspath(p).encode() for p in env_paths])
         check(self.lib.mc_env_multi(self.h, arr, len(env_paths), os.fspath(seq_fasta).encode(), gene_id, os.fspath(out_dir).encode()))

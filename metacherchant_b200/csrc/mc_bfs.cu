@@ -1,0 +1,302 @@
+// K5: the BFS that grows an environment from the target's k-mers.
+//
+// Restates OneSequenceCalculator.runBfs (src/algo/OneSequenceCalculator.java:154-220), getNeighborsByDir (:222-239),
+// TerminationMode.allowsAddition (src/algo/TerminationMode.java:31-47) and StringUtils.{left,right,all}Neighbors
+// (src/utils/StringUtils.java:8-32) as a batch-synchronous frontier expansion, one persistent CTA per (target, pass):
+//
+//   * the queue holds ORIENTED k-mers (2-bit); the visited set is keyed by the oriented k-mer
+//     (distanceToKmer is a HashMap<String,..> over oriented strings, :156,165,207);
+//   * a CTA step takes the next P queue entries, generates their 4 (or 8) neighbours in the reference's order
+//     A,G,C,T (dir 0: L[A],R[A],L[G],R[G],...), probes the count table with the CANONICAL key (getKmerKey :89-96),
+//     drops those below --coverage or beyond --maxradius, and orders the survivors by (parent queue index, slot);
+//   * first occurrence wins (atomicMin of the candidate rank on the visited slot), a block scan gives every winner its
+//     queue position, and winners are accepted while |visited| < --maxkmers.
+// This is the sequential FIFO rule, batch by batch: same visited set AND same discovery order, also when --maxkmers
+// truncates (simulated against the literal loop in tests/test_oracle_vs_pyref.py::test_level_synchronous_rule_equals_fifo_rule).
+// Once a candidate is refused for the budget nothing can ever be added again (|visited| never shrinks), so the pass ends.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mc_common.cuh"
+#include "mc_env.hpp"
+
+#define BFS_THREADS 256
+#define BFS_OVERFLOW 0xFFFFFFFFu
+
+struct McBfsJobDev {
+    const uint8_t* seq;    // target as nucleotide codes (A0 G1 C2 T3), one byte per base
+    uint32_t seq_len;
+    int dir;               // -1 left, +1 right, 0 both
+    uint64_t* queue;       // oriented k-mers in discovery order
+    int32_t* dist;
+    int16_t* count;
+    uint64_t* vis_keys;    // open addressing: oriented k-mer + 1 (0 = empty)
+    uint32_t* vis_val;     // < 2^31: queue index; >= 2^31: claim of candidate (val & 0x7FFFFFFF) in the running step; ~0: untouched
+    uint32_t cap;          // queue capacity
+    uint32_t vis_mask;
+    uint32_t* n_out;       // visited count, or BFS_OVERFLOW when cap was too small
+};
+
+__device__ __forceinline__ uint32_t vis_find_or_claim(const McBfsJobDev& j, uint64_t kmer, uint32_t code) {
+    const uint64_t want = kmer + 1;
+    uint32_t pos = (uint32_t)(mc_mix62(kmer) >> 20) & j.vis_mask;
+    while (true) {
+        uint64_t cur = atomicCAS((unsigned long long*)&j.vis_keys[pos], 0ULL, (unsigned long long)want);
+        if (cur == 0 || cur == want) {
+            atomicMin(&j.vis_val[pos], code);
+            return pos;
+        }
+        pos = (pos + 1) & j.vis_mask;   // table is at most half full: terminates
+    }
+}
+
+// block-wide exclusive scan of a 0/1 flag in thread order; returns my offset, total in *total
+__device__ __forceinline__ uint32_t block_scan_flag(bool flag, uint32_t* total) {
+    __shared__ uint32_t s_w[BFS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < BFS_THREADS / 32; i++) {
+        uint32_t c = s_w[i];
+        if (i < warp) off += c;
+        tot += c;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + __popc(m & ((1u << lane) - 1));
+}
+
+__global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t shard_id, int k, int min_cov, long long max_kmers, long long max_radius,
+                                                    const McBfsJobDev* __restrict__ jobs) {
+    const McBfsJobDev j = jobs[blockIdx.x];
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    __shared__ uint32_t s_head, s_tail, s_stop;
+    if (threadIdx.x == 0) { s_head = 0; s_tail = 0; s_stop = 0; }
+    __syncthreads();
+    (void)shard_id;
+
+    // ---- seeds: every window of the target whose count >= min_cov, in order, first occurrence only (:160-167) ----
+    const uint32_t n_win = j.seq_len >= (uint32_t)k ? j.seq_len - k + 1 : 0;
+    for (uint32_t base = 0; base < n_win; base += BFS_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        bool cand = false;
+        uint64_t kmer = 0;
+        int c = -1;
+        uint32_t slot = 0;
+        if (i < n_win) {
+            for (int t = 0; t < k; t++) kmer = (kmer << 2) | (uint64_t)(j.seq[i + t] & 3);
+            c = mc_table_lookup(table, mc_mix62(mc_canonical(kmer, k)));
+            cand = c >= min_cov;
+        }
+        if (cand) slot = vis_find_or_claim(j, kmer, 0x80000000u | threadIdx.x);
+        __syncthreads();
+        bool win = cand && __ldcg(&j.vis_val[slot]) == (0x80000000u | threadIdx.x);
+        uint32_t total;
+        uint32_t pos = block_scan_flag(win, &total);
+        uint32_t tail = s_tail;
+        if (tail + total > j.cap) {
+            if (threadIdx.x == 0) *j.n_out = BFS_OVERFLOW;
+            return;
+        }
+        if (win) {
+            j.queue[tail + pos] = kmer;
+            j.dist[tail + pos] = 0;
+            j.count[tail + pos] = (int16_t)c;
+            j.vis_val[slot] = tail + pos;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_tail = tail + total;
+        __syncthreads();
+    }
+
+    // ---- queue loop (:197-213) ----------------------------------------------------------------------------------
+    const int NB = j.dir == 0 ? 8 : 4;
+    const uint32_t PARENTS = BFS_THREADS / NB;
+    while (true) {
+        const uint32_t head = s_head, tail = s_tail;
+        if (head >= tail || s_stop) break;
+        const uint32_t P = min(tail - head, PARENTS);
+        const uint32_t t = threadIdx.x;
+        bool cand = false;
+        uint64_t nb = 0;
+        int c = -1;
+        int32_t nd = 0;
+        uint32_t slot = 0;
+        if (t < P * NB) {
+            const uint32_t pi = head + t / NB, s = t % NB;
+            const uint64_t kmer = j.queue[pi];
+            nd = j.dist[pi] + 1;
+            const uint64_t nuc = (NB == 8) ? (s >> 1) : s;
+            const bool left = (j.dir == -1) || (j.dir == 0 && (s & 1) == 0);
+            nb = left ? ((nuc << (2 * k - 2)) | (kmer >> 2)) : (((kmer << 2) | nuc) & kmask);
+            if (max_radius < 0 || nd <= max_radius) {
+                c = mc_table_lookup(table, mc_mix62(mc_canonical(nb, k)));
+                cand = c >= min_cov;
+            }
+        }
+        if (cand) slot = vis_find_or_claim(j, nb, 0x80000000u | t);
+        __syncthreads();
+        bool win = cand && __ldcg(&j.vis_val[slot]) == (0x80000000u | t);
+        uint32_t total;
+        uint32_t pos = block_scan_flag(win, &total);
+        uint32_t accept = total;
+        bool stop = false;
+        if (max_kmers >= 0) {
+            long long room = max_kmers - (long long)tail;   // allowsAddition: refuse when distanceToKmer.size() >= threshold
+            if (room < 0) room = 0;
+            if ((long long)total > room) { accept = (uint32_t)room; stop = true; }
+        }
+        if (tail + accept > j.cap) {
+            if (threadIdx.x == 0) *j.n_out = BFS_OVERFLOW;
+            return;
+        }
+        if (win && pos < accept) {
+            j.queue[tail + pos] = nb;
+            j.dist[tail + pos] = nd;
+            j.count[tail + pos] = (int16_t)c;
+            j.vis_val[slot] = tail + pos;
+        }
+        // all remaining parents are at least as far: once a whole step is beyond the radius the pass is over
+        bool radius_done = max_radius >= 0 && (long long)j.dist[head] + 1 > max_radius;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_head = head + P;
+            s_tail = tail + accept;
+            if (stop || radius_done) s_stop = 1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *j.n_out = s_tail;
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+std::vector<uint8_t> mc_codes_from_target(const std::string& seq) {
+    // DnaQ(str, 0) (ITMO!/dna/DnaQ.java:21-30): N, n, '.' become nucleotide 0; other chars go through DnaTools.fromChar
+    std::vector<uint8_t> codes(seq.size());
+    for (size_t i = 0; i < seq.size(); i++) {
+        char ch = seq[i];
+        if (ch == 'N' || ch == 'n' || ch == '.') { codes[i] = 0; continue; }
+        int c = mc_nuc_code((uint8_t)ch);
+        if (c >= 4) mc_throw(MC_ERR_FORMAT, "Incorrect nucleotide char: \"%c\" in a target sequence", ch);
+        codes[i] = (uint8_t)c;
+    }
+    return codes;
+}
+
+static uint32_t pow2_at_least(uint64_t x) {
+    uint32_t p = 1024;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
+                       const std::vector<McBfsRequest>& reqs, std::vector<McBfsResult>& results) {
+    if (max_kmers < 0 && max_radius < 0) mc_throw(MC_ERR_ARG, "At least one of --maxkmers and --maxradius parameters should be set");
+    if (k != t->k) mc_throw(MC_ERR_ARG, "k (%d) differs from the table's k (%d)", k, t->k);
+    MC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = reqs.size();
+    results.assign(n, McBfsResult{});
+    std::vector<uint32_t> caps(n);
+    std::vector<size_t> todo(n);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t seeds = reqs[i].codes.size() >= (size_t)k ? reqs[i].codes.size() - k + 1 : 0;
+        uint64_t cap = max_kmers >= 0 ? seeds + (uint64_t)max_kmers + 8 : std::max<uint64_t>(seeds * 2 + 1024, 1u << 16);
+        if (cap > 0x3FFFFFFFull) mc_throw(MC_ERR_ARG, "--maxkmers too large for the GPU path");
+        caps[i] = (uint32_t)cap;
+        todo[i] = i;
+    }
+    while (!todo.empty()) {
+        // one allocation for the whole wave
+        std::vector<McBfsJobDev> jobs(todo.size());
+        size_t bytes = 0;
+        auto take = [&](size_t sz) { size_t o = bytes; bytes += (sz + 255) / 256 * 256; return o; };
+        struct Off { size_t seq, queue, dist, count, vk, vv, nout; uint32_t vis_cap; };
+        std::vector<Off> offs(todo.size());
+        for (size_t w = 0; w < todo.size(); w++) {
+            size_t i = todo[w];
+            uint32_t cap = caps[i];
+            uint32_t vis_cap = pow2_at_least((uint64_t)cap * 2);
+            offs[w] = Off{take(reqs[i].codes.size() + 1), take((size_t)cap * 8), take((size_t)cap * 4), take((size_t)cap * 2),
+                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(4), vis_cap};
+        }
+        size_t jobs_off = take(jobs.size() * sizeof(McBfsJobDev));
+        uint8_t* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); mc_throw(MC_ERR_NOMEM, "cannot allocate %.1f MiB of BFS work memory", (double)bytes / (1 << 20)); }
+        for (size_t w = 0; w < todo.size(); w++) {
+            size_t i = todo[w];
+            const Off& o = offs[w];
+            if (!reqs[i].codes.empty())
+                MC_CUDA(cudaMemcpyAsync(d + o.seq, reqs[i].codes.data(), reqs[i].codes.size(), cudaMemcpyHostToDevice, st));
+            MC_CUDA(cudaMemsetAsync(d + o.vk, 0, (size_t)o.vis_cap * 8, st));
+            MC_CUDA(cudaMemsetAsync(d + o.vv, 0xFF, (size_t)o.vis_cap * 4, st));
+            MC_CUDA(cudaMemsetAsync(d + o.nout, 0, 4, st));
+            jobs[w] = McBfsJobDev{d + o.seq, (uint32_t)reqs[i].codes.size(), reqs[i].dir, (uint64_t*)(d + o.queue), (int32_t*)(d + o.dist),
+                                  (int16_t*)(d + o.count), (uint64_t*)(d + o.vk), (uint32_t*)(d + o.vv), caps[i], o.vis_cap - 1,
+                                  (uint32_t*)(d + o.nout)};
+        }
+        MC_CUDA(cudaMemcpyAsync(d + jobs_off, jobs.data(), jobs.size() * sizeof(McBfsJobDev), cudaMemcpyHostToDevice, st));
+        k_bfs<<<(unsigned)jobs.size(), BFS_THREADS, 0, st>>>(t->dev, t->shard_id, k, min_cov, (long long)max_kmers, (long long)max_radius,
+                                                            (const McBfsJobDev*)(d + jobs_off));
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        std::vector<uint32_t> n_out(todo.size());
+        for (size_t w = 0; w < todo.size(); w++)
+            MC_CUDA(cudaMemcpyAsync(&n_out[w], d + offs[w].nout, 4, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        std::vector<size_t> again;
+        for (size_t w = 0; w < todo.size(); w++) {
+            size_t i = todo[w];
+            if (n_out[w] == BFS_OVERFLOW) {
+                if (caps[i] > 0x1FFFFFFFu) { cudaFree(d); mc_throw(MC_ERR_NOMEM, "environment larger than 2^29 k-mers"); }
+                caps[i] *= 4;
+                again.push_back(i);
+                continue;
+            }
+            McBfsResult& r = results[i];
+            r.kmers.resize(n_out[w]);
+            r.dist.resize(n_out[w]);
+            r.counts.resize(n_out[w]);
+            if (n_out[w]) {
+                MC_CUDA(cudaMemcpyAsync(r.kmers.data(), d + offs[w].queue, (size_t)n_out[w] * 8, cudaMemcpyDeviceToHost, st));
+                MC_CUDA(cudaMemcpyAsync(r.dist.data(), d + offs[w].dist, (size_t)n_out[w] * 4, cudaMemcpyDeviceToHost, st));
+                MC_CUDA(cudaMemcpyAsync(r.counts.data(), d + offs[w].count, (size_t)n_out[w] * 2, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        MC_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d);
+        todo.swap(again);
+    }
+}
+
+extern "C" int mc_bfs(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int dir,
+                      uint64_t* kmers, int32_t* dist, int16_t* counts, size_t cap, size_t* n) {
+    try {
+        if (!ctx || !t || !seq || !n) mc_throw(MC_ERR_ARG, "null argument");
+        if (dir < -1 || dir > 1) mc_throw(MC_ERR_ARG, "dir must be -1, 0 or +1");
+        std::vector<McBfsRequest> reqs(1);
+        reqs[0].codes = mc_codes_from_target(seq);
+        reqs[0].dir = dir;
+        std::vector<McBfsResult> res;
+        mc_run_bfs_passes(ctx, t, k, min_cov, max_kmers, max_radius, reqs, res);
+        *n = res[0].kmers.size();
+        if (*n > cap) mc_throw(MC_ERR_CAPACITY, "BFS visited %zu k-mers, room for %zu", *n, cap);
+        for (size_t i = 0; i < *n; i++) {
+            if (kmers) kmers[i] = res[0].kmers[i];
+            if (dist) dist[i] = res[0].dist[i];
+            if (counts) counts[i] = res[0].counts[i];
+        }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}

@@ -1,0 +1,789 @@
+// Seam 3 / Seam 4 host side: target loading, environment assembly in the reference's iteration order, the merge
+// sweep over the device-computed neighbour lists, and the writers (graph.txt/env.txt, seqs.fasta, graph.gfa, tsvs/).
+//
+// What runs where:
+//   device  BFS passes for all targets at once (mc_bfs.cu); node hash, neighbour lists, degrees, gene flags and
+//           chain ranks of every environment (mc_unitig.cu)
+//   host    string formatting, java.util.HashMap iteration order (it fixes node ids and line order of every output),
+//           the O(n) merge sweep over the device's neighbour lists, file writing
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mc_env.hpp"
+
+namespace {
+
+const char NUC[4] = {'A', 'G', 'C', 'T'};   // ITMO!/dna/DnaTools.java:31
+
+std::string kmer_string(uint64_t code, int k) {   // KmerUtils.kmer2String
+    std::string s((size_t)k, 'A');
+    for (int i = 0; i < k; i++) s[(size_t)i] = NUC[(code >> (2 * (k - 1 - i))) & 3];
+    return s;
+}
+uint64_t kmer_code(const std::string& s) {
+    uint64_t r = 0;
+    for (char c : s) r = (r << 2) | (uint64_t)(mc_nuc_code((uint8_t)c) & 3);
+    return r;
+}
+std::string rc_string(const std::string& s) {
+    std::string r(s.size(), 'A');
+    for (size_t i = 0; i < s.size(); i++) {
+        int c = mc_nuc_code((uint8_t)s[i]);
+        if (c >= 4) mc_throw(MC_ERR_FORMAT, "Incorrect nucleotide char: \"%c\"", s[i]);
+        r[s.size() - 1 - i] = NUC[c ^ 3];
+    }
+    return r;
+}
+// StringUtils.normalizeDna (src/utils/StringUtils.java:34-41): ASCII order, A < C < G < T — NOT the 2-bit order
+std::string normalize_dna(const std::string& s) {
+    std::string rc = rc_string(s);
+    return s.compare(rc) < 0 ? s : rc;
+}
+int32_t java_string_hash(const std::string& s) {
+    uint32_t h = 0;
+    for (unsigned char c : s) h = 31u * h + c;
+    return (int32_t)h;
+}
+
+// Iteration order of a java.util.HashMap<String,V> (bucket index, then insertion order inside a bucket; capacity 16
+// doubling at load 0.75; treeified bins not modelled).  Pinned on the reference's committed graph.txt by the tests.
+template <class V>
+struct JavaMap {
+    std::unordered_map<std::string, uint32_t> index;
+    std::vector<std::pair<std::string, V>> entries;
+    void put(const std::string& k, const V& v) {
+        auto it = index.find(k);
+        if (it == index.end()) {
+            index.emplace(k, (uint32_t)entries.size());
+            entries.emplace_back(k, v);
+        } else {
+            entries[it->second].second = v;
+        }
+    }
+    const V* get(const std::string& k) const {
+        auto it = index.find(k);
+        return it == index.end() ? nullptr : &entries[it->second].second;
+    }
+    size_t size() const { return entries.size(); }
+    std::vector<uint32_t> order() const {
+        size_t cap = 16;
+        while ((double)entries.size() > 0.75 * (double)cap) cap <<= 1;
+        std::vector<std::pair<uint32_t, uint32_t>> v(entries.size());
+        for (size_t i = 0; i < entries.size(); i++) {
+            uint32_t h = (uint32_t)java_string_hash(entries[i].first);
+            v[i] = {(h ^ (h >> 16)) & (uint32_t)(cap - 1), (uint32_t)i};
+        }
+        std::stable_sort(v.begin(), v.end(), [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; });
+        std::vector<uint32_t> o(v.size());
+        for (size_t i = 0; i < v.size(); i++) o[i] = v[i].second;
+        return o;
+    }
+};
+
+void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i < path.size(); i++) {
+        cur.push_back(path[i]);
+        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0777);
+    }
+}
+
+// BufferedReader.readLine over a whole file
+std::vector<std::string> read_lines(const std::string& path, const char* what) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) mc_throw(MC_ERR_IO, "%s %s", what, path.c_str());
+    std::string data;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, got);
+    fclose(f);
+    std::vector<std::string> lines;
+    size_t p = 0;
+    while (p < data.size()) {
+        size_t s = p;
+        while (p < data.size() && data[p] != '\n' && data[p] != '\r') p++;
+        lines.emplace_back(data, s, p - s);
+        if (p < data.size()) p += (data[p] == '\r' && p + 1 < data.size() && data[p + 1] == '\n') ? 2 : 1;
+    }
+    return lines;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The merge sweep (doMerge, OneSequenceCalculator.java:434-451 / MultiSequenceCalculator.java:102-137) over the
+// device's neighbour lists.  One ascending sweep does all the work (a node that is alive when visited and has a
+// mergeable start is merged on the spot; the merge conditions are static), the reference's second sweep finds nothing.
+// Sequences are kept as linked lists of original nodes, so a merge is O(1).
+// ------------------------------------------------------------------------------------------------
+struct Graph {
+    int k = 0;
+    uint32_t n2 = 0;
+    std::vector<std::vector<int32_t>> nbrs;   // expanded neighbour lists (palindromes as two ids)
+    std::vector<uint8_t> gene, deleted;
+    std::vector<int32_t> rc;                  // current reverse-complement partner (stale for deleted nodes, like the reference)
+    // A node's sequence is an immutable concatenation tree over the original nodes (leaf v = original node v, id >= n2 =
+    // cat[id - n2]); mergeLabels(a, b) = a + b[k-1:] becomes a new tree node, so assignments behave exactly like the
+    // reference's String assignments (also in the self-referential corner cases) and a merge stays O(1).
+    std::vector<std::pair<int32_t, int32_t>> cat;
+    std::vector<int32_t> seq_id;
+    std::vector<std::string> seq;             // materialised for alive nodes and for the rc partners of alive nodes
+    std::vector<uint64_t> node_code;          // oriented k-mer of every original node
+
+    void build(const McUnitigInput& in, const McUnitigNodes& nodes) {
+        k = in.k;
+        n2 = (uint32_t)in.kmers.size() * 2;
+        nbrs.assign(n2, {});
+        gene = nodes.gene;
+        deleted.assign(n2, 0);
+        rc.resize(n2);
+        seq_id.resize(n2);
+        node_code.resize(n2);
+        for (uint32_t v = 0; v < n2; v++) {
+            rc[v] = (int32_t)(v ^ 1);
+            seq_id[v] = (int32_t)v;
+            node_code[v] = (v & 1) ? mc_revcomp(in.kmers[v >> 1], k) : in.kmers[v >> 1];
+            for (int s = 0; s < 4; s++) {
+                int32_t x = nodes.nbr[4 * (size_t)v + s];
+                if (x < 0) continue;
+                nbrs[v].push_back(x);
+                if (nodes.nbr_pal[v] & (1u << s)) nbrs[v].push_back(x + 1);
+            }
+        }
+    }
+    int32_t concat(int32_t a, int32_t b) {
+        cat.emplace_back(a, b);
+        return (int32_t)(n2 + cat.size() - 1);
+    }
+    void merge(int32_t first_plus, int32_t second_minus) {   // mergeNodes (:312-324), statement by statement
+        int32_t first_minus = rc[first_plus], second_plus = rc[second_minus];
+        int32_t new_seq = concat(seq_id[second_plus], seq_id[first_plus]);
+        int32_t new_seq_rc = concat(seq_id[first_minus], seq_id[second_minus]);
+        seq_id[second_plus] = new_seq;
+        seq_id[first_minus] = new_seq_rc;
+        rc[second_plus] = first_minus;
+        rc[first_minus] = second_plus;
+        deleted[first_plus] = deleted[second_minus] = 1;
+    }
+    void sweep(const std::vector<uint64_t>* colors) {
+        for (uint32_t i = 0; i < n2; i++) {
+            if (deleted[i] || nbrs[i].size() != 1) continue;
+            int32_t other = nbrs[i][0];
+            if (nbrs[other].size() != 1 || gene[i] != gene[other]) continue;
+            if (colors && (*colors)[i >> 1] != (*colors)[(uint32_t)other >> 1]) continue;
+            merge((int32_t)i, other);
+        }
+    }
+    // leaves of a concatenation tree, left to right
+    void leaves(int32_t id, std::vector<int32_t>& out) const {
+        std::vector<int32_t> stack{id};
+        while (!stack.empty()) {
+            int32_t x = stack.back();
+            stack.pop_back();
+            if ((uint32_t)x < n2) { out.push_back(x); continue; }
+            const std::pair<int32_t, int32_t>& c = cat[(uint32_t)x - n2];
+            stack.push_back(c.second);
+            stack.push_back(c.first);
+        }
+    }
+    std::string materialise(int32_t v) const {
+        std::vector<int32_t> lv;
+        leaves(seq_id[v], lv);
+        std::string s = kmer_string(node_code[lv[0]], k);
+        for (size_t i = 1; i < lv.size(); i++) s.push_back(NUC[node_code[lv[i]] & 3]);
+        return s;
+    }
+    void assemble() {
+        seq.assign(n2, std::string());
+        std::vector<uint8_t> need(n2, 0);
+        for (uint32_t v = 0; v < n2; v++)
+            if (!deleted[v]) need[v] = need[(uint32_t)rc[v]] = 1;
+        for (uint32_t v = 0; v < n2; v++)
+            if (need[v]) seq[v] = materialise((int32_t)v);
+    }
+    // original nodes whose k-mers make up node v's sequence, in order
+    std::vector<int32_t> path(int32_t v) const {
+        std::vector<int32_t> lv;
+        leaves(seq_id[v], lv);
+        return lv;
+    }
+    int32_t min_id(int32_t v) const { return std::min(v, rc[v]) + 1; }
+    std::string neighbor_ids(int32_t v) const {   // getNeighborIds (:375-385): TreeSet<Integer>.toString()
+        std::set<int32_t> r;
+        for (int32_t x : nbrs[v]) r.insert(min_id(x));
+        for (int32_t x : nbrs[rc[v]]) r.insert(min_id(x));
+        r.erase(min_id(v));
+        std::string s = "[";
+        bool first = true;
+        for (int32_t x : r) {
+            if (!first) s += ", ";
+            s += std::to_string(x);
+            first = false;
+        }
+        return s + "]";
+    }
+};
+
+std::vector<uint64_t> target_windows(const std::vector<std::string>& targets, int k) {
+    std::vector<uint64_t> w;
+    for (const std::string& t : targets)
+        for (size_t i = 0; i + k <= t.size(); i++) w.push_back(kmer_code(t.substr(i, k)));
+    std::sort(w.begin(), w.end());
+    w.erase(std::unique(w.begin(), w.end()), w.end());
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-environment writers
+// ------------------------------------------------------------------------------------------------
+void write_environment(const JavaMap<int>& subgraph, const std::vector<uint32_t>& ord, const std::string& prefix) {   // printEnvironment (:297-310)
+    mkdirs(prefix);
+    std::string body;
+    body.reserve(ord.size() * 40);
+    for (uint32_t p : ord) {
+        body += subgraph.entries[p].first;
+        body += ' ';
+        body += std::to_string(subgraph.entries[p].second);
+        body += '\n';
+    }
+    for (const char* name : {"/graph.txt", "/env.txt"}) {   // the reference writes graph.txt; README/BASELINE call it env.txt
+        std::ofstream out(prefix + name, std::ios::binary);
+        out << body;
+    }
+}
+
+void write_single_outputs(const Graph& g, const JavaMap<int>& subgraph, int chunk_len, const std::string& prefix) {
+    const int k = g.k;
+    auto node_id = [&](int32_t v) { return std::to_string(g.min_id(v)) + (g.gene[v] ? "_start" : ""); };
+    auto fwd = [&](int32_t v) { return g.seq[v].compare(g.seq[g.rc[v]]) <= 0; };
+    auto cov = [&](const std::string& kmer) -> long {
+        const int* c = subgraph.get(normalize_dna(kmer));
+        if (!c) mc_throw(MC_ERR_FORMAT, "k-mer %s of a unitig is not in the environment", kmer.c_str());
+        return *c;
+    };
+    mkdirs(prefix);
+    {   // outputNodeSequences (:354-373)
+        std::ofstream out(prefix + "/seqs.fasta", std::ios::binary);
+        for (uint32_t v = 0; v < g.n2; v++)
+            if (!g.deleted[v] && (int32_t)v < g.rc[v] && (int)g.seq[v].size() >= chunk_len)
+                out << "> Id" << node_id((int32_t)v) << " Length:" << g.seq[v].size() << " Neighbors:" << g.neighbor_ids((int32_t)v) << "\n" << g.seq[v] << "\n";
+    }
+    {   // GFAWriter.printGraph (src/io/writers/GFAWriter.java:47-99)
+        std::ofstream out(prefix + "/graph.gfa", std::ios::binary);
+        for (uint32_t v = 0; v < g.n2; v++)
+            if (!g.deleted[v] && fwd((int32_t)v)) {
+                const std::string& s = g.seq[v];
+                long coverage = 0;
+                for (size_t i = 0; i + k <= s.size(); i++) coverage += cov(s.substr(i, k));
+                coverage += cov(s.substr(s.size() - k)) * (k - 1);
+                out << "S\t" << node_id((int32_t)v) << "\t" << s << "\tLN:i:" << s.size() << "\tKC:i:" << coverage << (g.gene[v] ? "\tCL:Z:GREEN" : "") << "\n";
+            }
+        for (uint32_t i = 0; i < g.n2; i++)
+            if (!g.deleted[i])
+                for (int32_t j : g.nbrs[i])
+                    if (!g.deleted[j])
+                        out << "L\t" << node_id((int32_t)i) << "\t" << (g.seq[i].compare(g.seq[g.rc[i]]) >= 0 ? "+" : "-") << "\t" << node_id(j) << "\t"
+                            << (fwd(j) ? "+" : "-") << "\t" << (k - 1) << "M\n";
+    }
+    {   // TSVWriter (src/io/writers/TSVWriter.java:27-78)
+        mkdirs(prefix + "/tsvs");
+        auto tsv_id = [&](int32_t v) { return (fwd(v) ? std::to_string(v + 1) : "-" + std::to_string(g.rc[v] + 1)) + (g.gene[v] ? "_start" : ""); };
+        std::ofstream edges(prefix + "/tsvs/edges.tsv", std::ios::binary);
+        edges << "source\ttarget\n";
+        for (uint32_t i = 0; i < g.n2; i++)
+            if (!g.deleted[i])
+                for (int32_t j : g.nbrs[i])
+                    if (!g.deleted[j]) edges << tsv_id(g.rc[i]) << "\t" << tsv_id(j) << "\tpp\n";
+        std::ofstream nodes(prefix + "/tsvs/nodes.tsv", std::ios::binary);
+        nodes << "id\tlength\tseq\n";
+        for (uint32_t v = 0; v < g.n2; v++)
+            if (!g.deleted[v] && fwd((int32_t)v)) nodes << (v + 1) << "\t" << g.seq[v].size() << "\t" << g.seq[v] << "\n";
+    }
+}
+
+// subgraph of one target from its BFS passes: for (kmer : distanceToKmer.keySet()) subgraph.put(normalize(kmer), count) (:217-219,146-148)
+bool build_subgraph(const std::vector<const McBfsResult*>& passes, int k, JavaMap<int>& subgraph) {
+    for (const McBfsResult* r : passes) {
+        if (r->kmers.empty()) return false;   // "fail": no seed k-mer in the reads
+        JavaMap<int> dist;                   // insertion order = discovery order
+        std::vector<std::string> strs(r->kmers.size());
+        for (size_t i = 0; i < r->kmers.size(); i++) {
+            strs[i] = kmer_string(r->kmers[i], k);
+            dist.put(strs[i], (int)i);
+        }
+        for (uint32_t p : dist.order()) subgraph.put(normalize_dna(dist.entries[p].first), (int)r->counts[(size_t)dist.entries[p].second]);
+    }
+    return true;
+}
+
+void unitig_input_from_subgraph(const JavaMap<int>& subgraph, const std::vector<uint32_t>& ord, const std::vector<std::string>& targets, int k,
+                                McUnitigInput& in) {
+    in.k = k;
+    in.kmers.resize(ord.size());
+    in.counts.resize(ord.size());
+    for (size_t i = 0; i < ord.size(); i++) {
+        in.kmers[i] = kmer_code(subgraph.entries[ord[i]].first);
+        in.counts[i] = subgraph.entries[ord[i]].second;
+    }
+    in.gene_windows = target_windows(targets, k);
+}
+
+struct Target {
+    std::string seq, name;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// targets (RichFastaReader.readAll, src/io/RichFastaReader.java:38-76; DnaQ(str,0).toString())
+// ------------------------------------------------------------------------------------------------
+struct mc_targets {
+    std::vector<std::string> dnas, comments;
+};
+
+static std::string dnaq_to_string(const std::string& raw) {
+    std::string s(raw.size(), 'A');
+    for (size_t i = 0; i < raw.size(); i++) {
+        char c = raw[i];
+        if (c == 'N' || c == 'n' || c == '.') { s[i] = 'A'; continue; }
+        int code = mc_nuc_code((uint8_t)c);
+        if (code >= 4) mc_throw(MC_ERR_FORMAT, "Incorrect nucleotide char: \"%c\" in a target sequence", c);
+        s[i] = NUC[code];
+    }
+    return s;
+}
+
+static void load_targets(const std::string& path, mc_targets& t) {
+    std::vector<std::string> lines = read_lines(path, "Could not load sequences from");
+    bool last_comment = true;
+    std::string cur_comment, cur_dna;
+    for (const std::string& line : lines) {
+        if (!line.empty() && (line[0] == '>' || line[0] == ';')) {
+            if (!last_comment) {
+                t.dnas.push_back(dnaq_to_string(cur_dna));
+                cur_dna.clear();
+                cur_comment.clear();
+            }
+            cur_comment += line.substr(1);
+            last_comment = true;
+        } else {
+            if (last_comment) {
+                t.comments.push_back(cur_comment);
+                cur_dna.clear();
+                cur_comment.clear();
+            }
+            cur_dna += line;
+            last_comment = false;
+        }
+    }
+    if (!cur_comment.empty()) t.comments.push_back(cur_comment);
+    if (!cur_dna.empty()) t.dnas.push_back(dnaq_to_string(cur_dna));
+}
+
+extern "C" int mc_targets_load(const char* fasta_path, mc_targets** out) {
+    try {
+        if (!fasta_path || !out) mc_throw(MC_ERR_ARG, "null argument");
+        mc_targets* t = new mc_targets();
+        try {
+            load_targets(fasta_path, *t);
+        } catch (...) {
+            delete t;
+            throw;
+        }
+        *out = t;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+extern "C" int mc_targets_count(const mc_targets* t) { return t ? (int)t->dnas.size() : 0; }
+extern "C" const char* mc_targets_seq(const mc_targets* t, int i) { return (t && i >= 0 && i < (int)t->dnas.size()) ? t->dnas[(size_t)i].c_str() : nullptr; }
+extern "C" const char* mc_targets_name(const mc_targets* t, int i) {
+    return (t && i >= 0 && i < (int)t->comments.size()) ? t->comments[(size_t)i].c_str() : nullptr;
+}
+extern "C" void mc_targets_free(mc_targets* t) { delete t; }
+
+// ------------------------------------------------------------------------------------------------
+// Seam 3
+// ------------------------------------------------------------------------------------------------
+static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target>& targets, int k, int min_cov, int64_t max_kmers,
+                        int64_t max_radius, bool both_dirs, std::vector<JavaMap<int>>& subgraphs, std::vector<int>& found) {
+    std::vector<McBfsRequest> reqs;
+    for (const Target& tg : targets) {
+        std::vector<uint8_t> codes = mc_codes_from_target(tg.seq);
+        if (both_dirs) {
+            reqs.push_back(McBfsRequest{codes, 0});
+        } else {   // buildEnvironment (:137-144): runBfs(-1) then runBfs(+1), each with its own visited set and budget
+            reqs.push_back(McBfsRequest{codes, -1});
+            reqs.push_back(McBfsRequest{codes, 1});
+        }
+    }
+    std::vector<McBfsResult> res;
+    mc_run_bfs_passes(ctx, t, k, min_cov, max_kmers, max_radius, reqs, res);
+    const size_t per = both_dirs ? 1 : 2;
+    subgraphs.assign(targets.size(), JavaMap<int>());
+    found.assign(targets.size(), 0);
+    for (size_t i = 0; i < targets.size(); i++) {
+        std::vector<const McBfsResult*> passes;
+        for (size_t p = 0; p < per; p++) passes.push_back(&res[i * per + p]);
+        found[i] = build_subgraph(passes, k, subgraphs[i]) ? 1 : 0;
+    }
+}
+
+extern "C" int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets, int k, int min_cov,
+                           int64_t max_kmers, int64_t max_radius, int both_dirs, int chunk_len, const char* out_dir, int* found_out) {
+    try {
+        if (!ctx || !t || !out_dir || (n_targets && (!seqs || !names))) mc_throw(MC_ERR_ARG, "null argument");
+        std::vector<Target> targets((size_t)n_targets);
+        for (int i = 0; i < n_targets; i++) targets[(size_t)i] = Target{seqs[i], names[i]};
+        std::vector<JavaMap<int>> subgraphs;
+        std::vector<int> found;
+        run_targets(ctx, t, targets, k, min_cov, max_kmers, max_radius, both_dirs != 0, subgraphs, found);
+        for (int i = 0; i < n_targets; i++) {
+            if (found_out) found_out[i] = found[(size_t)i];
+            if (!found[(size_t)i]) continue;   // "Could not find any k-mers of the target gene in the input, halting."
+            const JavaMap<int>& sub = subgraphs[(size_t)i];
+            std::string prefix = std::string(out_dir) + "/" + targets[(size_t)i].name + "/";   // getOutputPrefix (EnvironmentFinderMain.java:245-249)
+            std::vector<uint32_t> ord = sub.order();
+            write_environment(sub, ord, prefix);
+            McUnitigInput in;
+            unitig_input_from_subgraph(sub, ord, {targets[(size_t)i].seq}, k, in);
+            McUnitigNodes nodes;
+            mc_unitig_nodes(ctx, in, nodes);
+            Graph g;
+            g.build(in, nodes);
+            g.sweep(nullptr);
+            g.assemble();
+            write_single_outputs(g, sub, chunk_len, prefix);
+        }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
+                            int both_dirs, uint64_t* kmers, int32_t* counts, size_t cap, size_t* n) {
+    try {
+        if (!ctx || !t || !seq || !n) mc_throw(MC_ERR_ARG, "null argument");
+        std::vector<JavaMap<int>> subgraphs;
+        std::vector<int> found;
+        run_targets(ctx, t, {Target{seq, ""}}, k, min_cov, max_kmers, max_radius, both_dirs != 0, subgraphs, found);
+        if (!found[0]) {
+            *n = 0;
+            return MC_OK;
+        }
+        std::vector<uint32_t> ord = subgraphs[0].order();
+        *n = ord.size();
+        if (ord.size() > cap) mc_throw(MC_ERR_CAPACITY, "environment has %zu k-mers, room for %zu", ord.size(), cap);
+        for (size_t i = 0; i < ord.size(); i++) {
+            if (kmers) kmers[i] = kmer_code(subgraphs[0].entries[ord[i]].first);
+            if (counts) counts[i] = subgraphs[0].entries[ord[i]].second;
+        }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+// stage D alone, from an environment file (test surface for the reference's committed graph.txt): exported for tests/CLI
+extern "C" int mc_env_from_graph_txt(mc_ctx* ctx, const char* graph_txt, const char* target_seq, int k, int chunk_len, const char* out_dir) {
+    try {
+        if (!ctx || !graph_txt || !target_seq || !out_dir) mc_throw(MC_ERR_ARG, "null argument");
+        JavaMap<int> sub;
+        for (const std::string& line : read_lines(graph_txt, "Couldn't load graph from file")) {
+            size_t sp = line.find(' ');
+            if (sp == std::string::npos) mc_throw(MC_ERR_FORMAT, "malformed environment line \"%s\"", line.c_str());
+            sub.put(line.substr(0, sp), atoi(line.c_str() + sp + 1));
+        }
+        std::vector<uint32_t> ord = sub.order();
+        std::string prefix = std::string(out_dir) + "/";
+        write_environment(sub, ord, prefix);
+        McUnitigInput in;
+        unitig_input_from_subgraph(sub, ord, {std::string(target_seq)}, k, in);
+        McUnitigNodes nodes;
+        mc_unitig_nodes(ctx, in, nodes);
+        Graph g;
+        g.build(in, nodes);
+        g.sweep(nullptr);
+        g.assemble();
+        write_single_outputs(g, sub, chunk_len, prefix);
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Seam 4: environment-finder-multi
+// ------------------------------------------------------------------------------------------------
+static std::string java_format_6_2f(float v) {   // String.format("%6.2f ", float): shortest digits of the widened double, HALF_UP
+    if (std::isnan(v)) return "   NaN ";
+    if (std::isinf(v)) return v > 0 ? "Infinity " : "-Infinity ";
+    double dv = (double)v;
+    bool neg = std::signbit(dv);
+    dv = std::fabs(dv);
+    char sci[64];
+    for (int prec = 0; prec <= 17; prec++) {
+        snprintf(sci, sizeof sci, "%.*e", prec, dv);
+        if (strtod(sci, nullptr) == dv) break;
+    }
+    std::string m(sci);
+    size_t epos = m.find('e');
+    int exp10 = atoi(m.c_str() + epos + 1);
+    std::string digits;
+    for (size_t i = 0; i < epos; i++)
+        if (m[i] != '.') digits.push_back(m[i]);
+    int point = exp10 + 1;
+    std::string ip, fp;
+    if (point <= 0) { ip = "0"; fp = std::string((size_t)(-point), '0') + digits; }
+    else if ((size_t)point >= digits.size()) { ip = digits + std::string((size_t)point - digits.size(), '0'); fp = ""; }
+    else { ip = digits.substr(0, (size_t)point); fp = digits.substr((size_t)point); }
+    while (fp.size() < 3) fp.push_back('0');
+    bool up = fp[2] >= '5';
+    std::string all = ip + fp.substr(0, 2);
+    if (up) {
+        int i = (int)all.size() - 1;
+        while (i >= 0) {
+            if (all[(size_t)i] == '9') { all[(size_t)i] = '0'; i--; }
+            else { all[(size_t)i]++; break; }
+        }
+        if (i < 0) all = "1" + all;
+    }
+    std::string r = all.substr(0, all.size() - 2) + "." + all.substr(all.size() - 2);
+    if (neg) r = "-" + r;
+    while (r.size() < 6) r = " " + r;
+    return r + " ";
+}
+
+extern "C" int mc_env_multi(mc_ctx* ctx, const char* const* env_paths, int n_envs, const char* seq_fasta, int gene_id, const char* out_dir) {
+    try {
+        if (!ctx || !seq_fasta || !out_dir || (n_envs && !env_paths)) mc_throw(MC_ERR_ARG, "null argument");
+        // loadInput (src/tools/EnvironmentFinderMultiMain.java:49-78)
+        std::vector<JavaMap<int>> graphs((size_t)n_envs);
+        for (int i = 0; i < n_envs; i++)
+            for (const std::string& line : read_lines(env_paths[i], "Couldn't load graph from file")) {   // DeBruijnGraphUtils.loadGraph
+                size_t sp = line.find(' ');
+                if (sp == std::string::npos) mc_throw(MC_ERR_FORMAT, "malformed environment line \"%s\" in %s", line.c_str(), env_paths[i]);
+                std::string rest = line.substr(sp + 1);
+                size_t sp2 = rest.find(' ');
+                if (sp2 != std::string::npos) rest = rest.substr(0, sp2);
+                char* endp = nullptr;
+                long depth = strtol(rest.c_str(), &endp, 10);
+                if (rest.empty() || *endp) mc_throw(MC_ERR_FORMAT, "For input string: \"%s\" in %s", rest.c_str(), env_paths[i]);
+                graphs[(size_t)i].put(line.substr(0, sp), (int)depth);
+            }
+        if (graphs.empty()) mc_throw(MC_ERR_ARG, "Zero environments given");
+        if (graphs[0].size() == 0) mc_throw(MC_ERR_FORMAT, "first environment is empty");
+        const int k = (int)graphs[0].entries[graphs[0].order()[0]].first.size();
+        if (k < 1 || k > 31) mc_throw(MC_ERR_UNSUPPORTED, "k = %d is outside the GPU path's 1..31", k);
+        for (auto& g : graphs)
+            for (auto& e : g.entries)
+                if ((int)e.first.size() != k) mc_throw(MC_ERR_FORMAT, "K-mers of different lengths encountered: %d and %d", k, (int)e.first.size());
+        mc_targets tg;
+        load_targets(seq_fasta, tg);
+        if (gene_id < 1 || gene_id > (int)tg.dnas.size() || gene_id > (int)tg.comments.size()) mc_throw(MC_ERR_ARG, "--geneid %d is out of range", gene_id);
+        const std::string sequence = tg.dnas[(size_t)gene_id - 1], comment = tg.comments[(size_t)gene_id - 1];
+
+        // MultiSequenceCalculator.initializeStructures (src/algo/MultiSequenceCalculator.java:51-100): node order
+        JavaMap<int> node_by_kmer;
+        for (auto& g : graphs)
+            for (uint32_t p : g.order()) {
+                const std::string& kmer = g.entries[p].first;
+                node_by_kmer.put(kmer, -1);
+                node_by_kmer.put(rc_string(kmer), -1);
+            }
+        McUnitigInput in;
+        in.k = k;
+        in.order_by_nucleotide = true;
+        std::unordered_map<std::string, uint32_t> pair_of;   // either strand -> env index
+        for (uint32_t p : node_by_kmer.order()) {
+            const std::string& kmer = node_by_kmer.entries[p].first;
+            std::string rc = rc_string(kmer);
+            if (kmer.compare(rc) > 0) continue;
+            if (kmer == rc) mc_throw(MC_ERR_UNSUPPORTED, "palindromic k-mer %s: the reference dereferences a null node here (even k)", kmer.c_str());
+            pair_of[kmer] = pair_of[rc] = (uint32_t)in.kmers.size();
+            in.kmers.push_back(kmer_code(kmer));
+        }
+        const size_t n = in.kmers.size();
+        in.counts.assign(n, 0);
+        in.colors.assign(n, 0);
+        std::vector<std::vector<uint8_t>> member(n_envs > 64 ? n : 0);
+        std::vector<uint32_t> n_graphs(n, 0);
+        for (int gi = 0; gi < n_envs; gi++) {
+            std::vector<uint8_t> seen(n, 0);
+            for (auto& e : graphs[(size_t)gi].entries) {
+                uint32_t idx = pair_of.at(e.first);
+                if (!seen[idx]) { seen[idx] = 1; n_graphs[idx]++; }
+                // colour = the SET of environments; 64-bit FNV-style fold keeps sets of up to 64 exact, beyond that hashed
+                if (n_envs <= 64) in.colors[idx] |= 1ULL << gi;
+                else in.colors[idx] = (in.colors[idx] ^ (uint64_t)(gi + 1)) * 0x100000001B3ULL + (uint64_t)gi;
+            }
+        }
+        // KC of a node = sum over environments of graph.get(normalizeDna(kmer)) (GFAWriterMulti.java:80-88)
+        for (size_t i = 0; i < n; i++) {
+            std::string canon = kmer_string(in.kmers[i], k);
+            for (auto& g : graphs) {
+                const int* c = g.get(canon);
+                if (c) in.counts[i] += *c;
+            }
+        }
+        in.gene_windows = target_windows({sequence}, k);
+        McUnitigNodes nodes;
+        mc_unitig_nodes(ctx, in, nodes);
+        Graph g;
+        g.build(in, nodes);
+        g.sweep(&in.colors);   // canBeMerged: equal gene flag AND equal environment set (:120-122)
+        g.assemble();
+
+        const std::string prefix = out_dir;
+        mkdirs(prefix);
+        auto gene_sfx = [&](int32_t v) { return g.gene[v] ? "_start" : ""; };
+        {   // outputNodeSequences (:139-175)
+            std::ofstream out(prefix + "/seqs.fasta", std::ios::binary);
+            for (uint32_t v = 0; v < g.n2; v++)
+                if (!g.deleted[v] && (int32_t)v < g.rc[v])
+                    out << "> Id" << g.min_id((int32_t)v) << gene_sfx((int32_t)v) << " Length:" << g.seq[v].size() << " Neighbors:" << g.neighbor_ids((int32_t)v) << "\n" << g.seq[v] << "\n";
+        }
+        {   // GFAWriterMulti.printGraph (src/io/writers/GFAWriterMulti.java:39-133)
+            std::ofstream out(prefix + "/graph.gfa", std::ios::binary);
+            const size_t G = graphs.size();
+            for (uint32_t v = 0; v < g.n2; v++)
+                if (!g.deleted[v] && (int32_t)v < g.rc[v]) {
+                    long coverage = 0;
+                    for (int32_t w : g.path((int32_t)v)) coverage += in.counts[(uint32_t)w >> 1];
+                    size_t gs = n_graphs[v >> 1];
+                    std::string color;
+                    if (G == 2) color = g.gene[v] ? "#00ff00" : gs == 1 ? "#ff0000" : gs == 2 ? "#0000ff" : "#000000";
+                    else if (G == 3) color = g.gene[v] ? "#00ff00" : gs == 1 ? "#ff0000" : gs == 2 ? "#0000ff" : gs == 3 ? "#ff00ff" : "#000000";
+                    else if (g.gene[v]) color = "#00ff00";
+                    else {
+                        int value = (int)(256 * gs / G);
+                        char b[32];
+                        snprintf(b, sizeof b, "#%02X%02X%02X", value, value, value);
+                        color = b;
+                    }
+                    out << "S\t" << g.min_id((int32_t)v) << gene_sfx((int32_t)v) << "\t" << g.seq[v] << "\tLN:i:" << g.seq[v].size() << "\tKC:i:" << coverage
+                        << "\tCL:Z:" << color << "\tC2:Z:" << color << "\n";
+                }
+            for (uint32_t i = 0; i < g.n2; i++)
+                if (!g.deleted[i])
+                    for (int32_t j : g.nbrs[i])   // no deleted-target check (GFAWriterMulti.java:51-57)
+                        out << "L\t" << g.min_id((int32_t)i) << gene_sfx((int32_t)i) << "\t" << ((int32_t)i < g.rc[i] ? "+" : "-") << "\t" << g.min_id(j) << gene_sfx(j)
+                            << "\t" << (j > g.rc[j] ? "+" : "-") << "\t" << (k - 1) << "M\n";
+        }
+        {   // printGene (EnvironmentFinderMultiMain.java:93-104)
+            std::ofstream out(prefix + "/gene.fasta", std::ios::binary);
+            out << ">" << comment << "\n" << sequence << "\n";
+        }
+        {   // printProbability (:106-168): int32 sums, float division, "%6.2f "
+            const size_t G = graphs.size();
+            std::ofstream sym(prefix + "/Jacard_sym.txt", std::ios::binary), alt(prefix + "/Jacard_alt.txt", std::ios::binary);
+            sym << "The[31mWarning! symmetric <<Jaccard distance>> (1 - AB/AUB):\n\n";
+            alt << "The[31mWarning! alternative <<Jaccard distance>> (1 - AB/A):\n\n";
+            for (size_t i = 0; i < G; i++) {
+                sym << env_paths[i];
+                alt << env_paths[i];
+                for (size_t j = 0; j < G; j++) {
+                    int32_t diff = 0, diff_alt = 0, uni = 0;
+                    for (auto& e : graphs[i].entries) {
+                        const int* o = graphs[j].get(e.first);
+                        if (!o) { diff += e.second; diff_alt += e.second; uni += e.second; }
+                        else { diff += std::abs(e.second - *o); diff_alt += std::abs(e.second - *o); uni += std::max(e.second, *o); }
+                    }
+                    for (auto& e : graphs[j].entries)
+                        if (!graphs[i].get(e.first)) { diff += e.second; uni += e.second; }
+                    int32_t inter = uni - diff;
+                    sym << java_format_6_2f(1 - inter / (float)uni);
+                    alt << java_format_6_2f(1 - inter / (float)(uni - diff_alt));
+                }
+                sym << "\n";
+                alt << "\n";
+            }
+        }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// "next" row f-1: kmer-counter's .kmers.bin (src/io/IOUtils.java:39-65) and loadKmers (:94-126)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mc_table_print_kmers(const mc_table* t, int threshold, const char* out_file, const char* stat_file, uint64_t* good_out) {
+    try {
+        if (!t || !out_file) mc_throw(MC_ERR_ARG, "null argument");
+        size_t n = 0;
+        int rc = mc_table_dump(t, 0, nullptr, nullptr, 0, &n);
+        if (rc != MC_OK) return rc;
+        std::vector<uint64_t> keys(n);
+        std::vector<int16_t> counts(n);
+        if (n) {
+            rc = mc_table_dump(t, 0, keys.data(), counts.data(), n, &n);
+            if (rc != MC_OK) return rc;
+        }
+        FILE* f = fopen(out_file, "wb");
+        if (!f) mc_throw(MC_ERR_IO, "cannot open %s", out_file);
+        std::vector<uint64_t> hist(32768, 0);
+        uint64_t good = 0;
+        std::vector<uint8_t> buf;
+        buf.reserve(10 << 16);
+        for (size_t i = 0; i < n; i++) {
+            hist[(size_t)counts[i]]++;
+            if (counts[i] > threshold) {
+                for (int b = 0; b < 8; b++) buf.push_back((uint8_t)(keys[i] >> (56 - 8 * b)));   // DataOutputStream: big-endian
+                buf.push_back((uint8_t)((uint16_t)counts[i] >> 8));
+                buf.push_back((uint8_t)counts[i]);
+                good++;
+                if (buf.size() >= (10u << 16)) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+            }
+        }
+        if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+        fclose(f);
+        if (stat_file) {
+            std::ofstream st(stat_file, std::ios::binary);
+            st << "# k-mer frequency\tnumber of such k-mers\n";
+            for (size_t c = 0; c < hist.size(); c++)
+                if (hist[c]) st << c << "\t" << hist[c] << "\n";
+        }
+        if (good_out) *good_out = good;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" int mc_table_load_kmers(mc_table* t, const char* path, int freq_threshold) {
+    try {
+        if (!t || !path) mc_throw(MC_ERR_ARG, "null argument");
+        FILE* f = fopen(path, "rb");
+        if (!f) mc_throw(MC_ERR_IO, "Can't load k-mers file %s", path);
+        std::vector<uint64_t> keys;
+        std::vector<int16_t> counts;
+        uint8_t rec[10];
+        while (fread(rec, 1, 10, f) == 10) {
+            uint64_t key = 0;
+            for (int b = 0; b < 8; b++) key = (key << 8) | rec[b];
+            int16_t freq = (int16_t)((rec[8] << 8) | rec[9]);
+            if (freq > freq_threshold) { keys.push_back(key); counts.push_back(freq); }   // Kmers2HMWorker.processKmer (:84-91)
+        }
+        fclose(f);
+        return mc_table_add_pairs(t, keys.data(), counts.data(), keys.size());
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
