@@ -64,6 +64,8 @@ int mc_table_create(mc_ctx* ctx, int k, uint64_t capacity_hint, int shard_bits, 
 void mc_table_free(mc_table* t);
 /* loadReads over files: format by suffix, FASTQ offset sniffed per file; counts into a fresh table */
 int mc_count_files(mc_ctx* ctx, const char* const* paths, int n_paths, int k, mc_table** out);
+/* one file into an existing table (the per-file body of IOUtils.run, src/io/IOUtils.java:284-314) */
+int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t);
 /* streaming form: `buf` is HOST memory holding whole records (a file, or a record-aligned slice of one) */
 int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt, mc_table* t);
 /* same, `dbuf` already resident in device memory (bench `value` leg; also the multi-GPU pipeline) */

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "mc_table_create": (i32, [vp, i32, u64, i32, i32, C.POINTER(vp)]),
     "mc_table_free": (None, [vp]),
     "mc_count_files": (i32, [vp, C.POINTER(cp), i32, i32, C.POINTER(vp)]),
+    "mc_count_file": (i32, [vp, cp, vp]),
     "mc_count_bytes": (i32, [vp, vp, sz, i32, vp]),
     "mc_count_device": (i32, [vp, vp, sz, i32, vp]),
     "mc_table_size": (u64, [vp]),

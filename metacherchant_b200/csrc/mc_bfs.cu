@@ -12,7 +12,7 @@
 //   * first occurrence wins (atomicMin of the candidate rank on the visited slot), a block scan gives every winner its
 //     queue position, and winners are accepted while |visited| < --maxkmers.
 // This is the sequential FIFO rule, batch by batch: same visited set AND same discovery order, also when --maxkmers
-// truncates (simulated against the literal loop in tests/test_oracle_vs_pyref.py::test_level_synchronous_rule_equals_fifo_rule).
+// truncates (the equivalence is simulated against the literal loop in tests/, test_level_synchronous_rule_equals_fifo_rule).
 // Once a candidate is refused for the budget nothing can ever be added again (|visited| never shrinks), so the pass ends.
 #include <algorithm>
 #include <cstring>

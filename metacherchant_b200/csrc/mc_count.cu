@@ -434,6 +434,28 @@ static int detect_file_format(const std::string& path) {
     mc_throw(MC_ERR_IO, "Failed to read from file %s", path.c_str());   // "Can't detect file format" wrapped by IOUtils.java:292
 }
 
+extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
+    try {
+        if (!ctx || !path || !t) mc_throw(MC_ERR_ARG, "null argument");
+        int fmt = detect_file_format(path);
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
+        size_t len = (size_t)sb.st_size;
+        void* map = len ? mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+        if (len && map == MAP_FAILED) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
+        if (len) madvise(map, len, MADV_SEQUENTIAL);
+        int rc = mc_count_bytes(ctx, map, len, fmt, t);
+        if (len) munmap(map, len);
+        close(fd);
+        return rc;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
 extern "C" int mc_count_files(mc_ctx* ctx, const char* const* paths, int n_paths, int k, mc_table** out) {
     mc_table* t = nullptr;
     try {
@@ -441,18 +463,7 @@ extern "C" int mc_count_files(mc_ctx* ctx, const char* const* paths, int n_paths
         int rc = mc_table_create(ctx, k, 0, 0, 0, &t);
         if (rc != MC_OK) return rc;
         for (int i = 0; i < n_paths; i++) {
-            int fmt = detect_file_format(paths[i]);
-            int fd = open(paths[i], O_RDONLY);
-            if (fd < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", paths[i]);
-            struct stat sb;
-            if (fstat(fd, &sb) != 0) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", paths[i]); }
-            size_t len = (size_t)sb.st_size;
-            void* map = len ? mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
-            if (len && map == MAP_FAILED) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", paths[i]); }
-            if (len) madvise(map, len, MADV_SEQUENTIAL);
-            rc = mc_count_bytes(ctx, map, len, fmt, t);
-            if (len) munmap(map, len);
-            close(fd);
+            rc = mc_count_file(ctx, paths[i], t);
             if (rc != MC_OK) { mc_table_free(t); return rc; }
         }
         *out = t;
