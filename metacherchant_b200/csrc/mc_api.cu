@@ -35,6 +35,16 @@ extern "C" int mc_ctx_create(int device, mc_ctx** out) {
             if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
             cudaGetLastError();
         }
+        // tables, rehash targets and temporaries come from the device's stream-ordered pool; keep freed blocks cached
+        // (cudaFree/cudaMalloc of multi-GB tables cost 20-800 ms each on this part, measured)
+        {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            cudaGetLastError();
+        }
         MC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         MC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) MC_CUDA(cudaEventCreate(&ev));

@@ -107,11 +107,17 @@ struct McTableDev {
     uint64_t* stash_keys;     // hashed key + 1 (0 = empty), stash_mask + 1 entries
     uint32_t* stash_counts;
     uint32_t stash_mask;
-    unsigned long long* counters;   // [0] distinct keys, [1] stash entries, [2] reads, [3] runs, [4] bases, [5] kmers
-    unsigned int* flags;            // bit 0: stash full (table overflow)
+    unsigned long long* counters;   // [0] distinct keys, [1] stash entries, [2] reads, [3] runs, [4] bases, [5] kmers, [6] overflow-list entries
+    unsigned int* flags;            // bit 0: an update could not be stored anywhere (fatal)
+    // Overflow list (only attached while reads are being counted): hashed keys whose 8-bucket window AND stash
+    // neighbourhood were full.  The host grows the table and re-inserts them, so no update is ever lost and the table
+    // never has to be grown pessimistically ahead of a chunk.
+    uint64_t* ovf_keys;
+    unsigned long long ovf_cap;
 };
-enum { MC_CNT_KEYS = 0, MC_CNT_STASH = 1, MC_CNT_READS = 2, MC_CNT_RUNS = 3, MC_CNT_BASES = 4, MC_CNT_KMERS = 5, MC_CNT_N = 8 };
+enum { MC_CNT_KEYS = 0, MC_CNT_STASH = 1, MC_CNT_READS = 2, MC_CNT_RUNS = 3, MC_CNT_BASES = 4, MC_CNT_KMERS = 5, MC_CNT_OVF = 6, MC_CNT_N = 8 };
 #define MC_FLAG_OVERFLOW 1u
+#define MC_STASH_PROBES 64u
 
 __device__ __forceinline__ void mc_load_bucket(const uint64_t* p, uint64_t w[4]) {
     // one 32-byte sector, straight from L2 (atomics live there): LDG.E.256
@@ -121,7 +127,7 @@ __device__ __forceinline__ void mc_load_bucket(const uint64_t* p, uint64_t w[4])
 __device__ __forceinline__ bool mc_stash_add(const McTableDev& t, uint64_t h, uint32_t inc) {
     uint64_t want = h + 1;
     uint32_t pos = (uint32_t)(h * 0x9E3779B97F4A7C15ULL >> 40) & t.stash_mask;
-    for (uint32_t probe = 0; probe <= t.stash_mask; probe++, pos = (pos + 1) & t.stash_mask) {
+    for (uint32_t probe = 0; probe < MC_STASH_PROBES; probe++, pos = (pos + 1) & t.stash_mask) {
         uint64_t cur = atomicCAS((unsigned long long*)&t.stash_keys[pos], 0ULL, (unsigned long long)want);
         if (cur == 0 || cur == want) {
             if (cur == 0) atomicAdd(&t.counters[MC_CNT_STASH], 1ULL);
@@ -130,13 +136,17 @@ __device__ __forceinline__ bool mc_stash_add(const McTableDev& t, uint64_t h, ui
             return cur == 0;
         }
     }
+    if (inc == 1 && t.ovf_keys) {
+        unsigned long long pos2 = atomicAdd(&t.counters[MC_CNT_OVF], 1ULL);
+        if (pos2 < t.ovf_cap) { t.ovf_keys[pos2] = h; return false; }
+    }
     atomicOr(t.flags, MC_FLAG_OVERFLOW);
     return false;
 }
 __device__ __forceinline__ int mc_stash_get(const McTableDev& t, uint64_t h) {
     uint64_t want = h + 1;
     uint32_t pos = (uint32_t)(h * 0x9E3779B97F4A7C15ULL >> 40) & t.stash_mask;
-    for (uint32_t probe = 0; probe <= t.stash_mask; probe++, pos = (pos + 1) & t.stash_mask) {
+    for (uint32_t probe = 0; probe < MC_STASH_PROBES; probe++, pos = (pos + 1) & t.stash_mask) {
         uint64_t cur = __ldcg(&t.stash_keys[pos]);
         if (cur == 0) return -1;
         if (cur == want) {
@@ -245,7 +255,11 @@ struct mc_table {
 };
 
 // kernels / host helpers shared across translation units
-void mc_table_reserve(mc_table* t, uint64_t additional_keys_upper_bound);   // grow (rehash) until it fits
+void mc_table_reserve(mc_table* t, uint64_t additional_keys_upper_bound);   // grow (rehash) until it fits at load <= 0.7
+void mc_table_prepare_chunk(mc_table* t, uint64_t chunk_kmers_upper_bound);  // amortised growth + attach the overflow list
+void mc_table_finish_chunk(mc_table* t);                                     // re-insert overflowed keys (growing), detach the list
+void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what);            // stream-ordered pool allocation on ctx->stream
+void mc_dev_free(mc_ctx* ctx, void* p);
 uint64_t mc_table_keys(const mc_table* t);                                  // synchronising read of the key counter
 void* mc_scratch(mc_ctx* ctx, int slot, size_t bytes);                      // grows ctx->d_scratch[slot]; contents are lost on growth
 #define MC_LAUNCH(ctx) ((ctx)->launches++)

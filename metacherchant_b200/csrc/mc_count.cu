@@ -285,7 +285,7 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
     MC_CUDA(cudaEventRecord(ctx->stage_ev[1], st));
     if (P.h.n_records > 0) {
         uint64_t ub = fasta ? P.h.total_seq_bytes : (uint64_t)n / 2;
-        mc_table_reserve(t, ub);
+        mc_table_prepare_chunk(t, ub);
         McExtractArgs a{};
         a.base = P.base;
         a.recs = P.recs;
@@ -305,6 +305,7 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->stage_ev[2], ctx->stage_ev[3]);
         ctx->stage_ms[1] += ms;
+        mc_table_finish_chunk(t);
     }
     float ms = 0;
     cudaEventSynchronize(ctx->stage_ev[1]);

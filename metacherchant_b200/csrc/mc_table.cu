@@ -57,7 +57,20 @@ static int q_for_keys(uint64_t keys, int shard_bits) {
     return q;
 }
 
-static void alloc_slots(McTableDev& d, int q, int shard_bits, cudaStream_t s) {
+void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        mc_throw(MC_ERR_NOMEM, "%s of %.2f GiB does not fit in device memory", what, (double)bytes / (1 << 30));
+    }
+    return p;
+}
+void mc_dev_free(mc_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+static void alloc_slots(mc_ctx* ctx, McTableDev& d, int q, int shard_bits, cudaStream_t s) {
     d.q = q;
     d.shard_bits = shard_bits;
     d.tag_bits = 62 - shard_bits - q;
@@ -65,11 +78,7 @@ static void alloc_slots(McTableDev& d, int q, int shard_bits, cudaStream_t s) {
     d.tag_mask = d.tag_bits == 0 ? 0 : ((1ULL << d.tag_bits) - 1);
     d.nb_mask = (1ULL << q) - 1;
     size_t bytes = ((size_t)1 << q) * 32;
-    cudaError_t e = cudaMalloc(&d.slots, bytes);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        mc_throw(MC_ERR_NOMEM, "k-mer table of %.1f GiB does not fit in device memory", (double)bytes / (1 << 30));
-    }
+    d.slots = (uint64_t*)mc_dev_alloc(ctx, bytes, "k-mer table");
     MC_CUDA(cudaMemsetAsync(d.slots, 0, bytes, s));
 }
 
@@ -83,13 +92,15 @@ extern "C" int mc_table_create(mc_ctx* ctx, int k, uint64_t capacity_hint, int s
         t->ctx = ctx;
         t->k = k;
         t->shard_id = (uint32_t)shard_id;
-        alloc_slots(t->dev, q_for_keys(capacity_hint, shard_bits), shard_bits, ctx->stream);
+        alloc_slots(ctx, t->dev, q_for_keys(capacity_hint, shard_bits), shard_bits, ctx->stream);
         t->nb = 1ULL << t->dev.q;
         t->dev.stash_mask = MC_STASH_SLOTS - 1;
-        MC_CUDA(cudaMalloc(&t->dev.stash_keys, MC_STASH_SLOTS * sizeof(uint64_t)));
-        MC_CUDA(cudaMalloc(&t->dev.stash_counts, MC_STASH_SLOTS * sizeof(uint32_t)));
-        MC_CUDA(cudaMalloc(&t->dev.counters, MC_CNT_N * sizeof(unsigned long long)));
-        MC_CUDA(cudaMalloc(&t->dev.flags, sizeof(unsigned int)));
+        t->dev.ovf_keys = nullptr;
+        t->dev.ovf_cap = 0;
+        t->dev.stash_keys = (uint64_t*)mc_dev_alloc(ctx, MC_STASH_SLOTS * sizeof(uint64_t), "stash");
+        t->dev.stash_counts = (uint32_t*)mc_dev_alloc(ctx, MC_STASH_SLOTS * sizeof(uint32_t), "stash");
+        t->dev.counters = (unsigned long long*)mc_dev_alloc(ctx, MC_CNT_N * sizeof(unsigned long long), "counters");
+        t->dev.flags = (unsigned int*)mc_dev_alloc(ctx, sizeof(unsigned int), "flags");
         MC_CUDA(cudaMemsetAsync(t->dev.stash_keys, 0, MC_STASH_SLOTS * sizeof(uint64_t), ctx->stream));
         MC_CUDA(cudaMemsetAsync(t->dev.stash_counts, 0, MC_STASH_SLOTS * sizeof(uint32_t), ctx->stream));
         MC_CUDA(cudaMemsetAsync(t->dev.counters, 0, MC_CNT_N * sizeof(unsigned long long), ctx->stream));
@@ -105,12 +116,12 @@ extern "C" int mc_table_create(mc_ctx* ctx, int k, uint64_t capacity_hint, int s
 extern "C" void mc_table_free(mc_table* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
-    cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->dev.slots);
-    cudaFree(t->dev.stash_keys);
-    cudaFree(t->dev.stash_counts);
-    cudaFree(t->dev.counters);
-    cudaFree(t->dev.flags);
+    // stream-ordered frees: the memory goes back to the context's pool once the work queued so far is done
+    mc_dev_free(t->ctx, t->dev.slots);
+    mc_dev_free(t->ctx, t->dev.stash_keys);
+    mc_dev_free(t->ctx, t->dev.stash_counts);
+    mc_dev_free(t->ctx, t->dev.counters);
+    mc_dev_free(t->ctx, t->dev.flags);
     delete t;
 }
 
@@ -157,18 +168,23 @@ extern "C" int mc_table_stats(const mc_table* t, uint64_t* reads, uint64_t* runs
 // rehash: every live slot of `src` re-inserted into `dst` (bigger, or filtered by min_count)
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rehash(McTableDev src, McTableDev dst, uint32_t min_count) {
-    const uint64_t n_slots = (src.nb_mask + 1) * 4;
+    const uint64_t nb = src.nb_mask + 1;
     unsigned long long added = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t w = src.slots[i];
-        if (w == 0) continue;
-        uint32_t c = (uint32_t)(w & MC_COUNT_MASK);
-        if (c > MC_SAT) c = MC_SAT;
-        if (c < min_count) continue;
-        uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
-        uint64_t home = ((i >> 2) - d) & src.nb_mask;
-        uint64_t hl = (home << src.tag_bits) | (w >> MC_TAG_SHIFT);
-        if (mc_table_add(dst, hl, c)) added++;
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t w4[4];
+        mc_load_bucket(src.slots + b * 4, w4);   // one 32-byte bucket per thread
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            uint64_t w = w4[s];
+            if (w == 0) continue;
+            uint32_t c = (uint32_t)(w & MC_COUNT_MASK);
+            if (c > MC_SAT) c = MC_SAT;
+            if (c < min_count) continue;
+            uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
+            uint64_t home = (b - d) & src.nb_mask;
+            uint64_t hl = (home << src.tag_bits) | (w >> MC_TAG_SHIFT);
+            if (mc_table_add(dst, hl, c)) added++;
+        }
     }
     // stash entries
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= src.stash_mask; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -200,41 +216,91 @@ static void grow_to(mc_table* t, int new_q) {
     mc_ctx* ctx = t->ctx;
     McTableDev old = t->dev;
     McTableDev nw = old;
-    alloc_slots(nw, new_q, old.shard_bits, ctx->stream);
+    alloc_slots(ctx, nw, new_q, old.shard_bits, ctx->stream);
     // fresh stash + key counter for the new geometry; the statistics counters carry over
-    MC_CUDA(cudaMalloc(&nw.stash_keys, MC_STASH_SLOTS * sizeof(uint64_t)));
-    MC_CUDA(cudaMalloc(&nw.stash_counts, MC_STASH_SLOTS * sizeof(uint32_t)));
+    nw.stash_keys = (uint64_t*)mc_dev_alloc(ctx, MC_STASH_SLOTS * sizeof(uint64_t), "stash");
+    nw.stash_counts = (uint32_t*)mc_dev_alloc(ctx, MC_STASH_SLOTS * sizeof(uint32_t), "stash");
+    nw.ovf_keys = nullptr;   // a rehash into a table twice the size never needs the overflow list
+    nw.ovf_cap = 0;
     MC_CUDA(cudaMemsetAsync(nw.stash_keys, 0, MC_STASH_SLOTS * sizeof(uint64_t), ctx->stream));
     MC_CUDA(cudaMemsetAsync(nw.stash_counts, 0, MC_STASH_SLOTS * sizeof(uint32_t), ctx->stream));
     MC_CUDA(cudaMemsetAsync(&nw.counters[MC_CNT_KEYS], 0, 2 * sizeof(unsigned long long), ctx->stream));
-    k_rehash<<<grid_for(ctx, (old.nb_mask + 1) * 4, 256, 16), 256, 0, ctx->stream>>>(old, nw, 0);
+    k_rehash<<<grid_for(ctx, old.nb_mask + 1, 256, 16), 256, 0, ctx->stream>>>(old, nw, 0);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
-    MC_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(old.slots);
-    cudaFree(old.stash_keys);
-    cudaFree(old.stash_counts);
+    mc_dev_free(ctx, old.slots);
+    mc_dev_free(ctx, old.stash_keys);
+    mc_dev_free(ctx, old.stash_counts);
+    nw.ovf_keys = old.ovf_keys;
+    nw.ovf_cap = old.ovf_cap;
     t->dev = nw;
     t->nb = 1ULL << new_q;
+}
+
+static void timed_grow(mc_table* t, int q) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, t->ctx->stream);
+    grow_to(t, q);
+    cudaEventRecord(b, t->ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    t->ctx->stage_ms[2] += ms;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
 }
 
 void mc_table_reserve(mc_table* t, uint64_t additional) {
     uint64_t keys = mc_table_keys(t);
     int q = q_for_keys(keys + additional, t->dev.shard_bits);
-    if (q > t->dev.q) {
-        cudaEvent_t a, b;
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
-        cudaEventRecord(a, t->ctx->stream);
-        grow_to(t, q);
-        cudaEventRecord(b, t->ctx->stream);
-        cudaEventSynchronize(b);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, a, b);
-        t->ctx->stage_ms[2] += ms;
-        cudaEventDestroy(a);
-        cudaEventDestroy(b);
+    if (q > t->dev.q) timed_grow(t, q);
+}
+
+// Chunk protocol of the counting path.  Growth is amortised (double when the table is more than 55 % full) instead
+// of reserving room for the worst case "every k-mer of the chunk is new"; an update that finds neither a free slot in
+// its 8-bucket window nor room in the stash lands in the overflow list and is re-inserted after the table has grown.
+static const double MC_GROW_LOAD = 0.55;
+static const uint64_t MC_OVF_MAX = 64ull << 20;
+
+void mc_table_prepare_chunk(mc_table* t, uint64_t ub) {
+    mc_ctx* ctx = t->ctx;
+    uint64_t keys = mc_table_keys(t);
+    uint64_t ovf_cap = std::min<uint64_t>(std::max<uint64_t>(ub, 1024), MC_OVF_MAX);
+    int q = t->dev.q;
+    // (a) amortised doubling, (b) never start a chunk that could not physically fit in table + overflow list
+    while ((double)keys > MC_GROW_LOAD * 4.0 * (double)(1ULL << q) || (double)(keys + ub) > 0.9 * 4.0 * (double)(1ULL << q) + (double)ovf_cap) q++;
+    if (q > t->dev.q) timed_grow(t, q);
+    t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
+    t->dev.ovf_cap = ovf_cap;
+    MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), ctx->stream));
+}
+
+__global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);
+
+void mc_table_finish_chunk(mc_table* t) {
+    mc_ctx* ctx = t->ctx;
+    while (true) {
+        unsigned long long c[MC_CNT_N];
+        read_counters(t, c);
+        check_overflow(t);
+        unsigned long long n = c[MC_CNT_OVF];
+        if (n == 0) break;
+        if (n > t->dev.ovf_cap) mc_throw(MC_ERR_NOMEM, "k-mer table overflow: pass a capacity hint for this input");
+        // move the list aside, double the table, insert the list (which may overflow again, into the now empty list)
+        uint64_t* tmp = (uint64_t*)mc_dev_alloc(ctx, n * sizeof(uint64_t), "overflow list");
+        MC_CUDA(cudaMemcpyAsync(tmp, t->dev.ovf_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), ctx->stream));
+        timed_grow(t, t->dev.q + 1);
+        uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        k_insert_hashed<<<(unsigned)blocks, 256, 0, ctx->stream>>>(t->dev, tmp, n);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        mc_dev_free(ctx, tmp);
     }
+    t->dev.ovf_keys = nullptr;
+    t->dev.ovf_cap = 0;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -257,16 +323,16 @@ extern "C" int mc_table_get(const mc_table* t, const uint64_t* keys, size_t n, i
         MC_CUDA(cudaSetDevice(ctx->device));
         uint64_t* d_keys;
         int16_t* d_out;
-        MC_CUDA(cudaMalloc(&d_keys, n * sizeof(uint64_t)));
-        MC_CUDA(cudaMalloc(&d_out, n * sizeof(int16_t)));
+        d_keys = (decltype(d_keys))mc_dev_alloc(ctx, n * sizeof(uint64_t), "scratch");
+        d_out = (decltype(d_out))mc_dev_alloc(ctx, n * sizeof(int16_t), "scratch");
         MC_CUDA(cudaMemcpyAsync(d_keys, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         k_get<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(t->dev, d_keys, n, d_out, t->shard_id);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
         MC_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
         MC_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_keys);
-        cudaFree(d_out);
+        mc_dev_free(ctx, d_keys);
+        mc_dev_free(ctx, d_out);
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());
@@ -274,61 +340,77 @@ extern "C" int mc_table_get(const mc_table* t, const uint64_t* keys, size_t n, i
     }
 }
 
-// pass 1: count matching entries; pass 2: write (key, count) with warp-aggregated appends
+// pass 1: count matching entries; pass 2: write (key, count) with warp-aggregated appends.  One 32-byte bucket per thread.
 template <bool WRITE>
 __global__ void __launch_bounds__(256) k_dump(McTableDev t, uint32_t min_count, unsigned long long* cursor, uint64_t* keys, int16_t* counts,
                                              uint64_t shard_prefix) {
-    const uint64_t n_slots = (t.nb_mask + 1) * 4;
-    const uint64_t total = n_slots + t.stash_mask + 1;
+    const uint64_t nb = t.nb_mask + 1;
+    const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
+    const uint64_t total = nb + stash_units;   // work units of 4 entries
     unsigned long long local = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     // every lane of a warp runs the same number of iterations so the ballots below are convergent
     const uint64_t iters = (total + stride - 1) / stride;
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    for (uint64_t it = 0; it < iters; it++, i += stride) {
-        bool hit = false;
-        uint64_t hl = 0;
-        uint32_t c = 0;
-        if (i < n_slots) {
-            uint64_t w = t.slots[i];
-            if (w != 0) {
-                c = (uint32_t)(w & MC_COUNT_MASK);
+    uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t it = 0; it < iters; it++, u += stride) {
+        uint64_t hl[4];
+        uint32_t c[4];
+        bool hit[4] = {false, false, false, false};
+        if (u < nb) {
+            uint64_t w4[4];
+            mc_load_bucket(t.slots + u * 4, w4);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                uint64_t w = w4[s];
+                c[s] = (uint32_t)(w & MC_COUNT_MASK);
                 uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
-                uint64_t home = ((i >> 2) - d) & t.nb_mask;
-                hl = (home << t.tag_bits) | (w >> MC_TAG_SHIFT);
-                hit = true;
+                hl[s] = (((u - d) & t.nb_mask) << t.tag_bits) | (w >> MC_TAG_SHIFT);
+                hit[s] = w != 0;
             }
-        } else if (i < total) {
-            uint64_t kx = t.stash_keys[i - n_slots];
-            if (kx != 0) {
-                hl = kx - 1;
-                c = t.stash_counts[i - n_slots];
-                hit = true;
+        } else if (u < total) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                uint64_t i = (u - nb) * 4 + s;
+                uint64_t kx = i <= t.stash_mask ? t.stash_keys[i] : 0;
+                hit[s] = kx != 0;
+                hl[s] = kx - 1;
+                c[s] = hit[s] ? t.stash_counts[i] : 0;
             }
         }
-        if (c > MC_SAT) c = MC_SAT;
-        hit = hit && c >= min_count;
+        uint32_t n_hit = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (c[s] > MC_SAT) c[s] = MC_SAT;
+            hit[s] = hit[s] && c[s] >= min_count;
+            n_hit += hit[s];
+        }
         if (!WRITE) {
-            local += hit;
+            local += n_hit;
         } else {
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                int lane = threadIdx.x & 31;
-                int leader = __ffs(m) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (hit) {
-                    unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
-                    keys[pos] = mc_unmix62_dev(shard_prefix | hl);
-                    counts[pos] = (int16_t)c;
-                }
+            // warp-aggregated reservation: exclusive scan of n_hit over the warp
+            uint32_t incl = n_hit;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
+            uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned long long base = 0;
+            if (lane == 0 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned long long pos = base + incl - n_hit;
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (hit[s]) {
+                    keys[pos] = mc_unmix62_dev(shard_prefix | hl[s]);
+                    counts[pos] = (int16_t)c[s];
+                    pos++;
+                }
         }
     }
     if (!WRITE) {
         for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-        if ((threadIdx.x & 31) == 0 && local) atomicAdd(cursor, local);
+        if (lane == 0 && local) atomicAdd(cursor, local);
     }
 }
 
@@ -336,7 +418,7 @@ static uint64_t count_matching(const mc_table* t, int min_count, unsigned long l
     mc_ctx* ctx = t->ctx;
     MC_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
     uint32_t mc = min_count < 0 ? 0 : (uint32_t)min_count;
-    k_dump<false><<<grid_for(ctx, t->capacity_slots(), 256, 16), 256, 0, ctx->stream>>>(t->dev, mc, d_cursor, nullptr, nullptr, 0);
+    k_dump<false><<<grid_for(ctx, t->nb, 256, 16), 256, 0, ctx->stream>>>(t->dev, mc, d_cursor, nullptr, nullptr, 0);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
     unsigned long long n = 0;
@@ -352,25 +434,25 @@ extern "C" int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, i
         MC_CUDA(cudaSetDevice(ctx->device));
         check_overflow(t);
         unsigned long long* d_cursor;
-        MC_CUDA(cudaMalloc(&d_cursor, sizeof(unsigned long long)));
+        d_cursor = (decltype(d_cursor))mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");
         uint64_t n = count_matching(t, min_count, d_cursor);
         *n_out = n;
         if (cap == 0 || n == 0) {
-            cudaFree(d_cursor);
+            mc_dev_free(ctx, d_cursor);
             return MC_OK;
         }
         if (cap < n) {
-            cudaFree(d_cursor);
+            mc_dev_free(ctx, d_cursor);
             mc_throw(MC_ERR_CAPACITY, "dump needs room for %llu entries", (unsigned long long)n);
         }
         uint64_t* d_keys;
         int16_t* d_counts;
-        MC_CUDA(cudaMalloc(&d_keys, n * sizeof(uint64_t)));
-        MC_CUDA(cudaMalloc(&d_counts, n * sizeof(int16_t)));
+        d_keys = (decltype(d_keys))mc_dev_alloc(ctx, n * sizeof(uint64_t), "scratch");
+        d_counts = (decltype(d_counts))mc_dev_alloc(ctx, n * sizeof(int16_t), "scratch");
         MC_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
         uint64_t prefix = t->dev.shard_bits ? ((uint64_t)t->shard_id << (62 - t->dev.shard_bits)) : 0;
         uint32_t mc = min_count < 0 ? 0 : (uint32_t)min_count;
-        k_dump<true><<<grid_for(ctx, t->capacity_slots(), 256, 16), 256, 0, ctx->stream>>>(t->dev, mc, d_cursor, d_keys, d_counts, prefix);
+        k_dump<true><<<grid_for(ctx, t->nb, 256, 16), 256, 0, ctx->stream>>>(t->dev, mc, d_cursor, d_keys, d_counts, prefix);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
         std::vector<uint64_t> hk(n);
@@ -378,9 +460,9 @@ extern "C" int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, i
         MC_CUDA(cudaMemcpyAsync(hk.data(), d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         MC_CUDA(cudaMemcpyAsync(hc.data(), d_counts, n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
         MC_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_keys);
-        cudaFree(d_counts);
-        cudaFree(d_cursor);
+        mc_dev_free(ctx, d_keys);
+        mc_dev_free(ctx, d_counts);
+        mc_dev_free(ctx, d_cursor);
         // sorted by key for parity checks (the reference iterates in map order; consumers treat it as a set)
         std::vector<uint32_t> idx(n);
         for (uint64_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
@@ -403,15 +485,15 @@ extern "C" int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc
         MC_CUDA(cudaSetDevice(ctx->device));
         check_overflow(t);
         unsigned long long* d_cursor;
-        MC_CUDA(cudaMalloc(&d_cursor, sizeof(unsigned long long)));
+        d_cursor = (decltype(d_cursor))mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");
         uint64_t n = count_matching(t, min_count, d_cursor);
-        cudaFree(d_cursor);
+        mc_dev_free(ctx, d_cursor);
         mc_table* s = nullptr;
         // dense but comfortably probe-able: load <= 0.35 keeps almost every lookup inside one sector
         int rc = mc_table_create(ctx, t->k, n * 2, t->dev.shard_bits, (int)t->shard_id, &s);
         if (rc != MC_OK) return rc;
         uint32_t mc = min_count < 1 ? 1 : (uint32_t)min_count;
-        k_rehash<<<grid_for(ctx, t->capacity_slots(), 256, 16), 256, 0, ctx->stream>>>(t->dev, s->dev, mc);
+        k_rehash<<<grid_for(ctx, t->nb, 256, 16), 256, 0, ctx->stream>>>(t->dev, s->dev, mc);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
         // statistics travel with the filtered table
@@ -445,16 +527,16 @@ extern "C" int mc_table_add_pairs(mc_table* t, const uint64_t* keys, const int16
         mc_table_reserve(t, n);
         uint64_t* d_keys;
         int16_t* d_counts;
-        MC_CUDA(cudaMalloc(&d_keys, n * sizeof(uint64_t)));
-        MC_CUDA(cudaMalloc(&d_counts, n * sizeof(int16_t)));
+        d_keys = (decltype(d_keys))mc_dev_alloc(ctx, n * sizeof(uint64_t), "scratch");
+        d_counts = (decltype(d_counts))mc_dev_alloc(ctx, n * sizeof(int16_t), "scratch");
         MC_CUDA(cudaMemcpyAsync(d_keys, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         MC_CUDA(cudaMemcpyAsync(d_counts, counts, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
         k_add_pairs<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(t->dev, d_keys, d_counts, n);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
         MC_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_keys);
-        cudaFree(d_counts);
+        mc_dev_free(ctx, d_keys);
+        mc_dev_free(ctx, d_counts);
         check_overflow(t);
         return MC_OK;
     } catch (const McError& e) {
@@ -485,10 +567,11 @@ extern "C" int mc_table_insert_hashed_device(mc_table* t, const uint64_t* d_hkey
         if (n == 0) return MC_OK;
         mc_ctx* ctx = t->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
-        mc_table_reserve(t, n);
+        mc_table_prepare_chunk(t, n);
         k_insert_hashed<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(t->dev, d_hkeys, n);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
+        mc_table_finish_chunk(t);
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());
