@@ -197,7 +197,7 @@ def main():
 
     def step_device():
         if world > 1:
-            return counter.count_device_step(d_reads, nbytes, FMT_FASTQ, cov, batch_bytes=args.chunk_mib << 20)
+            return counter.count_device_step(d_reads, nbytes, FMT_FASTQ, cov, batch_bytes=args.chunk_mib << 20, record_bytes=rb)
         t = ctx.new_table(k, capacity_hint=hint)
         t.count_device(d_reads, nbytes, FMT_FASTQ)
         solid = t.filter(cov)

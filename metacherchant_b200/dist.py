@@ -1,0 +1,107 @@
+"""One process per GPU: hash-sharded k-mer counting.
+
+Every rank parses and extracts the canonical k-mers of ITS OWN slice of the reads (libmcgpu, on its GPU), groups the
+hashed keys by owner — owner(key) = top log2(world) bits of the bijective 62-bit hash, so each GPU owns one slice of
+the table — and the ranks swap key groups with ONE all-to-all per read batch (torch.distributed: NCCL over
+NVLink/NVSwitch on GPUs, gloo in the CPU tests).  The receiver inserts what it was sent into its table shard.
+Counts are exact sums, so the union of the shards equals the single-GPU table whatever the world size or batching.
+
+The exchange itself (`exchange_keys`) is device-agnostic and is what the world_size-2 gloo tests exercise on CPU.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bits_for(world: int) -> int:
+    if world < 1 or world & (world - 1):
+        raise ValueError(f"world size must be a power of two (got {world}): owners are the top bits of the k-mer hash")
+    return int(math.log2(world))
+
+
+def owner_of(hashed_key: int, shard_bits: int) -> int:
+    """Rank that owns a hashed key (62-bit): its top shard_bits bits."""
+    return 0 if shard_bits == 0 else (hashed_key >> (62 - shard_bits)) & ((1 << shard_bits) - 1)
+
+
+def plan_batches(nbytes: int, batch_bytes: int, record_bytes: int | None):
+    """Record-aligned (offset, length) slices of a local read buffer.  With fixed-size records (the synthetic
+    workload) slices are multiples of the record size; otherwise the caller must cut at record boundaries itself."""
+    if nbytes == 0:
+        return []
+    if record_bytes:
+        per = max(record_bytes, batch_bytes // record_bytes * record_bytes)
+    else:
+        per = max(1, batch_bytes)
+    return [(off, min(per, nbytes - off)) for off in range(0, nbytes, per)]
+
+
+def exchange_keys(send: torch.Tensor, send_counts, group=None):
+    """All-to-all of owner-grouped hashed keys.  `send` (int64, 1-D) holds the keys grouped by destination rank,
+    send_counts[r] of them for rank r.  Returns (recv tensor, recv_counts)."""
+    world = dist.get_world_size(group)
+    assert len(send_counts) == world
+    dev = send.device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    recv = torch.empty(sum(recv_counts), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send[: sum(send_counts)], output_split_sizes=recv_counts, input_split_sizes=[int(x) for x in send_counts], group=group)
+    return recv, recv_counts
+
+
+class ShardedCounter:
+    """Rank-local driver of the sharded counting step (GPU only; there is no CPU fallback)."""
+
+    def __init__(self, ctx, k: int, world: int, rank: int, capacity_hint: int = 0):
+        self.ctx, self.k, self.world, self.rank = ctx, k, world, rank
+        self.shard_bits = shard_bits_for(world)
+        self.capacity_hint = capacity_hint
+        self.table = None
+        self.bytes_exchanged = 0
+
+    def new_table(self):
+        if self.table is not None:
+            self.table.free()
+        self.table = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint, shard_bits=self.shard_bits, shard_id=self.rank)
+        return self.table
+
+    def count_device(self, d_reads: int, nbytes: int, fmt: int, batch_bytes: int, record_bytes: int | None = None):
+        """Counts this rank's device-resident reads into the distributed table (collective: every rank must call it
+        with the same number of batches; ranks with fewer batches send empty groups)."""
+        lib = self.ctx.lib
+        batches = plan_batches(nbytes, batch_bytes, record_bytes)
+        n_batches = torch.tensor([len(batches)], dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(n_batches, op=dist.ReduceOp.MAX)
+        for b in range(int(n_batches.item())):
+            off, n = batches[b] if b < len(batches) else (0, 0)
+            ub = int(lib.mc_max_kmers(n, fmt, self.k)) if n else 1
+            send = torch.empty(ub, dtype=torch.int64, device="cuda")
+            counts = self.table.extract_partition_device(d_reads + off, n, fmt, self.shard_bits, send.data_ptr()) if n else [0] * self.world
+            if self.world > 1:
+                recv, _ = exchange_keys(send, counts)
+                torch.cuda.current_stream().synchronize()      # NCCL ran on torch's stream; the insert runs on the library's
+                self.bytes_exchanged += 8 * (sum(counts) - counts[self.rank])
+            else:
+                recv = send[: counts[0]]
+            if recv.numel():
+                self.table.insert_hashed_device(recv.data_ptr(), recv.numel())
+            self.ctx.sync()
+            del send, recv
+
+    def count_device_step(self, d_reads: int, nbytes: int, fmt: int, min_cov: int, batch_bytes: int, record_bytes: int | None = None):
+        """One bench step: fresh shard, count, coverage compaction; returns (global solid k-mers, stage times)."""
+        self.new_table()
+        self.count_device(d_reads, nbytes, fmt, batch_bytes, record_bytes)
+        solid = self.table.filter(min_cov)
+        n = torch.tensor([solid.size()], dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(n)
+        stage = self.ctx.stage_ms()
+        solid.free()
+        return int(n.item()), stage

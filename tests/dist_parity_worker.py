@@ -1,0 +1,64 @@
+"""Run under torchrun with N ranks (N = 2, 4, 8) on one box: checks that the hash-sharded table (union of the
+shards after the NCCL all-to-all) equals the oracle's single table bit-exactly, whatever N.
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_parity_worker.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import oracle_ffi
+    from metacherchant_b200 import Context
+    from metacherchant_b200.dist import ShardedCounter
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    o = oracle_ffi.load()
+    s = o.synth(genome_unit=20_000, n_targets=2)
+    total_reads, k = 120_000, 31
+    per = total_reads // world
+    ctx = Context(local)
+    rb = s.record_bytes
+    d = ctx.device_alloc(per * rb)
+    ctx.synth_generate_device(s.params_bytes(), rank * per, per, d)
+    counter = ShardedCounter(ctx, k, world, rank)
+    counter.new_table()
+    counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)   # several batches
+    keys, counts = counter.table.dump()
+    # gather the shards on rank 0
+    n = torch.tensor([keys.size], dtype=torch.int64, device="cuda")
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, n)
+    m = int(max(x.item() for x in sizes))
+    kbuf = torch.zeros(m, dtype=torch.int64, device="cuda")
+    cbuf = torch.zeros(m, dtype=torch.int32, device="cuda")   # NCCL has no int16
+    kbuf[: keys.size] = torch.from_numpy(keys.view(np.int64)).cuda()
+    cbuf[: keys.size] = torch.from_numpy(counts.astype(np.int32)).cuda()
+    ks = [torch.zeros(m, dtype=torch.int64, device="cuda") for _ in range(world)]
+    cs = [torch.zeros(m, dtype=torch.int32, device="cuda") for _ in range(world)]
+    dist.all_gather(ks, kbuf)
+    dist.all_gather(cs, cbuf)
+    ok = True
+    if rank == 0:
+        allk = np.concatenate([ks[r][: int(sizes[r].item())].cpu().numpy().view(np.uint64) for r in range(world)])
+        allc = np.concatenate([cs[r][: int(sizes[r].item())].cpu().numpy().astype(np.int16) for r in range(world)])
+        order = np.argsort(allk, kind="stable")
+        allk, allc = allk[order], allc[order]
+        ref = o.table(k, threads=8).count_bytes(s.generate(0, per * world), oracle_ffi.FMT_FASTQ)
+        rk, rc = ref.dump()
+        ok = np.array_equal(allk, rk) and np.array_equal(allc, rc) and len(np.unique(allk)) == allk.size
+        print(f"DIST_PARITY world={world} distinct={allk.size} oracle={rk.size} exchanged_bytes_rank0={counter.bytes_exchanged} {'OK' if ok else 'MISMATCH'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
