@@ -145,6 +145,9 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--direct", action="store_true", help="A/B: the round-1a fused direct-probing path instead of binned updates")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="mc_ctx_set_tuning knob (part_bits, batch_keys, segment_keys)")
+    ap.add_argument("--hint-div", type=int, default=4, help="table capacity hint = bases / this")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -182,6 +185,11 @@ def main():
     bases_per_step = reads * READ_LEN
 
     ctx = Context(local_rank, chunk_bytes=args.chunk_mib << 20)
+    if args.direct:
+        ctx.set_tuning("direct", 1)
+    for kv in args.tune:
+        name, v = kv.split("=")
+        ctx.set_tuning(name, int(v))
     d_reads = ctx.device_alloc(nbytes)
     first = rank * reads
     GEN = 4_000_000
@@ -189,7 +197,7 @@ def main():
         n = min(GEN, reads - off)
         ctx.synth_generate_device(params, first + off, n, d_reads + off * rb)
     # no rehash when memory allows: distinct k-mers <= k-mer instances <= bases (what mc_count_files does from the file size)
-    hint = bases_per_step // 4   # expected distinct k-mers; the table still grows (rehash) on demand beyond this
+    hint = bases_per_step // args.hint_div if args.hint_div > 0 else 0   # expected distinct k-mers; the table still grows (rehash) on demand beyond this
 
     if world > 1:
         from metacherchant_b200.dist import ShardedCounter
@@ -224,9 +232,14 @@ def main():
     t0 = time.perf_counter()
     kernel_ms = 0.0
     n_solid = 0
+    stages = {}
     for _ in range(args.steps):
         n_solid, stage = step_device()
-        kernel_ms += stage["extract_count"]
+        # the counting pipeline = extract (k-mers -> hashed keys) + scatter (keys -> bins) + count (bins -> table):
+        # together they do what SURVEY 8d's per-read byte figure describes (record read + one table update per k-mer)
+        kernel_ms += stage["extract"] + stage["scatter"] + stage["count"]
+        for name, v in stage.items():
+            stages[name] = stages.get(name, 0.0) + v
     ctx.event_record(1)
     barrier()
     wall = time.perf_counter() - t0
@@ -273,9 +286,10 @@ def main():
     peak, peak_src = load_peaks()
     alg_bytes = algorithmic_bytes_per_read(k, rb) * reads * args.steps   # per rank
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
-    roofline = {"kernel": "k_extract<fastq,count>", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "counting pipeline: k_extract<fastq,flat> + k_bin_scatter + k_bin_count" if not args.direct else "k_extract<fastq,count>", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_read": algorithmic_bytes_per_read(k, rb), "kernel_ms_per_step": round(kernel_ms / args.steps, 2)}
+                "algorithmic_bytes_per_read": algorithmic_bytes_per_read(k, rb), "kernel_ms_per_step": round(kernel_ms / args.steps, 2),
+                "stage_ms_per_step": {name: round(v / args.steps, 2) for name, v in stages.items()}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:

@@ -160,8 +160,16 @@ int mc_ctx_sync(mc_ctx* ctx);
 /* CUDA-event timing on the context's stream (bench.py times kernels on the stream they are launched on) */
 int mc_event_record(mc_ctx* ctx, int slot /*0..15*/);
 int mc_event_elapsed_ms(mc_ctx* ctx, int slot_a, int slot_b, float* ms);
-/* per-stage device times of the last mc_count_* call, milliseconds: [0]=parse [1]=extract+count [2]=grow/rehash */
-int mc_ctx_stage_ms(mc_ctx* ctx, float* ms3);
+/* per-stage device times since the start of the last mc_count_* call, milliseconds:
+ * [0]=parse [1]=extract [2]=grow/rehash [3]=bin scatter [4]=bin count [5]=coverage filter [6..7] reserved */
+int mc_ctx_stage_ms(mc_ctx* ctx, float* ms3);          /* first three only (kept for older callers) */
+int mc_ctx_stage_ms_all(mc_ctx* ctx, float* ms8);
+/* tuning knobs of the binned update path (NOT reference API; tests and profiles use them):
+ *   "part_bits" (-1 = automatic, else P = 2^value bins), "batch_keys" (capacity of one batch, 0 = automatic),
+ *   "segment_keys" (keys applied per count launch, 0 = automatic), "direct" (1 = round-1a fused direct probing) */
+int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);
+/* table updates are buffered in bins; every read of the table applies them first, this call does so explicitly */
+int mc_table_flush_pending(mc_table* t);
 
 #ifdef __cplusplus
 }

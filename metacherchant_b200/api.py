@@ -57,10 +57,17 @@ class Context:
     def sync(self):
         check(self.lib.mc_ctx_sync(self.h))
 
+    STAGES = ("parse", "extract", "grow", "scatter", "count", "filter")
+
     def stage_ms(self):
-        v = (C.c_float * 3)()
-        check(self.lib.mc_ctx_stage_ms(self.h, v))
-        return {"parse": v[0], "extract_count": v[1], "grow": v[2]}
+        """Device milliseconds per stage since the start of the last count call (CUDA events on the library's stream)."""
+        v = (C.c_float * 8)()
+        check(self.lib.mc_ctx_stage_ms_all(self.h, v))
+        return {name: v[i] for i, name in enumerate(self.STAGES)}
+
+    def set_tuning(self, name: str, value: int):
+        """Knobs of the binned update path: part_bits, batch_keys, segment_keys, direct (see include/mc_b200.h)."""
+        check(self.lib.mc_ctx_set_tuning(self.h, name.encode(), value))
 
     def event_record(self, slot):
         check(self.lib.mc_event_record(self.h, slot))

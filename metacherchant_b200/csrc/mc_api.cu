@@ -63,6 +63,7 @@ extern "C" void mc_ctx_destroy(mc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    mc_resolve_timers(c);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_chunk[i]);
         cudaFreeHost(c->h_stage[i]);
@@ -164,7 +165,15 @@ extern "C" int mc_event_elapsed_ms(mc_ctx* c, int a, int b, float* ms) {
 extern "C" int mc_ctx_stage_ms(mc_ctx* c, float* ms3) {
     MC_API_TRY
     if (!c || !ms3) mc_throw(MC_ERR_ARG, "null argument");
+    mc_resolve_timers(c);
     for (int i = 0; i < 3; i++) ms3[i] = c->stage_ms[i];
+    MC_API_END
+}
+extern "C" int mc_ctx_stage_ms_all(mc_ctx* c, float* ms8) {
+    MC_API_TRY
+    if (!c || !ms8) mc_throw(MC_ERR_ARG, "null argument");
+    mc_resolve_timers(c);
+    for (int i = 0; i < MC_N_STAGES; i++) ms8[i] = c->stage_ms[i];
     MC_API_END
 }
 

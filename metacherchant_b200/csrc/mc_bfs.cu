@@ -202,6 +202,7 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
     if (k != t->k) mc_throw(MC_ERR_ARG, "k (%d) differs from the table's k (%d)", k, t->k);
     MC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    mc_table_flush(const_cast<mc_table*>(t));   // pending binned updates first
     const size_t n = reqs.size();
     results.assign(n, McBfsResult{});
     std::vector<uint32_t> caps(n);

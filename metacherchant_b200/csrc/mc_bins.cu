@@ -1,0 +1,421 @@
+// Binned table updates: the write-combining front end of the count table (K3 in two phases).
+//
+//   phase 1  k_bin_scatter : hashed keys -> P bins by the top bits of the hash (one tile of 4096 keys per CTA step,
+//                            shared-memory histogram, one global reservation per non-empty bin, scattered 8-byte stores
+//                            that the L2 merges into full sectors at each bin's append frontier)
+//   phase 2  k_bin_count   : bins applied in order; the table slice of a bin (table_bytes / P) is L2 resident while
+//                            the resident CTAs sweep it, so the bucket probe (LDG.E.256) and the count update (RED / CAS)
+//                            are L2 hits and each slice crosses the HBM bus once per batch in each direction.
+//
+// Semantics are those of mc_table_add (BigLong2ShortHashMap.addAndBound(key, 1), ITMO!/structures/map/
+// BigLong2ShortHashMap.java:67-77): exact counts saturating at 32767, any order of application gives the same table.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "mc_common.cuh"
+
+#define BIN_TILE 2048u          // keys per k_bin_count work unit
+#define SC_THREADS 256
+#define SC_TILE 8192u           // keys per k_bin_scatter tile (sorted by bin in shared memory)
+
+void mc_resolve_timers(mc_ctx* ctx) {
+    for (auto& t : ctx->timers) {
+        float ms = 0;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) ctx->stage_ms[t.stage] += ms;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    cudaGetLastError();
+    ctx->timers.clear();
+}
+
+// --------------------------------------------------------------------------------------------
+// phase 1
+//
+// Measured on B200 (profiles/micro/l2ops.cu): a divergent 8-byte store costs as much as a divergent 32-byte one
+// (~6 cycles per request and SM when the target lines are not resident), so the bins are appended to in whole,
+// aligned 32-byte sectors only: a tile of SC_TILE keys is counting-sorted by bin in shared memory, every bin's run
+// is padded to a multiple of four keys with sentinels, and each lane then moves one full sector.
+// --------------------------------------------------------------------------------------------
+struct McScatterSmem {   // carved out of dynamic shared memory; P = number of bins
+    uint32_t* hist;      // [P]   keys per bin in this tile, then reused as the insertion cursor
+    uint32_t* off;       // [P+1] start of each bin's padded run inside `sorted`
+    unsigned long long* gbase;   // [P] position reserved in the bin's global run
+    uint16_t* secbin;    // [(SC_TILE + 3P) / 4] bin of every sector of `sorted`
+    uint64_t* sorted;    // [SC_TILE + 3P]
+};
+static size_t scatter_smem_bytes(uint32_t P) {
+    size_t keys = SC_TILE + 3 * (size_t)P;
+    return keys * 8 + (size_t)P * 8 + (size_t)P * 4 + ((size_t)P + 1) * 4 + (keys / 4) * 2 + 64;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
+                                                            unsigned int* flags) {
+    extern __shared__ unsigned long long s_mem[];
+    const uint32_t P = 1u << B.pbits;
+    McScatterSmem S;
+    S.sorted = (uint64_t*)s_mem;
+    S.gbase = s_mem + SC_TILE + 3 * P;
+    S.hist = (uint32_t*)(S.gbase + P);
+    S.off = S.hist + P;
+    S.secbin = (uint16_t*)(S.off + P + 1 + ((P + 1) & 1));
+    __shared__ uint32_t s_warp_tot[SC_THREADS / 32];
+    const int bshift = B.hbits - B.pbits;        // <= 62
+    const uint64_t lmask = (1ULL << B.hbits) - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // bins are scanned in contiguous groups of `per` per thread
+    const uint32_t per = (P + SC_THREADS - 1) / SC_THREADS;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * SC_TILE; t0 < n; t0 += (uint64_t)gridDim.x * SC_TILE) {
+        const uint32_t tn = (uint32_t)(n - t0 < SC_TILE ? n - t0 : SC_TILE);
+        for (uint32_t i = threadIdx.x; i < P; i += SC_THREADS) S.hist[i] = 0;
+        __syncthreads();
+        // pass A: histogram
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < tn; i += SC_THREADS) {
+            const uint64_t h = __ldg(flat + t0 + i);
+            const bool valid = h != MC_HASH_SENTINEL && (shard_bits == 0 || (uint32_t)(h >> (62 - shard_bits)) == shard_id);
+            if (valid) atomicAdd(&S.hist[(uint32_t)((h & lmask) >> bshift) & (P - 1)], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of the padded run lengths; reserve the global runs; write pads and the sector -> bin map
+        {
+            const uint32_t b0 = threadIdx.x * per;
+            uint32_t mine = 0;
+            for (uint32_t b = b0; b < b0 + per && b < P; b++) mine += (S.hist[b] + 3) & ~3u;
+            uint32_t incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0;
+            for (int w = 0; w < warp; w++) wbase += s_warp_tot[w];
+            uint32_t run = wbase + incl - mine;
+            for (uint32_t b = b0; b < b0 + per && b < P; b++) {
+                const uint32_t c = S.hist[b], pc = (c + 3) & ~3u;
+                S.off[b] = run;
+                S.gbase[b] = pc ? atomicAdd(&B.cursors[b], (unsigned long long)pc) : 0ULL;
+                for (uint32_t j = c; j < pc; j++) S.sorted[run + j] = MC_HASH_SENTINEL;
+                for (uint32_t j = 0; j < pc; j += 4) S.secbin[(run + j) >> 2] = (uint16_t)b;
+                S.hist[b] = 0;
+                run += pc;
+            }
+            if (threadIdx.x == SC_THREADS - 1) S.off[P] = run;   // the last thread owns the last bins
+        }
+        __syncthreads();
+        // pass B: keys to their sorted position (the tile was just read: these loads hit L2)
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < tn; i += SC_THREADS) {
+            const uint64_t h = __ldcs(flat + t0 + i);
+            const bool valid = h != MC_HASH_SENTINEL && (shard_bits == 0 || (uint32_t)(h >> (62 - shard_bits)) == shard_id);
+            if (valid) {
+                const uint64_t hl = h & lmask;
+                const uint32_t bin = (uint32_t)(hl >> bshift) & (P - 1);
+                S.sorted[S.off[bin] + atomicAdd(&S.hist[bin], 1u)] = hl;
+            }
+        }
+        __syncthreads();
+        // pass C: one aligned 32-byte sector per lane
+        const uint32_t n_sec = S.off[P] >> 2;
+        for (uint32_t j = threadIdx.x; j < n_sec; j += SC_THREADS) {
+            const uint32_t bin = S.secbin[j];
+            const unsigned long long pos = S.gbase[bin] + (j * 4 - S.off[bin]);
+            const ulonglong2 lo2 = *(const ulonglong2*)&S.sorted[j * 4], hi2 = *(const ulonglong2*)&S.sorted[j * 4 + 2];
+            const uint64_t k0 = lo2.x, k1 = lo2.y, k2 = hi2.x, k3 = hi2.y;
+            if (pos + 4 <= B.cap) {
+                uint64_t* dst = B.keys + (uint64_t)bin * B.cap + pos;
+                asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
+            } else {   // bin full (heavy hitter or undersized batch): shared spill list, applied with direct updates
+                const uint64_t kk[4] = {k0, k1, k2, k3};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (kk[q] == MC_HASH_SENTINEL) continue;
+                    const unsigned long long sp = atomicAdd(&B.cursors[P], 1ULL);
+                    if (sp < B.spill_cap) B.spill[sp] = kk[q];
+                    else atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// phase 2
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_count(McTableDev t, McBinsDev B, const uint64_t* __restrict__ tile_prefix, uint64_t tile_lo, uint64_t tile_hi) {
+    const uint32_t P = 1u << B.pbits;
+    unsigned long long added = 0;
+    for (uint64_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+        // the bin of this tile: largest b with tile_prefix[b] <= tile (empty bins have no tiles)
+        uint32_t lo = 0, hi = P;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(tile_prefix + mid) <= tile) lo = mid;
+            else hi = mid;
+        }
+        const unsigned long long attempts = B.cursors[lo];
+        const uint64_t n_bin = attempts < B.cap ? attempts : B.cap;
+        const uint64_t start = (tile - __ldg(tile_prefix + lo)) * BIN_TILE;
+        const uint64_t* keys = B.keys + (uint64_t)lo * B.cap + start;
+        const uint32_t n = (uint32_t)(n_bin - start < BIN_TILE ? n_bin - start : BIN_TILE);
+#pragma unroll 1
+        for (uint32_t base = 0; base < n; base += 1024) {
+            uint64_t h[4];
+            uint64_t w[4][4];
+            bool live[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t idx = base + u * 256 + threadIdx.x;
+                h[u] = idx < n ? __ldcs(keys + idx) : MC_HASH_SENTINEL;
+                live[u] = h[u] != MC_HASH_SENTINEL;   // pads of the sector-aligned runs
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (live[u]) mc_load_bucket(t.slots + ((h[u] >> t.tag_bits) & t.nb_mask) * 4, w[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (live[u] && mc_table_add_impl<true>(t, h[u], 1, w[u])) added++;
+        }
+    }
+    __shared__ unsigned long long s_added;
+    if (threadIdx.x == 0) s_added = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&s_added, added);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+static uint64_t available_device_bytes(mc_ctx* ctx) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (uint64_t)1 << 30; }
+    uint64_t avail = free_b;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        uint64_t reserved = 0, used = 0;   // blocks cached by the stream-ordered pool are reusable
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            avail += reserved - used;
+    }
+    cudaGetLastError();
+    return avail;
+}
+
+static void batch_free_buffers(mc_ctx* ctx, McBatch* B) {
+    mc_dev_free(ctx, B->dev.keys);
+    mc_dev_free(ctx, B->dev.cursors);
+    mc_dev_free(ctx, B->dev.spill);
+    B->dev.keys = nullptr;
+    B->dev.cursors = nullptr;
+    B->dev.spill = nullptr;
+}
+
+static void batch_create(mc_table* t, uint64_t ub, uint64_t total_hint) {
+    mc_ctx* ctx = t->ctx;
+    McBatch* B = t->batch ? t->batch : (t->batch = new McBatch());
+    // capacity: everything the caller expects to add when memory allows, at most half of what is free now
+    uint64_t want = total_hint ? std::max(total_hint, ub) : std::max<uint64_t>(ub * 16, (uint64_t)1 << 28);
+    if (ctx->tune_batch_keys) want = ctx->tune_batch_keys;
+    const uint64_t budget = available_device_bytes(ctx) / 2;
+    const uint64_t spill_bytes = (ub + 1024) * 8;
+    uint64_t room = budget > spill_bytes ? (budget - spill_bytes) / 10 : 0;   // 8 bytes per key + slack for pads
+    uint64_t capacity = std::min(want, std::max<uint64_t>(room, ub / 8 + 1024));
+    if (capacity < 1024) capacity = 1024;
+    int pbits = 0;
+    while (pbits < 9 && ((uint64_t)1 << (pbits + 21)) < capacity) pbits++;   // ~2 M keys per bin, at most SC_TILE / 16 bins (pads stay < 10 %)
+    if (ctx->tune_part_bits >= 0) pbits = (int)std::min<long>(ctx->tune_part_bits, MC_MAX_PBITS);
+    const int hbits = 62 - t->dev.shard_bits;
+    if (pbits > hbits) pbits = hbits;
+    B->P = 1u << pbits;
+    B->capacity = capacity;
+    // per-bin room: the mean + 3 % + the expected sentinel pads + a constant; whatever exceeds it takes the spill list
+    uint64_t cap = capacity / B->P;
+    cap = cap + cap / 32 + (capacity / SC_TILE + 1) * 8 / 5 + 4096;   // pads: 1.5 expected per bin and tile
+    cap = (cap + 15) & ~15ull;
+    B->dev.pbits = pbits;
+    B->dev.hbits = hbits;
+    B->dev.cap = cap;
+    B->dev.spill_cap = ub + 1024;
+    B->dev.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)B->P * cap * 8, "k-mer bins");
+    B->dev.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)B->dev.spill_cap * 8, "k-mer spill list");
+    // cursors [P+1] followed by the tile prefix [P+1] used by k_bin_count
+    B->dev.cursors = (unsigned long long*)mc_dev_alloc(ctx, (size_t)(B->P + 1) * 16, "bin cursors");
+    MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(B->P + 1) * 8, ctx->stream));
+    B->used = 0;
+    B->spill_used = 0;
+}
+
+static uint64_t read_spill_cursor(mc_table* t) {
+    McBatch* B = t->batch;
+    unsigned long long v = 0;
+    MC_CUDA(cudaMemcpyAsync(&v, &B->dev.cursors[B->P], sizeof v, cudaMemcpyDeviceToHost, t->ctx->stream));
+    MC_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    return v;
+}
+
+void mc_batch_reserve(mc_table* t, uint64_t ub, uint64_t total_hint) {
+    McBatch* B = t->batch;
+    if (B && B->dev.keys) {
+        if (B->used) B->spill_used = read_spill_cursor(t);
+        const bool fits = B->used + ub <= B->capacity && B->spill_used + ub <= B->dev.spill_cap;
+        if (fits) return;
+        mc_table_flush(t);
+        if (ub <= B->dev.spill_cap) return;
+        batch_free_buffers(t->ctx, B);   // a larger chunk than the buffers were made for
+    }
+    batch_create(t, ub, total_hint);
+}
+
+void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
+    if (n == 0) return;
+    mc_ctx* ctx = t->ctx;
+    McBatch* B = t->batch;
+    if (!B || !B->dev.keys || B->dev.spill_cap < n) mc_throw(MC_ERR_ARG, "internal: scatter without a reserved batch");
+    McStageTimer tm(ctx, MC_ST_SCATTER);
+    const size_t smem = scatter_smem_bytes(B->P);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
+        attr_set = true;
+    }
+    const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
+    k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, B->dev, t->dev.shard_bits, t->shard_id, t->dev.flags);
+    MC_LAUNCH(ctx);
+    MC_CUDA(cudaGetLastError());
+    B->used += n;
+}
+
+__global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);
+
+static const double MC_FLUSH_TARGET_LOAD = 0.50;   // table load aimed at when a flush has to grow the table
+extern const double MC_GROW_LOAD;
+extern const uint64_t MC_OVF_MAX;
+
+void mc_table_flush(mc_table* t) {
+    McBatch* B = t->batch;
+    if (!B || !B->dev.keys || B->used == 0) return;
+    mc_ctx* ctx = t->ctx;
+    MC_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t P = B->P;
+    std::vector<unsigned long long> cur(P + 1);
+    MC_CUDA(cudaMemcpyAsync(cur.data(), B->dev.cursors, (size_t)(P + 1) * 8, cudaMemcpyDeviceToHost, st));
+    MC_CUDA(cudaStreamSynchronize(st));
+    if (cur[P] > B->dev.spill_cap) mc_throw(MC_ERR_NOMEM, "internal: k-mer spill list overflow (%llu > %llu)", cur[P], (unsigned long long)B->dev.spill_cap);
+    std::vector<uint64_t> prefix(P + 1);
+    prefix[0] = 0;
+    for (uint32_t b = 0; b < P; b++) {
+        const uint64_t c = std::min<uint64_t>(cur[b], B->dev.cap);
+        prefix[b + 1] = prefix[b] + (c + BIN_TILE - 1) / BIN_TILE;
+    }
+    const uint64_t total_tiles = prefix[P];
+    uint64_t* d_prefix = (uint64_t*)(B->dev.cursors + (P + 1));
+    MC_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
+
+    const uint64_t seg_keys_max = ctx->tune_segment_keys ? std::min(std::max<uint64_t>(ctx->tune_segment_keys, BIN_TILE), MC_OVF_MAX) : MC_OVF_MAX;
+    const uint64_t seg_tiles_max = std::max<uint64_t>(seg_keys_max / BIN_TILE, 1);
+    const uint64_t keys_before = mc_table_keys(t);
+    uint64_t tile = 0;
+    bool first = true;
+    while (tile < total_tiles) {
+        // the first segment is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
+        uint64_t seg = first ? std::max<uint64_t>(total_tiles / 64, 1) : seg_tiles_max;
+        seg = std::min(std::min(seg, seg_tiles_max), total_tiles - tile);
+        mc_table_prepare_chunk(t, seg * BIN_TILE);
+        {
+            McStageTimer tm(ctx, MC_ST_COUNT);
+            // exactly the co-resident CTAs: with a static tile stride the sweep window then moves monotonically over the slices
+            static int per_sm = 0;
+            if (per_sm == 0) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+                cudaGetLastError();
+            }
+            const int grid = (int)std::min<uint64_t>(seg, (uint64_t)ctx->sm_count * per_sm);
+            k_bin_count<<<grid, 256, 0, st>>>(t->dev, B->dev, d_prefix, tile, tile + seg);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+        }
+        tile += seg;
+        first = false;
+        // predicted size at the end of this batch: hashes are uniform, so the slices not swept yet gain what the swept ones did
+        unsigned long long c[MC_CNT_N];
+        MC_CUDA(cudaMemcpyAsync(c, t->dev.counters, sizeof c, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        const uint64_t now = c[MC_CNT_KEYS] + c[MC_CNT_OVF];
+        const double gained = now > keys_before ? (double)(now - keys_before) : 0.0;
+        const double predicted = (double)keys_before + gained * ((double)total_tiles / (double)tile);
+        bool grown = false;
+        if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
+            int q = mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD);
+            if (q > t->dev.q) {
+                mc_table_grow_to(t, q);
+                grown = true;
+            }
+        }
+        mc_table_finish_chunk(t, grown);
+    }
+    // spill list: direct updates
+    uint64_t sp = cur[P];
+    for (uint64_t off = 0; off < sp;) {
+        const uint64_t n = std::min<uint64_t>(sp - off, seg_keys_max);
+        mc_table_prepare_chunk(t, n);
+        {
+            McStageTimer tm(ctx, MC_ST_COUNT);
+            const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            k_insert_hashed<<<grid, 256, 0, st>>>(t->dev, B->dev.spill + off, n);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+        }
+        mc_table_finish_chunk(t, false);
+        off += n;
+    }
+    MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(P + 1) * 8, st));
+    B->used = 0;
+    B->spill_used = 0;
+}
+
+void mc_batch_release(mc_table* t) {
+    if (!t->batch) return;
+    mc_table_flush(t);
+    batch_free_buffers(t->ctx, t->batch);
+    delete t->batch;
+    t->batch = nullptr;
+}
+
+// --------------------------------------------------------------------------------------------
+// tuning knobs (tests force tiny batches / many bins; profiles compare against the direct path)
+// --------------------------------------------------------------------------------------------
+extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value) {
+    if (!ctx || !name) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    std::string n(name);
+    if (n == "part_bits" && value >= -1 && value <= MC_MAX_PBITS) ctx->tune_part_bits = (long)value;
+    else if (n == "batch_keys" && value >= 0) ctx->tune_batch_keys = (uint64_t)value;
+    else if (n == "segment_keys" && value >= 0) ctx->tune_segment_keys = (uint64_t)value;
+    else if (n == "direct" && (value == 0 || value == 1)) ctx->tune_direct = (int)value;
+    else {
+        mc_set_error("unknown tuning parameter or value out of range: " + n);
+        return MC_ERR_ARG;
+    }
+    return MC_OK;
+}
+extern "C" int mc_table_flush_pending(mc_table* t) {
+    try {
+        if (!t) mc_throw(MC_ERR_ARG, "null argument");
+        mc_table_flush(t);
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}

@@ -5,6 +5,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/mc_b200.h"
 
@@ -161,8 +162,10 @@ __device__ __forceinline__ int mc_stash_get(const McTableDev& t, uint64_t h) {
 // mask inside).  Returns true when the key was new.  Lock-free: slots only ever go empty -> occupied and the
 // tag|disp part is immutable, so probing in a fixed order and resolving stale "empty" reads through
 // atomicCAS never creates a duplicate.
-__device__ __forceinline__ bool mc_table_add(const McTableDev& t, uint64_t h, uint32_t inc) {
-    const uint64_t hl = h & ((1ULL << (62 - t.shard_bits)) - 1);
+// `w0` (optional) = the words of the home bucket, loaded earlier by the caller so that several probes of one
+// thread are in flight at once (k_bin_count); a stale copy is fine for the same reason a stale load is.
+template <bool PREFETCHED>
+__device__ __forceinline__ bool mc_table_add_impl(const McTableDev& t, uint64_t hl, uint32_t inc, const uint64_t* w0) {
     const uint64_t tag = hl & t.tag_mask;
     const uint64_t b0 = hl >> t.tag_bits;
 #pragma unroll 1
@@ -170,7 +173,8 @@ __device__ __forceinline__ bool mc_table_add(const McTableDev& t, uint64_t h, ui
         const uint64_t b = (b0 + d) & t.nb_mask;
         uint64_t* bucket = t.slots + b * 4;
         uint64_t w[4];
-        mc_load_bucket(bucket, w);
+        if (PREFETCHED && d == 0) { w[0] = w0[0]; w[1] = w0[1]; w[2] = w0[2]; w[3] = w0[3]; }
+        else mc_load_bucket(bucket, w);
         const uint64_t want = (tag << MC_TAG_SHIFT) | ((uint64_t)d << MC_COUNT_BITS);
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -199,6 +203,10 @@ __device__ __forceinline__ bool mc_table_add(const McTableDev& t, uint64_t h, ui
     }
     return mc_stash_add(t, hl, inc);
 }
+__device__ __forceinline__ bool mc_table_add(const McTableDev& t, uint64_t h, uint32_t inc) {
+    const uint64_t hl = h & ((1ULL << (62 - t.shard_bits)) - 1);
+    return mc_table_add_impl<false>(t, hl, inc, nullptr);
+}
 
 // count of hashed key h clamped to 32767, or -1 when absent (Long2ShortHashMap.get)
 __device__ __forceinline__ int mc_table_lookup(const McTableDev& t, uint64_t h) {
@@ -224,8 +232,31 @@ __device__ __forceinline__ int mc_table_lookup(const McTableDev& t, uint64_t h) 
 }
 
 // --------------------------------------------------------------------------------------------
+// Binned updates (the write-combining front end of the table, mc_bins.cu).
+//
+// A random probe of an HBM-sized table costs a 128-byte line fill + a write-back per update (profiles/r1a), which
+// caps direct counting near 20 G updates/s.  Instead, hashed keys are first scattered into P = 2^pbits bins by the
+// TOP bits of their local hash -- bin b covers the contiguous table slice of buckets [b*nb/P, (b+1)*nb/P) -- and the
+// bins are then applied in order, so that the resident CTAs of k_bin_count work on one or two slices at a time and
+// every probe and atomic hits L2.  Each slice is read from and written back to HBM once per batch.
+// A bin that is full (heavy hitters) diverts to the shared spill list, which is applied with plain direct updates.
+// --------------------------------------------------------------------------------------------
+#define MC_MAX_PBITS 11
+struct McBinsDev {
+    uint64_t* keys;                 // P * cap hashed LOCAL keys (shard bits stripped)
+    unsigned long long* cursors;    // [0..P): append attempts per bin (may exceed cap), [P]: spill cursor
+    uint64_t* spill;
+    uint64_t cap;                   // entries per bin
+    uint64_t spill_cap;
+    int pbits;
+    int hbits;                      // 62 - shard_bits; bin = hl >> (hbits - pbits)
+};
+
+// --------------------------------------------------------------------------------------------
 // host-side objects behind the opaque handles
 // --------------------------------------------------------------------------------------------
+enum { MC_ST_PARSE = 0, MC_ST_EXTRACT = 1, MC_ST_GROW = 2, MC_ST_SCATTER = 3, MC_ST_COUNT = 4, MC_ST_FILTER = 5, MC_N_STAGES = 8 };
+struct McPendingTimer { int stage; cudaEvent_t a, b; };
 struct mc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -233,7 +264,13 @@ struct mc_ctx {
     cudaEvent_t stage_ev[8] = {};
     size_t chunk_bytes = (size_t)256 << 20;
     uint64_t launches = 0;
-    float stage_ms[3] = {0, 0, 0};
+    float stage_ms[MC_N_STAGES] = {};
+    std::vector<McPendingTimer> timers;   // recorded, not yet resolved (mc_resolve_timers)
+    // tuning knobs (mc_ctx_set_tuning); 0 = automatic
+    long tune_part_bits = -1;        // P = 2^bits bins
+    uint64_t tune_batch_keys = 0;    // capacity of one batch of binned keys
+    uint64_t tune_segment_keys = 0;  // keys applied per k_bin_count launch
+    int tune_direct = 0;             // 1 = the old fused direct-probing path (kept for A/B measurements)
     int sm_count = 148;
     // reusable device scratch for the parser (grown on demand)
     void* d_chunk[2] = {nullptr, nullptr};
@@ -252,14 +289,51 @@ struct mc_table {
     McTableDev dev{};
     uint64_t nb = 0;
     uint64_t capacity_slots() const { return nb * 4; }
+    struct McBatch* batch = nullptr;   // pending binned updates (mc_bins.cu); applied by mc_table_flush
 };
 
 // kernels / host helpers shared across translation units
 void mc_table_reserve(mc_table* t, uint64_t additional_keys_upper_bound);   // grow (rehash) until it fits at load <= 0.7
 void mc_table_prepare_chunk(mc_table* t, uint64_t chunk_kmers_upper_bound);  // amortised growth + attach the overflow list
-void mc_table_finish_chunk(mc_table* t);                                     // re-insert overflowed keys (growing), detach the list
+void mc_table_finish_chunk(mc_table* t, bool grown_already = false);         // re-insert overflowed keys (growing), detach the list
 void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what);            // stream-ordered pool allocation on ctx->stream
 void mc_dev_free(mc_ctx* ctx, void* p);
 uint64_t mc_table_keys(const mc_table* t);                                  // synchronising read of the key counter
 void* mc_scratch(mc_ctx* ctx, int slot, size_t bytes);                      // grows ctx->d_scratch[slot]; contents are lost on growth
 #define MC_LAUNCH(ctx) ((ctx)->launches++)
+
+// pending binned updates of one table (host side)
+struct McBatch {
+    McBinsDev dev{};
+    uint32_t P = 1;
+    uint64_t capacity = 0;      // total keys the batch is meant to hold (P * cap has slack on top)
+    uint64_t used = 0;          // keys scattered so far (upper bound: includes sentinels and foreign-shard keys)
+    uint64_t spill_used = 0;
+};
+// make sure the table's batch has room for `ub` more keys (flushing if needed); total_hint = all keys the caller expects to add
+void mc_batch_reserve(mc_table* t, uint64_t ub, uint64_t total_hint);
+// scatter n flat hashed keys (global hashes; sentinels and keys of other shards are dropped) into the batch
+void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n);
+// apply every pending update to the table (growing it as needed) and keep the buffers for reuse
+void mc_table_flush(mc_table* t);
+// flush + release the batch buffers
+void mc_batch_release(mc_table* t);
+void mc_table_grow_to(mc_table* t, int new_q);   // timed rehash into 2^new_q buckets
+int mc_q_for_keys(uint64_t keys, int shard_bits, double load);
+
+// accumulate the device time between two points of ctx->stream into ctx->stage_ms[stage] (resolved lazily)
+struct McStageTimer {
+    mc_ctx* ctx;
+    McPendingTimer t;
+    McStageTimer(mc_ctx* c, int stage) : ctx(c) {
+        t.stage = stage;
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, c->stream);
+    }
+    ~McStageTimer() {
+        cudaEventRecord(t.b, ctx->stream);
+        ctx->timers.push_back(t);
+    }
+};
+void mc_resolve_timers(mc_ctx* ctx);   // synchronises with the recorded events and folds them into ctx->stage_ms

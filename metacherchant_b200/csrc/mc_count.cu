@@ -27,6 +27,8 @@
 //   FASTA (FastaReader.java:54-64): a record containing N or n is dropped whole; any other non-ACGT char throws.
 //   k-mers (ShortKmer.java:68-71,122-149): fw=((fw<<2)|b)&mask, rc=(rc>>2)|((3-b)<<(2k-2)), key=min(fw,rc).
 // --------------------------------------------------------------------------------------------
+extern "C" uint64_t mc_max_kmers(size_t len, int fmt, int k);
+
 struct McExtractArgs {
     const uint8_t* base;
     const McRec* recs;
@@ -261,11 +263,16 @@ static int resolve_qoff_device(mc_ctx* ctx, const uint8_t* dbuf, size_t len, int
 // --------------------------------------------------------------------------------------------
 // one device chunk: parse -> reserve table room -> extract+count.  Returns bytes consumed.
 // --------------------------------------------------------------------------------------------
-static void check_k2_errors(mc_ctx* ctx, McParseHeader* d_header, const uint8_t* d_buf, uint32_t n) {
+// reads back K2's error word (and, when given, the flat-key cursor) with one synchronisation
+static unsigned long long check_k2_errors(mc_ctx* ctx, McParseHeader* d_header, const uint8_t* d_buf, uint32_t n, const unsigned long long* d_cursor = nullptr) {
     McParseHeader* hp = (McParseHeader*)ctx->h_pinned_small;
+    unsigned long long* hc = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 512);
+    *hc = 0;
     MC_CUDA(cudaMemcpyAsync(hp, d_header, sizeof(McParseHeader), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_cursor) MC_CUDA(cudaMemcpyAsync(hc, d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     MC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (hp->err_packed != MC_NO_ERROR) mc_throw_parse_error(hp->err_packed, d_buf, n, ctx);
+    return *hc;
 }
 
 static int extract_grid(const mc_ctx* ctx, uint32_t n_records) {
@@ -276,16 +283,38 @@ static int extract_grid(const mc_ctx* ctx, uint32_t n_records) {
     return (int)std::min(blocks, cap);
 }
 
-static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint32_t n, bool fasta, int qoff, bool final_chunk) {
+#define MC_FLAT_HEAD 8192   // cursor + per-owner counters and cursors in front of the flat keys
+// Launches k_extract in its flat-key mode into scratch slot 2; returns the device buffer, *n_flat = keys written (sentinels included)
+static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint64_t ub, const uint8_t* d_buf, uint32_t n, uint64_t* n_flat) {
     cudaStream_t st = ctx->stream;
-    MC_CUDA(cudaEventRecord(ctx->stage_ev[0], st));
+    uint8_t* s2 = (uint8_t*)mc_scratch(ctx, 2, MC_FLAT_HEAD + ub * sizeof(uint64_t));
+    unsigned long long* d_cursor = (unsigned long long*)s2;
+    uint64_t* d_flat = (uint64_t*)(s2 + MC_FLAT_HEAD);
+    MC_CUDA(cudaMemsetAsync(s2, 0, MC_FLAT_HEAD, st));
+    a.out_keys = d_flat;
+    a.out_cursor = d_cursor;
+    {
+        McStageTimer tm(ctx, MC_ST_EXTRACT);
+        if (fasta) k_extract<true, 1><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
+        else k_extract<false, 1><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+    }
+    *n_flat = check_k2_errors(ctx, a.header, d_buf, n, d_cursor);
+    if (*n_flat > ub) mc_throw(MC_ERR_CUDA, "internal: %llu k-mers extracted from a chunk bounded by %llu", (unsigned long long)*n_flat, (unsigned long long)ub);
+    return d_flat;
+}
+
+static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint32_t n, bool fasta, int qoff, bool final_chunk, uint64_t total_hint) {
+    cudaStream_t st = ctx->stream;
     McParsed P;
-    mc_parse_chunk(ctx, d_buf, n, fasta, final_chunk, &P);
+    {
+        McStageTimer tm(ctx, MC_ST_PARSE);
+        mc_parse_chunk(ctx, d_buf, n, fasta, final_chunk, &P);
+    }
     if (P.h.err_packed != MC_NO_ERROR) mc_throw_parse_error(P.h.err_packed, d_buf, n, ctx);
-    MC_CUDA(cudaEventRecord(ctx->stage_ev[1], st));
     if (P.h.n_records > 0) {
         uint64_t ub = fasta ? P.h.total_seq_bytes : (uint64_t)n / 2;
-        mc_table_prepare_chunk(t, ub);
         McExtractArgs a{};
         a.base = P.base;
         a.recs = P.recs;
@@ -295,28 +324,36 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
         a.header = P.d_header;
         a.table = t->dev;
         a.shard_id = t->shard_id;
-        MC_CUDA(cudaEventRecord(ctx->stage_ev[2], st));
-        if (fasta) k_extract<true, 0><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-        else k_extract<false, 0><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-        MC_LAUNCH(ctx);
-        MC_CUDA(cudaGetLastError());
-        MC_CUDA(cudaEventRecord(ctx->stage_ev[3], st));
-        check_k2_errors(ctx, P.d_header, d_buf, n);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->stage_ev[2], ctx->stage_ev[3]);
-        ctx->stage_ms[1] += ms;
-        mc_table_finish_chunk(t);
+        if (ctx->tune_direct) {
+            // the round-1a design, kept for A/B measurements: extraction fused with direct probing of the HBM-sized table
+            mc_table_prepare_chunk(t, ub);
+            a.table = t->dev;
+            {
+                McStageTimer tm(ctx, MC_ST_EXTRACT);
+                if (fasta) k_extract<true, 0><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
+                else k_extract<false, 0><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
+                MC_LAUNCH(ctx);
+                MC_CUDA(cudaGetLastError());
+            }
+            check_k2_errors(ctx, P.d_header, d_buf, n);
+            mc_table_finish_chunk(t);
+        } else {
+            // extract -> flat hashed keys -> bins; the table itself is touched only when the batch is flushed
+            mc_batch_reserve(t, ub + 1, total_hint);
+            a.table = t->dev;   // a flush may have grown the table (the extractor only uses its statistics counters)
+            uint64_t n_flat = 0;
+            uint64_t* d_flat = extract_flat(ctx, a, fasta, ub + 1, d_buf, n, &n_flat);
+            mc_batch_scatter(t, d_flat, n_flat);
+        }
     }
-    float ms = 0;
-    cudaEventSynchronize(ctx->stage_ev[1]);
-    cudaEventElapsedTime(&ms, ctx->stage_ev[0], ctx->stage_ev[1]);
-    ctx->stage_ms[0] += ms;
     uint32_t consumed = P.h.consumed;
     if (!final_chunk && consumed == 0 && n >= ctx->chunk_bytes / 2) mc_throw_parse_error(((unsigned long long)0 << 8) | MC_PE_TOO_LONG, nullptr, 0, ctx);
     return consumed;
 }
 
 static void finish_table(mc_table* t) {
+    mc_table_flush(t);
+    mc_resolve_timers(t->ctx);
     unsigned int f = 0;
     MC_CUDA(cudaMemcpyAsync(&f, t->dev.flags, sizeof f, cudaMemcpyDeviceToHost, t->ctx->stream));
     MC_CUDA(cudaStreamSynchronize(t->ctx->stream));
@@ -332,7 +369,8 @@ extern "C" int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fm
         if (!ctx || !t || (len && !dbuf)) mc_throw(MC_ERR_ARG, "null argument");
         validate_fmt(fmt);
         MC_CUDA(cudaSetDevice(ctx->device));
-        ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
+        mc_resolve_timers(ctx);
+        for (auto& v : ctx->stage_ms) v = 0;
         const uint8_t* p = (const uint8_t*)dbuf;
         bool fasta = fmt == MC_FMT_FASTA;
         int qoff = fasta ? 0 : resolve_qoff_device(ctx, p, len, fmt);
@@ -340,7 +378,7 @@ extern "C" int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fm
         while (pos < len) {
             size_t n = std::min(len - pos, ctx->chunk_bytes);
             bool final_chunk = pos + n == len;
-            uint32_t consumed = count_chunk(ctx, t, p + pos, (uint32_t)n, fasta, qoff, final_chunk);
+            uint32_t consumed = count_chunk(ctx, t, p + pos, (uint32_t)n, fasta, qoff, final_chunk, mc_max_kmers(len, fmt, t->k));
             if (final_chunk) break;
             if (consumed == 0) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", ctx->chunk_bytes);
             pos += consumed;
@@ -359,11 +397,13 @@ extern "C" int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fm
 // moved device-to-device right in front of that slice, so every chunk the kernels see starts at a record boundary.
 extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt, mc_table* t) {
     cudaEvent_t copied[2] = {nullptr, nullptr};
+    cudaEvent_t consumed_ev = nullptr;   // the compute stream is done reading the buffer the next prefetch overwrites
     try {
         if (!ctx || !t || (len && !buf)) mc_throw(MC_ERR_ARG, "null argument");
         validate_fmt(fmt);
         MC_CUDA(cudaSetDevice(ctx->device));
-        ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
+        mc_resolve_timers(ctx);
+        for (auto& v : ctx->stage_ms) v = 0;
         const uint8_t* p = (const uint8_t*)buf;
         const bool fasta = fmt == MC_FMT_FASTA;
         const int qoff = fasta ? 0 : resolve_qoff_host(p, len, fmt);
@@ -380,6 +420,7 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
                 ctx->d_chunk_cap[i] = cap;
             }
         for (int i = 0; i < 2; i++) MC_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        MC_CUDA(cudaEventCreateWithFlags(&consumed_ev, cudaEventDisableTiming));
         size_t pos = 0;      // next host byte to upload
         size_t carry = 0;    // bytes of the previous chunk sitting right in front of offset `chunk`
         int cur = 0;
@@ -393,28 +434,33 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
             size_t n_next = 0;
             if (!final_chunk) {   // prefetch the next slice; the idle buffer's kernels finished (count_chunk synchronises)
                 n_next = std::min(len - pos, chunk);
+                // buffer `nxt` held the previous chunk: its kernels and the carry copy out of it must have finished
+                MC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, consumed_ev, 0));
                 MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[nxt] + chunk, p + pos, n_next, cudaMemcpyHostToDevice, ctx->copy_stream));
                 MC_CUDA(cudaEventRecord(copied[nxt], ctx->copy_stream));
             }
             MC_CUDA(cudaStreamWaitEvent(ctx->stream, copied[cur], 0));
             const uint8_t* d_start = (const uint8_t*)ctx->d_chunk[cur] + chunk - carry;
             const size_t n = carry + n_slice;
-            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk);
+            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, mc_max_kmers(len, fmt, t->k));
             if (final_chunk) break;
             size_t left = n - consumed;
             if (left > chunk) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", chunk);
             if (left) MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[nxt] + chunk - left, d_start + consumed, left, cudaMemcpyDeviceToDevice, ctx->stream));
+            MC_CUDA(cudaEventRecord(consumed_ev, ctx->stream));
             carry = left;
             pos += n_next;
             n_slice = n_next;
             cur = nxt;
         }
         for (int i = 0; i < 2; i++) cudaEventDestroy(copied[i]);
+        cudaEventDestroy(consumed_ev);
         finish_table(t);
         return MC_OK;
     } catch (const McError& e) {
         cudaStreamSynchronize(ctx->copy_stream);
         for (int i = 0; i < 2; i++) if (copied[i]) cudaEventDestroy(copied[i]);
+        if (consumed_ev) cudaEventDestroy(consumed_ev);
         mc_set_error(e.what());
         return e.code;
     }
@@ -548,13 +594,6 @@ extern "C" int mc_extract_partition_device(mc_ctx* ctx, const void* dbuf, size_t
         if (P.h.err_packed != MC_NO_ERROR) mc_throw_parse_error(P.h.err_packed, p, (uint32_t)len, ctx);
         if (P.h.n_records == 0) return MC_OK;
         const uint64_t ub = mc_max_kmers(len, fmt, k);
-        // slot 2: flat keys + cursor + per-owner counters
-        uint8_t* s2 = (uint8_t*)mc_scratch(ctx, 2, 4096 + ub * sizeof(uint64_t));
-        unsigned long long* d_cursor = (unsigned long long*)s2;
-        unsigned long long* d_counts = d_cursor + 8;
-        unsigned long long* d_cursors = d_counts + MC_MAX_OWNERS;
-        uint64_t* d_flat = (uint64_t*)(s2 + 4096);
-        MC_CUDA(cudaMemsetAsync(s2, 0, 4096, st));
         McExtractArgs a{};
         a.base = P.base;
         a.recs = P.recs;
@@ -563,16 +602,11 @@ extern "C" int mc_extract_partition_device(mc_ctx* ctx, const void* dbuf, size_t
         a.qoff = qoff;
         a.header = P.d_header;
         a.table = stats_sink->dev;
-        a.out_keys = d_flat;
-        a.out_cursor = d_cursor;
-        if (fasta) k_extract<true, 1><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-        else k_extract<false, 1><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-        MC_LAUNCH(ctx);
-        MC_CUDA(cudaGetLastError());
-        check_k2_errors(ctx, P.d_header, p, (uint32_t)len);
-        unsigned long long n_flat = 0;
-        MC_CUDA(cudaMemcpyAsync(&n_flat, d_cursor, sizeof n_flat, cudaMemcpyDeviceToHost, st));
-        MC_CUDA(cudaStreamSynchronize(st));
+        uint64_t n_flat = 0;
+        uint64_t* d_flat = extract_flat(ctx, a, fasta, ub, p, (uint32_t)len, &n_flat);
+        // the head of slot 2 (8 KiB, zeroed by extract_flat): [0] flat cursor, [8..) per-owner counters, then cursors
+        unsigned long long* d_counts = (unsigned long long*)((uint8_t*)d_flat - MC_FLAT_HEAD) + 8;
+        unsigned long long* d_cursors = d_counts + MC_MAX_OWNERS;
         if (n_flat == 0) return MC_OK;
         int grid = (int)std::min<uint64_t>((n_flat + 4095) / 4096, (uint64_t)ctx->sm_count * 8);
         k_owner_count<<<grid, 256, 0, st>>>(d_flat, n_flat, shard_bits, d_counts);

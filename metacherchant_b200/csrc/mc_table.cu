@@ -49,13 +49,14 @@ __device__ uint64_t mc_unmix62_dev(uint64_t h) { return unmix62_impl(h); }
 static const double MC_MAX_LOAD = 0.70;
 static const uint32_t MC_STASH_SLOTS = 1u << 16;
 
-static int q_for_keys(uint64_t keys, int shard_bits) {
+int mc_q_for_keys(uint64_t keys, int shard_bits, double load) {
     int q_min = 21 - shard_bits;   // tag must fit 41 bits
     if (q_min < 10) q_min = 10;
     int q = q_min;
-    while ((double)keys > MC_MAX_LOAD * 4.0 * (double)(1ULL << q)) q++;
+    while ((double)keys > load * 4.0 * (double)(1ULL << q)) q++;
     return q;
 }
+static int q_for_keys(uint64_t keys, int shard_bits) { return mc_q_for_keys(keys, shard_bits, MC_MAX_LOAD); }
 
 void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what) {
     void* p = nullptr;
@@ -116,6 +117,13 @@ extern "C" int mc_table_create(mc_ctx* ctx, int k, uint64_t capacity_hint, int s
 extern "C" void mc_table_free(mc_table* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
+    if (t->batch) {   // pending updates die with the table
+        mc_dev_free(t->ctx, t->batch->dev.keys);
+        mc_dev_free(t->ctx, t->batch->dev.cursors);
+        mc_dev_free(t->ctx, t->batch->dev.spill);
+        delete t->batch;
+        t->batch = nullptr;
+    }
     // stream-ordered frees: the memory goes back to the context's pool once the work queued so far is done
     mc_dev_free(t->ctx, t->dev.slots);
     mc_dev_free(t->ctx, t->dev.stash_keys);
@@ -143,6 +151,7 @@ static void check_overflow(const mc_table* t) {
 
 extern "C" uint64_t mc_table_size(const mc_table* t) {
     try {
+        mc_table_flush(const_cast<mc_table*>(t));
         return mc_table_keys(t);
     } catch (const McError& e) {
         mc_set_error(e.what());
@@ -152,6 +161,7 @@ extern "C" uint64_t mc_table_size(const mc_table* t) {
 extern "C" int mc_table_stats(const mc_table* t, uint64_t* reads, uint64_t* runs, uint64_t* bases, uint64_t* kmers) {
     try {
         unsigned long long c[MC_CNT_N];
+        mc_table_flush(const_cast<mc_table*>(t));
         read_counters(t, c);
         if (reads) *reads = c[MC_CNT_READS];
         if (runs) *runs = c[MC_CNT_RUNS];
@@ -237,7 +247,7 @@ static void grow_to(mc_table* t, int new_q) {
     t->nb = 1ULL << new_q;
 }
 
-static void timed_grow(mc_table* t, int q) {
+void mc_table_grow_to(mc_table* t, int q) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -247,7 +257,7 @@ static void timed_grow(mc_table* t, int q) {
     cudaEventSynchronize(b);
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
-    t->ctx->stage_ms[2] += ms;
+    t->ctx->stage_ms[MC_ST_GROW] += ms;
     cudaEventDestroy(a);
     cudaEventDestroy(b);
 }
@@ -255,14 +265,14 @@ static void timed_grow(mc_table* t, int q) {
 void mc_table_reserve(mc_table* t, uint64_t additional) {
     uint64_t keys = mc_table_keys(t);
     int q = q_for_keys(keys + additional, t->dev.shard_bits);
-    if (q > t->dev.q) timed_grow(t, q);
+    if (q > t->dev.q) mc_table_grow_to(t, q);
 }
 
 // Chunk protocol of the counting path.  Growth is amortised (double when the table is more than 55 % full) instead
 // of reserving room for the worst case "every k-mer of the chunk is new"; an update that finds neither a free slot in
 // its 8-bucket window nor room in the stash lands in the overflow list and is re-inserted after the table has grown.
-static const double MC_GROW_LOAD = 0.55;
-static const uint64_t MC_OVF_MAX = 64ull << 20;
+extern const double MC_GROW_LOAD = 0.55;
+extern const uint64_t MC_OVF_MAX = 64ull << 20;
 
 void mc_table_prepare_chunk(mc_table* t, uint64_t ub) {
     mc_ctx* ctx = t->ctx;
@@ -271,7 +281,7 @@ void mc_table_prepare_chunk(mc_table* t, uint64_t ub) {
     int q = t->dev.q;
     // (a) amortised doubling, (b) never start a chunk that could not physically fit in table + overflow list
     while ((double)keys > MC_GROW_LOAD * 4.0 * (double)(1ULL << q) || (double)(keys + ub) > 0.9 * 4.0 * (double)(1ULL << q) + (double)ovf_cap) q++;
-    if (q > t->dev.q) timed_grow(t, q);
+    if (q > t->dev.q) mc_table_grow_to(t, q);
     t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
     t->dev.ovf_cap = ovf_cap;
     MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), ctx->stream));
@@ -279,7 +289,7 @@ void mc_table_prepare_chunk(mc_table* t, uint64_t ub) {
 
 __global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);
 
-void mc_table_finish_chunk(mc_table* t) {
+void mc_table_finish_chunk(mc_table* t, bool grown_already) {
     mc_ctx* ctx = t->ctx;
     while (true) {
         unsigned long long c[MC_CNT_N];
@@ -292,7 +302,8 @@ void mc_table_finish_chunk(mc_table* t) {
         uint64_t* tmp = (uint64_t*)mc_dev_alloc(ctx, n * sizeof(uint64_t), "overflow list");
         MC_CUDA(cudaMemcpyAsync(tmp, t->dev.ovf_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
         MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), ctx->stream));
-        timed_grow(t, t->dev.q + 1);
+        if (!grown_already) mc_table_grow_to(t, t->dev.q + 1);
+        grown_already = false;
         uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
         k_insert_hashed<<<(unsigned)blocks, 256, 0, ctx->stream>>>(t->dev, tmp, n);
         MC_LAUNCH(ctx);
@@ -321,6 +332,7 @@ extern "C" int mc_table_get(const mc_table* t, const uint64_t* keys, size_t n, i
         if (n == 0) return MC_OK;
         mc_ctx* ctx = t->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(const_cast<mc_table*>(t));
         uint64_t* d_keys;
         int16_t* d_out;
         d_keys = (decltype(d_keys))mc_dev_alloc(ctx, n * sizeof(uint64_t), "scratch");
@@ -432,6 +444,7 @@ extern "C" int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, i
         if (!t || !n_out) mc_throw(MC_ERR_ARG, "null argument");
         mc_ctx* ctx = t->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(const_cast<mc_table*>(t));
         check_overflow(t);
         unsigned long long* d_cursor;
         d_cursor = (decltype(d_cursor))mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");
@@ -483,7 +496,9 @@ extern "C" int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc
     try {
         if (!ctx || !t || !solid) mc_throw(MC_ERR_ARG, "null argument");
         MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(const_cast<mc_table*>(t));
         check_overflow(t);
+        McStageTimer tm(ctx, MC_ST_FILTER);
         unsigned long long* d_cursor;
         d_cursor = (decltype(d_cursor))mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");
         uint64_t n = count_matching(t, min_count, d_cursor);
@@ -524,6 +539,7 @@ extern "C" int mc_table_add_pairs(mc_table* t, const uint64_t* keys, const int16
         if (n == 0) return MC_OK;
         mc_ctx* ctx = t->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(t);
         mc_table_reserve(t, n);
         uint64_t* d_keys;
         int16_t* d_counts;
@@ -567,11 +583,18 @@ extern "C" int mc_table_insert_hashed_device(mc_table* t, const uint64_t* d_hkey
         if (n == 0) return MC_OK;
         mc_ctx* ctx = t->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
-        mc_table_prepare_chunk(t, n);
-        k_insert_hashed<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(t->dev, d_hkeys, n);
-        MC_LAUNCH(ctx);
-        MC_CUDA(cudaGetLastError());
-        mc_table_finish_chunk(t);
+        if (ctx->tune_direct) {
+            mc_table_prepare_chunk(t, n);
+            k_insert_hashed<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(t->dev, d_hkeys, n);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+            mc_table_finish_chunk(t, false);
+            return MC_OK;
+        }
+        // buffered: the keys are binned now and applied by the next flush (any read of the table flushes)
+        mc_batch_reserve(t, n, 0);
+        mc_batch_scatter(t, d_hkeys, n);
+        MC_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse d_hkeys
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());

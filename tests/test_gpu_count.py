@@ -187,3 +187,62 @@ def test_synthetic_config1_slice(ctx, oracle):
     assert_same_table(g, o)
     assert g.stats() == o.stats()
     assert_same_table(g.filter(5), o, min_count=5)
+
+
+# ---- the binned update path (mc_bins.cu): bins, spill list, several batches, sampled growth ----------------------
+BIN_TUNINGS = [
+    dict(part_bits=0),
+    dict(part_bits=5),
+    dict(part_bits=11),
+    dict(part_bits=4, batch_keys=3000),                        # tiny batch: most keys take the spill list, many flushes
+    dict(part_bits=3, segment_keys=2048),                      # one k_bin_count launch per tile
+    dict(part_bits=6, batch_keys=50_000, segment_keys=4096),
+    dict(direct=1),                                            # the fused direct-probing path stays exact too
+]
+
+
+@pytest.mark.parametrize("tuning", BIN_TUNINGS, ids=lambda t: ",".join(f"{k}={v}" for k, v in t.items()))
+def test_binned_update_path_is_exact(oracle, tuning):
+    from metacherchant_b200 import Context
+    s = oracle.synth(genome_unit=5_000)
+    data = s.generate(0, 12_000)                               # 1.4 M k-mer instances, k = 31
+    o = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ)
+    c = Context(0, chunk_bytes=1 << 20)                        # 4 chunks
+    try:
+        for name, v in tuning.items():
+            c.set_tuning(name, v)
+        g = c.new_table(31).count_bytes(data, FMT_FASTQ)
+        assert_same_table(g, o)
+        assert g.stats() == o.stats()
+        # a second input into the same table (a second file of --reads): counts add up
+        g.count_bytes(data, FMT_FASTQ)
+        o2 = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ).count_bytes(data, FMT_FASTQ)
+        assert_same_table(g, o2)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("part_bits", [0, 7])
+def test_heavy_hitters_overflow_their_bin(oracle, part_bits):
+    """One k-mer repeated far beyond a bin's capacity diverts to the spill list; counts stay exact and saturate at 32767."""
+    from metacherchant_b200 import Context
+    rng = random.Random(3)
+    reads = [">h\n" + "ACGTTGCA" * 5000 + "\n"] + [f">r{i}\n" + "".join(rng.choice("ACGT") for _ in range(80)) + "\n" for i in range(2000)]
+    data = "".join(reads).encode()
+    c = Context(0)
+    try:
+        c.set_tuning("part_bits", part_bits)
+        c.set_tuning("batch_keys", 20_000)
+        g = c.new_table(8).count_bytes(data, FMT_FASTA)
+        assert_same_table(g, oracle.table(8).count_bytes(data, FMT_FASTA))
+    finally:
+        c.close()
+
+
+def test_binned_growth_from_an_empty_hint(ctx, oracle):
+    """No capacity hint and ~3 M distinct k-mers: the first sampled segment sizes the table, nothing is lost."""
+    s = oracle.synth(genome_unit=40_000, err_ppm=20_000)
+    data = s.generate(0, 50_000)
+    g = ctx.new_table(31).count_bytes(data, FMT_FASTQ)
+    o = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ)
+    assert_same_table(g, o)
