@@ -16,7 +16,7 @@
 
 #include "mc_common.cuh"
 
-#define BIN_TILE 2048u          // keys per k_bin_count work unit
+#define BIN_TILE_DEFAULT 2048u  // keys per k_bin_count work unit (tunable: count_tile)
 #define SC_THREADS 256
 #define SC_TILE 8192u           // keys per k_bin_scatter tile (sorted by bin in shared memory)
 
@@ -146,10 +146,22 @@ __global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __re
 // --------------------------------------------------------------------------------------------
 // phase 2
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin_count(McTableDev t, McBinsDev B, const uint64_t* __restrict__ tile_prefix, uint64_t tile_lo, uint64_t tile_hi) {
+// U = bucket probes a thread keeps in flight, MINB = CTAs per SM the register budget is cut for
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bin_count(McTableDev t, McBinsDev B, const uint64_t* __restrict__ tile_prefix, uint64_t tile_lo, uint64_t tile_hi,
+                                                          uint32_t BIN_TILE, unsigned long long* ticket) {
     const uint32_t P = 1u << B.pbits;
     unsigned long long added = 0;
-    for (uint64_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+    __shared__ unsigned long long s_tile;
+    for (;;) {
+        // Tiles are handed out in order through a global ticket, one per CTA step: the resident CTAs then always work on
+        // the lowest unprocessed tiles, so the set of table lines being updated (the sweep window) stays narrow and L2
+        // resident.  Without the barrier the warps of a CTA drift tiles apart and the L2 hit rate collapses (measured: 4.5x).
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = tile_lo + atomicAdd(ticket, 1ULL);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= tile_hi) break;
         // the bin of this tile: largest b with tile_prefix[b] <= tile (empty bins have no tiles)
         uint32_t lo = 0, hi = P;
         while (hi - lo > 1) {
@@ -163,22 +175,38 @@ __global__ void __launch_bounds__(256) k_bin_count(McTableDev t, McBinsDev B, co
         const uint64_t* keys = B.keys + (uint64_t)lo * B.cap + start;
         const uint32_t n = (uint32_t)(n_bin - start < BIN_TILE ? n_bin - start : BIN_TILE);
 #pragma unroll 1
-        for (uint32_t base = 0; base < n; base += 1024) {
-            uint64_t h[4];
-            uint64_t w[4][4];
-            bool live[4];
+        for (uint32_t base = 0; base < n; base += 256 * U) {
+            uint64_t h[U];
+            uint64_t w[U][4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < U; u++) {
                 const uint32_t idx = base + u * 256 + threadIdx.x;
-                h[u] = idx < n ? __ldcs(keys + idx) : MC_HASH_SENTINEL;
-                live[u] = h[u] != MC_HASH_SENTINEL;   // pads of the sector-aligned runs
+                h[u] = idx < n ? __ldcs(keys + idx) : MC_HASH_SENTINEL;   // sentinels also pad the sector-aligned runs
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (live[u]) mc_load_bucket(t.slots + ((h[u] >> t.tag_bits) & t.nb_mask) * 4, w[u]);
+            for (int u = 0; u < U; u++)
+                if (h[u] != MC_HASH_SENTINEL) mc_load_bucket(t.slots + ((h[u] >> t.tag_bits) & t.nb_mask) * 4, w[u]);
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (live[u] && mc_table_add_impl<true>(t, h[u], 1, w[u])) added++;
+            for (int u = 0; u < U; u++) {
+                if (h[u] == MC_HASH_SENTINEL) continue;
+                // fast path: the key sits in its home bucket (slots fill in order and are never freed, so a match always
+                // precedes the first empty slot) -> one RED; everything else takes the general lock-free insert
+                const uint64_t want = (h[u] & t.tag_mask) << MC_DISP_BITS;   // tag | disp 0
+                uint64_t* bucket = t.slots + ((h[u] >> t.tag_bits) & t.nb_mask) * 4;
+                int hit = -1;
+                uint64_t wm = 0;
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                    if ((w[u][s] >> MC_COUNT_BITS) == want && w[u][s] != 0) {
+                        hit = s;
+                        wm = w[u][s];
+                    }
+                if (hit >= 0) {
+                    if ((wm & MC_COUNT_MASK) < MC_SAT) atomicAdd((unsigned long long*)(bucket + hit), 1ULL);
+                } else if (mc_table_add_impl<true>(t, h[u], 1, w[u])) {
+                    added++;
+                }
+            }
         }
     }
     __shared__ unsigned long long s_added;
@@ -188,6 +216,16 @@ __global__ void __launch_bounds__(256) k_bin_count(McTableDev t, McBinsDev B, co
     if ((threadIdx.x & 31) == 0 && added) atomicAdd(&s_added, added);
     __syncthreads();
     if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
+}
+
+typedef void (*McBinCountKernel)(McTableDev, McBinsDev, const uint64_t*, uint64_t, uint64_t, uint32_t, unsigned long long*);
+static McBinCountKernel bin_count_variant(int v) {
+    switch (v) {
+        case 1: return k_bin_count<4, 4>;
+        case 2: return k_bin_count<2, 6>;
+        case 3: return k_bin_count<4, 3>;
+        default: return k_bin_count<2, 4>;   // best of the sweep in profiles/r1c_NOTES.md
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -228,8 +266,11 @@ static void batch_create(mc_table* t, uint64_t ub, uint64_t total_hint) {
     uint64_t room = budget > spill_bytes ? (budget - spill_bytes) / 10 : 0;   // 8 bytes per key + slack for pads
     uint64_t capacity = std::min(want, std::max<uint64_t>(room, ub / 8 + 1024));
     if (capacity < 1024) capacity = 1024;
+    // bins: the table slice of one bin (table_bytes / P) must sit in L2 while it is swept -> <= 64 MiB; and a bin should hold
+    // ~2 M keys or more (SC_TILE / P keys per bin and tile are padded to a multiple of 4: 10 % waste at P = 512)
     int pbits = 0;
-    while (pbits < 9 && ((uint64_t)1 << (pbits + 21)) < capacity) pbits++;   // ~2 M keys per bin, at most SC_TILE / 16 bins (pads stay < 10 %)
+    while (pbits < 9 && ((uint64_t)1 << (pbits + 21)) < capacity) pbits++;
+    while (pbits < 10 && (t->nb * 32) >> pbits > ((uint64_t)64 << 20)) pbits++;
     if (ctx->tune_part_bits >= 0) pbits = (int)std::min<long>(ctx->tune_part_bits, MC_MAX_PBITS);
     const int hbits = 62 - t->dev.shard_bits;
     if (pbits > hbits) pbits = hbits;
@@ -246,7 +287,7 @@ static void batch_create(mc_table* t, uint64_t ub, uint64_t total_hint) {
     B->dev.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)B->P * cap * 8, "k-mer bins");
     B->dev.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)B->dev.spill_cap * 8, "k-mer spill list");
     // cursors [P+1] followed by the tile prefix [P+1] used by k_bin_count
-    B->dev.cursors = (unsigned long long*)mc_dev_alloc(ctx, (size_t)(B->P + 1) * 16, "bin cursors");
+    B->dev.cursors = (unsigned long long*)mc_dev_alloc(ctx, (size_t)(B->P + 1) * 16 + 64, "bin cursors");   // + the tile ticket
     MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(B->P + 1) * 8, ctx->stream));
     B->used = 0;
     B->spill_used = 0;
@@ -306,6 +347,7 @@ void mc_table_flush(mc_table* t) {
     MC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t P = B->P;
+    const uint32_t BIN_TILE = ctx->tune_count_tile ? ctx->tune_count_tile : BIN_TILE_DEFAULT;
     std::vector<unsigned long long> cur(P + 1);
     MC_CUDA(cudaMemcpyAsync(cur.data(), B->dev.cursors, (size_t)(P + 1) * 8, cudaMemcpyDeviceToHost, st));
     MC_CUDA(cudaStreamSynchronize(st));
@@ -333,13 +375,14 @@ void mc_table_flush(mc_table* t) {
         {
             McStageTimer tm(ctx, MC_ST_COUNT);
             // exactly the co-resident CTAs: with a static tile stride the sweep window then moves monotonically over the slices
-            static int per_sm = 0;
-            if (per_sm == 0) {
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_count, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-                cudaGetLastError();
-            }
+            McBinCountKernel kern = bin_count_variant(ctx->tune_count_variant);
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+            cudaGetLastError();
             const int grid = (int)std::min<uint64_t>(seg, (uint64_t)ctx->sm_count * per_sm);
-            k_bin_count<<<grid, 256, 0, st>>>(t->dev, B->dev, d_prefix, tile, tile + seg);
+            unsigned long long* d_ticket = (unsigned long long*)(d_prefix + (P + 1));
+            MC_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned long long), st));
+            kern<<<grid, 256, 0, st>>>(t->dev, B->dev, d_prefix, tile, tile + seg, BIN_TILE, d_ticket);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
         }
@@ -403,6 +446,8 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "batch_keys" && value >= 0) ctx->tune_batch_keys = (uint64_t)value;
     else if (n == "segment_keys" && value >= 0) ctx->tune_segment_keys = (uint64_t)value;
     else if (n == "direct" && (value == 0 || value == 1)) ctx->tune_direct = (int)value;
+    else if (n == "count_variant" && value >= 0 && value <= 3) ctx->tune_count_variant = (int)value;
+    else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;
     else {
         mc_set_error("unknown tuning parameter or value out of range: " + n);
         return MC_ERR_ARG;

@@ -270,6 +270,8 @@ struct mc_ctx {
     long tune_part_bits = -1;        // P = 2^bits bins
     uint64_t tune_batch_keys = 0;    // capacity of one batch of binned keys
     uint64_t tune_segment_keys = 0;  // keys applied per k_bin_count launch
+    uint32_t tune_count_tile = 0;    // keys per k_bin_count work unit
+    int tune_count_variant = 0;      // k_bin_count instantiation (probes in flight / occupancy), for measurements
     int tune_direct = 0;             // 1 = the old fused direct-probing path (kept for A/B measurements)
     int sm_count = 148;
     // reusable device scratch for the parser (grown on demand)

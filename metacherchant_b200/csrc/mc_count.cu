@@ -33,6 +33,7 @@ struct McExtractArgs {
     const uint8_t* base;
     const McRec* recs;
     uint32_t n_records;
+    uint32_t n_bytes;         // readable bytes at `base` (the chunk, or the compacted FASTA sequence buffer)
     int k;
     int qoff;                 // 33 / 64 (FASTQ) ; ignored for FASTA
     McParseHeader* header;    // errors
@@ -49,8 +50,21 @@ __device__ __forceinline__ bool is_iupac(uint8_t c) {
     }
 }
 
+// The bytes of a warp's 8 consecutive records form one contiguous span of the chunk (2.5 KB for 150 bp FASTQ).  Reading
+// them lane by lane and byte by byte costs ~10 L1 wavefronts per load instruction; instead the warp copies the span into
+// shared memory with coalesced 16-byte loads and the per-base loop reads from there.  Spans that do not fit (long reads)
+// keep the direct global loads.
+#define EX_STAGE_BYTES 4096
+__device__ __forceinline__ uint4 ld_stream128(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <bool FASTA, int MODE>
 __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint8_t(*s_stage)[EX_STAGE_BYTES] = reinterpret_cast<uint8_t(*)[EX_STAGE_BYTES]>(s_dyn);
     const int lane = threadIdx.x & 31;
     const int part = lane & 3;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -68,6 +82,35 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
         McRec rec = live ? a.recs[r] : McRec{0, 0, 0, 0};
         const uint8_t* seq = a.base + rec.seq_off;
         const uint8_t* qual = a.base + rec.qual_off;
+        {
+            uint32_t lo = live ? rec.seq_off : 0xFFFFFFFFu;
+            uint32_t hi = !live ? 0u : FASTA ? rec.seq_off + rec.seq_len : max(rec.seq_off + rec.seq_len, rec.qual_off + rec.qual_len);
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (hi > lo && hi <= a.n_bytes) {
+                const uint8_t* g = a.base + lo;
+                const uint32_t al = (uint32_t)((uintptr_t)g & 15);
+                const uint32_t span = hi - lo + al;
+                if (span <= EX_STAGE_BYTES) {
+                    const uint8_t* g0 = g - al;
+                    const uint8_t* end = a.base + a.n_bytes;
+                    uint8_t* sw = s_stage[threadIdx.x >> 5];
+                    __syncwarp();   // the previous group's readers are done
+                    for (uint32_t off = lane * 16; off < span; off += 512) {
+                        const uint8_t* p = g0 + off;
+                        if (p >= a.base && p + 16 <= end) {
+                            *reinterpret_cast<uint4*>(sw + off) = ld_stream128(p);
+                        } else {
+                            for (int j = 0; j < 16; j++)
+                                if (p + j >= a.base && p + j < end) sw[off + j] = p[j];
+                        }
+                    }
+                    __syncwarp();
+                    seq = sw + al + (rec.seq_off - lo);
+                    qual = sw + al + (rec.qual_off - lo);
+                }
+            }
+        }
         uint32_t len = rec.seq_len;
         bool skip = !live;
         if (!FASTA && live && rec.qual_len != rec.seq_len) {
@@ -80,7 +123,7 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
         uint32_t good = 0, splits = 0, bad_pos = 0xFFFFFFFFu, bad_code = 0;
         if (!skip) {
             for (uint32_t j = q_lo; j < q_hi; j++) {
-                uint8_t c = __ldg(seq + j);
+                uint8_t c = seq[j];
                 int code = mc_nuc_code(c);
                 if (FASTA) {
                     if (code == 4) has_n = true;
@@ -89,7 +132,7 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
                     bool split = (code == 4) || (c == '.');
                     if (!split) {
                         if (code == 5) mc_report_error(a.header, is_iupac(c) ? MC_PE_IUPAC : MC_PE_NUC, rec.seq_off + j);
-                        uint8_t q = __ldg(qual + j);
+                        uint8_t q = qual[j];
                         if (q < a.qoff || q > 126) mc_report_error(a.header, MC_PE_QUAL, rec.qual_off + j);
                         split = (((uint32_t)q - (uint32_t)a.qoff) & 63u) == 0;
                     }
@@ -123,23 +166,26 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
                 uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
             unsigned long long base = 0;
             if (lane == 0 && warp_total) base = atomicAdd(a.out_cursor, (unsigned long long)warp_total);
             base = __shfl_sync(0xffffffffu, base, 0);
             out_pos = base + incl - reserve;
         }
+        // (collecting a warp's keys in shared memory for coalesced stores was measured slower: the extra 64 KB per CTA
+        // halves the occupancy this ALU/latency-bound loop needs, profiles/r1c_NOTES.md)
+        uint64_t* const my_out = (MODE == 1) ? a.out_keys + out_pos : nullptr;
         uint32_t emitted = 0;
         if (reserve) {
             uint64_t fw = 0, rc = 0;
             uint32_t run = 0;
             const uint32_t j_end = s_hi + k - 1;   // exclusive; <= len
             for (uint32_t j = s_lo; j < j_end; j++) {
-                uint8_t c = __ldg(seq + j);
+                uint8_t c = seq[j];
                 int code = mc_nuc_code(c);
                 bool bad = code >= 4;
                 if (!FASTA && !bad) {
-                    uint8_t q = __ldg(qual + j);
+                    uint8_t q = qual[j];
                     bad = (((uint32_t)q - (uint32_t)a.qoff) & 63u) == 0;
                 }
                 uint64_t b = (uint64_t)(code & 3);
@@ -154,14 +200,15 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
                         if (a.table.shard_bits == 0 || (h >> (62 - a.table.shard_bits)) == a.shard_id)
                             if (mc_table_add(a.table, h, 1)) st_new++;
                     } else {
-                        a.out_keys[out_pos + emitted] = h;
+                        my_out[emitted] = h;
                         emitted++;
                     }
                 }
             }
         }
-        if (MODE == 1)
-            for (uint32_t e = emitted; e < reserve; e++) a.out_keys[out_pos + e] = MC_HASH_SENTINEL;
+        if (MODE == 1) {
+            for (uint32_t e = emitted; e < reserve; e++) my_out[e] = MC_HASH_SENTINEL;
+        }
     }
 
     // ---- block-aggregated statistics ---------------------------------------------------------
@@ -275,13 +322,23 @@ static unsigned long long check_k2_errors(mc_ctx* ctx, McParseHeader* d_header, 
     return *hc;
 }
 
-static int extract_grid(const mc_ctx* ctx, uint32_t n_records) {
-    uint64_t warps = ((uint64_t)n_records + 7) / 8;
-    uint64_t blocks = (warps + 7) / 8;               // 8 warps per 256-thread CTA
-    uint64_t cap = (uint64_t)ctx->sm_count * 8 * 4;   // 8 resident CTAs per SM x 4 waves
+template <bool FASTA, int MODE>
+static void launch_extract(mc_ctx* ctx, McExtractArgs& a) {
+    const size_t smem = 8 * EX_STAGE_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(k_extract<FASTA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    uint64_t warps = ((uint64_t)a.n_records + 7) / 8;
+    uint64_t blocks = (warps + 7) / 8;                           // 8 warps per 256-thread CTA
+    uint64_t cap = (uint64_t)ctx->sm_count * 6 * 4;   // resident CTAs per SM x 4 waves
     if (blocks < 1) blocks = 1;
-    return (int)std::min(blocks, cap);
+    k_extract<FASTA, MODE><<<(unsigned)std::min(blocks, cap), 256, smem, ctx->stream>>>(a);
+    MC_LAUNCH(ctx);
+    MC_CUDA(cudaGetLastError());
 }
+
 
 #define MC_FLAT_HEAD 8192   // cursor + per-owner counters and cursors in front of the flat keys
 // Launches k_extract in its flat-key mode into scratch slot 2; returns the device buffer, *n_flat = keys written (sentinels included)
@@ -295,10 +352,8 @@ static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint64_
     a.out_cursor = d_cursor;
     {
         McStageTimer tm(ctx, MC_ST_EXTRACT);
-        if (fasta) k_extract<true, 1><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-        else k_extract<false, 1><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-        MC_LAUNCH(ctx);
-        MC_CUDA(cudaGetLastError());
+        if (fasta) launch_extract<true, 1>(ctx, a);
+        else launch_extract<false, 1>(ctx, a);
     }
     *n_flat = check_k2_errors(ctx, a.header, d_buf, n, d_cursor);
     if (*n_flat > ub) mc_throw(MC_ERR_CUDA, "internal: %llu k-mers extracted from a chunk bounded by %llu", (unsigned long long)*n_flat, (unsigned long long)ub);
@@ -306,7 +361,6 @@ static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint64_
 }
 
 static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint32_t n, bool fasta, int qoff, bool final_chunk, uint64_t total_hint) {
-    cudaStream_t st = ctx->stream;
     McParsed P;
     {
         McStageTimer tm(ctx, MC_ST_PARSE);
@@ -319,6 +373,7 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
         a.base = P.base;
         a.recs = P.recs;
         a.n_records = P.h.n_records;
+        a.n_bytes = fasta ? P.h.total_seq_bytes : n;
         a.k = t->k;
         a.qoff = qoff;
         a.header = P.d_header;
@@ -330,10 +385,8 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
             a.table = t->dev;
             {
                 McStageTimer tm(ctx, MC_ST_EXTRACT);
-                if (fasta) k_extract<true, 0><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-                else k_extract<false, 0><<<extract_grid(ctx, a.n_records), 256, 0, st>>>(a);
-                MC_LAUNCH(ctx);
-                MC_CUDA(cudaGetLastError());
+                if (fasta) launch_extract<true, 0>(ctx, a);
+                else launch_extract<false, 0>(ctx, a);
             }
             check_k2_errors(ctx, P.d_header, d_buf, n);
             mc_table_finish_chunk(t);
@@ -598,6 +651,7 @@ extern "C" int mc_extract_partition_device(mc_ctx* ctx, const void* dbuf, size_t
         a.base = P.base;
         a.recs = P.recs;
         a.n_records = P.h.n_records;
+        a.n_bytes = fasta ? P.h.total_seq_bytes : (uint32_t)len;
         a.k = k;
         a.qoff = qoff;
         a.header = P.d_header;
