@@ -145,7 +145,6 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--direct", action="store_true", help="A/B: the round-1a fused direct-probing path instead of binned updates")
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="mc_ctx_set_tuning knob (part_bits, batch_keys, segment_keys)")
     ap.add_argument("--hint-div", type=int, default=4, help="table capacity hint = bases / this")
     args = ap.parse_args()
@@ -185,8 +184,6 @@ def main():
     bases_per_step = reads * READ_LEN
 
     ctx = Context(local_rank, chunk_bytes=args.chunk_mib << 20)
-    if args.direct:
-        ctx.set_tuning("direct", 1)
     for kv in args.tune:
         name, v = kv.split("=")
         ctx.set_tuning(name, int(v))
@@ -286,7 +283,7 @@ def main():
     peak, peak_src = load_peaks()
     alg_bytes = algorithmic_bytes_per_read(k, rb) * reads * args.steps   # per rank
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
-    roofline = {"kernel": "counting pipeline: k_extract<fastq,flat> + k_bin_scatter + k_bin_count" if not args.direct else "k_extract<fastq,count>", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "counting pipeline: k_extract + k_bin_scatter + k_bin_count", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_read": algorithmic_bytes_per_read(k, rb), "kernel_ms_per_step": round(kernel_ms / args.steps, 2),
                 "stage_ms_per_step": {name: round(v / args.steps, 2) for name, v in stages.items()}}

@@ -166,7 +166,8 @@ int mc_ctx_stage_ms(mc_ctx* ctx, float* ms3);          /* first three only (kept
 int mc_ctx_stage_ms_all(mc_ctx* ctx, float* ms8);
 /* tuning knobs of the binned update path (NOT reference API; tests and profiles use them):
  *   "part_bits" (-1 = automatic, else P = 2^value bins), "batch_keys" (capacity of one batch, 0 = automatic),
- *   "segment_keys" (keys applied per count launch, 0 = automatic), "direct" (1 = round-1a fused direct probing) */
+ *   "segment_keys" (keys applied per count launch, 0 = automatic), "count_tile", "count_variant" (k_bin_count shape),
+ *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32) */
 int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);
 /* table updates are buffered in bins; every read of the table applies them first, this call does so explicitly */
 int mc_table_flush_pending(mc_table* t);

@@ -445,7 +445,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     if (n == "part_bits" && value >= -1 && value <= MC_MAX_PBITS) ctx->tune_part_bits = (long)value;
     else if (n == "batch_keys" && value >= 0) ctx->tune_batch_keys = (uint64_t)value;
     else if (n == "segment_keys" && value >= 0) ctx->tune_segment_keys = (uint64_t)value;
-    else if (n == "direct" && (value == 0 || value == 1)) ctx->tune_direct = (int)value;
+    else if (n == "extract_parts" && (value == 0 || value == 1 || value == 4 || value == 32)) ctx->tune_extract_parts = (int)value;
     else if (n == "count_variant" && value >= 0 && value <= 3) ctx->tune_count_variant = (int)value;
     else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;
     else {

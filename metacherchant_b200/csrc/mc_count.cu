@@ -38,8 +38,8 @@ struct McExtractArgs {
     int qoff;                 // 33 / 64 (FASTQ) ; ignored for FASTA
     McParseHeader* header;    // errors
     McTableDev table;
-    uint32_t shard_id;        // only keys whose top shard_bits hash bits equal shard_id are kept (shard_bits may be 0)
-    uint64_t* out_keys;       // MODE 1: flat hashed keys (sentinel-padded)
+    uint32_t shard_id;        // (kept for the statistics sink; keys are filtered by shard when they are binned)
+    uint64_t* out_keys;       // flat hashed keys (sentinel-padded)
     unsigned long long* out_cursor;
 };
 
@@ -50,52 +50,133 @@ __device__ __forceinline__ bool is_iupac(uint8_t c) {
     }
 }
 
-// The bytes of a warp's 8 consecutive records form one contiguous span of the chunk (2.5 KB for 150 bp FASTQ).  Reading
-// them lane by lane and byte by byte costs ~10 L1 wavefronts per load instruction; instead the warp copies the span into
-// shared memory with coalesced 16-byte loads and the per-base loop reads from there.  Spans that do not fit (long reads)
-// keep the direct global loads.
-#define EX_STAGE_BYTES 4096
+// --------------------------------------------------------------------------------------------
+// K2 kernel, second design (profiles/r1c_NOTES.md).  The first one (a quad per record, a validation pass followed by a
+// rolling pass, byte loads from global memory, nested branches) executed ~210 thread instructions per k-mer and was
+// issue-bound.  Now:
+//   * the byte span of a warp's records is copied to shared memory with coalesced 16-byte loads and the loops read from there;
+//   * PARTS lanes share one record; PARTS = 1 for short reads (one lane rolls over the whole read: no k-1 bases of
+//     context are re-read), 4 or 32 for longer ones.  Lane p owns the k-mer starts [p*S, (p+1)*S), S = ceil(nk/PARTS),
+//     and the reader statistics of the bases [p*S, (p+1)*S) (the last lane: up to the end of the read);
+//   * one pass, branch-free per base: a 256-entry class table (2-bit code | split | invalid) in shared memory, error
+//     conditions are only OR-ed into a flag and the exact first error is located by a rare re-scan;
+//   * keys always leave as flat hashed keys (the binned table update consumes them; there is no direct-probing mode).
+// --------------------------------------------------------------------------------------------
+#define EX_THREADS 128
+#define EX_WARPS (EX_THREADS / 32)
+#define EX_STAGE_BYTES 12288   // per warp: 32 x 150 bp FASTQ records are ~10 KB
+#define EX_CLS_SPLIT 4u        // no k-mer may span this base: N, n, '.' in FASTQ, and every invalid character
+#define EX_CLS_BAD 8u          // not a nucleotide character (an error unless the FASTA record is dropped for an N)
+#define EX_CLS_N 16u           // N or n
+#define EX_FLAG_QUAL 32u       // quality character outside [offset, 126] under a real base
 __device__ __forceinline__ uint4 ld_stream128(const uint8_t* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint8_t ex_class(uint32_t c, bool fasta) {
+    int code = mc_nuc_code((uint8_t)c);
+    if (code < 4) return (uint8_t)code;
+    if (code == 4) return EX_CLS_SPLIT | EX_CLS_N;
+    if (!fasta && c == '.') return EX_CLS_SPLIT;
+    return EX_CLS_SPLIT | EX_CLS_BAD;
+}
 
-template <bool FASTA, int MODE>
-__global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
+__device__ __forceinline__ uint32_t ex_lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+struct McRollOut {
+    uint32_t emitted, good, splits, flags;
+};
+// Where a lane's e-th key goes inside its warp's block of the flat key buffer.  Lanes emit in lockstep, so the first `rows`
+// keys of every active lane are interleaved (row e = `stride` consecutive slots, one per active lane: one coalesced store
+// per emission step instead of 32 scattered 8-byte stores); what a lane has beyond `rows` follows in a private tail.
+struct McOutSlots {
+    uint64_t* row;    // block + my rank among the active lanes
+    uint64_t* tail;   // my private tail
+    uint32_t rows, stride;
+    __device__ __forceinline__ uint64_t* at(uint32_t e) const { return e < rows ? row + (uint64_t)e * stride : tail + (e - rows); }
+};
+// One pass over bases [s_lo, j_end) of a read: reader statistics for [s_lo, own_hi), every k-mer that lies inside a run to `out`.
+// STAGED: seq/qual are shared-memory addresses (the warp's staged span), else global pointers.
+template <bool FASTA, bool STAGED>
+__device__ __forceinline__ McRollOut ex_roll(uint64_t seq, uint64_t qual, uint32_t cls_saddr, uint32_t s_lo, uint32_t j_end, uint32_t own_hi, uint32_t len,
+                                             int k, uint64_t kmask, int rc_shift, uint32_t qoff, uint32_t qspan, const McOutSlots& out) {
+    McRollOut o{0, 0, 0, 0};
+    uint64_t fw = 0, rc = 0;
+    uint32_t run = 0;
+#pragma unroll 2
+    for (uint32_t j = s_lo; j < j_end; j++) {
+        const uint32_t c = STAGED ? ex_lds_u8((uint32_t)seq + j) : (uint32_t) __ldg((const uint8_t*)seq + j);
+        const uint32_t cls = ex_lds_u8(cls_saddr + c);
+        uint32_t split = cls & EX_CLS_SPLIT;
+        if (!FASTA) {
+            const uint32_t q = STAGED ? ex_lds_u8((uint32_t)qual + j) : (uint32_t) __ldg((const uint8_t*)qual + j);
+            const uint32_t qd = q - qoff;
+            o.flags |= (cls & EX_CLS_BAD) | ((split == 0 && qd > qspan) ? EX_FLAG_QUAL : 0u);
+            split |= ((qd & 63u) == 0) ? 1u : 0u;
+            if (j < own_hi) {
+                o.good += split ? 0u : 1u;
+                o.splits += (split && j + 1 != len) ? 1u : 0u;
+            }
+        } else {
+            o.flags |= cls;   // EX_CLS_N: the record holds an N, EX_CLS_BAD: an invalid character
+        }
+        const uint64_t b = cls & 3u;
+        fw = ((fw << 2) | b) & kmask;
+        rc = (rc >> 2) | ((3ULL - b) << rc_shift);
+        run = split ? 0u : run + 1u;
+        if (run >= (uint32_t)k) {
+            *out.at(o.emitted) = mc_mix62(fw < rc ? fw : rc);
+            o.emitted++;
+        }
+    }
+    return o;
+}
+
+template <bool FASTA, int PARTS>
+__global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
-    uint8_t(*s_stage)[EX_STAGE_BYTES] = reinterpret_cast<uint8_t(*)[EX_STAGE_BYTES]>(s_dyn);
+    constexpr int RPW = 32 / PARTS;   // records per warp and step
+    uint8_t* const s_cls = s_dyn + EX_WARPS * EX_STAGE_BYTES;
+    for (int i = threadIdx.x; i < 256; i += EX_THREADS) s_cls[i] = ex_class((uint32_t)i, FASTA);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int part = lane & 3;
-    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int part = lane & (PARTS - 1);
+    const uint32_t group_mask = PARTS == 32 ? 0xffffffffu : (((1u << PARTS) - 1u) << (lane & ~(PARTS - 1)));
+    uint8_t* const sw = s_dyn + (threadIdx.x >> 5) * EX_STAGE_BYTES;
+    const uint32_t warps_total = (gridDim.x * EX_THREADS) >> 5;
+    const uint32_t warp_global = (blockIdx.x * EX_THREADS + threadIdx.x) >> 5;
     const int k = a.k;
     const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
     const int rc_shift = 2 * k - 2;
+    const uint32_t qoff = (uint32_t)a.qoff, qspan = 126u - qoff;
 
-    unsigned long long st_reads = 0, st_runs = 0, st_bases = 0, st_kmers = 0, st_new = 0;
+    unsigned long long st_reads = 0, st_runs = 0, st_bases = 0, st_kmers = 0;
 
-    // each warp takes 8 consecutive records per step; all lanes run the same number of steps
-    for (uint32_t g = warp_global; (uint64_t)g * 8 < a.n_records; g += warps_total) {
-        const uint32_t r = g * 8 + (lane >> 2);
+    for (uint32_t g = warp_global; (uint64_t)g * RPW < a.n_records; g += warps_total) {
+        const uint32_t r = g * RPW + lane / PARTS;
         const bool live = r < a.n_records;
-        McRec rec = live ? a.recs[r] : McRec{0, 0, 0, 0};
+        const McRec rec = live ? a.recs[r] : McRec{0, 0, 0, 0};
         const uint8_t* seq = a.base + rec.seq_off;
         const uint8_t* qual = a.base + rec.qual_off;
+        bool staged = false;
+        // ---- the warp's byte span -> shared memory ------------------------------------------------
         {
             uint32_t lo = live ? rec.seq_off : 0xFFFFFFFFu;
             uint32_t hi = !live ? 0u : FASTA ? rec.seq_off + rec.seq_len : max(rec.seq_off + rec.seq_len, rec.qual_off + rec.qual_len);
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
+            __syncwarp();   // the previous step's readers are done with the buffer
             if (hi > lo && hi <= a.n_bytes) {
-                const uint8_t* g = a.base + lo;
-                const uint32_t al = (uint32_t)((uintptr_t)g & 15);
+                const uint8_t* gp = a.base + lo;
+                const uint32_t al = (uint32_t)((uintptr_t)gp & 15);
                 const uint32_t span = hi - lo + al;
                 if (span <= EX_STAGE_BYTES) {
-                    const uint8_t* g0 = g - al;
+                    const uint8_t* g0 = gp - al;
                     const uint8_t* end = a.base + a.n_bytes;
-                    uint8_t* sw = s_stage[threadIdx.x >> 5];
-                    __syncwarp();   // the previous group's readers are done
                     for (uint32_t off = lane * 16; off < span; off += 512) {
                         const uint8_t* p = g0 + off;
                         if (p >= a.base && p + 16 <= end) {
@@ -105,119 +186,95 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
                                 if (p + j >= a.base && p + j < end) sw[off + j] = p[j];
                         }
                     }
-                    __syncwarp();
                     seq = sw + al + (rec.seq_off - lo);
                     qual = sw + al + (rec.qual_off - lo);
+                    staged = true;
                 }
             }
+            __syncwarp();
         }
-        uint32_t len = rec.seq_len;
+        const uint32_t len = rec.seq_len;
         bool skip = !live;
         if (!FASTA && live && rec.qual_len != rec.seq_len) {
             if (part == 0) mc_report_error(a.header, MC_PE_FQ_LEN, rec.seq_off);
             skip = true;
         }
-        // ---- validation + statistics over my quarter of the record ---------------------------
-        uint32_t q_lo = (uint32_t)(((uint64_t)len * part) >> 2), q_hi = (uint32_t)(((uint64_t)len * (part + 1)) >> 2);
-        bool has_n = false;
-        uint32_t good = 0, splits = 0, bad_pos = 0xFFFFFFFFu, bad_code = 0;
-        if (!skip) {
-            for (uint32_t j = q_lo; j < q_hi; j++) {
-                uint8_t c = seq[j];
-                int code = mc_nuc_code(c);
-                if (FASTA) {
-                    if (code == 4) has_n = true;
-                    else if (code == 5 && bad_pos == 0xFFFFFFFFu) { bad_pos = rec.seq_off + j; bad_code = is_iupac(c) ? MC_PE_IUPAC : MC_PE_NUC; }
-                } else {
-                    bool split = (code == 4) || (c == '.');
-                    if (!split) {
-                        if (code == 5) mc_report_error(a.header, is_iupac(c) ? MC_PE_IUPAC : MC_PE_NUC, rec.seq_off + j);
-                        uint8_t q = qual[j];
-                        if (q < a.qoff || q > 126) mc_report_error(a.header, MC_PE_QUAL, rec.qual_off + j);
-                        split = (((uint32_t)q - (uint32_t)a.qoff) & 63u) == 0;
-                    }
-                    if (split) { if (j + 1 != len) splits++; }
-                    else good++;
-                }
-            }
-        }
-        if (FASTA) {
-            // the whole quad must agree on has_n before anything is reported or counted
-            unsigned m = __ballot_sync(0xffffffffu, has_n);
-            bool rec_has_n = (m >> (lane & ~3)) & 0xF;
-            if (!skip && !rec_has_n && bad_pos != 0xFFFFFFFFu) mc_report_error(a.header, bad_code, bad_pos);
-            if (rec_has_n || len == 0) skip = true;
-            if (!skip && part == 0) { st_reads++; st_runs++; st_bases += len; }
-        } else if (!skip) {
-            if (part == 0) { st_reads++; st_runs++; }
-            st_runs += splits;
-            st_bases += good;
-        }
-        // ---- rolling extraction over my share of k-mer start positions ------------------------
-        uint32_t nk = (!skip && len >= (uint32_t)k) ? len - k + 1 : 0;
-        uint32_t S = (nk + 3) >> 2;
-        uint32_t s_lo = min(nk, part * S), s_hi = min(nk, s_lo + S);
-        uint32_t reserve = s_hi - s_lo;
-        unsigned long long out_pos = 0;
-        if (MODE == 1) {
-            // warp-aggregated reservation of `reserve` slots per lane in the flat key buffer
-            uint32_t incl = reserve;
+        // ---- my share of the record -------------------------------------------------------------
+        const uint32_t nk = (!skip && len >= (uint32_t)k) ? len - k + 1 : 0;
+        const uint32_t S = (nk + PARTS - 1) / PARTS;
+        const uint32_t s_lo = min(nk, part * S), s_hi = min(nk, s_lo + S);
+        const uint32_t reserve = s_hi - s_lo;
+        const uint32_t own_hi = skip ? s_lo : (part == PARTS - 1 ? len : s_hi);          // statistics: bases [s_lo, own_hi)
+        const uint32_t j_end = skip ? s_lo : (part == PARTS - 1 ? len : (reserve ? s_hi + k - 1 : s_lo));
+        // warp-aggregated reservation of the warp's flat-key block (sum of `reserve`), laid out as McOutSlots describes
+        McOutSlots out;
+        {
+            const uint32_t act = __ballot_sync(0xffffffffu, reserve > 0);
+            out.stride = __popc(act);
+            out.rows = act ? __reduce_min_sync(0xffffffffu, reserve ? reserve : 0xFFFFFFFFu) : 0u;
+            const uint32_t rest = reserve > out.rows ? reserve - out.rows : 0u;
+            uint32_t incl = rest;
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t warp_total = out.rows * out.stride + __shfl_sync(0xffffffffu, incl, 31);
             unsigned long long base = 0;
             if (lane == 0 && warp_total) base = atomicAdd(a.out_cursor, (unsigned long long)warp_total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            out_pos = base + incl - reserve;
+            out.row = a.out_keys + base + __popc(act & ((1u << lane) - 1u));
+            out.tail = a.out_keys + base + (uint64_t)out.rows * out.stride + (incl - rest);
         }
-        // (collecting a warp's keys in shared memory for coalesced stores was measured slower: the extra 64 KB per CTA
-        // halves the occupancy this ALU/latency-bound loop needs, profiles/r1c_NOTES.md)
-        uint64_t* const my_out = (MODE == 1) ? a.out_keys + out_pos : nullptr;
-        uint32_t emitted = 0;
-        if (reserve) {
-            uint64_t fw = 0, rc = 0;
-            uint32_t run = 0;
-            const uint32_t j_end = s_hi + k - 1;   // exclusive; <= len
-            for (uint32_t j = s_lo; j < j_end; j++) {
-                uint8_t c = seq[j];
-                int code = mc_nuc_code(c);
-                bool bad = code >= 4;
-                if (!FASTA && !bad) {
-                    uint8_t q = qual[j];
-                    bad = (((uint32_t)q - (uint32_t)a.qoff) & 63u) == 0;
-                }
-                uint64_t b = (uint64_t)(code & 3);
-                fw = ((fw << 2) | b) & kmask;
-                rc = (rc >> 2) | ((3ULL - b) << rc_shift);
-                run = bad ? 0 : run + 1;
-                if (run >= (uint32_t)k) {
-                    uint64_t key = fw < rc ? fw : rc;
-                    uint64_t h = mc_mix62(key);
-                    st_kmers++;
-                    if (MODE == 0) {
-                        if (a.table.shard_bits == 0 || (h >> (62 - a.table.shard_bits)) == a.shard_id)
-                            if (mc_table_add(a.table, h, 1)) st_new++;
-                    } else {
-                        my_out[emitted] = h;
-                        emitted++;
-                    }
+        const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(s_cls);
+        McRollOut ro;
+        if (staged)
+            ro = ex_roll<FASTA, true>((uint64_t)__cvta_generic_to_shared(seq), (uint64_t)__cvta_generic_to_shared(qual), cls_saddr, s_lo, j_end, own_hi, len, k,
+                                      kmask, rc_shift, qoff, qspan, out);
+        else
+            ro = ex_roll<FASTA, false>((uint64_t)seq, (uint64_t)qual, cls_saddr, s_lo, j_end, own_hi, len, k, kmask, rc_shift, qoff, qspan, out);
+        uint32_t emitted = ro.emitted;
+        const uint32_t good = ro.good, splits = ro.splits, flags = ro.flags;
+        // ---- record-level outcome ---------------------------------------------------------------
+        bool drop = false;
+        if (FASTA) {
+            // FastaReader.java:58-59: a record holding N or n is skipped whole; invalid characters only matter otherwise
+            drop = (__ballot_sync(0xffffffffu, (flags & EX_CLS_N) != 0) & group_mask) != 0;
+            if (!skip && !drop && (flags & EX_CLS_BAD)) {
+                for (uint32_t j = s_lo; j < own_hi; j++) {
+                    const uint8_t c = seq[j];
+                    if (s_cls[c] & EX_CLS_BAD) { mc_report_error(a.header, is_iupac(c) ? MC_PE_IUPAC : MC_PE_NUC, rec.seq_off + j); break; }
                 }
             }
+            if (drop || len == 0) skip = true;
+            if (!skip && part == 0) { st_reads++; st_runs++; st_bases += len; }
+        } else if (!skip) {
+            if (flags & (EX_CLS_BAD | EX_FLAG_QUAL)) {   // rare: locate the first offending base of my share, in the reader's order of checks
+                for (uint32_t j = s_lo; j < own_hi; j++) {
+                    const uint8_t c = seq[j];
+                    const uint32_t cls = s_cls[c];
+                    if (cls & EX_CLS_SPLIT) {
+                        if (cls & EX_CLS_BAD) { mc_report_error(a.header, is_iupac(c) ? MC_PE_IUPAC : MC_PE_NUC, rec.seq_off + j); break; }
+                        continue;
+                    }
+                    if ((uint32_t)qual[j] - qoff > qspan) { mc_report_error(a.header, MC_PE_QUAL, rec.qual_off + j); break; }
+                }
+            }
+            if (part == 0) { st_reads++; st_runs++; }
+            st_runs += splits;
+            st_bases += good;
         }
-        if (MODE == 1) {
-            for (uint32_t e = emitted; e < reserve; e++) my_out[e] = MC_HASH_SENTINEL;
-        }
+        if (drop) emitted = 0;   // FASTA record with an N: its k-mers are withdrawn
+        st_kmers += emitted;
+        for (uint32_t e = emitted; e < reserve; e++) *out.at(e) = MC_HASH_SENTINEL;
     }
 
     // ---- block-aggregated statistics ---------------------------------------------------------
-    __shared__ unsigned long long s_acc[5];
-    if (threadIdx.x < 5) s_acc[threadIdx.x] = 0;
+    __shared__ unsigned long long s_acc[4];
+    if (threadIdx.x < 4) s_acc[threadIdx.x] = 0;
     __syncthreads();
-    unsigned long long v[5] = {st_reads, st_runs, st_bases, st_kmers, st_new};
+    unsigned long long v[4] = {st_reads, st_runs, st_bases, st_kmers};
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < 4; i++) {
         unsigned long long x = v[i];
         for (int o = 16; o; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(&s_acc[i], x);
@@ -228,7 +285,6 @@ __global__ void __launch_bounds__(256) k_extract(McExtractArgs a) {
         if (s_acc[1]) atomicAdd(&a.table.counters[MC_CNT_RUNS], s_acc[1]);
         if (s_acc[2]) atomicAdd(&a.table.counters[MC_CNT_BASES], s_acc[2]);
         if (s_acc[3]) atomicAdd(&a.table.counters[MC_CNT_KMERS], s_acc[3]);
-        if (s_acc[4]) atomicAdd(&a.table.counters[MC_CNT_KEYS], s_acc[4]);
     }
 }
 
@@ -322,27 +378,35 @@ static unsigned long long check_k2_errors(mc_ctx* ctx, McParseHeader* d_header, 
     return *hc;
 }
 
-template <bool FASTA, int MODE>
-static void launch_extract(mc_ctx* ctx, McExtractArgs& a) {
-    const size_t smem = 8 * EX_STAGE_BYTES;
+template <bool FASTA, int PARTS>
+static void launch_extract_p(mc_ctx* ctx, McExtractArgs& a) {
+    const size_t smem = EX_WARPS * EX_STAGE_BYTES + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        MC_CUDA(cudaFuncSetAttribute(k_extract<FASTA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MC_CUDA(cudaFuncSetAttribute(k_extract<FASTA, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    uint64_t warps = ((uint64_t)a.n_records + 7) / 8;
-    uint64_t blocks = (warps + 7) / 8;                           // 8 warps per 256-thread CTA
-    uint64_t cap = (uint64_t)ctx->sm_count * 6 * 4;   // resident CTAs per SM x 4 waves
+    const uint64_t per_cta = (uint64_t)(32 / PARTS) * EX_WARPS;          // records per CTA step
+    uint64_t blocks = ((uint64_t)a.n_records + per_cta - 1) / per_cta;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 4 * 4;                 // resident CTAs per SM x 4 waves
     if (blocks < 1) blocks = 1;
-    k_extract<FASTA, MODE><<<(unsigned)std::min(blocks, cap), 256, smem, ctx->stream>>>(a);
+    k_extract<FASTA, PARTS><<<(unsigned)std::min(blocks, cap), EX_THREADS, smem, ctx->stream>>>(a);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
 }
-
+// lanes per record: one for short reads (no context bases re-read), more when a warp's records would not fit its shared-memory
+// window or a single lane would serialise a long read
+template <bool FASTA>
+static void launch_extract(mc_ctx* ctx, McExtractArgs& a, uint32_t max_seq_len) {
+    const uint32_t one = FASTA ? 380u : 170u;
+    if (ctx->tune_extract_parts == 1 || (ctx->tune_extract_parts == 0 && max_seq_len <= one)) launch_extract_p<FASTA, 1>(ctx, a);
+    else if (ctx->tune_extract_parts == 4 || (ctx->tune_extract_parts == 0 && max_seq_len <= 4 * one)) launch_extract_p<FASTA, 4>(ctx, a);
+    else launch_extract_p<FASTA, 32>(ctx, a);
+}
 
 #define MC_FLAT_HEAD 8192   // cursor + per-owner counters and cursors in front of the flat keys
 // Launches k_extract in its flat-key mode into scratch slot 2; returns the device buffer, *n_flat = keys written (sentinels included)
-static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint64_t ub, const uint8_t* d_buf, uint32_t n, uint64_t* n_flat) {
+static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint32_t max_seq_len, uint64_t ub, const uint8_t* d_buf, uint32_t n, uint64_t* n_flat) {
     cudaStream_t st = ctx->stream;
     uint8_t* s2 = (uint8_t*)mc_scratch(ctx, 2, MC_FLAT_HEAD + ub * sizeof(uint64_t));
     unsigned long long* d_cursor = (unsigned long long*)s2;
@@ -352,8 +416,8 @@ static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint64_
     a.out_cursor = d_cursor;
     {
         McStageTimer tm(ctx, MC_ST_EXTRACT);
-        if (fasta) launch_extract<true, 1>(ctx, a);
-        else launch_extract<false, 1>(ctx, a);
+        if (fasta) launch_extract<true>(ctx, a, max_seq_len);
+        else launch_extract<false>(ctx, a, max_seq_len);
     }
     *n_flat = check_k2_errors(ctx, a.header, d_buf, n, d_cursor);
     if (*n_flat > ub) mc_throw(MC_ERR_CUDA, "internal: %llu k-mers extracted from a chunk bounded by %llu", (unsigned long long)*n_flat, (unsigned long long)ub);
@@ -379,23 +443,12 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
         a.header = P.d_header;
         a.table = t->dev;
         a.shard_id = t->shard_id;
-        if (ctx->tune_direct) {
-            // the round-1a design, kept for A/B measurements: extraction fused with direct probing of the HBM-sized table
-            mc_table_prepare_chunk(t, ub);
-            a.table = t->dev;
-            {
-                McStageTimer tm(ctx, MC_ST_EXTRACT);
-                if (fasta) launch_extract<true, 0>(ctx, a);
-                else launch_extract<false, 0>(ctx, a);
-            }
-            check_k2_errors(ctx, P.d_header, d_buf, n);
-            mc_table_finish_chunk(t);
-        } else {
+        {
             // extract -> flat hashed keys -> bins; the table itself is touched only when the batch is flushed
             mc_batch_reserve(t, ub + 1, total_hint);
             a.table = t->dev;   // a flush may have grown the table (the extractor only uses its statistics counters)
             uint64_t n_flat = 0;
-            uint64_t* d_flat = extract_flat(ctx, a, fasta, ub + 1, d_buf, n, &n_flat);
+            uint64_t* d_flat = extract_flat(ctx, a, fasta, P.h.max_seq_len, ub + 1, d_buf, n, &n_flat);
             mc_batch_scatter(t, d_flat, n_flat);
         }
     }
@@ -657,7 +710,7 @@ extern "C" int mc_extract_partition_device(mc_ctx* ctx, const void* dbuf, size_t
         a.header = P.d_header;
         a.table = stats_sink->dev;
         uint64_t n_flat = 0;
-        uint64_t* d_flat = extract_flat(ctx, a, fasta, ub, p, (uint32_t)len, &n_flat);
+        uint64_t* d_flat = extract_flat(ctx, a, fasta, P.h.max_seq_len, ub, p, (uint32_t)len, &n_flat);
         // the head of slot 2 (8 KiB, zeroed by extract_flat): [0] flat cursor, [8..) per-owner counters, then cursors
         unsigned long long* d_counts = (unsigned long long*)((uint8_t*)d_flat - MC_FLAT_HEAD) + 8;
         unsigned long long* d_cursors = d_counts + MC_MAX_OWNERS;

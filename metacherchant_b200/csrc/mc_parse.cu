@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_counts, uint
         h->data_lines = 0;
         h->final_state = 0;
         h->total_seq_bytes = 0;
+        h->max_seq_len = 0;
     }
 }
 
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
         }
         if (first <= n_lines - 1 && n_lines - 1 < first + LINES_PER_THREAD) rec_off[D] = h->total_seq_bytes;
     } else {
-        uint32_t st = in.f & 1, d = in.c0;
+        uint32_t st = in.f & 1, d = in.c0, longest = 0;
 #pragma unroll
         for (uint32_t j = 0; j < LINES_PER_THREAD; j++) {
             uint32_t i = first + j;
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
                 if ((d & 1) == 0) {
                     recs[r].seq_off = s;
                     recs[r].seq_len = e - s;
+                    longest = max(longest, e - s);
                     if ((D & 1) && d == D - 1) {   // sequence line whose quality line is not in this chunk: carry the record
                         uint32_t ps, pe;
                         line_span(buf, n, line_end, i - 1, ps, pe);
@@ -333,6 +335,8 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
                 st = 0;
             }
         }
+        longest = __reduce_max_sync(__activemask(), longest);
+        if ((threadIdx.x & 31) == 0 && longest) atomicMax(&h->max_seq_len, longest);
     }
     (void)final_state;
     (void)final_chunk;
@@ -351,12 +355,16 @@ __global__ void __launch_bounds__(256) k_fa_copy(const uint8_t* __restrict__ buf
         for (uint32_t p = s + lane; p < e; p += 32) seqbuf[dst + (p - s)] = buf[p];
     }
 }
-__global__ void __launch_bounds__(256) k_fa_recs(const uint32_t* __restrict__ rec_off, uint32_t n_records, McRec* __restrict__ recs) {
+__global__ void __launch_bounds__(256) k_fa_recs(const uint32_t* __restrict__ rec_off, uint32_t n_records, McRec* __restrict__ recs, McParseHeader* h) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t l = 0;
     if (r < n_records) {
-        uint32_t o = rec_off[r], l = rec_off[r + 1] - o;
+        uint32_t o = rec_off[r];
+        l = rec_off[r + 1] - o;
         recs[r] = McRec{o, l, 0, l};
     }
+    l = __reduce_max_sync(0xffffffffu, l);
+    if ((threadIdx.x & 31) == 0 && l) atomicMax(&h->max_seq_len, l);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -435,9 +443,12 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     MC_CUDA(cudaStreamSynchronize(st));
     out->h = *hp;
     if (fasta && out->h.n_records > 0) {
-        k_fa_recs<<<(out->h.n_records + 255) / 256, 256, 0, st>>>(d_rec_off, out->h.n_records, d_recs);
+        k_fa_recs<<<(out->h.n_records + 255) / 256, 256, 0, st>>>(d_rec_off, out->h.n_records, d_recs, d_h);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
+        MC_CUDA(cudaMemcpyAsync(&hp->max_seq_len, &d_h->max_seq_len, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        out->h.max_seq_len = hp->max_seq_len;
     }
 }
 

@@ -29,6 +29,7 @@ struct McParseHeader {
     uint32_t data_lines;      // FASTQ: number of data lines seen; FASTA: number of records started
     uint32_t final_state;     // FASTQ reader FSM state after the last line
     uint32_t total_seq_bytes; // FASTA: bytes copied into the compacted sequence buffer
+    uint32_t max_seq_len;     // longest sequence of the chunk's records (picks the extractor's lanes-per-record)
 };
 
 struct McParsed {

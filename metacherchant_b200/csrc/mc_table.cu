@@ -583,14 +583,6 @@ extern "C" int mc_table_insert_hashed_device(mc_table* t, const uint64_t* d_hkey
         if (n == 0) return MC_OK;
         mc_ctx* ctx = t->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
-        if (ctx->tune_direct) {
-            mc_table_prepare_chunk(t, n);
-            k_insert_hashed<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(t->dev, d_hkeys, n);
-            MC_LAUNCH(ctx);
-            MC_CUDA(cudaGetLastError());
-            mc_table_finish_chunk(t, false);
-            return MC_OK;
-        }
         // buffered: the keys are binned now and applied by the next flush (any read of the table flushes)
         mc_batch_reserve(t, n, 0);
         mc_batch_scatter(t, d_hkeys, n);

@@ -197,7 +197,8 @@ BIN_TUNINGS = [
     dict(part_bits=4, batch_keys=3000),                        # tiny batch: most keys take the spill list, many flushes
     dict(part_bits=3, segment_keys=2048),                      # one k_bin_count launch per tile
     dict(part_bits=6, batch_keys=50_000, segment_keys=4096),
-    dict(direct=1),                                            # the fused direct-probing path stays exact too
+    dict(extract_parts=4),
+    dict(extract_parts=32, part_bits=2),
 ]
 
 
