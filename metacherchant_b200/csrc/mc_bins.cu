@@ -336,7 +336,8 @@ void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
 
 __global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);
 
-static const double MC_FLUSH_TARGET_LOAD = 0.50;   // table load aimed at when a flush has to grow the table
+static const double MC_FLUSH_TARGET_LOAD = 0.50;
+static const uint64_t MC_FLUSH_SEGMENT = 128ull << 20;   // keys per k_bin_count launch (and entries of the overflow list)   // table load aimed at when a flush has to grow the table
 extern const double MC_GROW_LOAD;
 extern const uint64_t MC_OVF_MAX;
 
@@ -362,25 +363,39 @@ void mc_table_flush(mc_table* t) {
     uint64_t* d_prefix = (uint64_t*)(B->dev.cursors + (P + 1));
     MC_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
 
-    const uint64_t seg_keys_max = ctx->tune_segment_keys ? std::min(std::max<uint64_t>(ctx->tune_segment_keys, BIN_TILE), MC_OVF_MAX) : MC_OVF_MAX;
+    // One k_bin_count launch per segment of at most seg_keys_max keys.  The overflow list attached to the table has room for a
+    // whole segment, so even a table that turns out far too small loses no update; after every segment the key counter
+    // tells how many keys the batch will add in total (hashes are uniform: the slices not swept yet gain what the swept
+    // ones did) and the table is grown to that size at once, while it is still mostly empty.
+    const uint64_t seg_keys_max = ctx->tune_segment_keys ? std::min(std::max<uint64_t>(ctx->tune_segment_keys, BIN_TILE), MC_FLUSH_SEGMENT) : MC_FLUSH_SEGMENT;
     const uint64_t seg_tiles_max = std::max<uint64_t>(seg_keys_max / BIN_TILE, 1);
+    const uint64_t ovf_cap = std::max<uint64_t>(std::min<uint64_t>(seg_keys_max, total_tiles * BIN_TILE), 1024);
+    auto attach_overflow_list = [&]() {
+        t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
+        t->dev.ovf_cap = ovf_cap;
+        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), st));
+    };
+    attach_overflow_list();
+    McBinCountKernel kern = bin_count_variant(ctx->tune_count_variant);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    cudaGetLastError();
+    unsigned long long* d_ticket = (unsigned long long*)(d_prefix + (P + 1));
+    unsigned long long* h_c = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 1024);   // counters + flags read-back
+    unsigned int* h_flags = (unsigned int*)(h_c + MC_CNT_N);
     const uint64_t keys_before = mc_table_keys(t);
+    uint64_t keys_known = keys_before;
     uint64_t tile = 0;
     bool first = true;
     while (tile < total_tiles) {
         // the first segment is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
         uint64_t seg = first ? std::max<uint64_t>(total_tiles / 64, 1) : seg_tiles_max;
         seg = std::min(std::min(seg, seg_tiles_max), total_tiles - tile);
-        mc_table_prepare_chunk(t, seg * BIN_TILE);
+        if ((double)keys_known > MC_GROW_LOAD * 4.0 * (double)t->nb) mc_table_grow_to(t, t->dev.q + 1);   // amortised doubling
         {
             McStageTimer tm(ctx, MC_ST_COUNT);
-            // exactly the co-resident CTAs: with a static tile stride the sweep window then moves monotonically over the slices
-            McBinCountKernel kern = bin_count_variant(ctx->tune_count_variant);
-            int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-            cudaGetLastError();
+            // exactly the co-resident CTAs; tiles are handed out in order by the ticket
             const int grid = (int)std::min<uint64_t>(seg, (uint64_t)ctx->sm_count * per_sm);
-            unsigned long long* d_ticket = (unsigned long long*)(d_prefix + (P + 1));
             MC_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned long long), st));
             kern<<<grid, 256, 0, st>>>(t->dev, B->dev, d_prefix, tile, tile + seg, BIN_TILE, d_ticket);
             MC_LAUNCH(ctx);
@@ -388,11 +403,12 @@ void mc_table_flush(mc_table* t) {
         }
         tile += seg;
         first = false;
-        // predicted size at the end of this batch: hashes are uniform, so the slices not swept yet gain what the swept ones did
-        unsigned long long c[MC_CNT_N];
-        MC_CUDA(cudaMemcpyAsync(c, t->dev.counters, sizeof c, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(h_flags, t->dev.flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaStreamSynchronize(st));
-        const uint64_t now = c[MC_CNT_KEYS] + c[MC_CNT_OVF];
+        if (*h_flags & MC_FLAG_OVERFLOW) mc_throw(MC_ERR_NOMEM, "k-mer table overflow (stash and overflow list full)");
+        const uint64_t ovf_n = h_c[MC_CNT_OVF];
+        const uint64_t now = h_c[MC_CNT_KEYS] + ovf_n;
         const double gained = now > keys_before ? (double)(now - keys_before) : 0.0;
         const double predicted = (double)keys_before + gained * ((double)total_tiles / (double)tile);
         bool grown = false;
@@ -403,12 +419,20 @@ void mc_table_flush(mc_table* t) {
                 grown = true;
             }
         }
-        mc_table_finish_chunk(t, grown);
+        if (ovf_n) {   // rare: the table was too small for this segment; re-insert what overflowed (grows until it fits)
+            mc_table_finish_chunk(t, grown);
+            attach_overflow_list();
+            keys_known = mc_table_keys(t);
+        } else {
+            keys_known = now;
+        }
     }
+    t->dev.ovf_keys = nullptr;
+    t->dev.ovf_cap = 0;
     // spill list: direct updates
     uint64_t sp = cur[P];
     for (uint64_t off = 0; off < sp;) {
-        const uint64_t n = std::min<uint64_t>(sp - off, seg_keys_max);
+        const uint64_t n = std::min<uint64_t>(sp - off, MC_OVF_MAX);
         mc_table_prepare_chunk(t, n);
         {
             McStageTimer tm(ctx, MC_ST_COUNT);
@@ -445,6 +469,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     if (n == "part_bits" && value >= -1 && value <= MC_MAX_PBITS) ctx->tune_part_bits = (long)value;
     else if (n == "batch_keys" && value >= 0) ctx->tune_batch_keys = (uint64_t)value;
     else if (n == "segment_keys" && value >= 0) ctx->tune_segment_keys = (uint64_t)value;
+    else if (n == "host_batch_chunks" && value >= 0 && value <= 1024) ctx->tune_host_batch_chunks = (uint32_t)value;
     else if (n == "extract_parts" && (value == 0 || value == 1 || value == 4 || value == 32)) ctx->tune_extract_parts = (int)value;
     else if (n == "count_variant" && value >= 0 && value <= 3) ctx->tune_count_variant = (int)value;
     else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;

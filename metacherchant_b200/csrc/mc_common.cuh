@@ -272,6 +272,7 @@ struct mc_ctx {
     uint64_t tune_segment_keys = 0;  // keys applied per k_bin_count launch
     uint32_t tune_count_tile = 0;    // keys per k_bin_count work unit
     int tune_count_variant = 0;      // k_bin_count instantiation (probes in flight / occupancy), for measurements
+    uint32_t tune_host_batch_chunks = 0;   // host input: chunks binned between two table sweeps (0 = default 1)
     int tune_extract_parts = 0;      // lanes per record in k_extract: 0 = by read length, else 1 / 4 / 32
     int sm_count = 148;
     // reusable device scratch for the parser (grown on demand)

@@ -527,6 +527,10 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
             }
         for (int i = 0; i < 2; i++) MC_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
         MC_CUDA(cudaEventCreateWithFlags(&consumed_ev, cudaEventDisableTiming));
+        // Host input is PCIe-bound (~20 ms per GiB): the bins are applied after every chunk (measured best: profiles/r1c_NOTES.md), so that the table sweep runs in the
+        // shadow of the uploads instead of after the last one (device-resident input is binned whole, one sweep)
+        const uint64_t host_chunks = ctx->tune_host_batch_chunks ? ctx->tune_host_batch_chunks : 1;
+        const uint64_t batch_hint = std::min<uint64_t>(mc_max_kmers(len, fmt, t->k), host_chunks * mc_max_kmers(chunk, fmt, t->k));
         size_t pos = 0;      // next host byte to upload
         size_t carry = 0;    // bytes of the previous chunk sitting right in front of offset `chunk`
         int cur = 0;
@@ -548,7 +552,7 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
             MC_CUDA(cudaStreamWaitEvent(ctx->stream, copied[cur], 0));
             const uint8_t* d_start = (const uint8_t*)ctx->d_chunk[cur] + chunk - carry;
             const size_t n = carry + n_slice;
-            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, mc_max_kmers(len, fmt, t->k));
+            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, batch_hint);
             if (final_chunk) break;
             size_t left = n - consumed;
             if (left > chunk) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", chunk);

@@ -28,14 +28,33 @@
 // `base` is an offset in aligned coordinates (multiple of 32); bit j of the result = logical byte base+j-mis is a line
 // terminator.  Bytes before the chunk read as 0; the byte after the chunk reads as `pad` ('\n' for a non-final chunk,
 // so a trailing '\r' stays part of the unfinished line and is carried over; 0 at end of input).
+// 0x80 in every byte of w that equals the (replicated) byte pattern; exact per byte (no carries between bytes)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t pat) {
+    const uint32_t x = w ^ pat;
+    const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
+    return ~t & 0x80808080u;
+}
 __device__ __forceinline__ uint32_t term_mask32(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint32_t base, uint8_t pad) {
     __align__(16) uint8_t b[48];
     const uint32_t lo = mis, hi = mis + n;   // valid aligned-coordinate range [lo, hi)
     if (base >= lo && base + 33 <= hi) {
+        // interior: eight 32-bit words, four bytes per step (SWAR); '\n', or '\r' not followed by '\n', ends a line
         const uint4* p = reinterpret_cast<const uint4*>(abuf + base);
-        *reinterpret_cast<uint4*>(b) = __ldg(p);
-        *reinterpret_cast<uint4*>(b + 16) = __ldg(p + 1);
-        b[32] = __ldg(abuf + base + 32);
+        const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t nl[9];
+#pragma unroll
+        for (int i = 0; i < 8; i++) nl[i] = eq_bytes(w[i], 0x0A0A0A0Au);
+        nl[8] = __ldg(abuf + base + 32) == '\n' ? 0x80u : 0u;
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t cr = eq_bytes(w[i], 0x0D0D0D0Du);
+            const uint32_t nl_next = (nl[i] >> 8) | (nl[i + 1] << 24);
+            const uint32_t term = nl[i] | (cr & ~nl_next);
+            m |= ((((term >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+        }
+        return m;
     } else {
 #pragma unroll
         for (int j = 0; j < 33; j++) {
@@ -56,10 +75,13 @@ __device__ __forceinline__ uint32_t term_mask32(const uint8_t* __restrict__ abuf
     return m;
 }
 
+// pass 1 of the line index: terminator bit masks (kept: pass 2 reads them instead of the bytes) and their count per tile
 __global__ void __launch_bounds__(256) k_count_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint8_t pad,
-                                                     uint32_t* __restrict__ tile_counts) {
+                                                     uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ masks) {
     uint32_t base = blockIdx.x * TILE_BYTES + threadIdx.x * 32;
-    uint32_t c = base < mis + n ? __popc(term_mask32(abuf, mis, n, base, pad)) : 0;
+    const uint32_t mask = base < mis + n ? term_mask32(abuf, mis, n, base, pad) : 0;
+    masks[blockIdx.x * 256u + threadIdx.x] = mask;
+    uint32_t c = __popc(mask);
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     __shared__ uint32_t s[8];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
@@ -109,12 +131,12 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_counts, uint
     }
 }
 
-__global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint8_t pad,
+__global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, const uint32_t* __restrict__ masks,
                                                      const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ line_end, uint32_t n_lines,
                                                      int final_chunk) {
     const uint8_t* buf = abuf + mis;
     uint32_t base = blockIdx.x * TILE_BYTES + threadIdx.x * 32;
-    uint32_t m = base < mis + n ? term_mask32(abuf, mis, n, base, pad) : 0;
+    uint32_t m = masks[blockIdx.x * 256u + threadIdx.x];
     uint32_t c = __popc(m);
     // block exclusive scan of c
     uint32_t incl = c;
@@ -381,10 +403,13 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     uint32_t n_tiles = (mis + n + TILE_BYTES - 1) / TILE_BYTES;
     if (n_tiles == 0) n_tiles = 1;
     // slot 1: header + tile counts
-    uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, 256 + (size_t)n_tiles * 4);
+    // slot 1: header + tile counts + one terminator mask per 32 input bytes
+    const size_t off_masks = (256 + (size_t)n_tiles * 4 + 255) & ~(size_t)255;
+    uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, off_masks + (size_t)n_tiles * 256 * 4);
     McParseHeader* d_h = (McParseHeader*)s1;
     uint32_t* d_tiles = (uint32_t*)(s1 + 256);
-    k_count_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles);
+    uint32_t* d_masks = (uint32_t*)(s1 + off_masks);
+    k_count_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks);
     MC_LAUNCH(ctx);
     k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_buf, n, d_h, fin);
     MC_LAUNCH(ctx);
@@ -423,7 +448,7 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
         if (!final_chunk) out->h.consumed = 0;   // no complete line yet: everything is carried over
         return;
     }
-    k_write_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_line_end, n_lines, fin);
+    k_write_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, d_masks, d_tiles, d_line_end, n_lines, fin);
     MC_LAUNCH(ctx);
     if (fasta) {
         k_block_summaries<true><<<n_blk, 256, 0, st>>>(d_buf, n, d_line_end, n_lines, d_blk);
