@@ -290,7 +290,10 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("k_extract_dram_bytes_per_launch")
+            per_read = json.load(open(prof)).get("pipeline_dram_bytes_per_read")
+            # measured DRAM bytes of the three pipeline kernels per read (ncu, profiles/r1c_NOTES.md) x reads of one step
+            roofline["traffic"] = int(per_read * reads) if per_read else None
+            roofline["traffic_note"] = "ncu dram bytes of k_extract + k_bin_scatter + k_bin_count per read (8 M-read capture) x reads per step"
         except Exception:
             pass
 

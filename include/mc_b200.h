@@ -164,6 +164,7 @@ int mc_event_elapsed_ms(mc_ctx* ctx, int slot_a, int slot_b, float* ms);
  * [0]=parse [1]=extract [2]=grow/rehash [3]=bin scatter [4]=bin count [5]=coverage filter [6..7] reserved */
 int mc_ctx_stage_ms(mc_ctx* ctx, float* ms3);          /* first three only (kept for older callers) */
 int mc_ctx_stage_ms_all(mc_ctx* ctx, float* ms8);
+int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the timers themselves; the multi-GPU building blocks do not */
 /* tuning knobs of the binned update path (NOT reference API; tests and profiles use them):
  *   "part_bits" (-1 = automatic, else P = 2^value bins), "batch_keys" (capacity of one batch, 0 = automatic),
  *   "segment_keys" (keys applied per count launch, 0 = automatic), "count_tile", "count_variant" (k_bin_count shape),

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "mc_event_elapsed_ms": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
     "mc_ctx_stage_ms": (i32, [vp, C.POINTER(C.c_float)]),
     "mc_ctx_stage_ms_all": (i32, [vp, C.POINTER(C.c_float)]),
+    "mc_ctx_stage_reset": (i32, [vp]),
     "mc_ctx_set_tuning": (i32, [vp, cp, C.c_longlong]),
     "mc_table_flush_pending": (i32, [vp]),
 }

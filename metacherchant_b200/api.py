@@ -65,6 +65,9 @@ class Context:
         check(self.lib.mc_ctx_stage_ms_all(self.h, v))
         return {name: v[i] for i, name in enumerate(self.STAGES)}
 
+    def stage_reset(self):
+        check(self.lib.mc_ctx_stage_reset(self.h))
+
     def set_tuning(self, name: str, value: int):
         """Knobs of the binned update path: part_bits, batch_keys, segment_keys, direct (see include/mc_b200.h)."""
         check(self.lib.mc_ctx_set_tuning(self.h, name.encode(), value))

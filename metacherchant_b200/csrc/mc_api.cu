@@ -169,6 +169,13 @@ extern "C" int mc_ctx_stage_ms(mc_ctx* c, float* ms3) {
     for (int i = 0; i < 3; i++) ms3[i] = c->stage_ms[i];
     MC_API_END
 }
+extern "C" int mc_ctx_stage_reset(mc_ctx* c) {
+    MC_API_TRY
+    if (!c) mc_throw(MC_ERR_ARG, "null argument");
+    mc_resolve_timers(c);
+    for (auto& v : c->stage_ms) v = 0;
+    MC_API_END
+}
 extern "C" int mc_ctx_stage_ms_all(mc_ctx* c, float* ms8) {
     MC_API_TRY
     if (!c || !ms8) mc_throw(MC_ERR_ARG, "null argument");

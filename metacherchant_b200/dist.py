@@ -11,6 +11,8 @@ The exchange itself (`exchange_keys`) is device-agnostic and is what the world_s
 from __future__ import annotations
 
 import math
+import os
+import time
 
 import torch
 import torch.distributed as dist
@@ -63,6 +65,8 @@ class ShardedCounter:
         self.capacity_hint = capacity_hint
         self.table = None
         self.bytes_exchanged = 0
+        # wall-clock seconds per phase of the last step (host view, each phase ends with a synchronisation)
+        self.phase_s = {"extract": 0.0, "exchange": 0.0, "insert": 0.0, "sweep_filter": 0.0}
 
     def new_table(self):
         if self.table is not None:
@@ -70,38 +74,97 @@ class ShardedCounter:
         self.table = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint, shard_bits=self.shard_bits, shard_id=self.rank)
         return self.table
 
+    def _buffers(self, ub: int):
+        """Two send and two receive buffers, allocated once per size class (a fresh torch.empty of a few GB per batch costs
+        a cudaMalloc each time the size changes, measured ~10 ms per batch)."""
+        cap = getattr(self, "_buf_cap", 0)
+        if cap < ub:
+            self._send = [torch.empty(ub, dtype=torch.int64, device="cuda") for _ in range(2)]
+            self._recv = [torch.empty(ub + ub // 4 + 1024, dtype=torch.int64, device="cuda") for _ in range(2)]
+            self._buf_cap = ub
+        return self._send, self._recv
+
+    def _start_exchange(self, slot: int, counts):
+        """Counts first (tiny all-to-all), then the keys, asynchronously on the communication stream."""
+        send, recv = self._send[slot], self._recv[slot]
+        with torch.cuda.stream(self._comm_stream):
+            sc = torch.tensor(list(counts), dtype=torch.int64, device="cuda")
+            rc = torch.empty(self.world, dtype=torch.int64, device="cuda")
+            dist.all_to_all_single(rc, sc)
+            recv_counts = [int(x) for x in rc.tolist()]
+            total = sum(recv_counts)
+            if total > recv.numel():   # unbalanced owners: make room (rare)
+                self._recv[slot] = recv = torch.empty(total + total // 8, dtype=torch.int64, device="cuda")
+            dist.all_to_all_single(recv[:total], send[: sum(counts)], output_split_sizes=recv_counts, input_split_sizes=[int(x) for x in counts])
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        self.bytes_exchanged += 8 * (sum(counts) - counts[self.rank])
+        return done, total
+
     def count_device(self, d_reads: int, nbytes: int, fmt: int, batch_bytes: int, record_bytes: int | None = None):
         """Counts this rank's device-resident reads into the distributed table (collective: every rank must call it
-        with the same number of batches; ranks with fewer batches send empty groups)."""
+        with the same number of batches; ranks with fewer batches send empty groups).
+        Software pipeline: while batch b's keys cross NVLink (communication stream), batch b+1 is parsed and extracted and
+        batch b-1's received keys are binned (library stream)."""
         lib = self.ctx.lib
         batches = plan_batches(nbytes, batch_bytes, record_bytes)
         n_batches = torch.tensor([len(batches)], dtype=torch.int64, device="cuda")
         if self.world > 1:
             dist.all_reduce(n_batches, op=dist.ReduceOp.MAX)
-        for b in range(int(n_batches.item())):
+        n_batches = int(n_batches.item())
+        ub = max([int(lib.mc_max_kmers(n, fmt, self.k)) for _, n in batches] + [1])
+        send, recv = self._buffers(ub)
+        if not hasattr(self, "_comm_stream"):
+            self._comm_stream = torch.cuda.Stream()
+        pending = None   # (event, slot, n_received) of the exchange in flight
+
+        def finish(p):
+            ev, slot, total = p
+            t0 = time.perf_counter()
+            ev.synchronize()
+            t1 = time.perf_counter()
+            if total:
+                self.table.insert_hashed_device(self._recv[slot].data_ptr(), total)
+            self.phase_s["exchange"] += t1 - t0
+            self.phase_s["insert"] += time.perf_counter() - t1
+
+        for b in range(n_batches):
             off, n = batches[b] if b < len(batches) else (0, 0)
-            ub = int(lib.mc_max_kmers(n, fmt, self.k)) if n else 1
-            send = torch.empty(ub, dtype=torch.int64, device="cuda")
-            counts = self.table.extract_partition_device(d_reads + off, n, fmt, self.shard_bits, send.data_ptr()) if n else [0] * self.world
-            if self.world > 1:
-                recv, _ = exchange_keys(send, counts)
-                torch.cuda.current_stream().synchronize()      # NCCL ran on torch's stream; the insert runs on the library's
-                self.bytes_exchanged += 8 * (sum(counts) - counts[self.rank])
-            else:
-                recv = send[: counts[0]]
-            if recv.numel():
-                self.table.insert_hashed_device(recv.data_ptr(), recv.numel())
-            self.ctx.sync()
-            del send, recv
+            slot = b & 1
+            t0 = time.perf_counter()
+            counts = self.table.extract_partition_device(d_reads + off, n, fmt, self.shard_bits, send[slot].data_ptr()) if n else [0] * self.world
+            self.phase_s["extract"] += time.perf_counter() - t0
+            if self.world == 1:
+                if counts[0]:
+                    t0 = time.perf_counter()
+                    self.table.insert_hashed_device(send[slot].data_ptr(), counts[0])
+                    self.phase_s["insert"] += time.perf_counter() - t0
+                continue
+            if pending is not None:
+                finish(pending)
+            t0 = time.perf_counter()
+            ev, total = self._start_exchange(slot, counts)
+            self.phase_s["exchange"] += time.perf_counter() - t0
+            pending = (ev, slot, total)
+        if pending is not None:
+            finish(pending)
+        self.ctx.sync()
 
     def count_device_step(self, d_reads: int, nbytes: int, fmt: int, min_cov: int, batch_bytes: int, record_bytes: int | None = None):
         """One bench step: fresh shard, count, coverage compaction; returns (global solid k-mers, stage times)."""
+        self.ctx.stage_reset()
+        for name in self.phase_s:
+            self.phase_s[name] = 0.0
         self.new_table()
         self.count_device(d_reads, nbytes, fmt, batch_bytes, record_bytes)
+        t0 = time.perf_counter()
         solid = self.table.filter(min_cov)
         n = torch.tensor([solid.size()], dtype=torch.int64, device="cuda")
+        self.phase_s["sweep_filter"] = time.perf_counter() - t0
         if self.world > 1:
             dist.all_reduce(n)
         stage = self.ctx.stage_ms()
+        if os.environ.get("MC_DIST_PROFILE"):
+            print(f"[rank {self.rank}] phases (s): {({k: round(v, 4) for k, v in self.phase_s.items()})} stages (ms): {({k: round(v, 1) for k, v in stage.items()})}", flush=True)
         solid.free()
         return int(n.item()), stage
