@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-env", action="store_true")
+    ap.add_argument("--maxkmers", type=int, default=100000)
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="mc_ctx_set_tuning knob (part_bits, batch_keys, segment_keys)")
     ap.add_argument("--hint-div", type=int, default=4, help="table capacity hint = bases / this")
     args = ap.parse_args()
@@ -251,6 +253,38 @@ def main():
         t_ms, kernel_ms = tt.tolist()
     value = bases_per_step * world * args.steps / (t_ms / 1e3) / 1e9
 
+    # ---- reads -> environments (the other half of BASELINE.json's metric), once, outside the timed region -----------
+    env = None
+    if world == 1 and not args.no_env:
+        import shutil
+        t = ctx.new_table(k, capacity_hint=hint)
+        t.count_device(d_reads, nbytes, FMT_FASTQ)
+        solid = t.filter(cov)
+        out_dir = tempfile.mkdtemp(prefix="mc_env_")
+        try:
+            fa = os.path.join(out_dir, "targets.fasta")
+            with open(fa, "w") as f:
+                f.write(s.targets_fasta())
+            targets = ctx.load_targets(fa)
+            ctx.sync()
+            t_env = time.perf_counter()
+            found = ctx.find_environments(solid, [x[1] for x in targets], [x[0] for x in targets], min_cov=cov, max_kmers=args.maxkmers,
+                                          both_dirs=False, out_dir=os.path.join(out_dir, "out"))
+            env_s = time.perf_counter() - t_env
+            n_env_kmers = 0
+            for name, _ in targets:
+                g = os.path.join(out_dir, "out", name, "env.txt")
+                if os.path.exists(g):
+                    with open(g) as f:
+                        n_env_kmers += sum(1 for _ in f)
+            env = {"targets": len(targets), "found": int(sum(found)), "maxkmers": args.maxkmers, "bothdirs": False, "env_kmers": n_env_kmers,
+                   "env_ms": round(1000 * env_s, 1), "what": "BFS + unitigs + graph.gfa/env.txt/seqs.fasta/tsvs for all targets (mc_env_find, files written to a tmpfs dir)",
+                   "reads_to_env_s": round(t_ms / args.steps / 1e3 + env_s, 3)}
+        finally:
+            shutil.rmtree(out_dir, ignore_errors=True)
+            solid.free()
+            t.free()
+
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------
     e2e = None
     if not args.no_e2e and world == 1:
@@ -315,9 +349,10 @@ def main():
                            "fastq_bytes_per_gpu_per_step": nbytes, "l2": "inputs (>= 0.3 GB per step) larger than the 126 MB L2; no explicit flush",
                            "chunk_mib": args.chunk_mib, "table": "pre-sized for bases/4 distinct k-mers, grows by rehash beyond",
                            "solid_kmers": int(n_solid), "wall_s": round(wall, 3)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "env": env}
         print(json.dumps(line), flush=True)
     if world > 1:
+        counter.close_exchange()
         dist.destroy_process_group()
     return 0
 

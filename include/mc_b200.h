@@ -146,6 +146,19 @@ uint64_t mc_max_kmers(size_t len, int fmt, int k);
 /* insert hashed keys (as produced above) that this table owns; device pointer */
 int mc_table_insert_hashed_device(mc_table* t, const uint64_t* d_hkeys, size_t n);
 
+/* Peer-memory exchange (one process per GPU of ONE node): the owner groups of a batch are written by the scatter kernel itself
+ * into the owners' receive regions over NVLink (CUDA IPC mappings) -- no collective moves keys.  Protocol per batch b, slot = b & 1:
+ *   every rank: mc_xchg_scatter_device(slot);   all ranks: barrier (host layer);   every rank: mc_xchg_insert(slot).
+ * Setup: mc_xchg_create, exchange the 64-byte handles of mc_xchg_handle between the ranks, mc_xchg_open for every peer.
+ * region_keys must be >= mc_max_kmers of the largest batch. */
+typedef struct mc_xchg mc_xchg;
+int mc_xchg_create(mc_ctx* ctx, int world, int rank, uint64_t region_keys, mc_xchg** out);
+int mc_xchg_handle(mc_xchg* x, void* out64);
+int mc_xchg_open(mc_xchg* x, int peer_rank, const void* handle64);
+int mc_xchg_scatter_device(mc_xchg* x, const void* dbuf, size_t len, int fmt, int k, int slot, mc_table* stats_sink);
+int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_received);
+void mc_xchg_destroy(mc_xchg* x);
+
 /* ------------------------------------------------------------------------------------------------
  * Bench/test utility (NOT reference API): synthetic metagenome reads generated on the device
  * (include/mc_synth.h).  `params` is a mc_synth_params blob built by mc_synth_init.

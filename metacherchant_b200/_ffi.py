@@ -62,6 +62,12 @@ _SIGNATURES = {
     "mc_extract_partition_device": (i32, [vp, vp, sz, i32, i32, i32, vp, C.POINTER(u64), vp]),
     "mc_max_kmers": (u64, [sz, i32, i32]),
     "mc_table_insert_hashed_device": (i32, [vp, vp, sz]),
+    "mc_xchg_create": (i32, [vp, i32, i32, u64, C.POINTER(vp)]),
+    "mc_xchg_handle": (i32, [vp, vp]),
+    "mc_xchg_open": (i32, [vp, i32, vp]),
+    "mc_xchg_scatter_device": (i32, [vp, vp, sz, i32, i32, i32, vp]),
+    "mc_xchg_insert": (i32, [vp, i32, vp, C.POINTER(u64)]),
+    "mc_xchg_destroy": (None, [vp]),
     "mc_synth_generate_device": (i32, [vp, vp, sz, u64, u64, vp]),
     "mc_device_alloc": (i32, [vp, sz, C.POINTER(vp)]),
     "mc_device_free": (i32, [vp, vp]),

@@ -51,8 +51,10 @@ static size_t scatter_smem_bytes(uint32_t P) {
     return keys * 8 + (size_t)P * 8 + (size_t)P * 4 + ((size_t)P + 1) * 4 + (keys / 4) * 2 + 64;
 }
 
+// `D.use` = the bins are the OWNER ranks of the multi-GPU exchange: bin o's run goes to D.base[o], the receive region this rank
+// owns inside rank o's buffer (peer memory mapped through CUDA IPC: the sector stores travel over NVLink), mc_xchg.cu.
 __global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
-                                                            unsigned int* flags) {
+                                                            unsigned int* flags, McBinDst D) {
     extern __shared__ unsigned long long s_mem[];
     const uint32_t P = 1u << B.pbits;
     McScatterSmem S;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __re
             const ulonglong2 lo2 = *(const ulonglong2*)&S.sorted[j * 4], hi2 = *(const ulonglong2*)&S.sorted[j * 4 + 2];
             const uint64_t k0 = lo2.x, k1 = lo2.y, k2 = hi2.x, k3 = hi2.y;
             if (pos + 4 <= B.cap) {
-                uint64_t* dst = B.keys + (uint64_t)bin * B.cap + pos;
+                uint64_t* dst = (D.use ? D.base[bin] : B.keys + (uint64_t)bin * B.cap) + pos;
                 asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
             } else {   // bin full (heavy hitter or undersized batch): shared spill list, applied with direct updates
                 const uint64_t kk[4] = {k0, k1, k2, k3};
@@ -328,10 +330,27 @@ void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
     }
     const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
-    k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, B->dev, t->dev.shard_bits, t->shard_id, t->dev.flags);
+    McBinDst none{};
+    k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, B->dev, t->dev.shard_bits, t->shard_id, t->dev.flags, none);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
     B->used += n;
+}
+
+void mc_launch_owner_scatter(mc_ctx* ctx, const uint64_t* d_flat, uint64_t n, const McBinsDev& owners, const McBinDst& dst, unsigned int* flags) {
+    if (n == 0) return;
+    const uint32_t P = 1u << owners.pbits;
+    const size_t smem = scatter_smem_bytes(P);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
+        attr_set = true;
+    }
+    const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
+    k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, owners, 0, 0, flags, dst);
+    MC_LAUNCH(ctx);
+    MC_CUDA(cudaGetLastError());
 }
 
 __global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);

@@ -252,6 +252,14 @@ struct McBinsDev {
     int hbits;                      // 62 - shard_bits; bin = hl >> (hbits - pbits)
 };
 
+#define MC_MAX_XCHG_RANKS 16
+struct McBinDst {   // per-bin destination override of k_bin_scatter (owner groups written straight into peer memory)
+    uint64_t* base[MC_MAX_XCHG_RANKS];
+    int use;
+};
+// pads (sentinels) a sector-aligned run may carry: k_bin_scatter rounds every bin's run of a tile up to 4 keys
+#define MC_SCATTER_TILE 8192u
+
 // --------------------------------------------------------------------------------------------
 // host-side objects behind the opaque handles
 // --------------------------------------------------------------------------------------------
@@ -322,6 +330,8 @@ void mc_table_flush(mc_table* t);
 // flush + release the batch buffers
 void mc_batch_release(mc_table* t);
 void mc_table_grow_to(mc_table* t, int new_q);   // timed rehash into 2^new_q buckets
+uint64_t* mc_extract_flat_device(mc_ctx* ctx, const void* dbuf, size_t len, int fmt, int k, mc_table* stats_sink, uint64_t* n_flat);
+void mc_launch_owner_scatter(mc_ctx* ctx, const uint64_t* d_flat, uint64_t n, const McBinsDev& owners, const McBinDst& dst, unsigned int* flags);
 int mc_q_for_keys(uint64_t keys, int shard_bits, double load);
 
 // accumulate the device time between two points of ctx->stream into ctx->stage_ms[stage] (resolved lazily)

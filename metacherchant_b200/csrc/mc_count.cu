@@ -684,37 +684,45 @@ __global__ void __launch_bounds__(256) k_owner_scatter(const uint64_t* __restric
     }
 }
 
+// parse + extract one device-resident, record-aligned batch; the flat hashed keys stay in scratch slot 2 (valid until the next
+// extraction on this context).  Shared by the NCCL path below and the peer-memory exchange (mc_xchg.cu).
+uint64_t* mc_extract_flat_device(mc_ctx* ctx, const void* dbuf, size_t len, int fmt, int k, mc_table* stats_sink, uint64_t* n_flat) {
+    if (len > ((size_t)3 << 30)) mc_throw(MC_ERR_ARG, "batch larger than 3 GiB");
+    if (k != stats_sink->k) mc_throw(MC_ERR_ARG, "k differs from the table's");
+    *n_flat = 0;
+    const uint8_t* p = (const uint8_t*)dbuf;
+    const bool fasta = fmt == MC_FMT_FASTA;
+    const int qoff = fasta ? 0 : resolve_qoff_device(ctx, p, len, fmt);
+    McParsed P;
+    mc_parse_chunk(ctx, p, (uint32_t)len, fasta, true, &P);
+    if (P.h.err_packed != MC_NO_ERROR) mc_throw_parse_error(P.h.err_packed, p, (uint32_t)len, ctx);
+    if (P.h.n_records == 0) return nullptr;
+    const uint64_t ub = mc_max_kmers(len, fmt, k);
+    McExtractArgs a{};
+    a.base = P.base;
+    a.recs = P.recs;
+    a.n_records = P.h.n_records;
+    a.n_bytes = fasta ? P.h.total_seq_bytes : (uint32_t)len;
+    a.k = k;
+    a.qoff = qoff;
+    a.header = P.d_header;
+    a.table = stats_sink->dev;
+    return extract_flat(ctx, a, fasta, P.h.max_seq_len, ub, p, (uint32_t)len, n_flat);
+}
+
 extern "C" int mc_extract_partition_device(mc_ctx* ctx, const void* dbuf, size_t len, int fmt, int k, int shard_bits, uint64_t* d_keys,
                                            uint64_t* counts, mc_table* stats_sink) {
     try {
         if (!ctx || !d_keys || !counts || !stats_sink || (len && !dbuf)) mc_throw(MC_ERR_ARG, "null argument");
         validate_fmt(fmt);
         if (shard_bits < 0 || shard_bits > 8) mc_throw(MC_ERR_ARG, "shard_bits must be in 0..8");
-        if (len > ((size_t)3 << 30)) mc_throw(MC_ERR_ARG, "batch larger than 3 GiB");
-        if (k != stats_sink->k) mc_throw(MC_ERR_ARG, "k differs from the table's");
         MC_CUDA(cudaSetDevice(ctx->device));
         cudaStream_t st = ctx->stream;
         const int owners = 1 << shard_bits;
         for (int i = 0; i < owners; i++) counts[i] = 0;
-        const uint8_t* p = (const uint8_t*)dbuf;
-        const bool fasta = fmt == MC_FMT_FASTA;
-        const int qoff = fasta ? 0 : resolve_qoff_device(ctx, p, len, fmt);
-        McParsed P;
-        mc_parse_chunk(ctx, p, (uint32_t)len, fasta, true, &P);
-        if (P.h.err_packed != MC_NO_ERROR) mc_throw_parse_error(P.h.err_packed, p, (uint32_t)len, ctx);
-        if (P.h.n_records == 0) return MC_OK;
-        const uint64_t ub = mc_max_kmers(len, fmt, k);
-        McExtractArgs a{};
-        a.base = P.base;
-        a.recs = P.recs;
-        a.n_records = P.h.n_records;
-        a.n_bytes = fasta ? P.h.total_seq_bytes : (uint32_t)len;
-        a.k = k;
-        a.qoff = qoff;
-        a.header = P.d_header;
-        a.table = stats_sink->dev;
         uint64_t n_flat = 0;
-        uint64_t* d_flat = extract_flat(ctx, a, fasta, P.h.max_seq_len, ub, p, (uint32_t)len, &n_flat);
+        uint64_t* d_flat = mc_extract_flat_device(ctx, dbuf, len, fmt, k, stats_sink, &n_flat);
+        if (!d_flat) return MC_OK;
         // the head of slot 2 (8 KiB, zeroed by extract_flat): [0] flat cursor, [8..) per-owner counters, then cursors
         unsigned long long* d_counts = (unsigned long long*)((uint8_t*)d_flat - MC_FLAT_HEAD) + 8;
         unsigned long long* d_cursors = d_counts + MC_MAX_OWNERS;

@@ -1,0 +1,186 @@
+// Multi-GPU key exchange over peer memory: compute and transfer in ONE kernel.
+//
+// Every rank owns a receive buffer of `world` regions per slot (two slots: double buffering).  Region (slot, src) of rank
+// d's buffer is written ONLY by rank src: k_bin_scatter, run with the owner ranks as its bins, sorts a tile of hashed keys
+// by owner in shared memory and stores each owner's run, whole 32-byte sectors, straight into that owner's region through a
+// CUDA-IPC mapping -- the stores travel over NVLink while the next tile is being sorted.  No NCCL call moves keys; the
+// ranks only need a barrier per batch (torch.distributed, a few bytes) so that a receiver knows its regions are complete.
+// Cursors are local to the writer (nobody else appends to its regions), so there are no cross-GPU atomics; the final
+// cursor values are posted into the receiver's mailbox after the kernel.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "mc_common.cuh"
+
+struct mc_xchg {
+    mc_ctx* ctx = nullptr;
+    int world = 1, rank = 0, shard_bits = 0;
+    uint64_t region_keys = 0;       // capacity of one (slot, src) region (pads included)
+    uint64_t max_batch_keys = 0;    // largest batch (in k-mers) a region is guaranteed to hold
+    uint8_t* local = nullptr;       // my receive buffer: [2 slots][world regions][region_keys] keys, then the mailbox
+    size_t local_bytes = 0;
+    uint8_t* peer[MC_MAX_XCHG_RANKS] = {};   // mapped base of every rank's buffer (peer[rank] == local)
+    unsigned long long* d_cursors = nullptr; // [world + 1] local append cursors of the batch being scattered
+    unsigned int* d_flags = nullptr;
+    uint64_t mailbox_off = 0;
+    uint64_t* region(uint8_t* base, int slot, int src) const { return (uint64_t*)base + ((uint64_t)slot * world + src) * region_keys; }
+    unsigned long long* mailbox(uint8_t* base, int slot) const { return (unsigned long long*)(base + mailbox_off) + (uint64_t)slot * MC_MAX_XCHG_RANKS; }
+};
+
+extern "C" int mc_xchg_create(mc_ctx* ctx, int world, int rank, uint64_t region_keys, mc_xchg** out) {
+    try {
+        if (!ctx || !out) mc_throw(MC_ERR_ARG, "null argument");
+        if (world < 1 || world > MC_MAX_XCHG_RANKS || (world & (world - 1)) || rank < 0 || rank >= world) mc_throw(MC_ERR_ARG, "world must be a power of two <= %d", MC_MAX_XCHG_RANKS);
+        MC_CUDA(cudaSetDevice(ctx->device));
+        mc_xchg* x = new mc_xchg();
+        x->ctx = ctx;
+        x->world = world;
+        x->rank = rank;
+        while ((1 << x->shard_bits) < world) x->shard_bits++;
+        x->max_batch_keys = region_keys;
+        // pads: every tile of the scatter may round a region's run up by 3 keys
+        region_keys += 3 * (region_keys / MC_SCATTER_TILE + 2) + 64;
+        x->region_keys = (region_keys + 15) & ~15ull;
+        x->mailbox_off = 2ull * world * x->region_keys * 8;
+        x->local_bytes = x->mailbox_off + 2 * MC_MAX_XCHG_RANKS * sizeof(unsigned long long);
+        cudaError_t e = cudaMalloc(&x->local, x->local_bytes);   // plain cudaMalloc: IPC cannot export pool memory
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            const double gib = (double)x->local_bytes / (1 << 30);
+            delete x;
+            mc_throw(MC_ERR_NOMEM, "exchange buffer of %.2f GiB does not fit in device memory", gib);
+        }
+        MC_CUDA(cudaMemset(x->local + x->mailbox_off, 0, 2 * MC_MAX_XCHG_RANKS * sizeof(unsigned long long)));
+        MC_CUDA(cudaMalloc(&x->d_cursors, (MC_MAX_XCHG_RANKS + 1) * sizeof(unsigned long long)));
+        MC_CUDA(cudaMalloc(&x->d_flags, sizeof(unsigned int)));
+        MC_CUDA(cudaMemset(x->d_flags, 0, sizeof(unsigned int)));
+        x->peer[rank] = x->local;
+        *out = x;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" int mc_xchg_handle(mc_xchg* x, void* out64) {
+    try {
+        if (!x || !out64) mc_throw(MC_ERR_ARG, "null argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        MC_CUDA(cudaIpcGetMemHandle(&h, x->local));
+        memcpy(out64, &h, 64);
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" int mc_xchg_open(mc_xchg* x, int peer_rank, const void* handle64) {
+    try {
+        if (!x || !handle64 || peer_rank < 0 || peer_rank >= x->world) mc_throw(MC_ERR_ARG, "bad argument");
+        if (peer_rank == x->rank) return MC_OK;
+        MC_CUDA(cudaSetDevice(x->ctx->device));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        void* p = nullptr;
+        MC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer[peer_rank] = (uint8_t*)p;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" void mc_xchg_destroy(mc_xchg* x) {
+    if (!x) return;
+    cudaSetDevice(x->ctx->device);
+    cudaStreamSynchronize(x->ctx->stream);
+    for (int r = 0; r < x->world; r++)
+        if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    cudaFree(x->local);
+    cudaFree(x->d_cursors);
+    cudaFree(x->d_flags);
+    cudaGetLastError();
+    delete x;
+}
+
+// posts my final cursors into every owner's mailbox (one 8-byte store per peer, system scope)
+__global__ void k_post_counts(const unsigned long long* __restrict__ cursors, McBinDst mail, int world, int rank) {
+    const int o = threadIdx.x;
+    if (o < world) {
+        unsigned long long* slot = (unsigned long long*)mail.base[o] + rank;
+        asm volatile("st.global.release.sys.u64 [%0], %1;" ::"l"(slot), "l"(cursors[o]) : "memory");
+    }
+}
+
+// parse + extract the batch, then sort its keys by owner and store every owner's run into that owner's region (slot, my rank)
+extern "C" int mc_xchg_scatter_device(mc_xchg* x, const void* dbuf, size_t len, int fmt, int k, int slot, mc_table* stats_sink) {
+    try {
+        if (!x || !stats_sink || (len && !dbuf) || slot < 0 || slot > 1) mc_throw(MC_ERR_ARG, "bad argument");
+        mc_ctx* ctx = x->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        for (int r = 0; r < x->world; r++)
+            if (!x->peer[r]) mc_throw(MC_ERR_ARG, "exchange: rank %d's buffer has not been opened", r);
+        if (mc_max_kmers(len, fmt, k) > x->max_batch_keys) mc_throw(MC_ERR_ARG, "exchange: batch of %zu bytes exceeds the region capacity", len);
+        MC_CUDA(cudaMemsetAsync(x->d_cursors, 0, (MC_MAX_XCHG_RANKS + 1) * sizeof(unsigned long long), st));
+        uint64_t n_flat = 0;
+        uint64_t* d_flat = len ? mc_extract_flat_device(ctx, dbuf, len, fmt, k, stats_sink, &n_flat) : nullptr;
+        McBinDst dst{}, mail{};
+        dst.use = 1;
+        for (int o = 0; o < x->world; o++) {
+            dst.base[o] = x->region(x->peer[o], slot, x->rank);
+            mail.base[o] = (uint64_t*)x->mailbox(x->peer[o], slot);
+        }
+        if (d_flat && n_flat) {
+            McStageTimer tm(ctx, MC_ST_SCATTER);
+            McBinsDev owners{};
+            owners.cursors = x->d_cursors;
+            owners.cap = x->region_keys;
+            owners.spill_cap = 0;
+            owners.pbits = x->shard_bits;
+            owners.hbits = 62;
+            mc_launch_owner_scatter(ctx, d_flat, n_flat, owners, dst, x->d_flags);
+        }
+        k_post_counts<<<1, 32, 0, st>>>(x->d_cursors, mail, x->world, x->rank);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        unsigned int f = 0;
+        MC_CUDA(cudaMemcpyAsync(&f, x->d_flags, sizeof f, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        if (f) mc_throw(MC_ERR_NOMEM, "exchange: a receive region overflowed");
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+// after the ranks' barrier: bin what every source wrote into my regions of `slot`
+extern "C" int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_received) {
+    try {
+        if (!x || !t || slot < 0 || slot > 1) mc_throw(MC_ERR_ARG, "bad argument");
+        mc_ctx* ctx = x->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        unsigned long long counts[MC_MAX_XCHG_RANKS];
+        MC_CUDA(cudaMemcpyAsync(counts, x->mailbox(x->local, slot), sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
+        MC_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint64_t total = 0;
+        for (int src = 0; src < x->world; src++) {
+            if (counts[src] > x->region_keys) mc_throw(MC_ERR_CUDA, "exchange: mailbox of rank %d is corrupt", src);
+            if (counts[src] == 0) continue;
+            int rc = mc_table_insert_hashed_device(t, x->region(x->local, slot, src), counts[src]);
+            if (rc != MC_OK) return rc;
+            total += counts[src];
+        }
+        if (n_received) *n_received = total;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}

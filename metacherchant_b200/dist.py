@@ -59,10 +59,15 @@ def exchange_keys(send: torch.Tensor, send_counts, group=None):
 class ShardedCounter:
     """Rank-local driver of the sharded counting step (GPU only; there is no CPU fallback)."""
 
-    def __init__(self, ctx, k: int, world: int, rank: int, capacity_hint: int = 0):
+    def __init__(self, ctx, k: int, world: int, rank: int, capacity_hint: int = 0, exchange: str = "peer"):
+        """exchange = "peer": the scatter kernel writes every owner's keys straight into that owner's receive region over
+        NVLink (CUDA-IPC mapped peer memory, csrc/mc_xchg.cu; ranks must share one node); "nccl": all_to_all_single."""
         self.ctx, self.k, self.world, self.rank = ctx, k, world, rank
         self.shard_bits = shard_bits_for(world)
         self.capacity_hint = capacity_hint
+        self.exchange = exchange if world > 1 else "local"
+        self._xchg = None
+        self._xchg_keys = 0
         self.table = None
         self.bytes_exchanged = 0
         # wall-clock seconds per phase of the last step (host view, each phase ends with a synchronisation)
@@ -101,11 +106,69 @@ class ShardedCounter:
         self.bytes_exchanged += 8 * (sum(counts) - counts[self.rank])
         return done, total
 
+    # ---- peer-memory exchange ------------------------------------------------------------------------
+    def _peer_setup(self, region_keys: int):
+        import ctypes as C
+        from ._ffi import check
+        lib = self.ctx.lib
+        if self._xchg is not None and self._xchg_keys >= region_keys:
+            return
+        self.close_exchange()
+        h = C.c_void_p()
+        check(lib.mc_xchg_create(self.ctx.h, self.world, self.rank, region_keys, C.byref(h)))
+        buf = C.create_string_buffer(64)
+        check(lib.mc_xchg_handle(h, buf))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(buf.raw))
+        for r, raw in enumerate(handles):
+            if r != self.rank:
+                check(lib.mc_xchg_open(h, r, C.create_string_buffer(raw, 64)))
+        self._xchg, self._xchg_keys = h, region_keys
+        dist.barrier()
+
+    def close_exchange(self):
+        if self._xchg is not None:
+            dist.barrier()                       # nobody may still be writing into my regions
+            self.ctx.lib.mc_xchg_destroy(self._xchg)
+            self._xchg = None
+
+    def _count_device_peer(self, d_reads: int, nbytes: int, fmt: int, batch_bytes: int, record_bytes):
+        import ctypes as C
+        from ._ffi import check
+        lib = self.ctx.lib
+        # regions are sized for the worst case of a batch, 2 slots x world regions of them: keep that near 16 GiB
+        batch_bytes = min(batch_bytes, (2 << 30) // self.world)
+        batches = plan_batches(nbytes, batch_bytes, record_bytes)
+        nb = torch.tensor([len(batches), max([n for _, n in batches] + [1])], dtype=torch.int64, device="cuda")
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        n_batches, max_bytes = int(nb[0].item()), int(nb[1].item())
+        self._peer_setup(int(lib.mc_max_kmers(max_bytes, fmt, self.k)))
+        got = C.c_uint64()
+        sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for b in range(n_batches):
+            off, n = batches[b] if b < len(batches) else (0, 0)
+            slot = b & 1
+            t0 = time.perf_counter()
+            check(lib.mc_xchg_scatter_device(self._xchg, C.c_void_p(d_reads + off), n, fmt, self.k, slot, self.table.h))
+            t1 = time.perf_counter()
+            dist.all_reduce(sync)                # every rank's stores into slot `slot` have completed
+            torch.cuda.current_stream().synchronize()
+            t2 = time.perf_counter()
+            check(lib.mc_xchg_insert(self._xchg, slot, self.table.h, C.byref(got)))
+            t3 = time.perf_counter()
+            self.phase_s["extract"] += t1 - t0
+            self.phase_s["exchange"] += t2 - t1
+            self.phase_s["insert"] += t3 - t2
+            self.bytes_exchanged += 8 * got.value
+        self.ctx.sync()
+
     def count_device(self, d_reads: int, nbytes: int, fmt: int, batch_bytes: int, record_bytes: int | None = None):
         """Counts this rank's device-resident reads into the distributed table (collective: every rank must call it
         with the same number of batches; ranks with fewer batches send empty groups).
         Software pipeline: while batch b's keys cross NVLink (communication stream), batch b+1 is parsed and extracted and
         batch b-1's received keys are binned (library stream)."""
+        if self.exchange == "peer":
+            return self._count_device_peer(d_reads, nbytes, fmt, batch_bytes, record_bytes)
         lib = self.ctx.lib
         batches = plan_batches(nbytes, batch_bytes, record_bytes)
         n_batches = torch.tensor([len(batches)], dtype=torch.int64, device="cuda")

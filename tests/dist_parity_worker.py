@@ -28,10 +28,16 @@ def main():
     rb = s.record_bytes
     d = ctx.device_alloc(per * rb)
     ctx.synth_generate_device(s.params_bytes(), rank * per, per, d)
-    counter = ShardedCounter(ctx, k, world, rank)
-    counter.new_table()
-    counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)   # several batches
-    keys, counts = counter.table.dump()
+    # both exchanges must give the same shards: NCCL all-to-all and the peer-memory scatter (MC_DIST_EXCHANGE picks one to dump)
+    tables = {}
+    for mode in ("nccl", "peer"):
+        counter = ShardedCounter(ctx, k, world, rank, exchange=mode)
+        counter.new_table()
+        counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)   # several batches
+        tables[mode] = counter.table.dump()
+        counter.close_exchange()
+    same = np.array_equal(tables["nccl"][0], tables["peer"][0]) and np.array_equal(tables["nccl"][1], tables["peer"][1])
+    keys, counts = tables["peer"]
     # gather the shards on rank 0
     n = torch.tensor([keys.size], dtype=torch.int64, device="cuda")
     sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
@@ -53,7 +59,7 @@ def main():
         allk, allc = allk[order], allc[order]
         ref = o.table(k, threads=8).count_bytes(s.generate(0, per * world), oracle_ffi.FMT_FASTQ)
         rk, rc = ref.dump()
-        ok = np.array_equal(allk, rk) and np.array_equal(allc, rc) and len(np.unique(allk)) == allk.size
+        ok = np.array_equal(allk, rk) and np.array_equal(allc, rc) and len(np.unique(allk)) == allk.size and same
         print(f"DIST_PARITY world={world} distinct={allk.size} oracle={rk.size} exchanged_bytes_rank0={counter.bytes_exchanged} {'OK' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
