@@ -101,6 +101,15 @@ int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc_table** so
 int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets, int k,
                 int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs, int chunk_len, const char* out_dir,
                 int* found);
+/* The same with the tool's remaining switches:
+ *   merge (--merge, EnvironmentFinderMain.java:226-233): ONE environment seeded by the k-mers of every target and then of every
+ *     Hi-C sequence (--hicseq, OneSequenceCalculator.java:168-192), written to <out_dir>/merged/; gene nodes are decided against
+ *     the targets only (:421-432); found[0] tells whether any seed was solid.  names may be NULL.
+ *   trim (--trim, :208-216,241-262): after each pass keep only the k-mers from which, walking against the pass direction
+ *     inside the visited set, a "last" k-mer (one with a solid neighbour that allowsAddition refused) is reached. */
+int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets,
+                   const char* const* hic_seqs, int n_hic, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
+                   int chunk_len, int merge, int trim, const char* out_dir, int* found);
 /* one BFS pass (runBfs, OneSequenceCalculator.java:154-220): oriented k-mers in discovery order.
  * dir: -1 left, +1 right, 0 both.  Returns in *n the number visited (0 = no seeds). */
 int mc_bfs(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int dir,

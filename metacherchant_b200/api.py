@@ -122,6 +122,19 @@ class Context:
                                    -1 if max_radius is None else max_radius, int(both_dirs), chunk_len, os.fspath(out_dir).encode(), found))
         return [bool(x) for x in found]
 
+    def find_environments_ex(self, table: "KmerTable", seqs, names=None, hic_seqs=(), min_cov=1, max_kmers=None, max_radius=None,
+                             both_dirs=False, chunk_len=1, merge=False, trim=False, out_dir="."):
+        """environment-finder with --merge / --hicseq / --trim (mc_env_find_ex)."""
+        n, nh = len(seqs), len(hic_seqs)
+        a_seqs = (C.c_char_p * n)(*[s.encode() for s in seqs])
+        a_names = (C.c_char_p * n)(*[s.encode() for s in names]) if names is not None else None
+        a_hic = (C.c_char_p * max(nh, 1))(*[s.encode() for s in hic_seqs]) if nh else None
+        found = (C.c_int * max(n, 1))()
+        check(self.lib.mc_env_find_ex(self.h, table.h, a_seqs, a_names, n, a_hic, nh, table.k, min_cov, -1 if max_kmers is None else max_kmers,
+                                      -1 if max_radius is None else max_radius, int(both_dirs), chunk_len, int(merge), int(trim),
+                                      os.fspath(out_dir).encode(), found))
+        return [bool(found[i]) for i in range(1 if merge else n)]
+
     def env_from_graph_txt(self, graph_txt, target_seq, k, chunk_len, out_dir):
         check(self.lib.mc_env_from_graph_txt(self.h, os.fspath(graph_txt).encode(), target_seq.encode(), k, chunk_len, os.fspath(out_dir).encode()))
 

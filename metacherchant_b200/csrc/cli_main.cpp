@@ -9,8 +9,10 @@
 // Option syntax follows commons-cli PosixParser as the ITMO Tool uses it: "--name value", "--name=value", short
 // options, multi-valued options taking every following non-option token and re-tokenised on "[, ]"
 // (Tool.java:853-855,888-895), booleans with an optional True/False argument (Parameter.java:51-58).
-// Reference flags outside the GPU path (--trim, --merge, --hicseq, --forcehash, --hash, k > 31) fail loudly.
+// Reference flags outside the GPU path (--forcehash, --hash, k > 31) fail loudly.
 #include <sys/stat.h>
+
+#include <algorithm>
 
 #include <cstdarg>
 #include <cstdio>
@@ -124,7 +126,7 @@ const Opt ENV_FINDER_OPTS[] = {
     {"k", "k", INT, true, "k-mer size"},
     {"reads", "i", FILES, false, "FASTQ, FASTA reads"},
     {"seq", nullptr, STR, true, "FASTA file with sequences"},
-    {"hicseq", nullptr, STR, false, "FASTA file with Hi-C sequences [not supported by the GPU path]"},
+    {"hicseq", nullptr, STR, false, "FASTA file with Hi-C sequences (seeds of the merged environment)"},
     {"output", "o", STR, true, "output directory"},
     {"maxkmers", nullptr, INT, false, "maximum number of k-mers in created subgraph"},
     {"maxradius", nullptr, INT, false, "maximum distance in k-mers from starting gene"},
@@ -133,8 +135,8 @@ const Opt ENV_FINDER_OPTS[] = {
     {"chunklength", nullptr, INT, false, "minimum node length for BLAST search (default 1)"},
     {"forcehash", nullptr, BOOL, false, "force k-mer hashing [not supported by the GPU path]"},
     {"hash", nullptr, STR, false, "hash function to use [not supported by the GPU path]"},
-    {"trim", nullptr, BOOL, false, "trim all not maximal paths? [not supported by the GPU path]"},
-    {"merge", nullptr, BOOL, false, "single environment for multiple input sequences? [not supported by the GPU path]"},
+    {"trim", nullptr, BOOL, false, "trim all not maximal paths?"},
+    {"merge", nullptr, BOOL, false, "single environment for multiple input sequences?"},
 };
 const Opt MULTI_OPTS[] = {
     {"env", "e", FILES, true, "environment files to build difference for"},
@@ -251,9 +253,10 @@ int run_environment_finder(const std::vector<std::string>& rest, const Args& lau
     Args a;
     parse_args(rest, opts, a);
     check_mandatory(opts, a);
-    for (const char* bad : {"hicseq", "forcehash", "hash", "trim", "merge"})
-        if (a.has(bad) && !((std::string(bad) == "forcehash" || std::string(bad) == "trim" || std::string(bad) == "merge") && !a.boolean(bad, false)))
-            die("--%s is not supported by the GPU path (only the plain environment-finder route of the reference is implemented)", bad);
+    for (const char* bad : {"forcehash", "hash"})
+        if (a.has(bad) && !(std::string(bad) == "forcehash" && !a.boolean(bad, false)))
+            die("--%s is not supported by the GPU path (the reference's lossy hashed k-mer mode is out of scope)", bad);
+    const bool merge = a.boolean("merge", false), trim = a.boolean("trim", false);
     long long k = 0, max_kmers = -1, max_radius = -1, coverage = 1, chunk_len = 1, device = 0;
     a.integer("k", k);
     bool has_mk = a.integer("maxkmers", max_kmers), has_mr = a.integer("maxradius", max_radius);
@@ -276,27 +279,42 @@ int run_environment_finder(const std::vector<std::string>& rest, const Args& lau
     mc_targets* targets = nullptr;
     MC(mc_targets_load(a.str("seq").c_str(), &targets));
     const int n = mc_targets_count(targets);
+    // --hicseq: its sequences seed the merged environment; loadInput also overwrites the output names with the Hi-C file's
+    // header list (EnvironmentFinderMain.java:146-150), reproduced here
+    mc_targets* hic = nullptr;
+    std::vector<const char*> hic_seqs;
+    if (a.has("hicseq")) {
+        MC(mc_targets_load(a.str("hicseq").c_str(), &hic));
+        for (int i = 0; i < mc_targets_count(hic); i++) hic_seqs.push_back(mc_targets_seq(hic, i));
+    }
     std::vector<const char*> seqs, names;
     for (int i = 0; i < n; i++) {
-        const char* name = mc_targets_name(targets, i);
-        if (!name) die("IndexOutOfBoundsException: sequence %d of %s has no header entry", i, a.str("seq").c_str());
         seqs.push_back(mc_targets_seq(targets, i));
+        if (merge) continue;
+        const char* name = mc_targets_name(hic ? hic : targets, i);
+        if (!name) die("IndexOutOfBoundsException: sequence %d of %s has no header entry", i, a.str("seq").c_str());
         names.push_back(name);
         std::string s = seqs.back();
         if ((long long)s.size() >= 2 * k) s = s.substr(0, (size_t)k) + "..." + s.substr(s.size() - (size_t)k) + " (length=" + std::to_string(s.size()) + ")";
         info("Finding environment for sequence %s", s.c_str());   // OneSequenceCalculator.java:101, StringUtils.shortenLabel
     }
+    if (merge) {
+        info("hicSequences = %d", (int)hic_seqs.size());                                    // EnvironmentFinderMain.java:227
+        info("Finding single environment for %d sequences", n);                               // OneSequenceCalculator.java:103
+    }
     // B2/K4: coverage-threshold compaction; the BFS and the unitig stage probe the small solid table
     mc_table* solid = nullptr;
     MC(mc_table_filter(ctx, table, (int)coverage, &solid));
     debug("%llu k-mers with coverage >= %lld", (unsigned long long)mc_table_size(solid), coverage);
-    std::vector<int> found((size_t)n, 0);
-    MC(mc_env_find(ctx, solid, seqs.data(), names.data(), n, (int)k, (int)coverage, max_kmers, max_radius, both ? 1 : 0, (int)chunk_len,
-                   a.str("output").c_str(), found.data()));
-    for (int i = 0; i < n; i++)
+    std::vector<int> found((size_t)std::max(n, 1), 0);
+    MC(mc_env_find_ex(ctx, solid, seqs.data(), merge ? nullptr : names.data(), n, hic_seqs.empty() ? nullptr : hic_seqs.data(), (int)hic_seqs.size(),
+                      (int)k, (int)coverage, max_kmers, max_radius, both ? 1 : 0, (int)chunk_len, merge ? 1 : 0, trim ? 1 : 0,
+                      a.str("output").c_str(), found.data()));
+    for (int i = 0; i < (merge ? 1 : n); i++)
         if (!found[(size_t)i]) info("Could not find any k-mers of the target gene in the input, halting.");
     info("Finished processing all sequences!");
     mc_targets_free(targets);
+    if (hic) mc_targets_free(hic);
     mc_table_free(solid);
     mc_table_free(table);
     mc_ctx_destroy(ctx);

@@ -37,7 +37,9 @@ struct McBfsJobDev {
     uint32_t cap;          // queue capacity
     uint32_t vis_mask;
     uint32_t* n_out;       // visited count, or BFS_OVERFLOW when cap was too small
+    uint8_t* last;         // --trim: 1 = "lastKmers" member (some solid neighbour was refused by allowsAddition), else null
 };
+#define BFS_SEPARATOR 4    // code between the sequences of a merged seed list: no seed window may span it
 
 __device__ __forceinline__ uint32_t vis_find_or_claim(const McBfsJobDev& j, uint64_t kmer, uint32_t code) {
     const uint64_t want = kmer + 1;
@@ -89,9 +91,15 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
         int c = -1;
         uint32_t slot = 0;
         if (i < n_win) {
-            for (int t = 0; t < k; t++) kmer = (kmer << 2) | (uint64_t)(j.seq[i + t] & 3);
-            c = mc_table_lookup(table, mc_mix62(mc_canonical(kmer, k)));
-            cand = c >= min_cov;
+            bool whole = true;
+            for (int t = 0; t < k; t++) {
+                whole = whole && j.seq[i + t] < BFS_SEPARATOR;
+                kmer = (kmer << 2) | (uint64_t)(j.seq[i + t] & 3);
+            }
+            if (whole) {
+                c = mc_table_lookup(table, mc_mix62(mc_canonical(kmer, k)));
+                cand = c >= min_cov;
+            }
         }
         if (cand) slot = vis_find_or_claim(j, kmer, 0x80000000u | threadIdx.x);
         __syncthreads();
@@ -110,6 +118,9 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
             j.vis_val[slot] = tail + pos;
         }
         __syncthreads();
+        // A k-mer that occurs twice among the seed windows is queued twice by the reference (:160-167); when it is popped the
+        // second time all its solid neighbours are refused, which makes it a lastKmers member: remember the duplicate (bit 1).
+        if (j.last && cand && !win) j.last[__ldcg(&j.vis_val[slot])] = 2;
         if (threadIdx.x == 0) s_tail = tail + total;
         __syncthreads();
     }
@@ -119,24 +130,30 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
     const uint32_t PARENTS = BFS_THREADS / NB;
     while (true) {
         const uint32_t head = s_head, tail = s_tail;
-        if (head >= tail || s_stop) break;
+        // --trim (runBfs :197-213 keeps popping after the budget is spent, only to collect lastKmers): once nothing can be
+        // added any more the loop goes on "frozen" over the rest of the queue, looking only at which parents have solid neighbours
+        const bool frozen = s_stop != 0;
+        if (head >= tail || (frozen && !j.last)) break;
         const uint32_t P = min(tail - head, PARENTS);
         const uint32_t t = threadIdx.x;
-        bool cand = false;
+        bool cand = false, solid = false;
         uint64_t nb = 0;
         int c = -1;
         int32_t nd = 0;
-        uint32_t slot = 0;
+        uint32_t slot = 0, pi = 0;
         if (t < P * NB) {
-            const uint32_t pi = head + t / NB, s = t % NB;
+            pi = head + t / NB;
+            const uint32_t s = t % NB;
             const uint64_t kmer = j.queue[pi];
             nd = j.dist[pi] + 1;
             const uint64_t nuc = (NB == 8) ? (s >> 1) : s;
             const bool left = (j.dir == -1) || (j.dir == 0 && (s & 1) == 0);
             nb = left ? ((nuc << (2 * k - 2)) | (kmer >> 2)) : (((kmer << 2) | nuc) & kmask);
-            if (max_radius < 0 || nd <= max_radius) {
+            const bool within = max_radius < 0 || nd <= max_radius;
+            if (within || j.last) {
                 c = mc_table_lookup(table, mc_mix62(mc_canonical(nb, k)));
-                cand = c >= min_cov;
+                solid = c >= min_cov;
+                cand = solid && within && !frozen;
             }
         }
         if (cand) slot = vis_find_or_claim(j, nb, 0x80000000u | t);
@@ -155,12 +172,16 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
             if (threadIdx.x == 0) *j.n_out = BFS_OVERFLOW;
             return;
         }
-        if (win && pos < accept) {
+        const bool added = win && pos < accept;
+        if (added) {
             j.queue[tail + pos] = nb;
             j.dist[tail + pos] = nd;
             j.count[tail + pos] = (int16_t)c;
             j.vis_val[slot] = tail + pos;
         }
+        // allowsAddition said no (already visited, budget or radius) -> lastKmers.add(kmer); a duplicated seed is popped again later
+        // and then every solid neighbour is refused
+        if (j.last && solid && (!added || (j.last[pi] & 2))) j.last[pi] |= 1;
         // all remaining parents are at least as far: once a whole step is beyond the radius the pass is over
         bool radius_done = max_radius >= 0 && (long long)j.dist[head] + 1 > max_radius;
         __syncthreads();
@@ -219,14 +240,14 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
         std::vector<McBfsJobDev> jobs(todo.size());
         size_t bytes = 0;
         auto take = [&](size_t sz) { size_t o = bytes; bytes += (sz + 255) / 256 * 256; return o; };
-        struct Off { size_t seq, queue, dist, count, vk, vv, nout; uint32_t vis_cap; };
+        struct Off { size_t seq, queue, dist, count, vk, vv, nout, last; uint32_t vis_cap; };
         std::vector<Off> offs(todo.size());
         for (size_t w = 0; w < todo.size(); w++) {
             size_t i = todo[w];
             uint32_t cap = caps[i];
             uint32_t vis_cap = pow2_at_least((uint64_t)cap * 2);
             offs[w] = Off{take(reqs[i].codes.size() + 1), take((size_t)cap * 8), take((size_t)cap * 4), take((size_t)cap * 2),
-                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(4), vis_cap};
+                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(4), take(reqs[i].trim ? (size_t)cap : 1), vis_cap};
         }
         size_t jobs_off = take(jobs.size() * sizeof(McBfsJobDev));
         uint8_t* d = nullptr;
@@ -240,9 +261,10 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
             MC_CUDA(cudaMemsetAsync(d + o.vk, 0, (size_t)o.vis_cap * 8, st));
             MC_CUDA(cudaMemsetAsync(d + o.vv, 0xFF, (size_t)o.vis_cap * 4, st));
             MC_CUDA(cudaMemsetAsync(d + o.nout, 0, 4, st));
+            if (reqs[i].trim) MC_CUDA(cudaMemsetAsync(d + o.last, 0, caps[i], st));
             jobs[w] = McBfsJobDev{d + o.seq, (uint32_t)reqs[i].codes.size(), reqs[i].dir, (uint64_t*)(d + o.queue), (int32_t*)(d + o.dist),
                                   (int16_t*)(d + o.count), (uint64_t*)(d + o.vk), (uint32_t*)(d + o.vv), caps[i], o.vis_cap - 1,
-                                  (uint32_t*)(d + o.nout)};
+                                  (uint32_t*)(d + o.nout), reqs[i].trim ? d + o.last : nullptr};
         }
         MC_CUDA(cudaMemcpyAsync(d + jobs_off, jobs.data(), jobs.size() * sizeof(McBfsJobDev), cudaMemcpyHostToDevice, st));
         k_bfs<<<(unsigned)jobs.size(), BFS_THREADS, 0, st>>>(t->dev, t->shard_id, k, min_cov, (long long)max_kmers, (long long)max_radius,
@@ -270,6 +292,10 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
                 MC_CUDA(cudaMemcpyAsync(r.kmers.data(), d + offs[w].queue, (size_t)n_out[w] * 8, cudaMemcpyDeviceToHost, st));
                 MC_CUDA(cudaMemcpyAsync(r.dist.data(), d + offs[w].dist, (size_t)n_out[w] * 4, cudaMemcpyDeviceToHost, st));
                 MC_CUDA(cudaMemcpyAsync(r.counts.data(), d + offs[w].count, (size_t)n_out[w] * 2, cudaMemcpyDeviceToHost, st));
+                if (reqs[i].trim) {
+                    r.last.resize(n_out[w]);
+                    MC_CUDA(cudaMemcpyAsync(r.last.data(), d + offs[w].last, (size_t)n_out[w], cudaMemcpyDeviceToHost, st));
+                }
             }
         }
         MC_CUDA(cudaStreamSynchronize(st));

@@ -60,11 +60,13 @@ template <class V>
 struct JavaMap {
     std::unordered_map<std::string, uint32_t> index;
     std::vector<std::pair<std::string, V>> entries;
+    size_t peak = 0;   // largest size ever: a java HashMap never shrinks its table when keys are removed
     void put(const std::string& k, const V& v) {
         auto it = index.find(k);
         if (it == index.end()) {
             index.emplace(k, (uint32_t)entries.size());
             entries.emplace_back(k, v);
+            peak = std::max(peak, entries.size());
         } else {
             entries[it->second].second = v;
         }
@@ -74,9 +76,18 @@ struct JavaMap {
         return it == index.end() ? nullptr : &entries[it->second].second;
     }
     size_t size() const { return entries.size(); }
+    // keySet().retainAll(...): the survivors keep their relative order
+    void retain(const std::vector<uint8_t>& keep) {
+        std::vector<std::pair<std::string, V>> kept;
+        for (size_t i = 0; i < entries.size(); i++)
+            if (keep[i]) kept.push_back(std::move(entries[i]));
+        entries.swap(kept);
+        index.clear();
+        for (size_t i = 0; i < entries.size(); i++) index.emplace(entries[i].first, (uint32_t)i);
+    }
     std::vector<uint32_t> order() const {
         size_t cap = 16;
-        while ((double)entries.size() > 0.75 * (double)cap) cap <<= 1;
+        while ((double)std::max(peak, entries.size()) > 0.75 * (double)cap) cap <<= 1;
         std::vector<std::pair<uint32_t, uint32_t>> v(entries.size());
         for (size_t i = 0; i < entries.size(); i++) {
             uint32_t h = (uint32_t)java_string_hash(entries[i].first);
@@ -309,8 +320,42 @@ void write_single_outputs(const Graph& g, const JavaMap<int>& subgraph, int chun
 }
 
 // subgraph of one target from its BFS passes: for (kmer : distanceToKmer.keySet()) subgraph.put(normalize(kmer), count) (:217-219,146-148)
-bool build_subgraph(const std::vector<const McBfsResult*>& passes, int k, JavaMap<int>& subgraph) {
-    for (const McBfsResult* r : passes) {
+// runTrimPaths (OneSequenceCalculator.java:241-262): from the lastKmers walk AGAINST the pass direction inside the visited
+// set; what is not reached is dropped (keySet().retainAll).  The visited set is at most seeds + --maxkmers k-mers: host work.
+static std::vector<uint8_t> trim_paths(const McBfsResult& r, int dir, int k) {
+    const size_t n = r.kmers.size();
+    std::unordered_map<uint64_t, uint32_t> at;
+    at.reserve(n * 2);
+    for (size_t i = 0; i < n; i++) at.emplace(r.kmers[i], (uint32_t)i);
+    std::vector<uint8_t> keep(n, 0);
+    std::vector<uint32_t> queue;
+    for (size_t i = 0; i < n; i++)
+        if (r.last[i] & 1) {
+            keep[i] = 1;
+            queue.push_back((uint32_t)i);
+        }
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    for (size_t head = 0; head < queue.size(); head++) {
+        const uint64_t kmer = r.kmers[queue[head]];
+        for (int s = 0; s < 8; s++) {
+            const bool left = (s & 1) == 0;
+            // getNeighborsByDir(-dir): dir -1 -> right neighbours, dir +1 -> left neighbours, dir 0 -> both
+            if ((dir == -1 && left) || (dir == 1 && !left)) continue;
+            const uint64_t nuc = (uint64_t)(s >> 1);
+            const uint64_t nb = left ? ((nuc << (2 * k - 2)) | (kmer >> 2)) : (((kmer << 2) | nuc) & kmask);
+            auto it = at.find(nb);
+            if (it != at.end() && !keep[it->second]) {
+                keep[it->second] = 1;
+                queue.push_back(it->second);
+            }
+        }
+    }
+    return keep;
+}
+
+bool build_subgraph(const std::vector<const McBfsResult*>& passes, const std::vector<int>& dirs, bool trim, int k, JavaMap<int>& subgraph) {
+    for (size_t pi = 0; pi < passes.size(); pi++) {
+        const McBfsResult* r = passes[pi];
         if (r->kmers.empty()) return false;   // "fail": no seed k-mer in the reads
         JavaMap<int> dist;                   // insertion order = discovery order
         std::vector<std::string> strs(r->kmers.size());
@@ -318,6 +363,7 @@ bool build_subgraph(const std::vector<const McBfsResult*>& passes, int k, JavaMa
             strs[i] = kmer_string(r->kmers[i], k);
             dist.put(strs[i], (int)i);
         }
+        if (trim) dist.retain(trim_paths(*r, dirs[pi], k));
         for (uint32_t p : dist.order()) subgraph.put(normalize_dna(dist.entries[p].first), (int)r->counts[(size_t)dist.entries[p].second]);
     }
     return true;
@@ -414,61 +460,106 @@ extern "C" void mc_targets_free(mc_targets* t) { delete t; }
 // ------------------------------------------------------------------------------------------------
 // Seam 3
 // ------------------------------------------------------------------------------------------------
-static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target>& targets, int k, int min_cov, int64_t max_kmers,
-                        int64_t max_radius, bool both_dirs, std::vector<JavaMap<int>>& subgraphs, std::vector<int>& found) {
+// One job = one environment: its seed sequences (one target, or with --merge every target followed by the Hi-C sequences).
+struct EnvJob {
+    std::vector<std::string> seeds;
+};
+static void run_jobs(mc_ctx* ctx, const mc_table* t, const std::vector<EnvJob>& jobs, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
+                     bool both_dirs, bool trim, std::vector<JavaMap<int>>& subgraphs, std::vector<int>& found) {
     std::vector<McBfsRequest> reqs;
-    for (const Target& tg : targets) {
-        std::vector<uint8_t> codes = mc_codes_from_target(tg.seq);
+    for (const EnvJob& job : jobs) {
+        std::vector<uint8_t> codes;
+        for (size_t i = 0; i < job.seeds.size(); i++) {
+            if (i) codes.push_back(4);   // no seed window spans two sequences (:168-192 loop over the sequences one by one)
+            std::vector<uint8_t> c = mc_codes_from_target(job.seeds[i]);
+            codes.insert(codes.end(), c.begin(), c.end());
+        }
         if (both_dirs) {
-            reqs.push_back(McBfsRequest{codes, 0});
+            reqs.push_back(McBfsRequest{codes, 0, trim});
         } else {   // buildEnvironment (:137-144): runBfs(-1) then runBfs(+1), each with its own visited set and budget
-            reqs.push_back(McBfsRequest{codes, -1});
-            reqs.push_back(McBfsRequest{codes, 1});
+            reqs.push_back(McBfsRequest{codes, -1, trim});
+            reqs.push_back(McBfsRequest{codes, 1, trim});
         }
     }
     std::vector<McBfsResult> res;
     mc_run_bfs_passes(ctx, t, k, min_cov, max_kmers, max_radius, reqs, res);
     const size_t per = both_dirs ? 1 : 2;
-    subgraphs.assign(targets.size(), JavaMap<int>());
-    found.assign(targets.size(), 0);
-    for (size_t i = 0; i < targets.size(); i++) {
+    subgraphs.assign(jobs.size(), JavaMap<int>());
+    found.assign(jobs.size(), 0);
+    for (size_t i = 0; i < jobs.size(); i++) {
         std::vector<const McBfsResult*> passes;
-        for (size_t p = 0; p < per; p++) passes.push_back(&res[i * per + p]);
-        found[i] = build_subgraph(passes, k, subgraphs[i]) ? 1 : 0;
+        std::vector<int> dirs;
+        for (size_t p = 0; p < per; p++) {
+            passes.push_back(&res[i * per + p]);
+            dirs.push_back(reqs[i * per + p].dir);
+        }
+        found[i] = build_subgraph(passes, dirs, trim, k, subgraphs[i]) ? 1 : 0;
     }
 }
+static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target>& targets, int k, int min_cov, int64_t max_kmers,
+                        int64_t max_radius, bool both_dirs, std::vector<JavaMap<int>>& subgraphs, std::vector<int>& found) {
+    std::vector<EnvJob> jobs;
+    for (const Target& tg : targets) jobs.push_back(EnvJob{{tg.seq}});
+    run_jobs(ctx, t, jobs, k, min_cov, max_kmers, max_radius, both_dirs, false, subgraphs, found);
+}
 
-extern "C" int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets, int k, int min_cov,
-                           int64_t max_kmers, int64_t max_radius, int both_dirs, int chunk_len, const char* out_dir, int* found_out) {
+// graph.txt/env.txt + unitig stage + writers of one environment; gene nodes are decided against `gene_seqs` (isGeneNode :421-432)
+static void write_one_environment(mc_ctx* ctx, const JavaMap<int>& sub, const std::vector<std::string>& gene_seqs, int k, int chunk_len,
+                                  const std::string& prefix) {
+    std::vector<uint32_t> ord = sub.order();
+    write_environment(sub, ord, prefix);
+    McUnitigInput in;
+    unitig_input_from_subgraph(sub, ord, gene_seqs, k, in);
+    McUnitigNodes nodes;
+    mc_unitig_nodes(ctx, in, nodes);
+    Graph g;
+    g.build(in, nodes);
+    g.sweep(nullptr);
+    g.assemble();
+    write_single_outputs(g, sub, chunk_len, prefix);
+}
+
+// --merge / --hicseq / --trim (EnvironmentFinderMain.java:218-233, OneSequenceCalculator.java:168-192,208-216,241-262)
+extern "C" int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets,
+                              const char* const* hic_seqs, int n_hic, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
+                              int chunk_len, int merge, int trim, const char* out_dir, int* found_out) {
     try {
-        if (!ctx || !t || !out_dir || (n_targets && (!seqs || !names))) mc_throw(MC_ERR_ARG, "null argument");
-        std::vector<Target> targets((size_t)n_targets);
-        for (int i = 0; i < n_targets; i++) targets[(size_t)i] = Target{seqs[i], names[i]};
+        if (!ctx || !t || !out_dir || (n_targets && !seqs) || (n_hic && !hic_seqs) || (!merge && n_targets && !names)) mc_throw(MC_ERR_ARG, "null argument");
+        std::vector<EnvJob> jobs;
+        std::vector<std::string> prefixes;
+        std::vector<std::vector<std::string>> gene_seqs;
+        if (merge) {   // one environment seeded by every target and every Hi-C sequence, written to <out>/merged/
+            EnvJob job;
+            for (int i = 0; i < n_targets; i++) job.seeds.push_back(seqs[i]);
+            gene_seqs.push_back(job.seeds);            // isGeneNode looks at `sequences` only, not at the Hi-C reads
+            for (int i = 0; i < n_hic; i++) job.seeds.push_back(hic_seqs[i]);
+            jobs.push_back(job);
+            prefixes.push_back(std::string(out_dir) + "/merged/");
+        } else {
+            for (int i = 0; i < n_targets; i++) {
+                jobs.push_back(EnvJob{{seqs[i]}});
+                gene_seqs.push_back({seqs[i]});
+                prefixes.push_back(std::string(out_dir) + "/" + names[i] + "/");   // getOutputPrefix (EnvironmentFinderMain.java:245-249)
+            }
+        }
         std::vector<JavaMap<int>> subgraphs;
         std::vector<int> found;
-        run_targets(ctx, t, targets, k, min_cov, max_kmers, max_radius, both_dirs != 0, subgraphs, found);
-        for (int i = 0; i < n_targets; i++) {
-            if (found_out) found_out[i] = found[(size_t)i];
-            if (!found[(size_t)i]) continue;   // "Could not find any k-mers of the target gene in the input, halting."
-            const JavaMap<int>& sub = subgraphs[(size_t)i];
-            std::string prefix = std::string(out_dir) + "/" + targets[(size_t)i].name + "/";   // getOutputPrefix (EnvironmentFinderMain.java:245-249)
-            std::vector<uint32_t> ord = sub.order();
-            write_environment(sub, ord, prefix);
-            McUnitigInput in;
-            unitig_input_from_subgraph(sub, ord, {targets[(size_t)i].seq}, k, in);
-            McUnitigNodes nodes;
-            mc_unitig_nodes(ctx, in, nodes);
-            Graph g;
-            g.build(in, nodes);
-            g.sweep(nullptr);
-            g.assemble();
-            write_single_outputs(g, sub, chunk_len, prefix);
+        run_jobs(ctx, t, jobs, k, min_cov, max_kmers, max_radius, both_dirs != 0, trim != 0, subgraphs, found);
+        for (size_t i = 0; i < jobs.size(); i++) {
+            if (found_out) found_out[i] = found[i];
+            if (!found[i]) continue;   // "Could not find any k-mers of the target gene in the input, halting."
+            write_one_environment(ctx, subgraphs[i], gene_seqs[i], k, chunk_len, prefixes[i]);
         }
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());
         return e.code;
     }
+}
+
+extern "C" int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets, int k, int min_cov,
+                           int64_t max_kmers, int64_t max_radius, int both_dirs, int chunk_len, const char* out_dir, int* found_out) {
+    return mc_env_find_ex(ctx, t, seqs, names, n_targets, nullptr, 0, k, min_cov, max_kmers, max_radius, both_dirs, chunk_len, 0, 0, out_dir, found_out);
 }
 
 extern "C" int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius,

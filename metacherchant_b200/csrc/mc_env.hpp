@@ -8,13 +8,15 @@
 #include "mc_common.cuh"
 
 struct McBfsRequest {
-    std::vector<uint8_t> codes;   // target sequence(s) as nucleotide codes
+    std::vector<uint8_t> codes;   // seed sequence(s) as nucleotide codes; code 4 separates the sequences of a merged seed list
     int dir = 0;                  // -1 left, +1 right, 0 both
+    bool trim = false;            // --trim: also report which k-mers are "lastKmers" (OneSequenceCalculator.java:208-216)
 };
 struct McBfsResult {
     std::vector<uint64_t> kmers;  // oriented, discovery order
     std::vector<int32_t> dist;
     std::vector<int16_t> counts;
+    std::vector<uint8_t> last;    // with trim: 1 = some solid neighbour of this k-mer was refused by allowsAddition
 };
 
 std::vector<uint8_t> mc_codes_from_target(const std::string& seq);

@@ -130,6 +130,7 @@ template <class V>
 struct JHashMap {
     std::unordered_map<std::string, size_t> index;   // key -> position in `entries`
     std::vector<std::pair<std::string, V>> entries;  // insertion order
+    size_t peak = 0;                                 // largest size ever (java.util.HashMap never shrinks its table on removal)
 
     bool contains(const std::string& k) const { return index.count(k) != 0; }
     size_t size() const { return entries.size(); }
@@ -138,9 +139,19 @@ struct JHashMap {
         if (it == index.end()) {
             index.emplace(k, entries.size());
             entries.emplace_back(k, v);
+            peak = std::max(peak, entries.size());
         } else {
             entries[it->second].second = v;
         }
+    }
+    // keySet().retainAll(keep): survivors keep their relative (bucket-internal) order
+    void retain_all(const std::unordered_set<std::string>& keep) {
+        std::vector<std::pair<std::string, V>> kept;
+        for (auto& e : entries)
+            if (keep.count(e.first)) kept.push_back(std::move(e));
+        entries.swap(kept);
+        index.clear();
+        for (size_t i = 0; i < entries.size(); i++) index.emplace(entries[i].first, i);
     }
     const V* get(const std::string& k) const {
         auto it = index.find(k);
@@ -153,7 +164,7 @@ struct JHashMap {
     static uint32_t spread(int32_t h) { return (uint32_t)h ^ ((uint32_t)h >> 16); }
     size_t capacity() const {
         size_t cap = 16;
-        while ((double)entries.size() > 0.75 * (double)cap) cap <<= 1;
+        while ((double)std::max(peak, entries.size()) > 0.75 * (double)cap) cap <<= 1;
         return cap;
     }
     // positions into `entries` in java iteration order
@@ -640,21 +651,44 @@ struct EnvCalc {
     JHashMap<int> subgraph;
     bool failed = false;
     int extend_additions = 0;
+    std::vector<std::string> hic_sequences;   // --hicseq (only used with --merge, :180-191)
+    bool trim = false;                        // --trim
 
     int occs(const std::string& kmer) const { return reads->get(kmer_key(to_long(kmer), k)); }   // :89-96
 
-    // runBfs (:154-220), --trim off.  distanceToKmer is a java HashMap (iteration order matters for subgraph order).
+    // runTrimPaths (:241-262)
+    void run_trim_paths(const std::unordered_set<std::string>& last_kmers, JHashMap<int>& distance, int dir) {
+        std::vector<std::string> queue(last_kmers.begin(), last_kmers.end());
+        std::unordered_set<std::string> visited(last_kmers.begin(), last_kmers.end());
+        size_t head = 0;
+        while (head < queue.size()) {
+            std::string kmer = queue[head++];
+            for (const std::string& nb : neighbors_by_dir(-dir, kmer))
+                if (distance.contains(nb) && !visited.count(nb)) {
+                    queue.push_back(nb);
+                    visited.insert(nb);
+                }
+        }
+        distance.retain_all(visited);
+    }
+
+    // runBfs (:154-220).  distanceToKmer is a java HashMap (iteration order matters for subgraph order).
     void run_bfs(int dir, std::vector<std::string>* order_out = nullptr, std::vector<int>* dist_out = nullptr) {
         std::vector<std::string> queue;
         JHashMap<int> distance;
-        for (const std::string& sequence : sequences)
-            for (size_t i = 0; i + k <= sequence.size(); i++) {
-                std::string kmer = sequence.substr(i, k);
-                if (occs(kmer) >= min_occ) {
-                    queue.push_back(kmer);
-                    distance.put(kmer, 0);
+        std::unordered_set<std::string> last_kmers;
+        auto seed = [&](const std::vector<std::string>& seqs) {
+            for (const std::string& sequence : seqs)
+                for (size_t i = 0; i + k <= sequence.size(); i++) {
+                    std::string kmer = sequence.substr(i, k);
+                    if (occs(kmer) >= min_occ) {
+                        queue.push_back(kmer);   // duplicates are queued again (:164,175,187)
+                        distance.put(kmer, 0);
+                    }
                 }
-            }
+        };
+        seed(sequences);
+        seed(hic_sequences);
         if (queue.empty()) { failed = true; return; }
         size_t head = 0;
         while (head < queue.size()) {
@@ -665,10 +699,13 @@ struct EnvCalc {
                     if (term.allows(distance, nb, d + 1)) {
                         queue.push_back(nb);
                         distance.put(nb, d + 1);
+                    } else {
+                        last_kmers.insert(kmer);
                     }
                 }
             }
         }
+        if (trim) run_trim_paths(last_kmers, distance, dir);
         if (order_out) {   // discovery order = insertion order of the map
             for (auto& e : distance.entries) {
                 order_out->push_back(e.first);
@@ -1204,7 +1241,7 @@ int64_t orc_bfs(const orc_table* t, const char* seq, int k, int min_cov, int64_t
                 char* out_kmers, int32_t* out_dist, uint64_t cap) {
     int64_t result = -1;
     int rc = guarded([&] {
-        EnvCalc c{t, {std::string(seq)}, k, min_cov, dir == 0, 1, {max_kmers, max_radius}, {}, false, 0};
+        EnvCalc c{t, {std::string(seq)}, k, min_cov, dir == 0, 1, {max_kmers, max_radius}, {}, false, 0, {}, false};
         std::vector<std::string> order;
         std::vector<int> dist;
         c.run_bfs(dir, &order, &dist);
@@ -1232,13 +1269,56 @@ int orc_env_find(const orc_table* t, const char* seq_fasta, int k, int min_cov, 
         for (size_t i = 0; i < rf.dnas.size(); i++) {
             if (i >= rf.comments.size()) fail("IndexOutOfBoundsException: comments.get(%zu)", i);
             std::string prefix = std::string(out_dir) + "/" + rf.comments[i] + "/";   // getOutputPrefix (:245-249)
-            EnvCalc c{t, {rf.dnas[i]}, k, min_cov, both_dirs != 0, chunk_len, {max_kmers, max_radius}, {}, false, 0};
+            EnvCalc c{t, {rf.dnas[i]}, k, min_cov, both_dirs != 0, chunk_len, {max_kmers, max_radius}, {}, false, 0, {}, false};
             c.build_environment();
             if (c.failed) continue;   // "Could not find any k-mers of the target gene in the input, halting."
             c.extend_environment();
             print_environment(c.subgraph, prefix);
             create_picture(c.subgraph, c.sequences, k, chunk_len, prefix);
             done++;
+        }
+        return done;
+    });
+}
+
+// environment-finder with --merge / --hicseq / --trim (EnvironmentFinderMain.java:126-156,218-233)
+int orc_env_find_ex(const orc_table* t, const char* seq_fasta, const char* hic_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
+                    int both_dirs, int chunk_len, int merge, int trim, const char* out_dir) {
+    return guarded([&] {
+        if (max_kmers < 0 && max_radius < 0) fail("At least one of --maxkmers and --maxradius parameters should be set");
+        FILE* f = fopen(seq_fasta, "rb");
+        if (!f) fail("Could not load sequences from %s", seq_fasta);
+        fclose(f);
+        RichFasta rf = rich_fasta_read(seq_fasta);
+        std::vector<std::string> comments = rf.comments, hic;
+        if (hic_fasta && *hic_fasta) {
+            FILE* g = fopen(hic_fasta, "rb");
+            if (!g) fail("Could not load Hi-C sequences from %s", hic_fasta);
+            fclose(g);
+            RichFasta hf = rich_fasta_read(hic_fasta);
+            hic = hf.dnas;
+            comments = hf.comments;   // loadInput overwrites this.comments with the Hi-C file's (:146-150)
+        }
+        int done = 0;
+        auto run_one = [&](EnvCalc& c, const std::string& prefix) {
+            c.trim = trim != 0;
+            c.build_environment();
+            if (c.failed) return;
+            c.extend_environment();
+            print_environment(c.subgraph, prefix);
+            create_picture(c.subgraph, c.sequences, k, chunk_len, prefix);
+            done++;
+        };
+        if (!merge) {
+            for (size_t i = 0; i < rf.dnas.size(); i++) {
+                if (i >= comments.size()) fail("IndexOutOfBoundsException: comments.get(%zu)", i);
+                EnvCalc c{t, {rf.dnas[i]}, k, min_cov, both_dirs != 0, chunk_len, {max_kmers, max_radius}, {}, false, 0, {}, false};
+                run_one(c, std::string(out_dir) + "/" + comments[i] + "/");
+            }
+        } else {
+            EnvCalc c{t, rf.dnas, k, min_cov, both_dirs != 0, chunk_len, {max_kmers, max_radius}, {}, false, 0, {}, false};
+            c.hic_sequences = hic;
+            run_one(c, std::string(out_dir) + "/merged/");
         }
         return done;
     });

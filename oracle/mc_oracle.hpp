@@ -67,6 +67,8 @@ int64_t orc_bfs(const orc_table*, const char* seq, int k, int min_cov, int64_t m
 // ---- C0..C6: whole environment for every target of a FASTA (EnvironmentFinderMain.runImpl) ---
 // Writes <out_dir>/<header>/{graph.txt,env.txt,seqs.fasta,graph.gfa,tsvs/nodes.tsv,tsvs/edges.tsv}.
 // Returns number of targets processed (>=0) or <0 on error.
+int orc_env_find_ex(const orc_table*, const char* seq_fasta, const char* hic_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
+                    int both_dirs, int chunk_len, int merge, int trim, const char* out_dir);
 int orc_env_find(const orc_table*, const char* seq_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
                  int both_dirs, int chunk_len, const char* out_dir);
 // stage D only: from an env file (graph.txt lines "KMER COUNT", order kept) + target sequence string

@@ -184,10 +184,11 @@ def java_hash(s: str) -> int:
     return h
 
 
-def java_order(keys):
-    """Iteration order of a java.util.HashMap<String,_> filled in `keys` order (no treeified bins)."""
+def java_order(keys, peak=None):
+    """Iteration order of a java.util.HashMap<String,_> filled in `keys` order (no treeified bins).
+    peak = the largest size the map ever had (removals never shrink the table)."""
     cap = 16
-    while len(keys) > 0.75 * cap:
+    while max(len(keys), peak or 0) > 0.75 * cap:
         cap *= 2
     def bucket(s):
         h = java_hash(s)
@@ -195,17 +196,31 @@ def java_order(keys):
     return sorted(keys, key=bucket)  # python's sort is stable
 
 
-def bfs(table: dict, seq: str, k: int, min_cov: int, max_kmers, max_radius, direction: int):
-    """src/algo/OneSequenceCalculator.java:154-220 with TerminationMode.allowsAddition, literal."""
+def neighbors_by_dir(kmer: str, direction: int):
+    """getNeighborsByDir (OneSequenceCalculator.java:222-239)."""
+    left = [n + kmer[:-1] for n in NUC]
+    right = [kmer[1:] + n for n in NUC]
+    if direction == -1:
+        return left
+    if direction == 1:
+        return right
+    return [x for pair in zip(left, right) for x in pair]
+
+
+def bfs(table: dict, seq, k: int, min_cov: int, max_kmers, max_radius, direction: int, trim: bool = False, info: dict | None = None):
+    """src/algo/OneSequenceCalculator.java:154-220 with TerminationMode.allowsAddition, literal.
+    seq: one target, or (--merge) the list of seed sequences; trim: runTrimPaths (:241-262).
+    info (optional) receives the peak size of distanceToKmer."""
     def occ(kmer):
         c = encode(kmer)
         return table.get(min(c, revcomp_code(c, k)), -1)
-    queue, dist = [], {}
-    for i in range(len(seq) - k + 1):
-        kmer = seq[i:i + k]
-        if occ(kmer) >= min_cov:
-            queue.append(kmer)
-            dist[kmer] = 0
+    queue, dist, last = [], {}, set()
+    for one in ([seq] if isinstance(seq, str) else seq):
+        for i in range(len(one) - k + 1):
+            kmer = one[i:i + k]
+            if occ(kmer) >= min_cov:
+                queue.append(kmer)
+                dist[kmer] = 0
     if not queue:
         return None
     head = 0
@@ -213,14 +228,7 @@ def bfs(table: dict, seq: str, k: int, min_cov: int, max_kmers, max_radius, dire
         kmer = queue[head]
         head += 1
         d = dist[kmer]
-        left = [n + kmer[:-1] for n in NUC]
-        right = [kmer[1:] + n for n in NUC]
-        if direction == -1:
-            nbs = left
-        elif direction == 1:
-            nbs = right
-        else:
-            nbs = [x for pair in zip(left, right) for x in pair]
+        nbs = neighbors_by_dir(kmer, direction)
         for nb in nbs:
             if occ(nb) >= min_cov:
                 ok = nb not in dist
@@ -231,10 +239,25 @@ def bfs(table: dict, seq: str, k: int, min_cov: int, max_kmers, max_radius, dire
                 if ok:
                     queue.append(nb)
                     dist[nb] = d + 1
+                else:
+                    last.add(kmer)
+    if info is not None:
+        info["peak"] = len(dist)
+    if trim:
+        q2, seen = list(last), set(last)
+        head = 0
+        while head < len(q2):
+            kmer = q2[head]
+            head += 1
+            for nb in neighbors_by_dir(kmer, -direction):
+                if nb in dist and nb not in seen:
+                    q2.append(nb)
+                    seen.add(nb)
+        dist = {kk: v for kk, v in dist.items() if kk in seen}
     return dist  # python dicts keep insertion (= discovery) order
 
 
-def environment(table: dict, seq: str, k: int, min_cov: int, max_kmers, max_radius, both_dirs: bool):
+def environment(table: dict, seq, k: int, min_cov: int, max_kmers, max_radius, both_dirs: bool, trim: bool = False):
     """buildEnvironment + addToSubgraph (OneSequenceCalculator.java:137-148,217-219) -> [(kmer, count)] in
     the java iteration order of `subgraph`."""
     sub = {}
@@ -242,9 +265,10 @@ def environment(table: dict, seq: str, k: int, min_cov: int, max_kmers, max_radi
         c = encode(kmer)
         return table.get(min(c, revcomp_code(c, k)), -1)
     for direction in ([0] if both_dirs else [-1, 1]):
-        dist = bfs(table, seq, k, min_cov, max_kmers, max_radius, direction)
+        info = {}
+        dist = bfs(table, seq, k, min_cov, max_kmers, max_radius, direction, trim, info)
         if dist is None:
             return None
-        for kmer in java_order(list(dist.keys())):
+        for kmer in java_order(list(dist.keys()), info["peak"]):
             sub[normalize(kmer)] = occ(kmer)
     return [(kmer, sub[kmer]) for kmer in java_order(list(sub.keys()))]

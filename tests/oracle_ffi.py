@@ -59,6 +59,7 @@ class Oracle:
         L.orc_bfs.restype = C.c_int64
         L.orc_bfs.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64]
         L.orc_env_find.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char_p]
+        L.orc_env_find_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.orc_env_from_graph_txt.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
         L.orc_env_multi.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int, C.c_char_p]
         L.orc_print_kmers.restype = C.c_int64
@@ -196,6 +197,11 @@ class OracleTable:
                                                     -1 if max_kmers is None else max_kmers,
                                                     -1 if max_radius is None else max_radius,
                                                     int(both_dirs), chunk_len, out_dir.encode()))
+
+    def env_find_ex(self, seq_fasta, hic_fasta, min_cov, max_kmers, max_radius, both_dirs, chunk_len, merge, trim, out_dir):
+        return self.o.check(self.o.lib.orc_env_find_ex(self.h, seq_fasta.encode(), hic_fasta.encode() if hic_fasta else None, self.k, min_cov,
+                                                       -1 if max_kmers is None else max_kmers, -1 if max_radius is None else max_radius,
+                                                       int(both_dirs), chunk_len, int(merge), int(trim), out_dir.encode()))
 
     def print_kmers(self, threshold, out_file, stat_file=None):
         return self.o.check(self.o.lib.orc_print_kmers(self.h, threshold, out_file.encode(), stat_file.encode() if stat_file else None))

@@ -71,7 +71,7 @@ def test_cli_flag_surface(tmp_path, lib):
     assert r.returncode == 1 and "Mandatory argument --k (-k) not set" in r.stderr
     r = run_cli("-k", "31", "--seq", "x.fa", "--output", "o", cwd=tmp_path)
     assert r.returncode == 1 and "At least one of --maxkmers and --maxradius parameters should be set" in r.stderr
-    for bad in (["--trim"], ["--merge", "true"], ["--hicseq", "h.fa"], ["--forcehash", "True"], ["--hash", "fnv1a"]):
+    for bad in (["--forcehash", "True"], ["--hash", "fnv1a"]):
         r = run_cli("-k", "31", "--seq", "x.fa", "--output", "o", "--maxkmers", "5", *bad, cwd=tmp_path)
         assert r.returncode == 1 and "not supported by the GPU path" in r.stderr, bad
     r = run_cli("-k", "33", "--seq", "x.fa", "--output", "o", "--maxkmers", "5", cwd=tmp_path)

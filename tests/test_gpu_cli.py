@@ -57,6 +57,34 @@ def test_environment_finder_cli(oracle, tmp_path):
     assert (tmp_path / "wd2" / "kmers" / "a.kmers.bin").read_bytes() == (tmp_path / "o.kmers.bin").read_bytes()
 
 
+@pytest.mark.parametrize("flags", [["--merge", "true"], ["--merge", "--hicseq", "HIC"], ["--trim"], ["--merge", "true", "--trim", "--hicseq", "HIC", "--bothdirs", "true"],
+                                   ["--hicseq", "HIC"]])
+def test_cli_merge_hicseq_trim(oracle, tmp_path, flags):
+    """SURVEY 8f rows 2 and 3 through the command line, byte for byte against the oracle."""
+    k = 13
+    rng = random.Random(5)
+    genome, data = small_graph(rng, k, genome_len=2500, n_reads=3500, read_len=60)
+    (tmp_path / "r.fasta").write_bytes(data)
+    (tmp_path / "genes.fa").write_text(f">geneA\n{genome[500:580]}\n>geneB\n{genome[560:640]}\n")
+    (tmp_path / "hic.fa").write_text(f">hicA\n{genome[1500:1560]}\n>hicB\n{genome[2000:2050]}\n")
+    flags = [str(tmp_path / "hic.fa") if f == "HIC" else f for f in flags]
+    merge, trim, hic = "--merge" in flags, "--trim" in flags, "--hicseq" in flags
+    both = "--bothdirs" in flags
+    r = subprocess.run([CLI, "-k", str(k), "-i", str(tmp_path / "r.fasta"), "--seq", str(tmp_path / "genes.fa"), "-o", str(tmp_path / "out"),
+                        "-w", str(tmp_path / "wd"), "--maxkmers", "200", "--coverage", "2", *flags], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    o = oracle.table(k, threads=4)
+    o.count_file(str(tmp_path / "r.fasta"))
+    n = o.env_find_ex(str(tmp_path / "genes.fa"), str(tmp_path / "hic.fa") if hic else None, 2, 200, None, both, 1, merge, trim, str(tmp_path / "orc"))
+    dirs = ["merged"] if merge else (["hicA", "hicB"] if hic else ["geneA", "geneB"])
+    assert n == len(dirs)
+    if merge:
+        assert "Finding single environment for 2 sequences" in r.stderr
+    for d in dirs:
+        for f in FILES:
+            assert (tmp_path / "out" / d / f).read_bytes() == (tmp_path / "orc" / d / f).read_bytes(), (d, f)
+
+
 def test_cli_reports_reader_errors(tmp_path):
     (tmp_path / "bad.fastq").write_text("@r\nACGT\n+\nIII\n")
     (tmp_path / "g.fa").write_text(">g\nACGTACGTACGTACGTACGT\n")

@@ -183,3 +183,32 @@ def test_synthetic_config1_environment(ctx, oracle, tmp_path):
         assert found == [True]
         same_files(str(tmp_path / f"gpu{tag}" / "gene0"), str(tmp_path / f"orc{tag}" / "gene0"))
         assert sum(1 for _ in open(tmp_path / f"gpu{tag}" / "gene0" / "env.txt")) > 900
+
+
+# ---- --merge (+ --hicseq) and --trim ------------------------------------------------------
+@pytest.mark.parametrize("k", [7, 11, 31])
+@pytest.mark.parametrize("both", [False, True])
+@pytest.mark.parametrize("merge,trim,hic", [(True, False, False), (True, False, True), (False, True, False), (True, True, True)])
+@pytest.mark.parametrize("limits", [(60, None), (None, 5), (100000, None), (25, 3)])
+def test_merge_hicseq_trim_identical_to_oracle(ctx, oracle, tmp_path, k, both, merge, trim, hic, limits):
+    rng = random.Random(7 * k + both + 3 * merge + 5 * trim)
+    genome, data = small_graph(rng, k, genome_len=1500, n_reads=1500, read_len=max(40, k + 10))
+    g = ctx.new_table(k).count_bytes(data, FMT_FASTA)
+    o = oracle.table(k).count_bytes(data, FMT_FASTA)
+    L = max(k + 8, 40)
+    targets = [genome[200:200 + L], genome[200 + L - k - 3:200 + 2 * L], genome[900:900 + L]]      # the first two overlap: duplicated seeds
+    hics = [genome[500:500 + L], "ACGT" * 12]
+    fa, hf = tmp_path / "seq.fasta", tmp_path / "hic.fasta"
+    fa.write_text("".join(f">g{i}\n{s}\n" for i, s in enumerate(targets)))
+    hf.write_text("".join(f">h{i}\n{s}\n" for i, s in enumerate(hics)))
+    max_kmers, max_radius = limits
+    n = o.env_find_ex(str(fa), str(hf) if hic else None, 2, max_kmers, max_radius, both, 1, merge, trim, str(tmp_path / "orc"))
+    names = [f"g{i}" for i in range(len(targets))]
+    found = ctx.find_environments_ex(g.filter(2), targets, None if merge else names, hics if hic else (), min_cov=2, max_kmers=max_kmers,
+                                     max_radius=max_radius, both_dirs=both, merge=merge, trim=trim, out_dir=tmp_path / "gpu")
+    assert sum(found) == n
+    for d, ok in zip(["merged"] if merge else names, found):
+        if ok:
+            same_files(str(tmp_path / "gpu" / d), str(tmp_path / "orc" / d))
+        else:
+            assert not os.path.exists(tmp_path / "orc" / d / "graph.txt")

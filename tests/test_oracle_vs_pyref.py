@@ -211,6 +211,38 @@ def test_environment_matches_pyref(oracle, both, tmp_path):
         assert (tmp_path / "out" / "gene one" / f).exists()
 
 
+@pytest.mark.parametrize("both", [False, True])
+@pytest.mark.parametrize("merge,trim,hic", [(True, False, False), (True, False, True), (False, True, False), (True, True, True)])
+def test_merge_hicseq_trim_match_pyref(oracle, both, merge, trim, hic, tmp_path):
+    """--merge (+ --hicseq) seeds one environment from every sequence; --trim keeps the k-mers that reach a
+    lastKmers member walking against the pass direction.  C++ oracle vs the independent Python transcription."""
+    k = 9
+    rng = random.Random(1234 + both)
+    genome, data = small_graph(rng, k, genome_len=1200, n_reads=1200)
+    t = oracle.table(k).count_bytes(data, FMT_FASTA)
+    targets = [genome[200:250], genome[235:290], genome[700:745]]      # two overlap: duplicated seed k-mers
+    hics = [genome[400:440], "ACGT" * 8]
+    fa = tmp_path / "seq.fasta"
+    fa.write_text("".join(f">g{i}\n{s}\n" for i, s in enumerate(targets)))
+    hf = tmp_path / "hic.fasta"
+    hf.write_text("".join(f">h{i}\n{s}\n" for i, s in enumerate(hics)))
+    out = tmp_path / "out"
+    n = t.env_find_ex(str(fa), str(hf) if hic else None, 2, 120, None, both, 1, merge, trim, str(out))
+    if merge:
+        assert n == 1
+        seeds = targets + (hics if hic else [])
+        want = pyref.environment(table_dict(t), seeds, k, 2, 120, None, both, trim)
+        lines = (out / "merged" / "graph.txt").read_text().splitlines()
+        assert lines == [f"{kmer} {c}" for kmer, c in want]
+    else:
+        assert n == len(targets)
+        names = [f"h{i}" for i in range(len(hics))] if hic else [f"g{i}" for i in range(len(targets))]
+        for i, target in enumerate(targets):
+            want = pyref.environment(table_dict(t), target, k, 2, 120, None, both, trim)
+            lines = (out / names[i] / "graph.txt").read_text().splitlines()
+            assert lines == [f"{kmer} {c}" for kmer, c in want]
+
+
 def test_level_synchronous_rule_equals_fifo_rule():
     """ordering a batch's candidates by (parent queue index, neighbour slot) and keeping the first
     occurrence gives the same set and discovery order as the sequential FIFO loop, also when --maxkmers is hit.
