@@ -11,14 +11,16 @@
 // BigLong2ShortHashMap.java:67-77): exact counts saturating at 32767, any order of application gives the same table.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "mc_common.cuh"
 
 #define BIN_TILE_DEFAULT 2048u  // keys per k_bin_count work unit (tunable: count_tile)
-#define SC_THREADS 256
+#define SC_THREADS 512
 #define SC_TILE 8192u           // keys per k_bin_scatter tile (sorted by bin in shared memory)
+#define SC_KPT (SC_TILE / SC_THREADS)   // keys per thread, held in registers between the histogram and the sort
 
 void mc_resolve_timers(mc_ctx* ctx) {
     for (auto& t : ctx->timers) {
@@ -53,8 +55,9 @@ static size_t scatter_smem_bytes(uint32_t P) {
 
 // `D.use` = the bins are the OWNER ranks of the multi-GPU exchange: bin o's run goes to D.base[o], the receive region this rank
 // owns inside rank o's buffer (peer memory mapped through CUDA IPC: the sector stores travel over NVLink), mc_xchg.cu.
-__global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
-                                                            unsigned int* flags, McBinDst D) {
+// tiles first_tile, first_tile + tile_stride, ... of `flat` (one CTA)
+__device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat, uint64_t n, const McBinsDev& B, int shard_bits, uint32_t shard_id,
+                                              unsigned int* flags, const McBinDst& D, uint32_t first_tile, uint32_t tile_stride) {
     extern __shared__ unsigned long long s_mem[];
     const uint32_t P = 1u << B.pbits;
     McScatterSmem S;
@@ -64,21 +67,51 @@ __global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __re
     S.off = S.hist + P;
     S.secbin = (uint16_t*)(S.off + P + 1 + ((P + 1) & 1));
     __shared__ uint32_t s_warp_tot[SC_THREADS / 32];
-    const int bshift = B.hbits - B.pbits;        // <= 62
+    const int bshift = B.shift;                  // <= 62
     const uint64_t lmask = (1ULL << B.hbits) - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // bins are scanned in contiguous groups of `per` per thread
     const uint32_t per = (P + SC_THREADS - 1) / SC_THREADS;
-    for (uint64_t t0 = (uint64_t)blockIdx.x * SC_TILE; t0 < n; t0 += (uint64_t)gridDim.x * SC_TILE) {
+    for (uint64_t t0 = (uint64_t)first_tile * SC_TILE; t0 < n; t0 += (uint64_t)tile_stride * SC_TILE) {
         const uint32_t tn = (uint32_t)(n - t0 < SC_TILE ? n - t0 : SC_TILE);
         for (uint32_t i = threadIdx.x; i < P; i += SC_THREADS) S.hist[i] = 0;
         __syncthreads();
-        // pass A: histogram
-#pragma unroll 4
-        for (uint32_t i = threadIdx.x; i < tn; i += SC_THREADS) {
-            const uint64_t h = __ldg(flat + t0 + i);
+        // pass A: the tile is read ONCE, 16 bytes per lane and SC_KPT / 2 loads in flight per thread; every key takes its rank
+        // inside its bin from the shared histogram and stays in registers until the run offsets are known
+        uint64_t key[SC_KPT];
+        uint32_t rk[SC_KPT / 2];   // two 16-bit ranks per word
+        const uint64_t* src = flat + t0;
+        const bool al16 = ((uintptr_t)src & 15) == 0;
+#pragma unroll
+        for (int j = 0; j < SC_KPT; j += 2) {
+            const uint32_t i = (uint32_t)j * SC_THREADS + threadIdx.x * 2;
+            key[j] = key[j + 1] = MC_HASH_SENTINEL;
+            if (i + 1 < tn) {
+                if (al16) {
+                    const ulonglong2 v = __ldcs((const ulonglong2*)(src + i));
+                    key[j] = v.x;
+                    key[j + 1] = v.y;
+                } else {   // a caller's own device buffer (mc_table_insert_hashed_device) may be only 8-byte aligned
+                    key[j] = __ldcs(src + i);
+                    key[j + 1] = __ldcs(src + i + 1);
+                }
+            } else if (i < tn) {
+                key[j] = __ldcs(src + i);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SC_KPT; j++) {
+            const uint64_t h = key[j];
             const bool valid = h != MC_HASH_SENTINEL && (shard_bits == 0 || (uint32_t)(h >> (62 - shard_bits)) == shard_id);
-            if (valid) atomicAdd(&S.hist[(uint32_t)((h & lmask) >> bshift) & (P - 1)], 1u);
+            uint32_t r = 0;
+            if (valid) {
+                key[j] = h & lmask;
+                r = atomicAdd(&S.hist[(uint32_t)(key[j] >> bshift) & (P - 1)], 1u);
+            } else {
+                key[j] = MC_HASH_SENTINEL;
+            }
+            if (j & 1) rk[j >> 1] |= r << 16;
+            else rk[j >> 1] = r;
         }
         __syncthreads();
         // exclusive scan of the padded run lengths; reserve the global runs; write pads and the sector -> bin map
@@ -102,22 +135,19 @@ __global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __re
                 S.gbase[b] = pc ? atomicAdd(&B.cursors[b], (unsigned long long)pc) : 0ULL;
                 for (uint32_t j = c; j < pc; j++) S.sorted[run + j] = MC_HASH_SENTINEL;
                 for (uint32_t j = 0; j < pc; j += 4) S.secbin[(run + j) >> 2] = (uint16_t)b;
-                S.hist[b] = 0;
                 run += pc;
             }
             if (threadIdx.x == SC_THREADS - 1) S.off[P] = run;   // the last thread owns the last bins
         }
         __syncthreads();
-        // pass B: keys to their sorted position (the tile was just read: these loads hit L2)
-#pragma unroll 4
-        for (uint32_t i = threadIdx.x; i < tn; i += SC_THREADS) {
-            const uint64_t h = __ldcs(flat + t0 + i);
-            const bool valid = h != MC_HASH_SENTINEL && (shard_bits == 0 || (uint32_t)(h >> (62 - shard_bits)) == shard_id);
-            if (valid) {
-                const uint64_t hl = h & lmask;
-                const uint32_t bin = (uint32_t)(hl >> bshift) & (P - 1);
-                S.sorted[S.off[bin] + atomicAdd(&S.hist[bin], 1u)] = hl;
-            }
+        // pass B: keys to their sorted position
+#pragma unroll
+        for (int j = 0; j < SC_KPT; j++) {
+            const uint64_t hl = key[j];
+            if (hl == MC_HASH_SENTINEL) continue;
+            const uint32_t bin = (uint32_t)(hl >> bshift) & (P - 1);
+            const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
+            S.sorted[S.off[bin] + r] = hl;
         }
         __syncthreads();
         // pass C: one aligned 32-byte sector per lane
@@ -132,16 +162,45 @@ __global__ void __launch_bounds__(SC_THREADS) k_bin_scatter(const uint64_t* __re
                 asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
             } else {   // bin full (heavy hitter or undersized batch): shared spill list, applied with direct updates
                 const uint64_t kk[4] = {k0, k1, k2, k3};
+                uint32_t real = 0;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (kk[q] == MC_HASH_SENTINEL) continue;
-                    const unsigned long long sp = atomicAdd(&B.cursors[P], 1ULL);
-                    if (sp < B.spill_cap) B.spill[sp] = kk[q];
-                    else atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
+                for (int q = 0; q < 4; q++) real += kk[q] != MC_HASH_SENTINEL;
+                unsigned long long sp = atomicAdd(B.spill_cursor, (unsigned long long)real);   // one reservation per sector
+                if (sp + real <= B.spill_cap) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (kk[q] != MC_HASH_SENTINEL) B.spill[sp++] = kk[q];
+                } else {
+                    atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
                 }
             }
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
+                                                            unsigned int* flags, McBinDst D) {
+    scatter_tiles(flat, n, B, shard_bits, shard_id, flags, D, blockIdx.x, gridDim.x);
+}
+
+// Second level: first-level bins b0 .. b0 + G - 1, each split into 2^B2.pbits sub-bins by the hash bits below the
+// first-level prefix.  Group slot g owns the sub-bin region and cursor block g of B2; the run lengths of the first level
+// are read on the device (no host round trip); the spill list is shared by the whole group.  The (bin, tile) pairs are
+// one flat index space walked by a persistent grid, so the CTAs work on the same one or two bins at any time.
+__global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter2(McBinsDev B1, uint32_t b0, uint32_t G, uint32_t tiles_per_bin, McBinsDev B2, unsigned int* flags) {
+    const uint32_t P2 = 1u << B2.pbits;
+    McBinDst none;
+    none.use = 0;
+    for (uint32_t vt = blockIdx.x; vt < G * tiles_per_bin; vt += gridDim.x) {
+        const uint32_t g = vt / tiles_per_bin, tile = vt - g * tiles_per_bin;
+        const unsigned long long attempts = B1.cursors[b0 + g];
+        const uint64_t n = attempts < B1.cap ? attempts : B1.cap;
+        if ((uint64_t)tile * SC_TILE >= n) continue;
+        McBinsDev S = B2;
+        S.keys = B2.keys + (uint64_t)g * P2 * B2.cap;
+        S.cursors = B2.cursors + (uint64_t)g * (P2 + 1);
+        scatter_tiles(B1.keys + (uint64_t)(b0 + g) * B1.cap, n, S, 0, 0, flags, none, tile, 0x40000000u);
     }
 }
 
@@ -220,6 +279,137 @@ __global__ void __launch_bounds__(256, MINB) k_bin_count(McTableDev t, McBinsDev
     if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
 }
 
+// --------------------------------------------------------------------------------------------
+// phase 2, aggregated: one CTA per sub-bin ("unit").  A unit is small enough (~24 K keys) for its DISTINCT keys to fit a
+// shared-memory hash table, so the repeats of a k-mer -- most of a metagenome's k-mer instances -- are summed in shared
+// memory and the count table in HBM receives ONE update per distinct key and batch (insert-or-add of the sum) instead of
+// one L2 probe + RED per instance.  Whatever does not fit the shared table (probe limit) is applied directly, so the
+// kernel is exact for any input; saturating adds commute, so the result does not depend on the grouping.
+// --------------------------------------------------------------------------------------------
+#define AGG_THREADS 512
+#define AGG_SLOTS 8192u      // 8 B key + 4 B count + 2 B list entry = 112 KB per CTA: two CTAs per SM
+#define AGG_PROBES 12
+#define AGG_U 4       // key loads in flight per thread (double buffered)
+#define AGG_FU 2      // bucket probes in flight per thread in the flush
+#define AGG_PREFETCH_MAX (512u << 10)   // table slices up to this size are pulled into L2 when their unit starts
+static size_t agg_smem_bytes() { return (size_t)AGG_SLOTS * 14; }
+
+__global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBinsDev B2, uint32_t b0, uint32_t n_units, unsigned long long* ticket) {
+    extern __shared__ unsigned long long a_mem[];
+    unsigned long long* s_key = a_mem;                       // hashed local key + 1, 0 = empty
+    uint32_t* s_cnt = (uint32_t*)(a_mem + AGG_SLOTS);
+    uint16_t* s_list = (uint16_t*)(s_cnt + AGG_SLOTS);       // claimed slots in claim order: the flush walks (and clears) only these
+    __shared__ unsigned long long s_unit;
+    __shared__ uint32_t s_used;
+    const uint32_t P2 = 1u << B2.pbits;
+    const int pbt = B2.hbits - B2.shift;                     // prefix bits shared by the keys of a unit
+    unsigned long long added = 0;
+    for (uint32_t i = threadIdx.x; i < AGG_SLOTS; i += AGG_THREADS) {
+        s_key[i] = 0;
+        s_cnt[i] = 0;
+    }
+    if (threadIdx.x == 0) s_used = 0;
+    for (;;) {
+        __syncthreads();                                     // the previous unit's flush is complete (table empty again)
+        if (threadIdx.x == 0) s_unit = atomicAdd(ticket, 1ULL);
+        __syncthreads();
+        if (s_unit >= n_units) break;
+        const uint32_t unit = (uint32_t)s_unit;
+        const uint32_t g = unit >> B2.pbits, sub = unit & (P2 - 1);
+        const unsigned long long attempts = B2.cursors[(uint64_t)g * (P2 + 1) + sub];
+        const uint32_t n = (uint32_t)(attempts < B2.cap ? attempts : B2.cap);
+        const uint64_t* keys = B2.keys + (uint64_t)unit * B2.cap;
+        if (n && pbt <= t.q) {
+            // the unit's keys all live in one contiguous table slice: start pulling it into L2 now, the flush probes it later
+            const uint64_t prefix = ((uint64_t)(b0 + g) << B2.pbits) | sub;
+            const uint64_t bytes = (32ull << (t.q - pbt));
+            if (bytes <= AGG_PREFETCH_MAX) {
+                const char* base = (const char*)(t.slots + ((prefix << (t.q - pbt)) & t.nb_mask) * 4);
+                for (uint64_t off = (uint64_t)threadIdx.x * 128; off < bytes; off += (uint64_t)AGG_THREADS * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            }
+        }
+        uint64_t h[AGG_U];
+#pragma unroll
+        for (int u = 0; u < AGG_U; u++) {
+            const uint32_t idx = u * AGG_THREADS + threadIdx.x;
+            h[u] = idx < n ? __ldcs(keys + idx) : MC_HASH_SENTINEL;
+        }
+#pragma unroll 1
+        for (uint32_t base = 0; base < n; base += AGG_THREADS * AGG_U) {
+            uint64_t hn[AGG_U];
+#pragma unroll
+            for (int u = 0; u < AGG_U; u++) {                // the next round's keys are in flight while this round is aggregated
+                const uint32_t idx = base + (AGG_U + u) * AGG_THREADS + threadIdx.x;
+                hn[u] = idx < n ? __ldcs(keys + idx) : MC_HASH_SENTINEL;
+            }
+#pragma unroll
+            for (int u = 0; u < AGG_U; u++) {
+                if (h[u] == MC_HASH_SENTINEL) continue;
+                const unsigned long long want = h[u] + 1;
+                uint32_t slot = (uint32_t)h[u] & (AGG_SLOTS - 1);   // low bits of the mixed hash: independent of the bin prefix
+                bool done = false;
+#pragma unroll 1
+                for (int p = 0; p < AGG_PROBES; p++, slot = (slot + 1) & (AGG_SLOTS - 1)) {
+                    unsigned long long cur = *(volatile unsigned long long*)&s_key[slot];
+                    if (cur == 0) {
+                        cur = atomicCAS(&s_key[slot], 0ULL, want);
+                        if (cur == 0) {
+                            s_list[atomicAdd(&s_used, 1u)] = (uint16_t)slot;
+                            cur = want;
+                        }
+                    }
+                    if (cur == want) {
+                        atomicAdd(&s_cnt[slot], 1u);
+                        done = true;
+                        break;
+                    }
+                }
+                if (!done && mc_table_add_impl<false>(t, h[u], 1, nullptr)) added++;
+            }
+#pragma unroll
+            for (int u = 0; u < AGG_U; u++) h[u] = hn[u];
+        }
+        __syncthreads();
+        // flush: one insert-or-add per distinct key, AGG_FU bucket probes in flight per thread; the slots are emptied on the way
+        const uint32_t used = s_used;
+#pragma unroll 1
+        for (uint32_t base = 0; base < used; base += AGG_THREADS * AGG_FU) {
+            uint64_t hk[AGG_FU];
+            uint32_t c[AGG_FU];
+            uint64_t w[AGG_FU][4];
+#pragma unroll
+            for (int u = 0; u < AGG_FU; u++) {
+                const uint32_t i = base + u * AGG_THREADS + threadIdx.x;
+                hk[u] = MC_HASH_SENTINEL;
+                c[u] = 0;
+                if (i < used) {
+                    const uint32_t slot = s_list[i];
+                    hk[u] = s_key[slot] - 1;
+                    c[u] = s_cnt[slot] < MC_SAT ? s_cnt[slot] : MC_SAT;   // min(min(a, S) + b, S) == min(a + b, S)
+                    s_key[slot] = 0;
+                    s_cnt[slot] = 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AGG_FU; u++)
+                if (hk[u] != MC_HASH_SENTINEL) mc_load_bucket(t.slots + ((hk[u] >> t.tag_bits) & t.nb_mask) * 4, w[u]);
+#pragma unroll
+            for (int u = 0; u < AGG_FU; u++)
+                if (hk[u] != MC_HASH_SENTINEL && mc_table_add_impl<true>(t, hk[u], c[u], w[u])) added++;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_used = 0;
+    }
+    __shared__ unsigned long long s_added;
+    if (threadIdx.x == 0) s_added = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&s_added, added);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
+}
+
 typedef void (*McBinCountKernel)(McTableDev, McBinsDev, const uint64_t*, uint64_t, uint64_t, uint32_t, unsigned long long*);
 static McBinCountKernel bin_count_variant(int v) {
     switch (v) {
@@ -284,12 +474,14 @@ static void batch_create(mc_table* t, uint64_t ub, uint64_t total_hint) {
     cap = (cap + 15) & ~15ull;
     B->dev.pbits = pbits;
     B->dev.hbits = hbits;
+    B->dev.shift = hbits - pbits;
     B->dev.cap = cap;
     B->dev.spill_cap = ub + 1024;
     B->dev.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)B->P * cap * 8, "k-mer bins");
     B->dev.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)B->dev.spill_cap * 8, "k-mer spill list");
     // cursors [P+1] followed by the tile prefix [P+1] used by k_bin_count
     B->dev.cursors = (unsigned long long*)mc_dev_alloc(ctx, (size_t)(B->P + 1) * 16 + 64, "bin cursors");   // + the tile ticket
+    B->dev.spill_cursor = B->dev.cursors + B->P;
     MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(B->P + 1) * 8, ctx->stream));
     B->used = 0;
     B->spill_used = 0;
@@ -360,6 +552,180 @@ static const uint64_t MC_FLUSH_SEGMENT = 128ull << 20;   // keys per k_bin_count
 extern const double MC_GROW_LOAD;
 extern const uint64_t MC_OVF_MAX;
 
+// direct updates from a list of hashed keys (spill lists: heavy hitters that overflowed their bin)
+static void insert_list(mc_table* t, const uint64_t* d_keys, uint64_t count) {
+    mc_ctx* ctx = t->ctx;
+    for (uint64_t off = 0; off < count;) {
+        const uint64_t n = std::min<uint64_t>(count - off, MC_OVF_MAX);
+        mc_table_prepare_chunk(t, n);
+        {
+            McStageTimer tm(ctx, MC_ST_COUNT);
+            const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            k_insert_hashed<<<grid, 256, 0, ctx->stream>>>(t->dev, d_keys + off, n);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+        }
+        mc_table_finish_chunk(t, false);
+        off += n;
+    }
+}
+// the first-level spill list, then the batch is empty again
+static void apply_spill_list(mc_table* t, uint64_t sp) {
+    McBatch* B = t->batch;
+    insert_list(t, B->dev.spill, sp);
+    MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(B->P + 1) * 8, t->ctx->stream));
+    B->used = 0;
+    B->spill_used = 0;
+}
+
+static const uint64_t MC_AGG_MIN_KEYS = 1ull << 25;   // batches below this are swept directly (k_bin_count)
+static const uint32_t MC_AGG_UNIT_KEYS = 24576;       // target keys per aggregation unit: ~3 x AGG_SLOTS instances
+
+// Groups of first-level bins (<= MC_FLUSH_SEGMENT keys): k_bin_scatter2 splits every bin of the group into 2^pb2 sub-bins
+// in a staging buffer, k_bin_agg sums each sub-bin in shared memory and applies the sums.  Table sizing is the same as in
+// the direct sweep: the first group is a sample of the hash space, and the overflow list has room for every instance.
+static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>& cur, uint64_t batch_keys) {
+    McBatch* B = t->batch;
+    mc_ctx* ctx = t->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t P1 = B->P;
+    const uint64_t cap1 = B->dev.cap;
+    uint64_t max_bin = 0;
+    for (uint32_t b = 0; b < P1; b++) max_bin = std::max<uint64_t>(max_bin, std::min<uint64_t>(cur[b], cap1));
+    if (max_bin == 0) return;
+    const uint32_t unit_keys = ctx->tune_agg_unit ? ctx->tune_agg_unit : MC_AGG_UNIT_KEYS;
+    int pb2 = 0;
+    while (pb2 < MC_MAX_PBITS && pb2 < B->dev.shift && (max_bin >> pb2) > unit_keys) pb2++;
+    const uint32_t P2 = 1u << pb2;
+    // sub-bin room: the mean of the fullest bin + 50 % + the sentinel pads of its tiles + a constant; the rest spills
+    uint64_t cap2 = max_bin / P2;
+    cap2 = cap2 + cap2 / 2 + (max_bin / SC_TILE + 1) * 8 / 5 + 1024;   // 50 %: a k-mer seen 1000 x is a tenth of a unit
+    cap2 = (cap2 + 15) & ~15ull;
+    const uint64_t seg_keys = ctx->tune_segment_keys ? std::min<uint64_t>(ctx->tune_segment_keys, MC_FLUSH_SEGMENT) : MC_FLUSH_SEGMENT;
+    const uint32_t g_max = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(P1, seg_keys / max_bin));
+    const uint64_t spill2_cap = (uint64_t)g_max * max_bin + 1024;
+    McBinsDev B2{};
+    B2.pbits = pb2;
+    B2.hbits = B->dev.hbits;
+    B2.shift = B->dev.shift - pb2;
+    B2.cap = cap2;
+    B2.spill_cap = spill2_cap;
+    B2.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)g_max * P2 * cap2 * 8, "k-mer sub-bins");
+    B2.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)spill2_cap * 8, "k-mer sub-bin spill list");
+    const size_t n_cursors = (size_t)g_max * (P2 + 1) + 2;   // + the shared spill cursor + the unit ticket
+    B2.cursors = (unsigned long long*)mc_dev_alloc(ctx, n_cursors * 8, "sub-bin cursors");
+    B2.spill_cursor = B2.cursors + (n_cursors - 2);
+    unsigned long long* d_ticket = B2.cursors + (n_cursors - 1);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(k_bin_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        attr_set = true;
+    }
+    int agg_per_sm = 0, sc_per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc_per_sm, k_bin_scatter2, SC_THREADS, scatter_smem_bytes(P2)) != cudaSuccess || sc_per_sm < 1) sc_per_sm = 1;
+    cudaGetLastError();
+
+    const uint64_t ovf_cap = std::max<uint64_t>((uint64_t)g_max * max_bin, 1024);   // every instance of a group
+    auto attach_overflow_list = [&]() {
+        t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
+        t->dev.ovf_cap = ovf_cap;
+        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), st));
+    };
+    attach_overflow_list();
+    unsigned long long* h_c = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 1024);   // counters + flags + spill cursor read-back
+    unsigned int* h_flags = (unsigned int*)(h_c + MC_CNT_N);
+    unsigned long long* h_spill2 = h_c + MC_CNT_N + 1;
+    const uint64_t keys_before = mc_table_keys(t);
+    uint64_t keys_known = keys_before;
+    uint64_t keys_done = 0;
+    bool first = true;
+    for (uint32_t b0 = 0; b0 < P1;) {
+        // the first group is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
+        uint32_t G = first ? std::max<uint32_t>(P1 / 64, 1) : g_max;
+        G = std::min(std::min(G, g_max), P1 - b0);
+        uint64_t group_keys = 0;
+        for (uint32_t b = b0; b < b0 + G; b++) group_keys += std::min<uint64_t>(cur[b], cap1);
+        if ((double)keys_known > MC_GROW_LOAD * 4.0 * (double)t->nb) mc_table_grow_to(t, t->dev.q + 1);   // amortised doubling
+        if (group_keys) {
+            MC_CUDA(cudaMemsetAsync(B2.cursors, 0, n_cursors * 8, st));
+            {
+                McStageTimer tm(ctx, MC_ST_SCATTER);
+                const uint32_t tiles = (uint32_t)((max_bin + SC_TILE - 1) / SC_TILE);
+                const uint32_t x = (uint32_t)std::min<uint64_t>((uint64_t)tiles * G, (uint64_t)ctx->sm_count * sc_per_sm);
+                k_bin_scatter2<<<x, SC_THREADS, scatter_smem_bytes(P2), st>>>(B->dev, b0, G, tiles, B2, t->dev.flags);
+                MC_LAUNCH(ctx);
+                MC_CUDA(cudaGetLastError());
+            }
+            {
+                McStageTimer tm(ctx, MC_ST_COUNT);
+                const uint32_t n_units = G * P2;
+                const int grid = (int)std::min<uint64_t>(n_units, (uint64_t)ctx->sm_count * agg_per_sm);
+                k_bin_agg<<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
+                MC_LAUNCH(ctx);
+                MC_CUDA(cudaGetLastError());
+            }
+        }
+        b0 += G;
+        keys_done += group_keys;
+        first = false;
+        MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(h_flags, t->dev.flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(h_spill2, B2.spill_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        if (*h_flags & MC_FLAG_OVERFLOW) mc_throw(MC_ERR_NOMEM, "k-mer table overflow (stash and overflow list full)");
+        const uint64_t spill2 = group_keys ? *h_spill2 : 0;
+        if (getenv("MC_TRACE") && b0 == G) {   // sub-bin fill of the first group
+            std::vector<unsigned long long> c2((size_t)G * (P2 + 1));
+            MC_CUDA(cudaMemcpy(c2.data(), B2.cursors, c2.size() * 8, cudaMemcpyDeviceToHost));
+            unsigned long long mx = 0, sum = 0, over = 0, mn = ~0ull;
+            for (uint32_t g = 0; g < G; g++)
+                for (uint32_t j = 0; j < P2; j++) {
+                    unsigned long long v = c2[(size_t)g * (P2 + 1) + j];
+                    mx = std::max(mx, v); mn = std::min(mn, v); sum += v; over += v > cap2;
+                }
+            fprintf(stderr, "[mc trace] sub-bin attempts: min %llu mean %.0f max %llu, %llu of %u over cap2; bin0 attempts %llu\n", mn, (double)sum / (G * P2), mx, over, G * P2, cur[0]);
+        }
+        if (getenv("MC_TRACE")) fprintf(stderr, "[mc trace] agg group b0=%u G=%u keys=%llu P2=%u cap2=%llu spill2=%llu ovf=%llu table_keys=%llu\n", b0 - G, G,
+                                        (unsigned long long)group_keys, P2, (unsigned long long)cap2, (unsigned long long)spill2,
+                                        (unsigned long long)h_c[MC_CNT_OVF], (unsigned long long)h_c[MC_CNT_KEYS]);
+        if (spill2 > spill2_cap) mc_throw(MC_ERR_NOMEM, "internal: sub-bin spill list overflow");
+        const uint64_t ovf_n = h_c[MC_CNT_OVF];
+        const uint64_t now = h_c[MC_CNT_KEYS] + ovf_n;   // an upper bound: the list holds instances
+        const double gained = now > keys_before ? (double)(now - keys_before) : 0.0;
+        const double predicted = (double)keys_before + (keys_done ? gained * ((double)batch_keys / (double)keys_done) : 0.0);
+        bool grown = false;
+        if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
+            int q = mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD);
+            if (q > t->dev.q) {
+                mc_table_grow_to(t, q);
+                grown = true;
+            }
+        }
+        if (ovf_n) {   // rare: the table was too small for this group; re-insert what overflowed (grows until it fits)
+            mc_table_finish_chunk(t, grown);
+            attach_overflow_list();
+            keys_known = mc_table_keys(t);
+        } else {
+            keys_known = now;
+        }
+        if (spill2) {   // a sub-bin was full (a heavy hitter): direct updates
+            t->dev.ovf_keys = nullptr;
+            t->dev.ovf_cap = 0;
+            insert_list(t, B2.spill, spill2);
+            attach_overflow_list();
+            keys_known = mc_table_keys(t);
+        }
+    }
+    t->dev.ovf_keys = nullptr;
+    t->dev.ovf_cap = 0;
+    mc_dev_free(ctx, B2.keys);
+    mc_dev_free(ctx, B2.spill);
+    mc_dev_free(ctx, B2.cursors);
+}
+
 void mc_table_flush(mc_table* t) {
     McBatch* B = t->batch;
     if (!B || !B->dev.keys || B->used == 0) return;
@@ -372,6 +738,15 @@ void mc_table_flush(mc_table* t) {
     MC_CUDA(cudaMemcpyAsync(cur.data(), B->dev.cursors, (size_t)(P + 1) * 8, cudaMemcpyDeviceToHost, st));
     MC_CUDA(cudaStreamSynchronize(st));
     if (cur[P] > B->dev.spill_cap) mc_throw(MC_ERR_NOMEM, "internal: k-mer spill list overflow (%llu > %llu)", cur[P], (unsigned long long)B->dev.spill_cap);
+    uint64_t batch_keys = 0;
+    for (uint32_t b = 0; b < P; b++) batch_keys += std::min<uint64_t>(cur[b], B->dev.cap);
+    // large batches: second-level bins + shared-memory aggregation (one table update per DISTINCT key of a sub-bin)
+    const bool aggregate = ctx->tune_agg < 0 ? batch_keys >= MC_AGG_MIN_KEYS : ctx->tune_agg != 0;
+    if (aggregate) {
+        flush_aggregated(t, cur, batch_keys);
+        apply_spill_list(t, cur[P]);
+        return;
+    }
     std::vector<uint64_t> prefix(P + 1);
     prefix[0] = 0;
     for (uint32_t b = 0; b < P; b++) {
@@ -448,24 +823,7 @@ void mc_table_flush(mc_table* t) {
     }
     t->dev.ovf_keys = nullptr;
     t->dev.ovf_cap = 0;
-    // spill list: direct updates
-    uint64_t sp = cur[P];
-    for (uint64_t off = 0; off < sp;) {
-        const uint64_t n = std::min<uint64_t>(sp - off, MC_OVF_MAX);
-        mc_table_prepare_chunk(t, n);
-        {
-            McStageTimer tm(ctx, MC_ST_COUNT);
-            const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
-            k_insert_hashed<<<grid, 256, 0, st>>>(t->dev, B->dev.spill + off, n);
-            MC_LAUNCH(ctx);
-            MC_CUDA(cudaGetLastError());
-        }
-        mc_table_finish_chunk(t, false);
-        off += n;
-    }
-    MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(P + 1) * 8, st));
-    B->used = 0;
-    B->spill_used = 0;
+    apply_spill_list(t, cur[P]);
 }
 
 void mc_batch_release(mc_table* t) {
@@ -491,6 +849,8 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "host_batch_chunks" && value >= 0 && value <= 1024) ctx->tune_host_batch_chunks = (uint32_t)value;
     else if (n == "extract_parts" && (value == 0 || value == 1 || value == 4 || value == 32)) ctx->tune_extract_parts = (int)value;
     else if (n == "count_variant" && value >= 0 && value <= 3) ctx->tune_count_variant = (int)value;
+    else if (n == "agg" && value >= -1 && value <= 1) ctx->tune_agg = (int)value;
+    else if (n == "agg_unit" && value >= 0 && value <= (1 << 24)) ctx->tune_agg_unit = (uint32_t)value;
     else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;
     else {
         mc_set_error("unknown tuning parameter or value out of range: " + n);

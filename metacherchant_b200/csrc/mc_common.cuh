@@ -137,9 +137,12 @@ __device__ __forceinline__ bool mc_stash_add(const McTableDev& t, uint64_t h, ui
             return cur == 0;
         }
     }
-    if (inc == 1 && t.ovf_keys) {
-        unsigned long long pos2 = atomicAdd(&t.counters[MC_CNT_OVF], 1ULL);
-        if (pos2 < t.ovf_cap) { t.ovf_keys[pos2] = h; return false; }
+    if (t.ovf_keys) {   // `inc` copies: the list is sized for every key INSTANCE of the segment being applied
+        unsigned long long pos2 = atomicAdd(&t.counters[MC_CNT_OVF], (unsigned long long)inc);
+        if (pos2 + inc <= t.ovf_cap) {
+            for (uint32_t i = 0; i < inc; i++) t.ovf_keys[pos2 + i] = h;
+            return false;
+        }
     }
     atomicOr(t.flags, MC_FLAG_OVERFLOW);
     return false;
@@ -249,7 +252,9 @@ struct McBinsDev {
     uint64_t cap;                   // entries per bin
     uint64_t spill_cap;
     int pbits;
-    int hbits;                      // 62 - shard_bits; bin = hl >> (hbits - pbits)
+    int hbits;                      // 62 - shard_bits: keys are stored as hl = h & (2^hbits - 1)
+    int shift;                      // bin = (hl >> shift) & (P - 1); hbits - pbits for the first level
+    unsigned long long* spill_cursor;   // &cursors[P] for the first level; shared by all sub-bin groups of the second level
 };
 
 #define MC_MAX_XCHG_RANKS 16
@@ -282,6 +287,8 @@ struct mc_ctx {
     int tune_count_variant = 0;      // k_bin_count instantiation (probes in flight / occupancy), for measurements
     uint32_t tune_host_batch_chunks = 0;   // host input: chunks binned between two table sweeps (0 = default 1)
     int tune_extract_parts = 0;      // lanes per record in k_extract: 0 = by read length, else 1 / 4 / 32
+    int tune_agg = -1;               // two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on
+    uint32_t tune_agg_unit = 0;      // target keys per aggregation unit (sub-bin); 0 = default
     int sm_count = 148;
     // reusable device scratch for the parser (grown on demand)
     void* d_chunk[2] = {nullptr, nullptr};

@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
+#include <cstdlib>
 #include <fstream>
 #include <set>
 #include <string>
@@ -21,6 +23,27 @@
 #include "mc_env.hpp"
 
 namespace {
+
+// MC_TRACE=1: accumulated host/device time of every environment stage on stderr (profiles/)
+struct EnvTrace {
+    static bool on() { static const bool v = getenv("MC_TRACE") != nullptr; return v; }
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
+    static std::vector<std::pair<const char*, double>>& acc() { static std::vector<std::pair<const char*, double>> a; return a; }
+    const char* name;
+    double t0;
+    explicit EnvTrace(const char* n) : name(n), t0(on() ? now() : 0) {}
+    ~EnvTrace() {
+        if (!on()) return;
+        const double dt = now() - t0;
+        for (auto& e : acc()) if (e.first == name) { e.second += dt; return; }
+        acc().emplace_back(name, dt);
+    }
+    static void report() {
+        if (!on()) return;
+        for (auto& e : acc()) fprintf(stderr, "[mc trace] %-28s %10.1f ms\n", e.first, e.second);
+        acc().clear();
+    }
+};
 
 const char NUC[4] = {'A', 'G', 'C', 'T'};   // ITMO!/dna/DnaTools.java:31
 
@@ -482,7 +505,11 @@ static void run_jobs(mc_ctx* ctx, const mc_table* t, const std::vector<EnvJob>& 
         }
     }
     std::vector<McBfsResult> res;
-    mc_run_bfs_passes(ctx, t, k, min_cov, max_kmers, max_radius, reqs, res);
+    {
+        EnvTrace tr("bfs passes (device)");
+        mc_run_bfs_passes(ctx, t, k, min_cov, max_kmers, max_radius, reqs, res);
+    }
+    EnvTrace tr("build_subgraph");
     const size_t per = both_dirs ? 1 : 2;
     subgraphs.assign(jobs.size(), JavaMap<int>());
     found.assign(jobs.size(), 0);
@@ -506,17 +533,18 @@ static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target
 // graph.txt/env.txt + unitig stage + writers of one environment; gene nodes are decided against `gene_seqs` (isGeneNode :421-432)
 static void write_one_environment(mc_ctx* ctx, const JavaMap<int>& sub, const std::vector<std::string>& gene_seqs, int k, int chunk_len,
                                   const std::string& prefix) {
-    std::vector<uint32_t> ord = sub.order();
-    write_environment(sub, ord, prefix);
+    std::vector<uint32_t> ord;
+    { EnvTrace tr("subgraph order"); ord = sub.order(); }
+    { EnvTrace tr("write env.txt/graph.txt"); write_environment(sub, ord, prefix); }
     McUnitigInput in;
-    unitig_input_from_subgraph(sub, ord, gene_seqs, k, in);
+    { EnvTrace tr("unitig input"); unitig_input_from_subgraph(sub, ord, gene_seqs, k, in); }
     McUnitigNodes nodes;
-    mc_unitig_nodes(ctx, in, nodes);
+    { EnvTrace tr("unitig nodes (device)"); mc_unitig_nodes(ctx, in, nodes); }
     Graph g;
-    g.build(in, nodes);
-    g.sweep(nullptr);
-    g.assemble();
-    write_single_outputs(g, sub, chunk_len, prefix);
+    { EnvTrace tr("graph build"); g.build(in, nodes); }
+    { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
+    { EnvTrace tr("assemble"); g.assemble(); }
+    { EnvTrace tr("write gfa/fasta/tsv"); write_single_outputs(g, sub, chunk_len, prefix); }
 }
 
 // --merge / --hicseq / --trim (EnvironmentFinderMain.java:218-233, OneSequenceCalculator.java:168-192,208-216,241-262)
@@ -550,6 +578,7 @@ extern "C" int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const*
             if (!found[i]) continue;   // "Could not find any k-mers of the target gene in the input, halting."
             write_one_environment(ctx, subgraphs[i], gene_seqs[i], k, chunk_len, prefixes[i]);
         }
+        EnvTrace::report();
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());

@@ -144,6 +144,8 @@ extern "C" int mc_xchg_scatter_device(mc_xchg* x, const void* dbuf, size_t len, 
             owners.spill_cap = 0;
             owners.pbits = x->shard_bits;
             owners.hbits = 62;
+            owners.shift = 62 - x->shard_bits;
+            owners.spill_cursor = x->d_cursors + ((size_t)1 << x->shard_bits);
             mc_launch_owner_scatter(ctx, d_flat, n_flat, owners, dst, x->d_flags);
         }
         k_post_counts<<<1, 32, 0, st>>>(x->d_cursors, mail, x->world, x->rank);

@@ -199,6 +199,12 @@ BIN_TUNINGS = [
     dict(part_bits=6, batch_keys=50_000, segment_keys=4096),
     dict(extract_parts=4),
     dict(extract_parts=32, part_bits=2),
+    # two-level bins + shared-memory aggregation (k_bin_scatter2 + k_bin_agg), forced on for a small input
+    dict(agg=1),
+    dict(agg=1, part_bits=5, agg_unit=512),
+    dict(agg=1, part_bits=3, agg_unit=64, segment_keys=100_000),    # 2^11 sub-bins per bin, several groups
+    dict(agg=1, part_bits=0, agg_unit=1 << 22),                     # one unit far larger than the shared table: direct fallback
+    dict(agg=1, part_bits=6, batch_keys=50_000, agg_unit=256),      # many flushes into a table that already holds the keys
 ]
 
 
@@ -223,8 +229,9 @@ def test_binned_update_path_is_exact(oracle, tuning):
         c.close()
 
 
+@pytest.mark.parametrize("agg", [0, 1])
 @pytest.mark.parametrize("part_bits", [0, 7])
-def test_heavy_hitters_overflow_their_bin(oracle, part_bits):
+def test_heavy_hitters_overflow_their_bin(oracle, part_bits, agg):
     """One k-mer repeated far beyond a bin's capacity diverts to the spill list; counts stay exact and saturate at 32767."""
     from metacherchant_b200 import Context
     rng = random.Random(3)
@@ -233,17 +240,26 @@ def test_heavy_hitters_overflow_their_bin(oracle, part_bits):
     c = Context(0)
     try:
         c.set_tuning("part_bits", part_bits)
-        c.set_tuning("batch_keys", 20_000)
+        c.set_tuning("batch_keys", 20_000 if not agg else 200_000)
+        c.set_tuning("agg", agg)
+        c.set_tuning("agg_unit", 128)
         g = c.new_table(8).count_bytes(data, FMT_FASTA)
         assert_same_table(g, oracle.table(8).count_bytes(data, FMT_FASTA))
     finally:
         c.close()
 
 
-def test_binned_growth_from_an_empty_hint(ctx, oracle):
+@pytest.mark.parametrize("agg", [0, 1])
+def test_binned_growth_from_an_empty_hint(oracle, agg):
     """No capacity hint and ~3 M distinct k-mers: the first sampled segment sizes the table, nothing is lost."""
+    from metacherchant_b200 import Context
     s = oracle.synth(genome_unit=40_000, err_ppm=20_000)
     data = s.generate(0, 50_000)
-    g = ctx.new_table(31).count_bytes(data, FMT_FASTQ)
-    o = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ)
-    assert_same_table(g, o)
+    c = Context(0)
+    try:
+        c.set_tuning("agg", agg)
+        g = c.new_table(31).count_bytes(data, FMT_FASTQ)
+        o = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ)
+        assert_same_table(g, o)
+    finally:
+        c.close()
