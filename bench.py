@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--no-env", action="store_true")
     ap.add_argument("--maxkmers", type=int, default=100000)
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="mc_ctx_set_tuning knob (part_bits, batch_keys, segment_keys)")
-    ap.add_argument("--hint-div", type=int, default=4, help="table capacity hint = bases / this")
+    ap.add_argument("--hint-div", type=int, default=0, help="table capacity hint = bases / this; 0 = none: the library sizes the table from a 1/64 sample of the first batch")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -317,7 +317,7 @@ def main():
     peak, peak_src = load_peaks()
     alg_bytes = algorithmic_bytes_per_read(k, rb) * reads * args.steps   # per rank
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
-    roofline = {"kernel": "counting pipeline: k_extract + k_bin_scatter + k_bin_count", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "counting pipeline: k_extract + k_bin_scatter + k_bin_scatter2 + k_bin_agg", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_read": algorithmic_bytes_per_read(k, rb), "kernel_ms_per_step": round(kernel_ms / args.steps, 2),
                 "stage_ms_per_step": {name: round(v / args.steps, 2) for name, v in stages.items()}}
@@ -347,7 +347,8 @@ def main():
                 "dtype": "int64", "data": "synthetic",
                 "config": {"workload": w["name"], "description": w["desc"], "k": k, "coverage": cov, "reads_per_gpu_per_step": reads,
                            "fastq_bytes_per_gpu_per_step": nbytes, "l2": "inputs (>= 0.3 GB per step) larger than the 126 MB L2; no explicit flush",
-                           "chunk_mib": args.chunk_mib, "table": "pre-sized for bases/4 distinct k-mers, grows by rehash beyond",
+                           "chunk_mib": args.chunk_mib, "table": (f"pre-sized for bases/{args.hint_div} distinct k-mers, grows by rehash beyond" if args.hint_div > 0 else
+                                     "no capacity hint: sized by the library from a counted 1/64 sample of the hash space (load 0.5), grows by rehash beyond"),
                            "solid_kmers": int(n_solid), "wall_s": round(wall, 3)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "env": env}
         print(json.dumps(line), flush=True)

@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(256, MINB) k_bin_count(McTableDev t, McBinsDev
 #define AGG_PREFETCH_MAX (512u << 10)   // table slices up to this size are pulled into L2 when their unit starts
 static size_t agg_smem_bytes() { return (size_t)AGG_SLOTS * 14; }
 
+// COUNT_ONLY: the same aggregation, but the table is only looked up: the kernel reports how many distinct keys of these units are
+// NOT in the table yet (counters[MC_CNT_OVF_KEYS]).  Run on the first group -- 1/64 of the hash space -- it tells the host how
+// large the table must be for the whole batch before anything is inserted.
+template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBinsDev B2, uint32_t b0, uint32_t n_units, unsigned long long* ticket) {
     extern __shared__ unsigned long long a_mem[];
     unsigned long long* s_key = a_mem;                       // hashed local key + 1, 0 = empty
@@ -365,7 +369,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBins
                         break;
                     }
                 }
-                if (!done && mc_table_add_impl<false>(t, h[u], 1, nullptr)) added++;
+                if (!done) {
+                    if (COUNT_ONLY) added += mc_table_lookup(t, h[u]) < 0;
+                    else if (mc_table_add_impl<false>(t, h[u], 1, nullptr)) added++;
+                }
             }
 #pragma unroll
             for (int u = 0; u < AGG_U; u++) h[u] = hn[u];
@@ -395,8 +402,11 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBins
             for (int u = 0; u < AGG_FU; u++)
                 if (hk[u] != MC_HASH_SENTINEL) mc_load_bucket(t.slots + ((hk[u] >> t.tag_bits) & t.nb_mask) * 4, w[u]);
 #pragma unroll
-            for (int u = 0; u < AGG_FU; u++)
-                if (hk[u] != MC_HASH_SENTINEL && mc_table_add_impl<true>(t, hk[u], c[u], w[u])) added++;
+            for (int u = 0; u < AGG_FU; u++) {
+                if (hk[u] == MC_HASH_SENTINEL) continue;
+                if (COUNT_ONLY) added += mc_table_lookup(t, hk[u]) < 0;
+                else if (mc_table_add_impl<true>(t, hk[u], c[u], w[u])) added++;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) s_used = 0;
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBins
     for (int o = 16; o; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
     if ((threadIdx.x & 31) == 0 && added) atomicAdd(&s_added, added);
     __syncthreads();
-    if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
+    if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[COUNT_ONLY ? MC_CNT_OVF_KEYS : MC_CNT_KEYS], s_added);
 }
 
 typedef void (*McBinCountKernel)(McTableDev, McBinsDev, const uint64_t*, uint64_t, uint64_t, uint32_t, unsigned long long*);
@@ -579,7 +589,7 @@ static void apply_spill_list(mc_table* t, uint64_t sp) {
 }
 
 static const uint64_t MC_AGG_MIN_KEYS = 1ull << 25;   // batches below this are swept directly (k_bin_count)
-static const uint32_t MC_AGG_UNIT_KEYS = 24576;       // target keys per aggregation unit: ~3 x AGG_SLOTS instances
+static const uint32_t MC_AGG_UNIT_KEYS = 32768;       // target keys per aggregation unit (sentinel pads included): 4 x AGG_SLOTS
 
 // Groups of first-level bins (<= MC_FLUSH_SEGMENT keys): k_bin_scatter2 splits every bin of the group into 2^pb2 sub-bins
 // in a staging buffer, k_bin_agg sums each sub-bin in shared memory and applies the sums.  Table sizing is the same as in
@@ -620,11 +630,12 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     static bool attr_set = false;
     if (!attr_set) {
         MC_CUDA(cudaFuncSetAttribute(k_bin_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
-        MC_CUDA(cudaFuncSetAttribute(k_bin_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
         attr_set = true;
     }
     int agg_per_sm = 0, sc_per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg<false>, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc_per_sm, k_bin_scatter2, SC_THREADS, scatter_smem_bytes(P2)) != cudaSuccess || sc_per_sm < 1) sc_per_sm = 1;
     cudaGetLastError();
 
@@ -632,7 +643,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     auto attach_overflow_list = [&]() {
         t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
         t->dev.ovf_cap = ovf_cap;
-        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), st));
+        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, 2 * sizeof(unsigned long long), st));
     };
     attach_overflow_list();
     unsigned long long* h_c = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 1024);   // counters + flags + spill cursor read-back
@@ -659,11 +670,33 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 MC_LAUNCH(ctx);
                 MC_CUDA(cudaGetLastError());
             }
+            const uint32_t n_units = G * P2;
+            const int grid = (int)std::min<uint64_t>(n_units, (uint64_t)ctx->sm_count * agg_per_sm);
+            if (first) {
+                // the sample is only COUNTED first: its distinct keys that the table does not hold yet, scaled to the whole batch,
+                // size the table before anything is inserted (no overflow churn, no rehash of a half-filled table)
+                {
+                    McStageTimer tm(ctx, MC_ST_COUNT);
+                    k_bin_agg<true><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
+                    MC_LAUNCH(ctx);
+                    MC_CUDA(cudaGetLastError());
+                }
+                MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                MC_CUDA(cudaStreamSynchronize(st));
+                const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)group_keys);
+                const double predicted = (double)keys_before + fresh;
+                if (getenv("MC_TRACE")) fprintf(stderr, "[mc trace] agg sample: %llu new distinct keys in %llu instances -> %.0f predicted for the batch\n",
+                                                (unsigned long long)h_c[MC_CNT_OVF_KEYS], (unsigned long long)group_keys, predicted);
+                if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
+                    const int q = mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD);
+                    if (q > t->dev.q) mc_table_grow_to(t, q);
+                }
+                attach_overflow_list();
+                MC_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned long long), st));
+            }
             {
                 McStageTimer tm(ctx, MC_ST_COUNT);
-                const uint32_t n_units = G * P2;
-                const int grid = (int)std::min<uint64_t>(n_units, (uint64_t)ctx->sm_count * agg_per_sm);
-                k_bin_agg<<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
+                k_bin_agg<false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
                 MC_LAUNCH(ctx);
                 MC_CUDA(cudaGetLastError());
             }
@@ -693,7 +726,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                                         (unsigned long long)h_c[MC_CNT_OVF], (unsigned long long)h_c[MC_CNT_KEYS]);
         if (spill2 > spill2_cap) mc_throw(MC_ERR_NOMEM, "internal: sub-bin spill list overflow");
         const uint64_t ovf_n = h_c[MC_CNT_OVF];
-        const uint64_t now = h_c[MC_CNT_KEYS] + ovf_n;   // an upper bound: the list holds instances
+        const uint64_t now = h_c[MC_CNT_KEYS] + h_c[MC_CNT_OVF_KEYS];   // every push is one distinct key of this group
         const double gained = now > keys_before ? (double)(now - keys_before) : 0.0;
         const double predicted = (double)keys_before + (keys_done ? gained * ((double)batch_keys / (double)keys_done) : 0.0);
         bool grown = false;
@@ -767,7 +800,7 @@ void mc_table_flush(mc_table* t) {
     auto attach_overflow_list = [&]() {
         t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
         t->dev.ovf_cap = ovf_cap;
-        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), st));
+        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, 2 * sizeof(unsigned long long), st));
     };
     attach_overflow_list();
     McBinCountKernel kern = bin_count_variant(ctx->tune_count_variant);

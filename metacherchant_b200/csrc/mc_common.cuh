@@ -108,7 +108,7 @@ struct McTableDev {
     uint64_t* stash_keys;     // hashed key + 1 (0 = empty), stash_mask + 1 entries
     uint32_t* stash_counts;
     uint32_t stash_mask;
-    unsigned long long* counters;   // [0] distinct keys, [1] stash entries, [2] reads, [3] runs, [4] bases, [5] kmers, [6] overflow-list entries
+    unsigned long long* counters;   // [0] distinct keys, [1] stash entries, [2] reads, [3] runs, [4] bases, [5] kmers, [6] overflow-list entries, [7] overflow-list pushes
     unsigned int* flags;            // bit 0: an update could not be stored anywhere (fatal)
     // Overflow list (only attached while reads are being counted): hashed keys whose 8-bucket window AND stash
     // neighbourhood were full.  The host grows the table and re-inserts them, so no update is ever lost and the table
@@ -116,7 +116,7 @@ struct McTableDev {
     uint64_t* ovf_keys;
     unsigned long long ovf_cap;
 };
-enum { MC_CNT_KEYS = 0, MC_CNT_STASH = 1, MC_CNT_READS = 2, MC_CNT_RUNS = 3, MC_CNT_BASES = 4, MC_CNT_KMERS = 5, MC_CNT_OVF = 6, MC_CNT_N = 8 };
+enum { MC_CNT_KEYS = 0, MC_CNT_STASH = 1, MC_CNT_READS = 2, MC_CNT_RUNS = 3, MC_CNT_BASES = 4, MC_CNT_KMERS = 5, MC_CNT_OVF = 6, MC_CNT_OVF_KEYS = 7, MC_CNT_N = 8 };
 #define MC_FLAG_OVERFLOW 1u
 #define MC_STASH_PROBES 64u
 
@@ -140,6 +140,7 @@ __device__ __forceinline__ bool mc_stash_add(const McTableDev& t, uint64_t h, ui
     if (t.ovf_keys) {   // `inc` copies: the list is sized for every key INSTANCE of the segment being applied
         unsigned long long pos2 = atomicAdd(&t.counters[MC_CNT_OVF], (unsigned long long)inc);
         if (pos2 + inc <= t.ovf_cap) {
+            atomicAdd(&t.counters[MC_CNT_OVF_KEYS], 1ULL);   // list entries are instances; this one counts the calls (sizing estimate)
             for (uint32_t i = 0; i < inc; i++) t.ovf_keys[pos2 + i] = h;
             return false;
         }

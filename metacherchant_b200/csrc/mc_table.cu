@@ -284,7 +284,7 @@ void mc_table_prepare_chunk(mc_table* t, uint64_t ub) {
     if (q > t->dev.q) mc_table_grow_to(t, q);
     t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
     t->dev.ovf_cap = ovf_cap;
-    MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), ctx->stream));
+    MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, 2 * sizeof(unsigned long long), ctx->stream));
 }
 
 __global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);
@@ -301,7 +301,7 @@ void mc_table_finish_chunk(mc_table* t, bool grown_already) {
         // move the list aside, double the table, insert the list (which may overflow again, into the now empty list)
         uint64_t* tmp = (uint64_t*)mc_dev_alloc(ctx, n * sizeof(uint64_t), "overflow list");
         MC_CUDA(cudaMemcpyAsync(tmp, t->dev.ovf_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, sizeof(unsigned long long), ctx->stream));
+        MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, 2 * sizeof(unsigned long long), ctx->stream));
         if (!grown_already) mc_table_grow_to(t, t->dev.q + 1);
         grown_already = false;
         uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
