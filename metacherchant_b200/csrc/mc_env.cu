@@ -9,6 +9,10 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
+#include <exception>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -32,9 +36,11 @@ struct EnvTrace {
     const char* name;
     double t0;
     explicit EnvTrace(const char* n) : name(n), t0(on() ? now() : 0) {}
+    static std::mutex& mu() { static std::mutex m; return m; }
     ~EnvTrace() {
         if (!on()) return;
-        const double dt = now() - t0;
+        const double dt = now() - t0;   // summed over the worker threads for the per-environment stages
+        std::lock_guard<std::mutex> lk(mu());
         for (auto& e : acc()) if (e.first == name) { e.second += dt; return; }
         acc().emplace_back(name, dt);
     }
@@ -44,6 +50,45 @@ struct EnvTrace {
         acc().clear();
     }
 };
+
+// The reference runs one OneSequenceCalculator per target on a pool of --available-processors threads
+// (EnvironmentFinderMain.java:188,218-225); the host half of an environment (HashMap order, merge sweep, writers) does the
+// same here.  MC_THREADS overrides the default (all host cores).
+unsigned env_threads(size_t n_items) {
+    unsigned n = std::thread::hardware_concurrency();
+    if (const char* e = getenv("MC_THREADS")) n = (unsigned)std::max(1, atoi(e));
+    if (n == 0) n = 1;
+    return (unsigned)std::min<size_t>(n, std::max<size_t>(n_items, 1));
+}
+template <class F>
+void parallel_for(size_t n, F&& body) {
+    const unsigned nt = env_threads(n);
+    if (nt <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; i++) body(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    auto worker = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) return;
+            try {
+                body(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (!err) err = std::current_exception();
+                next.store(n);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < nt; w++) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    if (err) std::rethrow_exception(err);
+}
 
 const char NUC[4] = {'A', 'G', 'C', 'T'};   // ITMO!/dna/DnaTools.java:31
 
@@ -65,11 +110,6 @@ std::string rc_string(const std::string& s) {
         r[s.size() - 1 - i] = NUC[c ^ 3];
     }
     return r;
-}
-// StringUtils.normalizeDna (src/utils/StringUtils.java:34-41): ASCII order, A < C < G < T — NOT the 2-bit order
-std::string normalize_dna(const std::string& s) {
-    std::string rc = rc_string(s);
-    return s.compare(rc) < 0 ? s : rc;
 }
 int32_t java_string_hash(const std::string& s) {
     uint32_t h = 0;
@@ -123,6 +163,122 @@ struct JavaMap {
     }
 };
 
+// The same java.util.HashMap<String,Integer>, for maps whose keys are all k-mers of one length: the key is held as its 2-bit
+// code (A0 G1 C2 T3, first base most significant -- one string <-> one code), String.hashCode is computed from the code, and
+// entries live in flat arrays, so an environment costs no per-k-mer allocation.  Same iteration order as JavaMap (tests pin
+// both on the reference's committed graph.txt).
+struct KmerMap {
+    int k = 0;
+    std::vector<uint64_t> keys;          // insertion order
+    std::vector<int32_t> vals;
+    std::vector<uint32_t> slots;         // open addressing over `keys`: index + 1, 0 = empty
+    size_t peak = 0;
+    uint32_t hash_tab[32][4];            // ascii(NUC[c]) * 31^(k-1-i) mod 2^32
+
+    void init(int k_, size_t expect) {
+        k = k_;
+        keys.clear();
+        vals.clear();
+        peak = 0;
+        keys.reserve(expect);
+        vals.reserve(expect);
+        size_t cap = 64;
+        while (cap < expect * 2 + 2) cap <<= 1;
+        slots.assign(cap, 0);
+        uint32_t pw = 1;
+        for (int i = k - 1; i >= 0; i--) {
+            for (int c = 0; c < 4; c++) hash_tab[i][c] = (uint32_t)(unsigned char)"AGCT"[c] * pw;
+            pw *= 31u;
+        }
+    }
+    static uint64_t mix(uint64_t x) {
+        x ^= x >> 33;
+        x *= 0xff51afd7ed558ccdULL;
+        x ^= x >> 29;
+        return x;
+    }
+    void grow() {
+        std::vector<uint32_t> ns(slots.size() * 2, 0);
+        const size_t m = ns.size() - 1;
+        for (size_t i = 0; i < keys.size(); i++) {
+            size_t p = mix(keys[i]) & m;
+            while (ns[p]) p = (p + 1) & m;
+            ns[p] = (uint32_t)i + 1;
+        }
+        slots.swap(ns);
+    }
+    // index of `code`, or -1
+    long find(uint64_t code) const {
+        const size_t m = slots.size() - 1;
+        for (size_t p = mix(code) & m;; p = (p + 1) & m) {
+            const uint32_t v = slots[p];
+            if (!v) return -1;
+            if (keys[v - 1] == code) return (long)v - 1;
+        }
+    }
+    void put(uint64_t code, int32_t v) {
+        const size_t m = slots.size() - 1;
+        size_t p = mix(code) & m;
+        for (;; p = (p + 1) & m) {
+            const uint32_t s = slots[p];
+            if (!s) break;
+            if (keys[s - 1] == code) { vals[s - 1] = v; return; }
+        }
+        keys.push_back(code);
+        vals.push_back(v);
+        slots[p] = (uint32_t)keys.size();
+        peak = std::max(peak, keys.size());
+        if (keys.size() * 2 > slots.size()) grow();
+    }
+    const int32_t* get(uint64_t code) const {
+        long i = find(code);
+        return i < 0 ? nullptr : &vals[(size_t)i];
+    }
+    void retain(const std::vector<uint8_t>& keep) {   // keySet().retainAll(...): the survivors keep their relative order
+        size_t n = 0;
+        for (size_t i = 0; i < keys.size(); i++)
+            if (keep[i]) { keys[n] = keys[i]; vals[n] = vals[i]; n++; }
+        keys.resize(n);
+        vals.resize(n);
+        std::fill(slots.begin(), slots.end(), 0u);
+        const size_t m = slots.size() - 1;
+        for (size_t i = 0; i < n; i++) {
+            size_t p = mix(keys[i]) & m;
+            while (slots[p]) p = (p + 1) & m;
+            slots[p] = (uint32_t)i + 1;
+        }
+    }
+    uint32_t java_hash(uint64_t code) const {         // String.hashCode() of the k-mer string
+        uint32_t h = 0;
+        for (int i = k - 1; i >= 0; i--, code >>= 2) h += hash_tab[i][code & 3];
+        return h;
+    }
+    std::vector<uint32_t> order() const {             // bucket index, then insertion order inside a bucket: a stable counting sort
+        size_t cap = 16;
+        while ((double)std::max(peak, keys.size()) > 0.75 * (double)cap) cap <<= 1;
+        std::vector<uint32_t> bucket(keys.size()), start(cap + 1, 0);
+        for (size_t i = 0; i < keys.size(); i++) {
+            const uint32_t h = java_hash(keys[i]);
+            bucket[i] = (h ^ (h >> 16)) & (uint32_t)(cap - 1);
+            start[bucket[i] + 1]++;
+        }
+        for (size_t b = 0; b < cap; b++) start[b + 1] += start[b];
+        std::vector<uint32_t> o(keys.size());
+        for (size_t i = 0; i < keys.size(); i++) o[start[bucket[i]]++] = (uint32_t)i;
+        return o;
+    }
+};
+
+// StringUtils.normalizeDna (src/utils/StringUtils.java:34-41) on codes: the ASCII order A < C < G < T is the code order with G (1) and C (2) exchanged
+inline uint64_t ascii_rank(uint64_t x) { return ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL); }
+inline uint64_t normalize_code(uint64_t code, int k) {
+    const uint64_t rc = mc_revcomp(code, k);
+    return ascii_rank(code) <= ascii_rank(rc) ? code : rc;   // s.compareTo(rc) < 0 ? s : rc  (equal strings are the same string)
+}
+inline void kmer_chars(uint64_t code, int k, char* out) {
+    for (int i = k - 1; i >= 0; i--, code >>= 2) out[i] = NUC[code & 3];
+}
+
 void mkdirs(const std::string& path) {
     std::string cur;
     for (size_t i = 0; i < path.size(); i++) {
@@ -160,7 +316,16 @@ std::vector<std::string> read_lines(const std::string& path, const char* what) {
 struct Graph {
     int k = 0;
     uint32_t n2 = 0;
-    std::vector<std::vector<int32_t>> nbrs;   // expanded neighbour lists (palindromes as two ids)
+    struct NbrList {                          // at most 4 neighbours, a palindromic one counts twice
+        int32_t v[8];
+        uint8_t n = 0;
+        size_t size() const { return n; }
+        int32_t operator[](size_t i) const { return v[i]; }
+        const int32_t* begin() const { return v; }
+        const int32_t* end() const { return v + n; }
+        void push_back(int32_t x) { v[n++] = x; }
+    };
+    std::vector<NbrList> nbrs;                // expanded neighbour lists (palindromes as two ids)
     std::vector<uint8_t> gene, deleted;
     std::vector<int32_t> rc;                  // current reverse-complement partner (stale for deleted nodes, like the reference)
     // A node's sequence is an immutable concatenation tree over the original nodes (leaf v = original node v, id >= n2 =
@@ -174,7 +339,7 @@ struct Graph {
     void build(const McUnitigInput& in, const McUnitigNodes& nodes) {
         k = in.k;
         n2 = (uint32_t)in.kmers.size() * 2;
-        nbrs.assign(n2, {});
+        nbrs.assign(n2, NbrList());
         gene = nodes.gene;
         deleted.assign(n2, 0);
         rc.resize(n2);
@@ -277,31 +442,48 @@ std::vector<uint64_t> target_windows(const std::vector<std::string>& targets, in
 // ------------------------------------------------------------------------------------------------
 // single-environment writers
 // ------------------------------------------------------------------------------------------------
-void write_environment(const JavaMap<int>& subgraph, const std::vector<uint32_t>& ord, const std::string& prefix) {   // printEnvironment (:297-310)
+void write_environment(const KmerMap& subgraph, const std::vector<uint32_t>& ord, const std::string& prefix) {   // printEnvironment (:297-310)
     mkdirs(prefix);
+    const int k = subgraph.k;
     std::string body;
-    body.reserve(ord.size() * 40);
+    body.resize(ord.size() * (size_t)(k + 8));
+    char* out = &body[0];
     for (uint32_t p : ord) {
-        body += subgraph.entries[p].first;
-        body += ' ';
-        body += std::to_string(subgraph.entries[p].second);
-        body += '\n';
+        kmer_chars(subgraph.keys[p], k, out);
+        out += k;
+        *out++ = ' ';
+        out += snprintf(out, 8, "%d", subgraph.vals[p]);   // counts are <= 32767
+        *out++ = '\n';
     }
+    body.resize((size_t)(out - &body[0]));
     for (const char* name : {"/graph.txt", "/env.txt"}) {   // the reference writes graph.txt; README/BASELINE call it env.txt
-        std::ofstream out(prefix + name, std::ios::binary);
-        out << body;
+        FILE* f = fopen((prefix + name).c_str(), "wb");
+        if (!f) mc_throw(MC_ERR_IO, "cannot write %s%s", prefix.c_str(), name);
+        fwrite(body.data(), 1, body.size(), f);
+        fclose(f);
     }
 }
 
-void write_single_outputs(const Graph& g, const JavaMap<int>& subgraph, int chunk_len, const std::string& prefix) {
+void write_single_outputs(const Graph& g, const KmerMap& subgraph, int chunk_len, const std::string& prefix) {
     const int k = g.k;
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    // KC (GFAWriter.java:90-95): sum of the coverage of every k-window + coverage of the last window * (k - 1); the windows are
+    // looked up in `subgraph` by their normalised form, rolling the 2-bit code along the sequence
+    auto kc = [&](const std::string& seq) -> long {
+        long total = 0, last = 0;
+        uint64_t code = 0;
+        for (size_t i = 0; i < seq.size(); i++) {
+            code = ((code << 2) | (uint64_t)(mc_nuc_code((uint8_t)seq[i]) & 3)) & kmask;
+            if (i + 1 < (size_t)k) continue;
+            const int32_t* c = subgraph.get(normalize_code(code, k));
+            if (!c) mc_throw(MC_ERR_FORMAT, "k-mer %s of a unitig is not in the environment", seq.substr(i + 1 - k, k).c_str());
+            last = *c;
+            total += last;
+        }
+        return total + last * (k - 1);
+    };
     auto node_id = [&](int32_t v) { return std::to_string(g.min_id(v)) + (g.gene[v] ? "_start" : ""); };
     auto fwd = [&](int32_t v) { return g.seq[v].compare(g.seq[g.rc[v]]) <= 0; };
-    auto cov = [&](const std::string& kmer) -> long {
-        const int* c = subgraph.get(normalize_dna(kmer));
-        if (!c) mc_throw(MC_ERR_FORMAT, "k-mer %s of a unitig is not in the environment", kmer.c_str());
-        return *c;
-    };
     mkdirs(prefix);
     {   // outputNodeSequences (:354-373)
         std::ofstream out(prefix + "/seqs.fasta", std::ios::binary);
@@ -314,9 +496,7 @@ void write_single_outputs(const Graph& g, const JavaMap<int>& subgraph, int chun
         for (uint32_t v = 0; v < g.n2; v++)
             if (!g.deleted[v] && fwd((int32_t)v)) {
                 const std::string& s = g.seq[v];
-                long coverage = 0;
-                for (size_t i = 0; i + k <= s.size(); i++) coverage += cov(s.substr(i, k));
-                coverage += cov(s.substr(s.size() - k)) * (k - 1);
+                const long coverage = kc(s);
                 out << "S\t" << node_id((int32_t)v) << "\t" << s << "\tLN:i:" << s.size() << "\tKC:i:" << coverage << (g.gene[v] ? "\tCL:Z:GREEN" : "") << "\n";
             }
         for (uint32_t i = 0; i < g.n2; i++)
@@ -376,30 +556,30 @@ static std::vector<uint8_t> trim_paths(const McBfsResult& r, int dir, int k) {
     return keep;
 }
 
-bool build_subgraph(const std::vector<const McBfsResult*>& passes, const std::vector<int>& dirs, bool trim, int k, JavaMap<int>& subgraph) {
+bool build_subgraph(const std::vector<const McBfsResult*>& passes, const std::vector<int>& dirs, bool trim, int k, KmerMap& subgraph) {
+    size_t total = 0;
+    for (const McBfsResult* r : passes) total += r->kmers.size();
+    subgraph.init(k, total);
     for (size_t pi = 0; pi < passes.size(); pi++) {
         const McBfsResult* r = passes[pi];
         if (r->kmers.empty()) return false;   // "fail": no seed k-mer in the reads
-        JavaMap<int> dist;                   // insertion order = discovery order
-        std::vector<std::string> strs(r->kmers.size());
-        for (size_t i = 0; i < r->kmers.size(); i++) {
-            strs[i] = kmer_string(r->kmers[i], k);
-            dist.put(strs[i], (int)i);
-        }
+        KmerMap dist;                         // distanceToKmer: insertion order = discovery order, value = queue index
+        dist.init(k, r->kmers.size());
+        for (size_t i = 0; i < r->kmers.size(); i++) dist.put(r->kmers[i], (int32_t)i);
         if (trim) dist.retain(trim_paths(*r, dirs[pi], k));
-        for (uint32_t p : dist.order()) subgraph.put(normalize_dna(dist.entries[p].first), (int)r->counts[(size_t)dist.entries[p].second]);
+        for (uint32_t p : dist.order()) subgraph.put(normalize_code(dist.keys[p], k), (int32_t)r->counts[(size_t)dist.vals[p]]);
     }
     return true;
 }
 
-void unitig_input_from_subgraph(const JavaMap<int>& subgraph, const std::vector<uint32_t>& ord, const std::vector<std::string>& targets, int k,
+void unitig_input_from_subgraph(const KmerMap& subgraph, const std::vector<uint32_t>& ord, const std::vector<std::string>& targets, int k,
                                 McUnitigInput& in) {
     in.k = k;
     in.kmers.resize(ord.size());
     in.counts.resize(ord.size());
     for (size_t i = 0; i < ord.size(); i++) {
-        in.kmers[i] = kmer_code(subgraph.entries[ord[i]].first);
-        in.counts[i] = subgraph.entries[ord[i]].second;
+        in.kmers[i] = subgraph.keys[ord[i]];
+        in.counts[i] = subgraph.vals[ord[i]];
     }
     in.gene_windows = target_windows(targets, k);
 }
@@ -488,7 +668,7 @@ struct EnvJob {
     std::vector<std::string> seeds;
 };
 static void run_jobs(mc_ctx* ctx, const mc_table* t, const std::vector<EnvJob>& jobs, int k, int min_cov, int64_t max_kmers, int64_t max_radius,
-                     bool both_dirs, bool trim, std::vector<JavaMap<int>>& subgraphs, std::vector<int>& found) {
+                     bool both_dirs, bool trim, std::vector<KmerMap>& subgraphs, std::vector<int>& found) {
     std::vector<McBfsRequest> reqs;
     for (const EnvJob& job : jobs) {
         std::vector<uint8_t> codes;
@@ -511,9 +691,9 @@ static void run_jobs(mc_ctx* ctx, const mc_table* t, const std::vector<EnvJob>& 
     }
     EnvTrace tr("build_subgraph");
     const size_t per = both_dirs ? 1 : 2;
-    subgraphs.assign(jobs.size(), JavaMap<int>());
+    subgraphs.assign(jobs.size(), KmerMap());
     found.assign(jobs.size(), 0);
-    for (size_t i = 0; i < jobs.size(); i++) {
+    parallel_for(jobs.size(), [&](size_t i) {
         std::vector<const McBfsResult*> passes;
         std::vector<int> dirs;
         for (size_t p = 0; p < per; p++) {
@@ -521,30 +701,54 @@ static void run_jobs(mc_ctx* ctx, const mc_table* t, const std::vector<EnvJob>& 
             dirs.push_back(reqs[i * per + p].dir);
         }
         found[i] = build_subgraph(passes, dirs, trim, k, subgraphs[i]) ? 1 : 0;
-    }
+    });
 }
 static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target>& targets, int k, int min_cov, int64_t max_kmers,
-                        int64_t max_radius, bool both_dirs, std::vector<JavaMap<int>>& subgraphs, std::vector<int>& found) {
+                        int64_t max_radius, bool both_dirs, std::vector<KmerMap>& subgraphs, std::vector<int>& found) {
     std::vector<EnvJob> jobs;
     for (const Target& tg : targets) jobs.push_back(EnvJob{{tg.seq}});
     run_jobs(ctx, t, jobs, k, min_cov, max_kmers, max_radius, both_dirs, false, subgraphs, found);
 }
 
-// graph.txt/env.txt + unitig stage + writers of one environment; gene nodes are decided against `gene_seqs` (isGeneNode :421-432)
-static void write_one_environment(mc_ctx* ctx, const JavaMap<int>& sub, const std::vector<std::string>& gene_seqs, int k, int chunk_len,
-                                  const std::string& prefix) {
+// graph.txt/env.txt + unitig stage + writers of the found environments; gene nodes are decided against `gene_seqs` (isGeneNode
+// :421-432).  Host stages run on the thread pool, one environment per task; the device stage in between (node hash, neighbour
+// lists, chain ranks: mc_unitig.cu) is issued from the calling thread, environment after environment, on the context's stream.
+struct EnvWork {
+    size_t job = 0;
     std::vector<uint32_t> ord;
-    { EnvTrace tr("subgraph order"); ord = sub.order(); }
-    { EnvTrace tr("write env.txt/graph.txt"); write_environment(sub, ord, prefix); }
     McUnitigInput in;
-    { EnvTrace tr("unitig input"); unitig_input_from_subgraph(sub, ord, gene_seqs, k, in); }
     McUnitigNodes nodes;
-    { EnvTrace tr("unitig nodes (device)"); mc_unitig_nodes(ctx, in, nodes); }
-    Graph g;
-    { EnvTrace tr("graph build"); g.build(in, nodes); }
-    { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
-    { EnvTrace tr("assemble"); g.assemble(); }
-    { EnvTrace tr("write gfa/fasta/tsv"); write_single_outputs(g, sub, chunk_len, prefix); }
+};
+static void write_environments(mc_ctx* ctx, const std::vector<KmerMap>& subs, const std::vector<int>& found,
+                               const std::vector<std::vector<std::string>>& gene_seqs, int k, int chunk_len, const std::vector<std::string>& prefixes) {
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < subs.size(); i++)
+        if (found[i]) todo.push_back(i);   // else: "Could not find any k-mers of the target gene in the input, halting."
+    const size_t wave = std::max<size_t>(2 * env_threads(todo.size()), 1);   // bounds the memory held between the phases
+    for (size_t w0 = 0; w0 < todo.size(); w0 += wave) {
+        const size_t nw = std::min(wave, todo.size() - w0);
+        std::vector<EnvWork> work(nw);
+        parallel_for(nw, [&](size_t w) {
+            EnvWork& e = work[w];
+            e.job = todo[w0 + w];
+            const KmerMap& sub = subs[e.job];
+            { EnvTrace tr("subgraph order"); e.ord = sub.order(); }
+            { EnvTrace tr("write env.txt/graph.txt"); write_environment(sub, e.ord, prefixes[e.job]); }
+            { EnvTrace tr("unitig input"); unitig_input_from_subgraph(sub, e.ord, gene_seqs[e.job], k, e.in); }
+        });
+        {
+            EnvTrace tr("unitig nodes (device)");
+            for (size_t w = 0; w < nw; w++) mc_unitig_nodes(ctx, work[w].in, work[w].nodes);
+        }
+        parallel_for(nw, [&](size_t w) {
+            EnvWork& e = work[w];
+            Graph g;
+            { EnvTrace tr("graph build"); g.build(e.in, e.nodes); }
+            { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
+            { EnvTrace tr("assemble"); g.assemble(); }
+            { EnvTrace tr("write gfa/fasta/tsv"); write_single_outputs(g, subs[e.job], chunk_len, prefixes[e.job]); }
+        });
+    }
 }
 
 // --merge / --hicseq / --trim (EnvironmentFinderMain.java:218-233, OneSequenceCalculator.java:168-192,208-216,241-262)
@@ -570,13 +774,14 @@ extern "C" int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const*
                 prefixes.push_back(std::string(out_dir) + "/" + names[i] + "/");   // getOutputPrefix (EnvironmentFinderMain.java:245-249)
             }
         }
-        std::vector<JavaMap<int>> subgraphs;
+        std::vector<KmerMap> subgraphs;
         std::vector<int> found;
         run_jobs(ctx, t, jobs, k, min_cov, max_kmers, max_radius, both_dirs != 0, trim != 0, subgraphs, found);
-        for (size_t i = 0; i < jobs.size(); i++) {
+        for (size_t i = 0; i < jobs.size(); i++)
             if (found_out) found_out[i] = found[i];
-            if (!found[i]) continue;   // "Could not find any k-mers of the target gene in the input, halting."
-            write_one_environment(ctx, subgraphs[i], gene_seqs[i], k, chunk_len, prefixes[i]);
+        {
+            EnvTrace tr("environments -> files (wall)");
+            write_environments(ctx, subgraphs, found, gene_seqs, k, chunk_len, prefixes);
         }
         EnvTrace::report();
         return MC_OK;
@@ -595,7 +800,7 @@ extern "C" int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int
                             int both_dirs, uint64_t* kmers, int32_t* counts, size_t cap, size_t* n) {
     try {
         if (!ctx || !t || !seq || !n) mc_throw(MC_ERR_ARG, "null argument");
-        std::vector<JavaMap<int>> subgraphs;
+        std::vector<KmerMap> subgraphs;
         std::vector<int> found;
         run_targets(ctx, t, {Target{seq, ""}}, k, min_cov, max_kmers, max_radius, both_dirs != 0, subgraphs, found);
         if (!found[0]) {
@@ -606,8 +811,8 @@ extern "C" int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int
         *n = ord.size();
         if (ord.size() > cap) mc_throw(MC_ERR_CAPACITY, "environment has %zu k-mers, room for %zu", ord.size(), cap);
         for (size_t i = 0; i < ord.size(); i++) {
-            if (kmers) kmers[i] = kmer_code(subgraphs[0].entries[ord[i]].first);
-            if (counts) counts[i] = subgraphs[0].entries[ord[i]].second;
+            if (kmers) kmers[i] = subgraphs[0].keys[ord[i]];
+            if (counts) counts[i] = subgraphs[0].vals[ord[i]];
         }
         return MC_OK;
     } catch (const McError& e) {
@@ -620,11 +825,16 @@ extern "C" int mc_env_kmers(mc_ctx* ctx, const mc_table* t, const char* seq, int
 extern "C" int mc_env_from_graph_txt(mc_ctx* ctx, const char* graph_txt, const char* target_seq, int k, int chunk_len, const char* out_dir) {
     try {
         if (!ctx || !graph_txt || !target_seq || !out_dir) mc_throw(MC_ERR_ARG, "null argument");
-        JavaMap<int> sub;
-        for (const std::string& line : read_lines(graph_txt, "Couldn't load graph from file")) {
+        KmerMap sub;
+        const std::vector<std::string> lines = read_lines(graph_txt, "Couldn't load graph from file");
+        sub.init(k, lines.size());
+        for (const std::string& line : lines) {
             size_t sp = line.find(' ');
             if (sp == std::string::npos) mc_throw(MC_ERR_FORMAT, "malformed environment line \"%s\"", line.c_str());
-            sub.put(line.substr(0, sp), atoi(line.c_str() + sp + 1));
+            if (sp != (size_t)k) mc_throw(MC_ERR_FORMAT, "environment k-mer \"%s\" is not %d bases long", line.substr(0, sp).c_str(), k);
+            for (size_t i = 0; i < sp; i++)
+                if (line[i] != 'A' && line[i] != 'C' && line[i] != 'G' && line[i] != 'T') mc_throw(MC_ERR_FORMAT, "Incorrect nucleotide char: \"%c\"", line[i]);
+            sub.put(kmer_code(line.substr(0, sp)), atoi(line.c_str() + sp + 1));
         }
         std::vector<uint32_t> ord = sub.order();
         std::string prefix = std::string(out_dir) + "/";
