@@ -190,10 +190,21 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
 /* tuning knobs of the binned update path (NOT reference API; tests and profiles use them):
  *   "part_bits" (-1 = automatic, else P = 2^value bins), "batch_keys" (capacity of one batch, 0 = automatic),
  *   "segment_keys" (keys applied per count launch, 0 = automatic), "count_tile", "count_variant" (k_bin_count shape),
- *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32) */
+ *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32),
+ *   "agg" (two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on), "agg_unit" (keys per
+ *   aggregation unit, 0 = automatic) */
 int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);
 /* table updates are buffered in bins; every read of the table applies them first, this call does so explicitly */
 int mc_table_flush_pending(mc_table* t);
+/* "About `n` more k-mer instances will be added to `t`" (0 = unknown).  Without a capacity hint the table is sized from a
+ * counted 1/64 sample of every batch of binned updates (mc_bins.cu); with this the estimate is scaled to the rest of the
+ * input, so a stream of batches does not grow the table by repeated doubling.  mc_count_bytes sets it itself. */
+int mc_table_expect_keys(mc_table* t, uint64_t n);
+/* Order-independent digest of the table's entries with count >= min_count, computed on the device (tests at sizes where a
+ * dump through the host is impractical): out[0] = entries, out[1] = sum of counts (each clamped to 32767, like get()),
+ * out[2] = sum of digest(key) * count mod 2^64 with digest(x) = (x ^ (x >> 29)) * 0xBF58476D1CE4E5B9 + 1, out[3] = largest
+ * count.  The sum of shard digests of a sharded table equals the digest of the whole table. */
+int mc_table_checksum(const mc_table* t, int min_count, uint64_t out[4]);
 
 #ifdef __cplusplus
 }

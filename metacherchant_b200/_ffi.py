@@ -82,6 +82,8 @@ _SIGNATURES = {
     "mc_ctx_stage_reset": (i32, [vp]),
     "mc_ctx_set_tuning": (i32, [vp, cp, C.c_longlong]),
     "mc_table_flush_pending": (i32, [vp]),
+    "mc_table_expect_keys": (i32, [vp, u64]),
+    "mc_table_checksum": (i32, [vp, i32, C.POINTER(u64)]),
 }
 
 

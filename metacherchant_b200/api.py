@@ -199,6 +199,16 @@ class KmerTable:
         check(self.lib.mc_table_stats(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("reads", "runs", "bases", "kmers"), [x.value for x in v]))
 
+    def checksum(self, min_count=0):
+        """Device-side digest of the entries with count >= min_count: dict(entries, sum_counts, digest, max_count)."""
+        out = (C.c_uint64 * 4)()
+        check(self.lib.mc_table_checksum(self.h, min_count, out))
+        return dict(zip(("entries", "sum_counts", "digest", "max_count"), [int(x) for x in out]))
+
+    def expect_keys(self, n: int):
+        """About n more k-mer instances will be added (sizes the table for a stream of batches); 0 = unknown."""
+        check(self.lib.mc_table_expect_keys(self.h, n))
+
     def add_pairs(self, keys, counts):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         counts = np.ascontiguousarray(counts, dtype=np.int16)

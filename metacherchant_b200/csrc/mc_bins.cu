@@ -448,6 +448,14 @@ static uint64_t available_device_bytes(mc_ctx* ctx) {
     return avail;
 }
 
+// a predicted table size is an estimate: never ask for more than 80 % of what the device can still give (the amortised
+// doubling in the flush loops takes over if the table really has to become that large)
+static int fit_q(mc_ctx* ctx, const mc_table* t, int q) {
+    const double room = 0.8 * (double)available_device_bytes(ctx);
+    while (q > t->dev.q + 1 && (double)(32ull << q) > room) q--;
+    return q;
+}
+
 static void batch_free_buffers(mc_ctx* ctx, McBatch* B) {
     mc_dev_free(ctx, B->dev.keys);
     mc_dev_free(ctx, B->dev.cursors);
@@ -683,12 +691,19 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 }
                 MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 MC_CUDA(cudaStreamSynchronize(st));
-                const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)group_keys);
+                // later batches of a stream are assumed to bring as many new keys as this one: an upper bound (the genomic k-mers
+                // saturate, the error k-mers keep coming), so the table is grown once instead of doubling batch after batch
+                // The first batch of a stream over-predicts most (everything is new): it is trusted for 4 batches only; the
+                // second batch already shows the marginal rate and the table is then grown to its final size.
+                double batches_left = 1.0;
+                if (t->expect_instances > t->seen_instances + batch_keys) batches_left = (double)(t->expect_instances - t->seen_instances) / (double)batch_keys;
+                if (t->stream_flushes == 0) batches_left = std::min(batches_left, 4.0);
+                const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)group_keys) * batches_left;
                 const double predicted = (double)keys_before + fresh;
                 if (getenv("MC_TRACE")) fprintf(stderr, "[mc trace] agg sample: %llu new distinct keys in %llu instances -> %.0f predicted for the batch\n",
                                                 (unsigned long long)h_c[MC_CNT_OVF_KEYS], (unsigned long long)group_keys, predicted);
                 if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
-                    const int q = mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD);
+                    const int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
                     if (q > t->dev.q) mc_table_grow_to(t, q);
                 }
                 attach_overflow_list();
@@ -731,7 +746,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
         const double predicted = (double)keys_before + (keys_done ? gained * ((double)batch_keys / (double)keys_done) : 0.0);
         bool grown = false;
         if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
-            int q = mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD);
+            int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
             if (q > t->dev.q) {
                 mc_table_grow_to(t, q);
                 grown = true;
@@ -754,6 +769,8 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     }
     t->dev.ovf_keys = nullptr;
     t->dev.ovf_cap = 0;
+    t->seen_instances += batch_keys;
+    t->stream_flushes++;
     mc_dev_free(ctx, B2.keys);
     mc_dev_free(ctx, B2.spill);
     mc_dev_free(ctx, B2.cursors);
@@ -840,7 +857,7 @@ void mc_table_flush(mc_table* t) {
         const double predicted = (double)keys_before + gained * ((double)total_tiles / (double)tile);
         bool grown = false;
         if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
-            int q = mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD);
+            int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
             if (q > t->dev.q) {
                 mc_table_grow_to(t, q);
                 grown = true;
@@ -889,6 +906,16 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
         mc_set_error("unknown tuning parameter or value out of range: " + n);
         return MC_ERR_ARG;
     }
+    return MC_OK;
+}
+extern "C" int mc_table_expect_keys(mc_table* t, uint64_t n) {
+    if (!t) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    t->expect_instances = n;
+    t->seen_instances = 0;
+    t->stream_flushes = 0;
     return MC_OK;
 }
 extern "C" int mc_table_flush_pending(mc_table* t) {

@@ -309,6 +309,9 @@ struct mc_table {
     uint64_t nb = 0;
     uint64_t capacity_slots() const { return nb * 4; }
     struct McBatch* batch = nullptr;   // pending binned updates (mc_bins.cu); applied by mc_table_flush
+    uint64_t expect_instances = 0;     // mc_table_expect_keys: k-mer instances the caller still expects to add (0 = unknown)
+    uint64_t seen_instances = 0;       // instances applied since the expectation was set
+    uint32_t stream_flushes = 0;       // flushes since the expectation was set
 };
 
 // kernels / host helpers shared across translation units

@@ -424,7 +424,8 @@ static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint32_
     return d_flat;
 }
 
-static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint32_t n, bool fasta, int qoff, bool final_chunk, uint64_t total_hint) {
+static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint32_t n, bool fasta, int qoff, bool final_chunk, uint64_t total_hint,
+                            uint64_t stream_bytes = 0) {
     McParsed P;
     {
         McStageTimer tm(ctx, MC_ST_PARSE);
@@ -449,6 +450,10 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
             a.table = t->dev;   // a flush may have grown the table (the extractor only uses its statistics counters)
             uint64_t n_flat = 0;
             uint64_t* d_flat = extract_flat(ctx, a, fasta, P.h.max_seq_len, ub + 1, d_buf, n, &n_flat);
+            // a stream of chunks (host input): the first chunk's k-mers per byte, scaled to the whole input, tells the flush how
+            // many more instances to expect
+            if (stream_bytes && t->expect_instances == 0 && P.h.consumed)
+                mc_table_expect_keys(t, (uint64_t)((double)n_flat * ((double)stream_bytes / (double)P.h.consumed)));
             mc_batch_scatter(t, d_flat, n_flat);
         }
     }
@@ -531,6 +536,7 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
         // shadow of the uploads instead of after the last one (device-resident input is binned whole, one sweep)
         const uint64_t host_chunks = ctx->tune_host_batch_chunks ? ctx->tune_host_batch_chunks : 1;
         const uint64_t batch_hint = std::min<uint64_t>(mc_max_kmers(len, fmt, t->k), host_chunks * mc_max_kmers(chunk, fmt, t->k));
+        mc_table_expect_keys(t, 0);   // set from the first chunk's k-mers per byte (count_chunk)
         size_t pos = 0;      // next host byte to upload
         size_t carry = 0;    // bytes of the previous chunk sitting right in front of offset `chunk`
         int cur = 0;
@@ -552,7 +558,7 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
             MC_CUDA(cudaStreamWaitEvent(ctx->stream, copied[cur], 0));
             const uint8_t* d_start = (const uint8_t*)ctx->d_chunk[cur] + chunk - carry;
             const size_t n = carry + n_slice;
-            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, batch_hint);
+            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, batch_hint, len);
             if (final_chunk) break;
             size_t left = n - consumed;
             if (left > chunk) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", chunk);
@@ -566,11 +572,13 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
         for (int i = 0; i < 2; i++) cudaEventDestroy(copied[i]);
         cudaEventDestroy(consumed_ev);
         finish_table(t);
+        mc_table_expect_keys(t, 0);
         return MC_OK;
     } catch (const McError& e) {
         cudaStreamSynchronize(ctx->copy_stream);
         for (int i = 0; i < 2; i++) if (copied[i]) cudaEventDestroy(copied[i]);
         if (consumed_ev) cudaEventDestroy(consumed_ev);
+        if (t) mc_table_expect_keys(t, 0);
         mc_set_error(e.what());
         return e.code;
     }

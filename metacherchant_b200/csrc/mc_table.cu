@@ -439,6 +439,86 @@ static uint64_t count_matching(const mc_table* t, int min_count, unsigned long l
     return n;
 }
 
+// Order-independent digest of the entries (mc_table_checksum): one 32-byte bucket per thread, like k_dump
+__global__ void __launch_bounds__(256) k_checksum(McTableDev t, uint32_t min_count, unsigned long long* acc, uint64_t shard_prefix) {
+    const uint64_t nb = t.nb_mask + 1;
+    const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
+    const uint64_t total = nb + stash_units;
+    unsigned long long n = 0, sum = 0, dig = 0, mx = 0;
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t hl[4];
+        uint32_t c[4];
+        if (u < nb) {
+            uint64_t w4[4];
+            mc_load_bucket(t.slots + u * 4, w4);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint64_t w = w4[s];
+                c[s] = (uint32_t)(w & MC_COUNT_MASK);
+                const uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
+                hl[s] = (((u - d) & t.nb_mask) << t.tag_bits) | (w >> MC_TAG_SHIFT);
+                if (w == 0) c[s] = 0;
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint64_t i = (u - nb) * 4 + s;
+                const uint64_t kx = i <= t.stash_mask ? t.stash_keys[i] : 0;
+                hl[s] = kx - 1;
+                c[s] = kx ? t.stash_counts[i] : 0;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (c[s] > MC_SAT) c[s] = MC_SAT;
+            if (c[s] == 0 || c[s] < min_count) continue;
+            const uint64_t key = mc_unmix62_dev(shard_prefix | hl[s]);
+            n++;
+            sum += c[s];
+            dig += ((key ^ (key >> 29)) * 0xBF58476D1CE4E5B9ULL + 1ULL) * (unsigned long long)c[s];
+            mx = mx > c[s] ? mx : c[s];
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        n += __shfl_down_sync(0xffffffffu, n, o);
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        dig += __shfl_down_sync(0xffffffffu, dig, o);
+        const unsigned long long m2 = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = mx > m2 ? mx : m2;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n) atomicAdd(&acc[0], n);
+        if (sum) atomicAdd(&acc[1], sum);
+        if (dig) atomicAdd(&acc[2], dig);
+        if (mx) atomicMax(&acc[3], mx);
+    }
+}
+
+extern "C" int mc_table_checksum(const mc_table* t, int min_count, uint64_t out[4]) {
+    try {
+        if (!t || !out) mc_throw(MC_ERR_ARG, "null argument");
+        mc_ctx* ctx = t->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(const_cast<mc_table*>(t));
+        check_overflow(t);
+        unsigned long long* d_acc = (unsigned long long*)mc_dev_alloc(ctx, 4 * sizeof(unsigned long long), "scratch");
+        MC_CUDA(cudaMemsetAsync(d_acc, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        const uint64_t prefix = t->dev.shard_bits ? ((uint64_t)t->shard_id << (62 - t->dev.shard_bits)) : 0;
+        k_checksum<<<grid_for(ctx, t->nb, 256, 16), 256, 0, ctx->stream>>>(t->dev, min_count < 0 ? 0u : (uint32_t)min_count, d_acc, prefix);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        unsigned long long h[4];
+        MC_CUDA(cudaMemcpyAsync(h, d_acc, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        MC_CUDA(cudaStreamSynchronize(ctx->stream));
+        mc_dev_free(ctx, d_acc);
+        for (int i = 0; i < 4; i++) out[i] = h[i];
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
 extern "C" int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, int16_t* counts, size_t cap, size_t* n_out) {
     try {
         if (!t || !n_out) mc_throw(MC_ERR_ARG, "null argument");

@@ -155,6 +155,8 @@ class ShardedCounter:
             torch.cuda.current_stream().synchronize()
             t2 = time.perf_counter()
             check(lib.mc_xchg_insert(self._xchg, slot, self.table.h, C.byref(got)))
+            if b == 0:   # what the first batch brought, times the batches: sizes the shard once (no capacity hint needed)
+                self.table.expect_keys(got.value * n_batches)
             t3 = time.perf_counter()
             self.phase_s["extract"] += t1 - t0
             self.phase_s["exchange"] += t2 - t1
@@ -180,6 +182,7 @@ class ShardedCounter:
         if not hasattr(self, "_comm_stream"):
             self._comm_stream = torch.cuda.Stream()
         pending = None   # (event, slot, n_received) of the exchange in flight
+        self._expect_set = False
 
         def finish(p):
             ev, slot, total = p
@@ -187,6 +190,9 @@ class ShardedCounter:
             ev.synchronize()
             t1 = time.perf_counter()
             if total:
+                if not self._expect_set:
+                    self.table.expect_keys(total * n_batches)
+                    self._expect_set = True
                 self.table.insert_hashed_device(self._recv[slot].data_ptr(), total)
             self.phase_s["exchange"] += t1 - t0
             self.phase_s["insert"] += time.perf_counter() - t1

@@ -1,0 +1,178 @@
+"""BASELINE.json's configurations at their full sizes, through size-independent properties, and their shapes at sizes
+the oracle finishes in seconds (bit-exact).
+
+The oracle cannot count 50 M reads inside a test, so at full size the table is checked through
+  * sum of counts == k-mer instances the extractor saw (no count saturates in these workloads: checked),
+  * an order-independent 64-bit digest of (key, count) that must agree between independent code paths
+    (direct sweep vs two-level bins + shared-memory aggregation, device-resident input vs host input in chunks),
+  * counting the input twice doubles every count: digest and sum double, the entries stay,
+and the digest itself is pinned against numpy on a dump and against the oracle on a slice.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_ffi import FMT_FASTQ
+
+pytestmark = pytest.mark.gpu
+
+M64 = (1 << 64) - 1
+
+
+def np_digest(keys, counts):
+    k = keys.astype(np.uint64)
+    d = ((k ^ (k >> np.uint64(29))) * np.uint64(0xBF58476D1CE4E5B9) + np.uint64(1)) * counts.astype(np.uint64)
+    return int(d.sum(dtype=np.uint64)), int(counts.astype(np.int64).sum()), int(counts.max()) if counts.size else 0
+
+
+def device_reads(ctx, synth, first, reads, gen=4_000_000):
+    rb = synth.record_bytes
+    d = ctx.device_alloc(reads * rb)
+    params = synth.params_bytes()
+    for off in range(0, reads, gen):
+        n = min(gen, reads - off)
+        ctx.synth_generate_device(params, first + off, n, d + off * rb)
+    return d, reads * rb
+
+
+def test_checksum_matches_numpy_and_oracle(oracle):
+    from metacherchant_b200 import Context
+    s = oracle.synth(genome_unit=20_000)
+    data = s.generate(0, 80_000)
+    c = Context(0)
+    try:
+        g = c.new_table(31).count_bytes(data, FMT_FASTQ)
+        o = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ)
+        ok, oc = o.dump(-32768)
+        for mc in (0, 3):
+            gk, gc = g.dump(mc)
+            dig, total, mx = np_digest(gk, gc)
+            got = g.checksum(mc)
+            assert got == dict(entries=gk.size, sum_counts=total, digest=dig, max_count=mx)
+            sel = oc >= max(mc, 1)
+            assert (got["digest"], got["sum_counts"]) == np_digest(ok[sel], oc[sel])[:2]
+        assert g.checksum()["sum_counts"] == g.stats()["kmers"]
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_full_size_counting_properties(oracle, cfg):
+    """cfg1 = 1 M reads (BASELINE configs[0]), cfg2 = 50 M reads (configs[1]): k = 31, coverage 5."""
+    from metacherchant_b200 import Context
+    reads, unit, n_targets = (1_000_000, 100_000, 1) if cfg == "cfg1" else (50_000_000, 1_000_000, 20)
+    if cfg == "cfg2" and os.environ.get("MC_SKIP_FULL_CFG2"):
+        pytest.skip("MC_SKIP_FULL_CFG2 set")
+    s = oracle.synth(genome_unit=unit, n_targets=n_targets)
+    c = Context(0, chunk_bytes=1 << 30)
+    try:
+        d, nbytes = device_reads(c, s, 0, reads)
+        sums = {}
+        for name, agg in (("direct sweep", 0), ("aggregated", 1)):
+            c.set_tuning("agg", agg)
+            # the direct sweep sizes its table from overflowed INSTANCES (a loose estimate): give it the usual hint
+            t = c.new_table(31, capacity_hint=0 if agg else reads * 150 // 8)
+            t.count_device(d, nbytes, FMT_FASTQ)
+            st = t.stats()
+            chk = t.checksum()
+            assert st["reads"] == reads
+            assert chk["max_count"] < 32767, "a count saturated: the sum property does not apply"
+            assert chk["sum_counts"] == st["kmers"], f"{name}: counts sum to {chk['sum_counts']}, the extractor saw {st['kmers']} k-mers"
+            assert chk["entries"] == t.size()
+            solid = t.filter(5)
+            assert solid.size() == t.checksum(5)["entries"] == solid.checksum()["entries"]
+            assert solid.checksum() == t.checksum(5)
+            sums[name] = (chk, solid.size())
+            solid.free()
+            if agg == 1:
+                # the same reads once more: every count doubles (still far from saturation), nothing new appears
+                t.count_device(d, nbytes, FMT_FASTQ)
+                twice = t.checksum()
+                assert twice["entries"] == chk["entries"]
+                assert twice["sum_counts"] == 2 * chk["sum_counts"]
+                assert twice["digest"] == (2 * chk["digest"]) & M64
+                assert twice["max_count"] == 2 * chk["max_count"]
+            t.free()
+        assert sums["direct sweep"] == sums["aggregated"]
+        if cfg == "cfg1":
+            # host input in small chunks (one table flush per chunk) gives the same table
+            c.set_tuning("agg", -1)
+            host = np.empty(nbytes, dtype=np.uint8)
+            c.d2h(host, d)
+            c2 = Context(0, chunk_bytes=32 << 20)
+            try:
+                t = c2.new_table(31).count_bytes(host, FMT_FASTQ)
+                assert t.checksum() == sums["aggregated"][0]
+                t.free()
+            finally:
+                c2.close()
+        c.device_free(d)
+    finally:
+        c.close()
+
+
+def same_tree(a, b, files):
+    for f in files:
+        x, y = open(os.path.join(a, f), "rb").read(), open(os.path.join(b, f), "rb").read()
+        assert x == y, f"{f} differs ({len(x)} vs {len(y)} bytes)"
+
+
+ENV_FILES = ("env.txt", "graph.txt", "graph.gfa", "seqs.fasta", "tsvs/nodes.tsv", "tsvs/edges.tsv")
+
+
+def test_config4_shape_deep_frontier(oracle, tmp_path):
+    """BASELINE configs[3] at 1/1000 scale: k = 23, --bothdirs, many targets next to planted 3 kb repeats, --maxkmers hit."""
+    from metacherchant_b200 import Context
+    s = oracle.synth(genome_unit=20_000, n_targets=12, repeat_len=3000)
+    data = s.generate(0, 200_000)          # ~27x over 1.1 Mbp
+    fa = tmp_path / "genes.fasta"
+    fa.write_text(s.targets_fasta())
+    c = Context(0)
+    try:
+        g = c.new_table(23).count_bytes(data, FMT_FASTQ)
+        o = oracle.table(23, threads=8).count_bytes(data, FMT_FASTQ)
+        assert g.checksum()["sum_counts"] == o.stats()["kmers"]
+        targets = c.load_targets(fa)
+        solid = g.filter(5)
+        hit_cap = 0
+        for mk in (400, 5000):
+            found = c.find_environments(solid, [t[1] for t in targets], [t[0] for t in targets], min_cov=5, max_kmers=mk, both_dirs=True,
+                                        out_dir=tmp_path / f"gpu{mk}")
+            n = o.env_find(str(fa), 5, mk, None, True, 1, str(tmp_path / f"orc{mk}"))
+            assert sum(found) == n == 12
+            for name, _ in targets:
+                same_tree(str(tmp_path / f"gpu{mk}" / name), str(tmp_path / f"orc{mk}" / name), ENV_FILES)
+                lines = sum(1 for _ in open(tmp_path / f"gpu{mk}" / name / "env.txt"))
+                hit_cap += lines >= mk // 2
+        assert hit_cap >= 12, "the planted repeats should drive most environments into the --maxkmers cap"
+    finally:
+        c.close()
+
+
+def test_config3_shape_two_time_points(oracle, tmp_path):
+    """BASELINE configs[2]: environment-finder on two synthetic time points, then environment-finder-multi on their env.txt."""
+    from metacherchant_b200 import Context
+    c = Context(0)
+    try:
+        envs_g = []
+        base = oracle.synth(genome_unit=10_000, n_targets=2)
+        fa = tmp_path / "genes.fasta"
+        fa.write_text(base.targets_fasta())
+        for tp, (first, n) in enumerate(((0, 60_000), (500_000, 35_000))):    # different read sets and depths of one community
+            data = base.generate(first, n)
+            g = c.new_table(31).count_bytes(data, FMT_FASTQ)
+            o = oracle.table(31, threads=8).count_bytes(data, FMT_FASTQ)
+            targets = c.load_targets(fa)
+            found = c.find_environments(g.filter(3), [t[1] for t in targets], [t[0] for t in targets], min_cov=3, max_kmers=3000, both_dirs=False,
+                                        out_dir=tmp_path / f"gpu_tp{tp}")
+            assert o.env_find(str(fa), 3, 3000, None, False, 1, str(tmp_path / f"orc_tp{tp}")) == sum(found) == 2
+            same_tree(str(tmp_path / f"gpu_tp{tp}" / "gene1"), str(tmp_path / f"orc_tp{tp}" / "gene1"), ENV_FILES)
+            envs_g.append(str(tmp_path / f"gpu_tp{tp}" / "gene1" / "env.txt"))
+        c.multi_environment(envs_g, fa, 2, tmp_path / "gpu_multi")
+        oracle.env_multi(envs_g, str(fa), 2, str(tmp_path / "orc_multi"))   # the Jaccard files quote the env paths: same inputs (identical bytes, checked above)
+        same_tree(str(tmp_path / "gpu_multi"), str(tmp_path / "orc_multi"), ("seqs.fasta", "graph.gfa", "gene.fasta", "Jacard_sym.txt", "Jacard_alt.txt"))
+        gfa = open(tmp_path / "gpu_multi" / "graph.gfa").read()
+        assert "CL:Z:#0000ff" in gfa, "k-mers shared by both time points are coloured blue"
+    finally:
+        c.close()
