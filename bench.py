@@ -10,7 +10,8 @@ compaction].  One "step" = one pass of that path over the synthetic metagenome o
   e2e    — the same job through the C ABI with HOST buffers (mc_count_bytes): H2D copies and the D2H read of
            the result (size of the coverage-filtered table) inside the timed region
 Inputs are >> L2 (15.75 GB of FASTQ per step at cfg2), so no explicit L2 flush is needed between steps.
-The roofline entry is for the dominant kernel (k_extract: extraction fused with the table update);
+The roofline entry is for the counting pipeline (k_extract + k_bin_scatter + k_bin_scatter2 + k_bin_agg: the kernels
+that together do what SURVEY.md 8d's per-read byte figure describes);
 cpu_baseline times the oracle's multi-threaded C++ restatement of the reference on a bounded sample.
 """
 from __future__ import annotations
@@ -148,6 +149,7 @@ def main():
     ap.add_argument("--no-env", action="store_true")
     ap.add_argument("--maxkmers", type=int, default=100000)
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="mc_ctx_set_tuning knob (part_bits, batch_keys, segment_keys)")
+    ap.add_argument("--exchange", default="merge", choices=["merge", "peer", "nccl"], help="N > 1: how the ranks' k-mers reach their owners (metacherchant_b200/dist.py)")
     ap.add_argument("--hint-div", type=int, default=0, help="table capacity hint = bases / this; 0 = none: the library sizes the table from a 1/64 sample of the first batch")
     args = ap.parse_args()
 
@@ -200,7 +202,7 @@ def main():
 
     if world > 1:
         from metacherchant_b200.dist import ShardedCounter
-        counter = ShardedCounter(ctx, k, world, rank, capacity_hint=hint)
+        counter = ShardedCounter(ctx, k, world, rank, capacity_hint=hint, exchange=args.exchange)
 
     def step_device():
         if world > 1:
@@ -324,12 +326,20 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            per_read = json.load(open(prof)).get("pipeline_dram_bytes_per_read")
-            # measured DRAM bytes of the three pipeline kernels per read (ncu, profiles/r1c_NOTES.md) x reads of one step
+            tj = json.load(open(prof))
+            per_read = tj.get("pipeline_dram_bytes_per_read")
+            # measured DRAM bytes of the four pipeline kernels per read (ncu over one full cfg2 step, profiles/r1d_NOTES.md) x reads of one step
             roofline["traffic"] = int(per_read * reads) if per_read else None
-            roofline["traffic_note"] = "ncu dram bytes of k_extract + k_bin_scatter + k_bin_count per read (8 M-read capture) x reads per step"
+            roofline["traffic_note"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of every launch of k_extract + k_bin_scatter + k_bin_scatter2 + k_bin_agg "
+                                        "in one step (profiles/r1d_launches.csv), per read x reads per step")
+            # what the pipeline really moved per second of its own time: the HBM utilisation behind `frac`
+            if per_read and kernel_ms > 0:
+                roofline["dram_gbs_measured_traffic"] = round(per_read * reads * args.steps / (kernel_ms / 1e3) / 1e9, 1)
         except Exception:
             pass
+    # per-stage share of the pipeline (CUDA events on the library's stream): scatter = both bin levels, count = aggregation + table updates
+    if kernel_ms > 0:
+        roofline["pipeline_share"] = {name: round(stages.get(name, 0.0) / kernel_ms, 3) for name in ("extract", "scatter", "count")}
 
     # ---- CPU baseline (rank 0, N = 1): the oracle's multi-threaded restatement on a bounded sample --------------
     cpu = None

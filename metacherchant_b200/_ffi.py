@@ -68,6 +68,9 @@ _SIGNATURES = {
     "mc_xchg_open": (i32, [vp, i32, vp]),
     "mc_xchg_scatter_device": (i32, [vp, vp, sz, i32, i32, i32, vp]),
     "mc_xchg_insert": (i32, [vp, i32, vp, C.POINTER(u64)]),
+    "mc_xchg_dump_owners": (i32, [vp, vp, i32, C.POINTER(u64)]),
+    "mc_xchg_merge": (i32, [vp, i32, vp, C.POINTER(u64)]),
+    "mc_table_copy_stats": (i32, [vp, vp]),
     "mc_xchg_destroy": (None, [vp]),
     "mc_synth_generate_device": (i32, [vp, vp, sz, u64, u64, vp]),
     "mc_device_alloc": (i32, [vp, sz, C.POINTER(vp)]),

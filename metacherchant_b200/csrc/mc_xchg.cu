@@ -186,3 +186,184 @@ extern "C" int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_rec
         return e.code;
     }
 }
+
+// --------------------------------------------------------------------------------------------
+// "count locally, then merge" (include/mc_b200.h): distinct (hashed key, count) pairs instead of key instances cross NVLink
+// --------------------------------------------------------------------------------------------
+// One 32-byte bucket per thread (plus the stash), like k_dump; every live entry is appended to its owner's region as a 16-byte
+// pair.  Appends are warp-aggregated per owner: one atomicAdd on a LOCAL cursor per warp, owner and iteration (the region
+// (slot, my rank) of every peer has this rank as its only writer), and the lanes of a warp store to consecutive positions,
+// so the NVLink stores are full 32-byte sectors.  The scan runs in bucket order = hash order, so a receiver sees its pairs
+// in nearly ascending order of ITS bucket index and the merge walks its shard table almost sequentially.
+__global__ void __launch_bounds__(256) k_dump_owners(McTableDev t, int sb, McBinDst dst, unsigned long long* __restrict__ cursors, uint64_t cap_pairs,
+                                                    unsigned int* flags) {
+    const uint64_t nb = t.nb_mask + 1;
+    const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
+    const uint64_t total = nb + stash_units;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t iters = (total + stride - 1) / stride;   // the same trip count for every lane: the ballots below are convergent
+    const int lane = threadIdx.x & 31;
+    const int world = 1 << sb;
+    uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t it = 0; it < iters; it++, u += stride) {
+        uint64_t h[4];
+        uint32_t c[4] = {0, 0, 0, 0};
+        if (u < nb) {
+            uint64_t w4[4];
+            mc_load_bucket(t.slots + u * 4, w4);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint64_t w = w4[s];
+                const uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
+                h[s] = (((u - d) & t.nb_mask) << t.tag_bits) | (w >> MC_TAG_SHIFT);
+                c[s] = w ? (uint32_t)(w & MC_COUNT_MASK) : 0;
+            }
+        } else if (u < total) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint64_t i = (u - nb) * 4 + s;
+                const uint64_t kx = i <= t.stash_mask ? t.stash_keys[i] : 0;
+                h[s] = kx - 1;
+                c[s] = kx ? t.stash_counts[i] : 0;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            if (c[s] > MC_SAT) c[s] = MC_SAT;
+        for (int o = 0; o < world; o++) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++) mine += c[s] != 0 && (int)(sb ? h[s] >> (62 - sb) : 0) == o;
+            uint32_t incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            if (warp_total == 0) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&cursors[o], (unsigned long long)warp_total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned long long pos = base + incl - mine;
+            if (base + warp_total > cap_pairs) {
+                if (lane == 0) atomicOr(flags, 1u);
+                continue;
+            }
+            ulonglong2* out = (ulonglong2*)dst.base[o];
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (c[s] != 0 && (int)(sb ? h[s] >> (62 - sb) : 0) == o) out[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, const ulonglong2* __restrict__ pairs, uint64_t n) {
+    unsigned long long added = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 p = __ldcs(pairs + i);
+        if (mc_table_add(t, p.x, (uint32_t)p.y)) added++;
+    }
+    __shared__ unsigned long long s_added;
+    if (threadIdx.x == 0) s_added = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&s_added, added);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
+}
+
+extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, uint64_t* n_pairs) {
+    try {
+        if (!x || !local || slot < 0 || slot > 1) mc_throw(MC_ERR_ARG, "bad argument");
+        if (local->dev.shard_bits != 0) mc_throw(MC_ERR_ARG, "exchange: the local table must be unsharded");
+        mc_ctx* ctx = x->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        mc_table_flush(const_cast<mc_table*>(local));
+        for (int r = 0; r < x->world; r++)
+            if (!x->peer[r]) mc_throw(MC_ERR_ARG, "exchange: rank %d's buffer has not been opened", r);
+        MC_CUDA(cudaMemsetAsync(x->d_cursors, 0, (MC_MAX_XCHG_RANKS + 1) * sizeof(unsigned long long), st));
+        McBinDst dst{}, mail{};
+        dst.use = 1;
+        for (int o = 0; o < x->world; o++) {
+            dst.base[o] = x->region(x->peer[o], slot, x->rank);
+            mail.base[o] = (uint64_t*)x->mailbox(x->peer[o], slot);
+        }
+        {
+            McStageTimer tm(ctx, MC_ST_SCATTER);
+            const uint64_t units = local->nb;
+            const int grid = (int)std::min<uint64_t>((units + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            k_dump_owners<<<grid, 256, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+        }
+        k_post_counts<<<1, 32, 0, st>>>(x->d_cursors, mail, x->world, x->rank);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        unsigned int f = 0;
+        unsigned long long cur[MC_MAX_XCHG_RANKS + 1];
+        MC_CUDA(cudaMemcpyAsync(&f, x->d_flags, sizeof f, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(cur, x->d_cursors, sizeof cur, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        if (f) mc_throw(MC_ERR_NOMEM, "exchange: a receive region overflowed");
+        if (n_pairs) {
+            *n_pairs = 0;
+            for (int o = 0; o < x->world; o++) *n_pairs += cur[o];
+        }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_pairs) {
+    try {
+        if (!x || !shard || slot < 0 || slot > 1) mc_throw(MC_ERR_ARG, "bad argument");
+        mc_ctx* ctx = x->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        mc_table_flush(shard);
+        unsigned long long counts[MC_MAX_XCHG_RANKS];
+        MC_CUDA(cudaMemcpyAsync(counts, x->mailbox(x->local, slot), sizeof counts, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        uint64_t total = 0;
+        for (int src = 0; src < x->world; src++) {
+            if (counts[src] > x->region_keys / 2) mc_throw(MC_ERR_CUDA, "exchange: mailbox of rank %d is corrupt", src);
+            total += counts[src];
+        }
+        mc_table_reserve(shard, total);   // every pair may be a new key: no overflow list needed
+        for (int src = 0; src < x->world; src++) {
+            if (counts[src] == 0) continue;
+            McStageTimer tm(ctx, MC_ST_COUNT);
+            const int grid = (int)std::min<uint64_t>((counts[src] + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            k_merge_pairs<<<grid, 256, 0, st>>>(shard->dev, (const ulonglong2*)x->region(x->local, slot, src), counts[src]);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+        }
+        unsigned int f = 0;
+        MC_CUDA(cudaMemcpyAsync(&f, shard->dev.flags, sizeof f, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        if (f & MC_FLAG_OVERFLOW) mc_throw(MC_ERR_NOMEM, "k-mer table overflow while merging the received pairs");
+        if (n_pairs) *n_pairs = total;
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+extern "C" int mc_table_copy_stats(mc_table* dst, const mc_table* src) {
+    try {
+        if (!dst || !src) mc_throw(MC_ERR_ARG, "null argument");
+        MC_CUDA(cudaSetDevice(dst->ctx->device));
+        // counters [2..5]: reads, runs, bases, k-mer instances (mc_table_stats)
+        MC_CUDA(cudaMemcpyAsync(&dst->dev.counters[MC_CNT_READS], &src->dev.counters[MC_CNT_READS], 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice,
+                                dst->ctx->stream));
+        MC_CUDA(cudaStreamSynchronize(dst->ctx->stream));
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}

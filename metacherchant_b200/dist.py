@@ -61,7 +61,9 @@ class ShardedCounter:
 
     def __init__(self, ctx, k: int, world: int, rank: int, capacity_hint: int = 0, exchange: str = "peer"):
         """exchange = "peer": the scatter kernel writes every owner's keys straight into that owner's receive region over
-        NVLink (CUDA-IPC mapped peer memory, csrc/mc_xchg.cu; ranks must share one node); "nccl": all_to_all_single."""
+        NVLink (CUDA-IPC mapped peer memory, csrc/mc_xchg.cu; ranks must share one node); "nccl": all_to_all_single;
+        "merge": count locally, then ship the distinct (key, count) pairs to their owners (also peer memory) -- the choice
+        when a rank's own k-mers fit its GPU: several times fewer bytes cross NVLink."""
         self.ctx, self.k, self.world, self.rank = ctx, k, world, rank
         self.shard_bits = shard_bits_for(world)
         self.capacity_hint = capacity_hint
@@ -164,6 +166,43 @@ class ShardedCounter:
             self.bytes_exchanged += 8 * got.value
         self.ctx.sync()
 
+    def _count_device_merge(self, d_reads: int, nbytes: int, fmt: int):
+        """Count locally, then merge (include/mc_b200.h, mc_xchg_dump_owners): this rank's reads go through the single-GPU
+        pipeline into a complete local table; the table scan then stores every DISTINCT (key, count) pair into its owner's
+        region over NVLink, and each rank adds what it received into its shard.  One barrier, no collective moves data."""
+        import ctypes as C
+        from ._ffi import check
+        lib = self.ctx.lib
+        t0 = time.perf_counter()
+        local = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint)
+        if nbytes:
+            local.count_device(d_reads, nbytes, fmt)
+        n_local = local.size()
+        t1 = time.perf_counter()
+        mx = torch.tensor([n_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        # an owner's share of a table is binomial around size / world: 25 % + a constant is far outside its spread
+        pairs = int(mx.item()) // self.world
+        pairs = pairs + pairs // 4 + (1 << 16)
+        self._peer_setup(2 * pairs)
+        got = C.c_uint64()
+        check(lib.mc_xchg_dump_owners(self._xchg, local.h, 0, C.byref(got)))
+        t2 = time.perf_counter()
+        sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+        dist.all_reduce(sync)                    # every rank's stores into my regions have completed
+        torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter()
+        check(lib.mc_xchg_merge(self._xchg, 0, self.table.h, C.byref(got)))
+        check(lib.mc_table_copy_stats(self.table.h, local.h))
+        local.free()
+        self.ctx.sync()
+        dist.barrier()                           # nobody reuses its regions (next step's dump) before every merge has read them
+        t4 = time.perf_counter()
+        self.bytes_exchanged += 16 * got.value * (self.world - 1) // self.world
+        self.phase_s["extract"] += t1 - t0
+        self.phase_s["exchange"] += t3 - t1
+        self.phase_s["insert"] += t4 - t3
+
     def count_device(self, d_reads: int, nbytes: int, fmt: int, batch_bytes: int, record_bytes: int | None = None):
         """Counts this rank's device-resident reads into the distributed table (collective: every rank must call it
         with the same number of batches; ranks with fewer batches send empty groups).
@@ -171,6 +210,8 @@ class ShardedCounter:
         batch b-1's received keys are binned (library stream)."""
         if self.exchange == "peer":
             return self._count_device_peer(d_reads, nbytes, fmt, batch_bytes, record_bytes)
+        if self.exchange == "merge":
+            return self._count_device_merge(d_reads, nbytes, fmt)
         lib = self.ctx.lib
         batches = plan_batches(nbytes, batch_bytes, record_bytes)
         n_batches = torch.tensor([len(batches)], dtype=torch.int64, device="cuda")

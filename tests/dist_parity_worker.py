@@ -30,13 +30,17 @@ def main():
     ctx.synth_generate_device(s.params_bytes(), rank * per, per, d)
     # both exchanges must give the same shards: NCCL all-to-all and the peer-memory scatter (MC_DIST_EXCHANGE picks one to dump)
     tables = {}
-    for mode in ("nccl", "peer"):
+    for mode in ("nccl", "peer", "merge"):
         counter = ShardedCounter(ctx, k, world, rank, exchange=mode)
         counter.new_table()
         counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)   # several batches
         tables[mode] = counter.table.dump()
+        stats = counter.table.stats()
+        tot = torch.tensor([stats["reads"], stats["kmers"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        assert int(tot[0].item()) == per * world, (mode, stats)
         counter.close_exchange()
-    same = np.array_equal(tables["nccl"][0], tables["peer"][0]) and np.array_equal(tables["nccl"][1], tables["peer"][1])
+    same = all(np.array_equal(tables["nccl"][i], tables[m][i]) for m in ("peer", "merge") for i in (0, 1))
     keys, counts = tables["peer"]
     # gather the shards on rank 0
     n = torch.tensor([keys.size], dtype=torch.int64, device="cuda")
