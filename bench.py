@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--no-env", action="store_true")
     ap.add_argument("--maxkmers", type=int, default=100000)
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE", help="mc_ctx_set_tuning knob (part_bits, batch_keys, segment_keys)")
+    ap.add_argument("--force-sharded", action="store_true", help="profiling: run the N > 1 code path on one rank")
     ap.add_argument("--exchange", default="merge", choices=["merge", "peer", "nccl"], help="N > 1: how the ranks' k-mers reach their owners (metacherchant_b200/dist.py)")
     ap.add_argument("--hint-div", type=int, default=0, help="table capacity hint = bases / this; 0 = none: the library sizes the table from a 1/64 sample of the first batch")
     args = ap.parse_args()
@@ -200,12 +201,13 @@ def main():
     # no rehash when memory allows: distinct k-mers <= k-mer instances <= bases (what mc_count_files does from the file size)
     hint = bases_per_step // args.hint_div if args.hint_div > 0 else 0   # expected distinct k-mers; the table still grows (rehash) on demand beyond this
 
-    if world > 1:
+    sharded = world > 1 or args.force_sharded
+    if sharded:
         from metacherchant_b200.dist import ShardedCounter
         counter = ShardedCounter(ctx, k, world, rank, capacity_hint=hint, exchange=args.exchange)
 
     def step_device():
-        if world > 1:
+        if sharded:
             return counter.count_device_step(d_reads, nbytes, FMT_FASTQ, cov, batch_bytes=args.chunk_mib << 20, record_bytes=rb)
         t = ctx.new_table(k, capacity_hint=hint)
         t.count_device(d_reads, nbytes, FMT_FASTQ)
@@ -362,8 +364,9 @@ def main():
                            "solid_kmers": int(n_solid), "wall_s": round(wall, 3)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "env": env}
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if sharded:
         counter.close_exchange()
+    if world > 1:
         dist.destroy_process_group()
     return 0
 

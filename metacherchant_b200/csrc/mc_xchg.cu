@@ -190,27 +190,31 @@ extern "C" int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_rec
 // --------------------------------------------------------------------------------------------
 // "count locally, then merge" (include/mc_b200.h): distinct (hashed key, count) pairs instead of key instances cross NVLink
 // --------------------------------------------------------------------------------------------
-// One 32-byte bucket per thread (plus the stash), like k_dump; every live entry is appended to its owner's region as a 16-byte
-// pair.  Appends are warp-aggregated per owner: one atomicAdd on a LOCAL cursor per warp, owner and iteration (the region
-// (slot, my rank) of every peer has this rank as its only writer), and the lanes of a warp store to consecutive positions,
-// so the NVLink stores are full 32-byte sectors.  The scan runs in bucket order = hash order, so a receiver sees its pairs
-// in nearly ascending order of ITS bucket index and the merge walks its shard table almost sequentially.
-__global__ void __launch_bounds__(256) k_dump_owners(McTableDev t, int sb, McBinDst dst, unsigned long long* __restrict__ cursors, uint64_t cap_pairs,
-                                                    unsigned int* flags) {
+// One 32-byte bucket per thread and step (plus the stash), like k_dump; every live entry is appended to its owner's region as
+// a 16-byte pair.  Appends are aggregated per CTA: one atomicAdd per owner, CTA and step on a LOCAL cursor (the region
+// (slot, my rank) of every peer has this rank as its only writer).  Per-warp appends were measured first: tens of millions of
+// atomics on ONE address, which the L2 serialises (20 ms for a 16 GB table, 17 % of DRAM peak).  The threads of a CTA store
+// to consecutive positions: whole 32-byte sectors on NVLink.  The grid walks the table in bucket order = hash order, so a
+// receiver sees its pairs in nearly ascending order of ITS bucket index and the merge streams through its shard table.
+#define DUMP_THREADS 512
+__global__ void __launch_bounds__(DUMP_THREADS) k_dump_owners(McTableDev t, int sb, McBinDst dst, unsigned long long* __restrict__ cursors, uint64_t cap_pairs,
+                                                             unsigned int* flags) {
+    __shared__ uint32_t s_tot[MC_MAX_XCHG_RANKS][DUMP_THREADS / 32];
+    __shared__ unsigned long long s_base[MC_MAX_XCHG_RANKS];
     const uint64_t nb = t.nb_mask + 1;
     const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
     const uint64_t total = nb + stash_units;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t iters = (total + stride - 1) / stride;   // the same trip count for every lane: the ballots below are convergent
-    const int lane = threadIdx.x & 31;
+    const uint64_t iters = (total + stride - 1) / stride;   // the same trip count for every thread: the barriers below are convergent
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int world = 1 << sb;
     uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t w4[4] = {0, 0, 0, 0};
+    if (u < nb) mc_load_bucket(t.slots + u * 4, w4);
     for (uint64_t it = 0; it < iters; it++, u += stride) {
         uint64_t h[4];
         uint32_t c[4] = {0, 0, 0, 0};
         if (u < nb) {
-            uint64_t w4[4];
-            mc_load_bucket(t.slots + u * 4, w4);
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 const uint64_t w = w4[s];
@@ -227,41 +231,70 @@ __global__ void __launch_bounds__(256) k_dump_owners(McTableDev t, int sb, McBin
                 c[s] = kx ? t.stash_counts[i] : 0;
             }
         }
+        if (u + stride < nb) mc_load_bucket(t.slots + (u + stride) * 4, w4);   // the next step's bucket is in flight during this one
+        uint32_t own = 0;   // owner of entry s in bits [8s, 8s+8), 0xFF = no entry
 #pragma unroll
-        for (int s = 0; s < 4; s++)
+        for (int s = 0; s < 4; s++) {
             if (c[s] > MC_SAT) c[s] = MC_SAT;
+            own |= (c[s] ? (uint32_t)(sb ? h[s] >> (62 - sb) : 0) : 0xFFu) << (8 * s);
+        }
+        // pass 1: entries per owner and warp (the offsets inside the warp are recomputed in pass 2: cheaper than keeping 16 of them)
         for (int o = 0; o < world; o++) {
             uint32_t mine = 0;
 #pragma unroll
-            for (int s = 0; s < 4; s++) mine += c[s] != 0 && (int)(sb ? h[s] >> (62 - sb) : 0) == o;
+            for (int s = 0; s < 4; s++) mine += ((own >> (8 * s)) & 0xFFu) == (uint32_t)o;
             uint32_t incl = mine;
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += v;
             }
-            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-            if (warp_total == 0) continue;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&cursors[o], (unsigned long long)warp_total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            unsigned long long pos = base + incl - mine;
-            if (base + warp_total > cap_pairs) {
-                if (lane == 0) atomicOr(flags, 1u);
-                continue;
+            if (lane == 31) s_tot[o][warp] = incl;
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            uint32_t tot = 0;
+            for (int w = 0; w < DUMP_THREADS / 32; w++) tot += s_tot[threadIdx.x][w];
+            unsigned long long base = tot ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)tot) : 0ULL;
+            if (base + tot > cap_pairs) {
+                atomicOr(flags, 1u);
+                base = ~0ULL;
             }
+            s_base[threadIdx.x] = base;
+        }
+        __syncthreads();
+        for (int o = 0; o < world; o++) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++) mine += ((own >> (8 * s)) & 0xFFu) == (uint32_t)o;
+            const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+            if (!any) continue;
+            uint32_t incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const unsigned long long base = s_base[o];
+            if (base == ~0ULL || mine == 0) continue;
+            uint32_t before = 0;
+            for (int w = 0; w < warp; w++) before += s_tot[o][w];
+            unsigned long long pos = base + before + incl - mine;
             ulonglong2* out = (ulonglong2*)dst.base[o];
 #pragma unroll
             for (int s = 0; s < 4; s++)
-                if (c[s] != 0 && (int)(sb ? h[s] >> (62 - sb) : 0) == o) out[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
+                if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) out[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
         }
+        __syncthreads();   // s_tot / s_base are rewritten by the next step
     }
 }
 
+// Adds (hashed key, count) pairs to the table; count-0 pairs are padding.  The pairs arrive in hash order, so neighbouring
+// lanes update the same few buckets at the same time: the bucket is read right before its CAS (a version that kept four
+// prefetched buckets per thread lost more to stale copies and failed CAS retries than it gained: 70 ms against 47 ms).
 __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, const ulonglong2* __restrict__ pairs, uint64_t n) {
     unsigned long long added = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const ulonglong2 p = __ldcs(pairs + i);
-        if (mc_table_add(t, p.x, (uint32_t)p.y)) added++;
+        if (p.y && mc_table_add(t, p.x, (uint32_t)p.y)) added++;
     }
     __shared__ unsigned long long s_added;
     if (threadIdx.x == 0) s_added = 0;
@@ -279,7 +312,7 @@ extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, 
         mc_ctx* ctx = x->ctx;
         MC_CUDA(cudaSetDevice(ctx->device));
         cudaStream_t st = ctx->stream;
-        mc_table_flush(const_cast<mc_table*>(local));
+        mc_batch_release(const_cast<mc_table*>(local));   // applies pending updates and returns the bins (tens of GB) to the pool: the shard table needs the room
         for (int r = 0; r < x->world; r++)
             if (!x->peer[r]) mc_throw(MC_ERR_ARG, "exchange: rank %d's buffer has not been opened", r);
         MC_CUDA(cudaMemsetAsync(x->d_cursors, 0, (MC_MAX_XCHG_RANKS + 1) * sizeof(unsigned long long), st));
@@ -292,8 +325,8 @@ extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, 
         {
             McStageTimer tm(ctx, MC_ST_SCATTER);
             const uint64_t units = local->nb;
-            const int grid = (int)std::min<uint64_t>((units + 255) / 256, (uint64_t)ctx->sm_count * 8);
-            k_dump_owners<<<grid, 256, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags);
+            const int grid = (int)std::min<uint64_t>((units + DUMP_THREADS - 1) / DUMP_THREADS, (uint64_t)ctx->sm_count * 4);
+            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
         }

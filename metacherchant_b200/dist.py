@@ -67,7 +67,7 @@ class ShardedCounter:
         self.ctx, self.k, self.world, self.rank = ctx, k, world, rank
         self.shard_bits = shard_bits_for(world)
         self.capacity_hint = capacity_hint
-        self.exchange = exchange if world > 1 else "local"
+        self.exchange = exchange if (world > 1 or exchange == "merge") else "local"   # "merge" also runs on one rank (profiling)
         self._xchg = None
         self._xchg_keys = 0
         self.table = None
@@ -120,17 +120,20 @@ class ShardedCounter:
         check(lib.mc_xchg_create(self.ctx.h, self.world, self.rank, region_keys, C.byref(h)))
         buf = C.create_string_buffer(64)
         check(lib.mc_xchg_handle(h, buf))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(buf.raw))
-        for r, raw in enumerate(handles):
-            if r != self.rank:
-                check(lib.mc_xchg_open(h, r, C.create_string_buffer(raw, 64)))
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(buf.raw))
+            for r, raw in enumerate(handles):
+                if r != self.rank:
+                    check(lib.mc_xchg_open(h, r, C.create_string_buffer(raw, 64)))
         self._xchg, self._xchg_keys = h, region_keys
-        dist.barrier()
+        if self.world > 1:
+            dist.barrier()
 
     def close_exchange(self):
         if self._xchg is not None:
-            dist.barrier()                       # nobody may still be writing into my regions
+            if self.world > 1:
+                dist.barrier()                   # nobody may still be writing into my regions
             self.ctx.lib.mc_xchg_destroy(self._xchg)
             self._xchg = None
 
@@ -180,7 +183,8 @@ class ShardedCounter:
         n_local = local.size()
         t1 = time.perf_counter()
         mx = torch.tensor([n_local], dtype=torch.int64, device="cuda")
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        if self.world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         # an owner's share of a table is binomial around size / world: 25 % + a constant is far outside its spread
         pairs = int(mx.item()) // self.world
         pairs = pairs + pairs // 4 + (1 << 16)
@@ -188,15 +192,17 @@ class ShardedCounter:
         got = C.c_uint64()
         check(lib.mc_xchg_dump_owners(self._xchg, local.h, 0, C.byref(got)))
         t2 = time.perf_counter()
-        sync = torch.zeros(1, dtype=torch.int32, device="cuda")
-        dist.all_reduce(sync)                    # every rank's stores into my regions have completed
-        torch.cuda.current_stream().synchronize()
+        if self.world > 1:
+            sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+            dist.all_reduce(sync)                # every rank's stores into my regions have completed
+            torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
         check(lib.mc_xchg_merge(self._xchg, 0, self.table.h, C.byref(got)))
         check(lib.mc_table_copy_stats(self.table.h, local.h))
         local.free()
         self.ctx.sync()
-        dist.barrier()                           # nobody reuses its regions (next step's dump) before every merge has read them
+        if self.world > 1:
+            dist.barrier()                       # nobody reuses its regions (next step's dump) before every merge has read them
         t4 = time.perf_counter()
         self.bytes_exchanged += 16 * got.value * (self.world - 1) // self.world
         self.phase_s["extract"] += t1 - t0
