@@ -178,10 +178,14 @@ class ShardedCounter:
         lib = self.ctx.lib
         t0 = time.perf_counter()
         local = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint)
+        ta = time.perf_counter()
         if nbytes:
             local.count_device(d_reads, nbytes, fmt)
+        tb = time.perf_counter()
         n_local = local.size()
         t1 = time.perf_counter()
+        if os.environ.get("MC_DIST_PROFILE"):
+            print(f"[rank {self.rank}] local count: new_table {ta - t0:.4f} s, count_device {tb - ta:.4f} s, size {t1 - tb:.4f} s", flush=True)
         mx = torch.tensor([n_local], dtype=torch.int64, device="cuda")
         if self.world > 1:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
