@@ -4,6 +4,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -587,12 +588,17 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
 // --------------------------------------------------------------------------------------------
 // files: format by suffix (ITMO!/io/ReadersUtils.java:27-54), one file after the other (src/io/IOUtils.java:283-316)
 // --------------------------------------------------------------------------------------------
-static int detect_file_format(const std::string& path) {
+static int detect_file_format(const std::string& path, bool* gz) {
     size_t slash = path.find_last_of('/');
     std::string name = slash == std::string::npos ? path : path.substr(slash + 1);
     for (auto& c : name) c = (char)tolower((unsigned char)c);
     auto ends = [&](const char* suf) { size_t m = strlen(suf); return name.size() >= m && name.compare(name.size() - m, m, suf) == 0; };
-    if (ends(".gz") || ends(".bz2")) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (compressed input is not supported by the GPU path)", path.c_str());
+    *gz = false;
+    if (ends(".gz")) {   // "fastq.gz" / "fasta.gz": the same readers over a GZIPInputStream (ReadersUtils.java:36-39, FastqGZReader.java:26-34)
+        *gz = true;
+        name.resize(name.size() - 3);
+    }
+    if (ends(".gz") || ends(".bz2")) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (bz2 input is not supported by the GPU path)", path.c_str());
     if (ends(".binq")) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (binq input is not supported by the GPU path)", path.c_str());
     if (ends(".fastq") || ends(".fq")) return MC_FMT_FASTQ;
     if (ends(".fasta") || ends(".fa") || ends(".fn") || ends(".fna")) return MC_FMT_FASTA;
@@ -602,7 +608,25 @@ static int detect_file_format(const std::string& path) {
 extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
     try {
         if (!ctx || !path || !t) mc_throw(MC_ERR_ARG, "null argument");
-        int fmt = detect_file_format(path);
+        bool gz = false;
+        int fmt = detect_file_format(path, &gz);
+        if (gz) {
+            // host-side inflate (zlib; concatenated members like java.util.zip.GZIPInputStream), then the usual chunked upload.
+            // The whole file is inflated first: the decompressor, not the GPU, bounds a .gz input either way.
+            gzFile g = gzopen(path, "rb");
+            if (!g) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
+            gzbuffer(g, 1 << 20);
+            std::vector<uint8_t> data;
+            std::vector<uint8_t> piece(16 << 20);
+            for (;;) {
+                int got = gzread(g, piece.data(), (unsigned)piece.size());
+                if (got < 0) { gzclose(g); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
+                if (got == 0) break;
+                data.insert(data.end(), piece.begin(), piece.begin() + got);
+            }
+            gzclose(g);
+            return mc_count_bytes(ctx, data.data(), data.size(), fmt, t);
+        }
         int fd = open(path, O_RDONLY);
         if (fd < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
         struct stat sb;

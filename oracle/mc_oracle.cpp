@@ -26,6 +26,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
+#include <zlib.h>
 
 namespace {
 
@@ -544,12 +545,35 @@ std::vector<uint8_t> read_file(const std::string& path) {
     return b;
 }
 
-// ITMO!/io/ReadersUtils.java:27-54
-int detect_format(const std::string& path) {
+// FastqGZReader / FastaGZReader (ITMO!/io/readers/FastqGZReader.java:26-34, FastaGZReader.java:24-32): the plain readers over a
+// java.util.zip.GZIPInputStream, which also reads concatenated members -- like zlib's gzread
+std::vector<uint8_t> read_gz_file(const std::string& path) {
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) fail("Failed to read from file %s", path.c_str());
+    gzbuffer(g, 1 << 20);
+    std::vector<uint8_t> b;
+    std::vector<uint8_t> piece(8 << 20);
+    for (;;) {
+        int got = gzread(g, piece.data(), (unsigned)piece.size());
+        if (got < 0) { gzclose(g); fail("Failed to read from file %s", path.c_str()); }
+        if (got == 0) break;
+        b.insert(b.end(), piece.begin(), piece.begin() + got);
+    }
+    gzclose(g);
+    return b;
+}
+
+// ITMO!/io/ReadersUtils.java:27-54; *gz = the ".gz" suffix was stripped first (:36-39)
+int detect_format(const std::string& path, bool* gz = nullptr) {
     size_t slash = path.find_last_of('/');
     std::string name = slash == std::string::npos ? path : path.substr(slash + 1);
     for (auto& c : name) c = (char)tolower((unsigned char)c);
     auto ends = [&](const char* s) { size_t n = strlen(s); return name.size() >= n && name.compare(name.size() - n, n, s) == 0; };
+    if (gz) *gz = false;
+    if (gz && ends(".gz")) {
+        *gz = true;
+        name.resize(name.size() - 3);
+    }
     if (ends(".gz") || ends(".bz2")) fail("compressed input is out of scope for the hot path: '%s'", name.c_str());
     if (ends(".binq")) fail("binq input is out of scope for the hot path: '%s'", name.c_str());
     if (ends(".fastq") || ends(".fq")) return 1;
@@ -1193,8 +1217,9 @@ int orc_count_bytes(orc_table* t, const uint8_t* buf, size_t len, int fmt) {
 }
 int orc_count_file(orc_table* t, const char* path) {
     return guarded([&] {
-        int fmt = detect_format(path);
-        std::vector<uint8_t> b = read_file(path);
+        bool gz = false;
+        int fmt = detect_format(path, &gz);
+        std::vector<uint8_t> b = gz ? read_gz_file(path) : read_file(path);
         count_source(t, b.data(), b.size(), fmt);
         return 0;
     });

@@ -296,3 +296,30 @@ def test_level_synchronous_rule_equals_fifo_rule():
                     assert (a is None) == (b is None)
                     if a is not None:
                         assert list(a.items()) == list(b.items())
+
+
+def test_gz_input_equals_plain_input(oracle, tmp_path):
+    """`.fastq.gz` / `.fa.gz` are the plain readers over a GZIPInputStream (ReadersUtils.java:36-39,
+    FastqGZReader.java:26-34), concatenated members included; `.bz2` stays outside the path and fails loudly."""
+    import gzip
+    import random
+    from helpers import make_fasta, make_fastq
+    rng = random.Random(11)
+    fq, fa = make_fastq(rng, 400, max_len=90), make_fasta(rng, 200)
+    (tmp_path / "a.fastq").write_bytes(fq)
+    (tmp_path / "a.FQ.gz").write_bytes(gzip.compress(fq[:7001]) + gzip.compress(fq[7001:]))     # two members, upper-case suffix
+    (tmp_path / "b.fa").write_bytes(fa)
+    (tmp_path / "b.fa.gz").write_bytes(gzip.compress(fa))
+    for plain, packed, k in (("a.fastq", "a.FQ.gz", 13), ("b.fa", "b.fa.gz", 9)):
+        p = oracle.table(k)
+        p.count_file(str(tmp_path / plain))
+        g = oracle.table(k)
+        g.count_file(str(tmp_path / packed))
+        assert p.size() > 0 and p.stats() == g.stats()
+        pk, pc = p.dump()
+        gk, gc = g.dump()
+        assert (pk == gk).all() and (pc == gc).all()
+    (tmp_path / "c.fastq.bz2").write_bytes(b"BZh9")
+    import oracle_ffi
+    with pytest.raises(oracle_ffi.OracleError):
+        oracle.table(13).count_file(str(tmp_path / "c.fastq.bz2"))
