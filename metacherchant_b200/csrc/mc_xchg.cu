@@ -197,7 +197,7 @@ extern "C" int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_rec
 // to consecutive positions: whole 32-byte sectors on NVLink.  The grid walks the table in bucket order = hash order, so a
 // receiver sees its pairs in nearly ascending order of ITS bucket index and the merge streams through its shard table.
 #define DUMP_THREADS 512
-__global__ void __launch_bounds__(DUMP_THREADS) k_dump_owners(McTableDev t, int sb, McBinDst dst, unsigned long long* __restrict__ cursors, uint64_t cap_pairs,
+__global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, int sb, McBinDst dst, unsigned long long* __restrict__ cursors, uint64_t cap_pairs,
                                                              unsigned int* flags) {
     __shared__ uint32_t s_tot[MC_MAX_XCHG_RANKS][DUMP_THREADS / 32];
     __shared__ unsigned long long s_base[MC_MAX_XCHG_RANKS];
