@@ -711,44 +711,35 @@ static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target
 }
 
 // graph.txt/env.txt + unitig stage + writers of the found environments; gene nodes are decided against `gene_seqs` (isGeneNode
-// :421-432).  Host stages run on the thread pool, one environment per task; the device stage in between (node hash, neighbour
-// lists, chain ranks: mc_unitig.cu) is issued from the calling thread, environment after environment, on the context's stream.
-struct EnvWork {
-    size_t job = 0;
-    std::vector<uint32_t> ord;
-    McUnitigInput in;
-    McUnitigNodes nodes;
-};
+// :421-432).  One task per environment on the thread pool: host stages run concurrently, the device stage in between (node
+// hash, neighbour lists, chain ranks: mc_unitig.cu) is taken in turns (one stream per context), so it overlaps the other
+// workers' host stages.
 static void write_environments(mc_ctx* ctx, const std::vector<KmerMap>& subs, const std::vector<int>& found,
                                const std::vector<std::vector<std::string>>& gene_seqs, int k, int chunk_len, const std::vector<std::string>& prefixes) {
     std::vector<size_t> todo;
     for (size_t i = 0; i < subs.size(); i++)
         if (found[i]) todo.push_back(i);   // else: "Could not find any k-mers of the target gene in the input, halting."
-    const size_t wave = std::max<size_t>(2 * env_threads(todo.size()), 1);   // bounds the memory held between the phases
-    for (size_t w0 = 0; w0 < todo.size(); w0 += wave) {
-        const size_t nw = std::min(wave, todo.size() - w0);
-        std::vector<EnvWork> work(nw);
-        parallel_for(nw, [&](size_t w) {
-            EnvWork& e = work[w];
-            e.job = todo[w0 + w];
-            const KmerMap& sub = subs[e.job];
-            { EnvTrace tr("subgraph order"); e.ord = sub.order(); }
-            { EnvTrace tr("write env.txt/graph.txt"); write_environment(sub, e.ord, prefixes[e.job]); }
-            { EnvTrace tr("unitig input"); unitig_input_from_subgraph(sub, e.ord, gene_seqs[e.job], k, e.in); }
-        });
+    std::mutex device_turn;
+    parallel_for(todo.size(), [&](size_t w) {
+        const size_t job = todo[w];
+        const KmerMap& sub = subs[job];
+        std::vector<uint32_t> ord;
+        McUnitigInput in;
+        McUnitigNodes nodes;
+        { EnvTrace tr("subgraph order"); ord = sub.order(); }
+        { EnvTrace tr("write env.txt/graph.txt"); write_environment(sub, ord, prefixes[job]); }
+        { EnvTrace tr("unitig input"); unitig_input_from_subgraph(sub, ord, gene_seqs[job], k, in); }
         {
+            std::lock_guard<std::mutex> turn(device_turn);
             EnvTrace tr("unitig nodes (device)");
-            for (size_t w = 0; w < nw; w++) mc_unitig_nodes(ctx, work[w].in, work[w].nodes);
+            mc_unitig_nodes(ctx, in, nodes);
         }
-        parallel_for(nw, [&](size_t w) {
-            EnvWork& e = work[w];
-            Graph g;
-            { EnvTrace tr("graph build"); g.build(e.in, e.nodes); }
-            { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
-            { EnvTrace tr("assemble"); g.assemble(); }
-            { EnvTrace tr("write gfa/fasta/tsv"); write_single_outputs(g, subs[e.job], chunk_len, prefixes[e.job]); }
-        });
-    }
+        Graph g;
+        { EnvTrace tr("graph build"); g.build(in, nodes); }
+        { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
+        { EnvTrace tr("assemble"); g.assemble(); }
+        { EnvTrace tr("write gfa/fasta/tsv"); write_single_outputs(g, sub, chunk_len, prefixes[job]); }
+    });
 }
 
 // --merge / --hicseq / --trim (EnvironmentFinderMain.java:218-233, OneSequenceCalculator.java:168-192,208-216,241-262)
