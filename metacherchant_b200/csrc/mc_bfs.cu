@@ -15,6 +15,8 @@
 // truncates (the equivalence is simulated against the literal loop in tests/, test_level_synchronous_rule_equals_fifo_rule).
 // Once a candidate is refused for the budget nothing can ever be added again (|visited| never shrinks), so the pass ends.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -267,10 +269,26 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
                                   (uint32_t*)(d + o.nout), reqs[i].trim ? d + o.last : nullptr};
         }
         MC_CUDA(cudaMemcpyAsync(d + jobs_off, jobs.data(), jobs.size() * sizeof(McBfsJobDev), cudaMemcpyHostToDevice, st));
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+        const bool trace = getenv("MC_TRACE") != nullptr;   // device time of the kernel alone on stderr
+        if (trace) {
+            cudaEventCreate(&ev_a);
+            cudaEventCreate(&ev_b);
+            cudaEventRecord(ev_a, st);
+        }
         k_bfs<<<(unsigned)jobs.size(), BFS_THREADS, 0, st>>>(t->dev, t->shard_id, k, min_cov, (long long)max_kmers, (long long)max_radius,
                                                             (const McBfsJobDev*)(d + jobs_off));
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
+        if (trace) {
+            cudaEventRecord(ev_b, st);
+            cudaEventSynchronize(ev_b);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_a, ev_b);
+            fprintf(stderr, "[mc trace] k_bfs: %zu passes, %.1f ms on the device, %.1f MiB of work memory\n", jobs.size(), ms, (double)bytes / (1 << 20));
+            cudaEventDestroy(ev_a);
+            cudaEventDestroy(ev_b);
+        }
         std::vector<uint32_t> n_out(todo.size());
         for (size_t w = 0; w < todo.size(); w++)
             MC_CUDA(cudaMemcpyAsync(&n_out[w], d + offs[w].nout, 4, cudaMemcpyDeviceToHost, st));
