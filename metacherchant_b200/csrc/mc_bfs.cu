@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
     // ---- queue loop (:197-213) ----------------------------------------------------------------------------------
     const int NB = j.dir == 0 ? 8 : 4;
     const uint32_t PARENTS = BFS_THREADS / NB;
+    uint32_t steps = 0;
     while (true) {
+        steps++;
         const uint32_t head = s_head, tail = s_tail;
         // --trim (runBfs :197-213 keeps popping after the budget is spent, only to collect lastKmers): once nothing can be
         // added any more the loop goes on "frozen" over the rest of the queue, looking only at which parents have solid neighbours
@@ -194,7 +196,10 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *j.n_out = s_tail;
+    if (threadIdx.x == 0) {
+        j.n_out[0] = s_tail;
+        j.n_out[1] = steps;
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -249,7 +254,7 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
             uint32_t cap = caps[i];
             uint32_t vis_cap = pow2_at_least((uint64_t)cap * 2);
             offs[w] = Off{take(reqs[i].codes.size() + 1), take((size_t)cap * 8), take((size_t)cap * 4), take((size_t)cap * 2),
-                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(4), take(reqs[i].trim ? (size_t)cap : 1), vis_cap};
+                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(8), take(reqs[i].trim ? (size_t)cap : 1), vis_cap};
         }
         size_t jobs_off = take(jobs.size() * sizeof(McBfsJobDev));
         uint8_t* d = nullptr;
@@ -262,7 +267,7 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
                 MC_CUDA(cudaMemcpyAsync(d + o.seq, reqs[i].codes.data(), reqs[i].codes.size(), cudaMemcpyHostToDevice, st));
             MC_CUDA(cudaMemsetAsync(d + o.vk, 0, (size_t)o.vis_cap * 8, st));
             MC_CUDA(cudaMemsetAsync(d + o.vv, 0xFF, (size_t)o.vis_cap * 4, st));
-            MC_CUDA(cudaMemsetAsync(d + o.nout, 0, 4, st));
+            MC_CUDA(cudaMemsetAsync(d + o.nout, 0, 8, st));   // [0] visited count, [1] steps of the queue loop (MC_TRACE)
             if (reqs[i].trim) MC_CUDA(cudaMemsetAsync(d + o.last, 0, caps[i], st));
             jobs[w] = McBfsJobDev{d + o.seq, (uint32_t)reqs[i].codes.size(), reqs[i].dir, (uint64_t*)(d + o.queue), (int32_t*)(d + o.dist),
                                   (int16_t*)(d + o.count), (uint64_t*)(d + o.vk), (uint32_t*)(d + o.vv), caps[i], o.vis_cap - 1,
@@ -285,7 +290,17 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
             cudaEventSynchronize(ev_b);
             float ms = 0;
             cudaEventElapsedTime(&ms, ev_a, ev_b);
-            fprintf(stderr, "[mc trace] k_bfs: %zu passes, %.1f ms on the device, %.1f MiB of work memory\n", jobs.size(), ms, (double)bytes / (1 << 20));
+            uint64_t steps = 0, visited = 0;
+            uint32_t most = 0;
+            for (size_t w = 0; w < todo.size(); w++) {
+                uint32_t v[2] = {0, 0};
+                cudaMemcpy(v, d + offs[w].nout, 8, cudaMemcpyDeviceToHost);
+                if (v[0] != BFS_OVERFLOW) visited += v[0];
+                steps += v[1];
+                most = std::max(most, v[1]);
+            }
+            fprintf(stderr, "[mc trace] k_bfs: %zu passes, %.1f ms on the device, %.1f MiB of work memory; %llu k-mers visited in %llu steps (longest pass %u steps: %.2f us per step)\n",
+                    jobs.size(), ms, (double)bytes / (1 << 20), (unsigned long long)visited, (unsigned long long)steps, most, most ? 1e3 * ms / most : 0.0);
             cudaEventDestroy(ev_a);
             cudaEventDestroy(ev_b);
         }

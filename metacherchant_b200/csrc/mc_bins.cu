@@ -628,6 +628,18 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     B2.shift = B->dev.shift - pb2;
     B2.cap = cap2;
     B2.spill_cap = spill2_cap;
+    struct Staging {   // returned to the pool, and the overflow list detached, also when a step below throws
+        mc_ctx* ctx;
+        mc_table* t;
+        McBinsDev* b;
+        ~Staging() {
+            t->dev.ovf_keys = nullptr;
+            t->dev.ovf_cap = 0;
+            mc_dev_free(ctx, b->keys);
+            mc_dev_free(ctx, b->spill);
+            mc_dev_free(ctx, b->cursors);
+        }
+    } staging{ctx, t, &B2};
     B2.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)g_max * P2 * cap2 * 8, "k-mer sub-bins");
     B2.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)spill2_cap * 8, "k-mer sub-bin spill list");
     const size_t n_cursors = (size_t)g_max * (P2 + 1) + 2;   // + the shared spill cursor + the unit ticket
@@ -767,13 +779,8 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
             keys_known = mc_table_keys(t);
         }
     }
-    t->dev.ovf_keys = nullptr;
-    t->dev.ovf_cap = 0;
     t->seen_instances += batch_keys;
     t->stream_flushes++;
-    mc_dev_free(ctx, B2.keys);
-    mc_dev_free(ctx, B2.spill);
-    mc_dev_free(ctx, B2.cursors);
 }
 
 void mc_table_flush(mc_table* t) {
