@@ -195,8 +195,6 @@ class ShardedCounter:
         self._peer_setup(2 * pairs)
         got = C.c_uint64()
         check(lib.mc_xchg_dump_owners(self._xchg, local.h, 0, C.byref(got)))
-        check(lib.mc_table_copy_stats(self.table.h, local.h))
-        local.free()                             # everything the peers need has left the local table
         t2 = time.perf_counter()
         if self.world > 1:
             sync = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -204,6 +202,8 @@ class ShardedCounter:
             torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
         check(lib.mc_xchg_merge(self._xchg, 0, self.table.h, C.byref(got)))
+        check(lib.mc_table_copy_stats(self.table.h, local.h))
+        local.free()      # after the merge: freeing the 16 GB table earlier cost 37 ms per step (the pool hands the block to the shard's grow, then has to find it again)
         self.ctx.sync()
         if self.world > 1:
             dist.barrier()                       # nobody reuses its regions (next step's dump) before every merge has read them
