@@ -24,7 +24,9 @@
 #include "mc_common.cuh"
 #include "mc_env.hpp"
 
+#ifndef BFS_THREADS
 #define BFS_THREADS 256
+#endif
 #define BFS_OVERFLOW 0xFFFFFFFFu
 
 struct McBfsJobDev {
