@@ -140,6 +140,88 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
         // added any more the loop goes on "frozen" over the rest of the queue, looking only at which parents have solid neighbours
         const bool frozen = s_stop != 0;
         if (head >= tail || (frozen && !j.last)) break;
+        // ---- linear stretch: the queue holds ONE unprocessed k-mer.  The general step below costs five block barriers and ~130
+        // instructions per warp for that one parent; here the first warp walks the chain alone -- same candidates, same order (slot
+        // = lane), same visited set, same budget and radius rules -- until the frontier widens, empties or the pass stops.
+        if (tail - head == 1 && !frozen && !j.last) {
+            if (threadIdx.x < 32) {
+                const uint32_t lane = threadIdx.x;
+                uint32_t h = head, tl = tail;
+                uint64_t kmer = j.queue[h];
+                int32_t dist = j.dist[h];
+                bool stop = false, overflow = false;
+                while (true) {
+                    const int32_t nd = dist + 1;
+                    const bool within = max_radius < 0 || nd <= max_radius;
+                    bool cand = false;
+                    uint64_t nb = 0xFFFFFFFFFFFFFF00ULL | lane;   // distinct per lane: never matches a k-mer or another lane
+                    int c = -1;
+                    if (lane < (uint32_t)NB && within) {
+                        const uint64_t nuc = (NB == 8) ? (lane >> 1) : lane;
+                        const bool left = (j.dir == -1) || (j.dir == 0 && (lane & 1) == 0);
+                        const uint64_t x = left ? ((nuc << (2 * k - 2)) | (kmer >> 2)) : (((kmer << 2) | nuc) & kmask);
+                        c = mc_table_lookup(table, mc_mix62(mc_canonical(x, k)));
+                        if (c >= min_cov) { cand = true; nb = x; }
+                    }
+                    // first occurrence among the neighbours of this parent, then "not visited before" (the same slot protocol as
+                    // vis_find_or_claim; vis_val gets the queue index so that the general step sees the k-mer as visited).
+                    // Claiming all neighbours before the probe answers, to overlap the two round trips, was measured slower
+                    // (2.39 us per step against 1.90: profiles/r1d_NOTES.md).
+                    const unsigned same = __match_any_sync(0xffffffffu, nb);
+                    bool win = cand && (uint32_t)(__ffs(same) - 1) == lane;
+                    uint32_t vpos = 0;
+                    if (win) {
+                        const uint64_t want = nb + 1;
+                        vpos = (uint32_t)(mc_mix62(nb) >> 20) & j.vis_mask;
+                        while (true) {
+                            const uint64_t cur = atomicCAS((unsigned long long*)&j.vis_keys[vpos], 0ULL, (unsigned long long)want);
+                            if (cur == 0) break;
+                            if (cur == want) { win = false; break; }
+                            vpos = (vpos + 1) & j.vis_mask;
+                        }
+                    }
+                    const unsigned winners = __ballot_sync(0xffffffffu, win);
+                    const uint32_t total = __popc(winners), pos = __popc(winners & ((1u << lane) - 1u));
+                    uint32_t accept = total;
+                    if (max_kmers >= 0) {
+                        long long room = max_kmers - (long long)tl;
+                        if (room < 0) room = 0;
+                        if ((long long)total > room) { accept = (uint32_t)room; stop = true; }
+                    }
+                    if (tl + accept > j.cap) { overflow = true; break; }
+                    const bool added = win && pos < accept;
+                    if (added) {
+                        j.queue[tl + pos] = nb;
+                        j.dist[tl + pos] = nd;
+                        j.count[tl + pos] = (int16_t)c;
+                        j.vis_val[vpos] = tl + pos;
+                    } else if (win) {
+                        j.vis_val[vpos] = 0x80000000u | lane;   // claimed but refused by the budget: what the general step leaves behind
+                    }
+                    if (max_radius >= 0 && (long long)dist + 1 > max_radius) stop = true;
+                    h += 1;
+                    tl += accept;
+                    steps++;
+                    if (stop || tl - h != 1) break;
+                    // exactly one k-mer was appended and it is the whole frontier: it is the next parent
+                    const int src = __ffs(__ballot_sync(0xffffffffu, added)) - 1;
+                    kmer = __shfl_sync(0xffffffffu, nb, src);
+                    dist = nd;
+                }
+                if (lane == 0) {
+                    s_head = h;
+                    s_tail = tl;
+                    if (stop) s_stop = 1;
+                    if (overflow) s_stop = 2;
+                }
+            }
+            __syncthreads();
+            if (s_stop == 2) {
+                if (threadIdx.x == 0) *j.n_out = BFS_OVERFLOW;
+                return;
+            }
+            continue;
+        }
         const uint32_t P = min(tail - head, PARENTS);
         const uint32_t t = threadIdx.x;
         bool cand = false, solid = false;
