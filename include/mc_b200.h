@@ -216,6 +216,12 @@ int mc_table_expect_keys(mc_table* t, uint64_t n);
  * out[2] = sum of digest(key) * count mod 2^64 with digest(x) = (x ^ (x >> 29)) * 0xBF58476D1CE4E5B9 + 1, out[3] = largest
  * count.  The sum of shard digests of a sharded table equals the digest of the whole table. */
 int mc_table_checksum(const mc_table* t, int min_count, uint64_t out[4]);
+/* Host only (no device needed; test surface of the environment stage's host logic): iteration order of a
+ * java.util.HashMap<String,Integer> whose keys are the k-mers `codes` (2-bit, A0 G1 C2 T3, first base most significant), put in
+ * this order -- the order of graph.txt / env.txt lines and of node ids (src/algo/OneSequenceCalculator.java:297-310,387-405).
+ * `peak` = the largest size the map ever had (a java HashMap never shrinks; 0 = its final size).  order[i] = index into `codes`
+ * of the i-th entry; *n_out = number of distinct keys. */
+int mc_kmer_hashmap_order(const uint64_t* codes, size_t n, int k, size_t peak, uint32_t* order, size_t* n_out);
 
 #ifdef __cplusplus
 }

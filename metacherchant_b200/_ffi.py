@@ -87,6 +87,7 @@ _SIGNATURES = {
     "mc_table_flush_pending": (i32, [vp]),
     "mc_table_expect_keys": (i32, [vp, u64]),
     "mc_table_checksum": (i32, [vp, i32, C.POINTER(u64)]),
+    "mc_kmer_hashmap_order": (i32, [vp, sz, i32, sz, vp, C.POINTER(sz)]),
 }
 
 

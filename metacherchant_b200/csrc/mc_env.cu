@@ -846,6 +846,30 @@ extern "C" int mc_env_from_graph_txt(mc_ctx* ctx, const char* graph_txt, const c
     }
 }
 
+// host-only test surface: the HashMap order emulation of the environment stage (KmerMap)
+extern "C" int mc_kmer_hashmap_order(const uint64_t* codes, size_t n, int k, size_t peak, uint32_t* order, size_t* n_out) {
+    try {
+        if ((n && (!codes || !order)) || !n_out || k < 1 || k > 31) mc_throw(MC_ERR_ARG, "bad argument");
+        KmerMap m;
+        m.init(k, n);
+        std::vector<uint32_t> first_index;
+        first_index.reserve(n);
+        for (size_t i = 0; i < n; i++) {
+            const size_t before = m.keys.size();
+            m.put(codes[i], (int32_t)i);
+            if (m.keys.size() != before) first_index.push_back((uint32_t)i);
+        }
+        m.peak = std::max(m.peak, peak);
+        const std::vector<uint32_t> ord = m.order();
+        for (size_t i = 0; i < ord.size(); i++) order[i] = first_index[ord[i]];
+        *n_out = ord.size();
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Seam 4: environment-finder-multi
 // ------------------------------------------------------------------------------------------------
