@@ -70,3 +70,84 @@ def test_bad_arguments():
     n = C.c_size_t()
     assert lib.mc_kmer_hashmap_order(None, 0, 32, 0, None, C.byref(n)) != 0
     assert lib.mc_kmer_hashmap_order(None, 0, 5, 0, None, C.byref(n)) == 0 and n.value == 0
+
+
+# ---- target loading: RichFastaReader.readAll (src/io/RichFastaReader.java:38-76) + new DnaQ(str, 0).toString() ---------------
+def rich_fasta_reader(text: str):
+    """Literal transcription of readAll: returns (dnas, comments)."""
+    dnas, comments = [], []
+    last_comment, cur_comment, cur_dna = True, "", ""
+    for line in pyref.java_lines(text.encode()):
+        if line.startswith(">") or line.startswith(";"):
+            if not last_comment:
+                dnas.append(cur_dna)
+                cur_dna, cur_comment = "", ""
+            cur_comment += line[1:]
+            last_comment = True
+        else:
+            if last_comment:
+                comments.append(cur_comment)
+                cur_dna, cur_comment = "", ""
+            cur_dna += line
+            last_comment = False
+    if cur_comment:
+        comments.append(cur_comment)
+    if cur_dna:
+        dnas.append(cur_dna)
+    # DnaQ(str, 0): N, n, '.' -> nucleotide 0 ('A'), lower case accepted, toString() upper case (ITMO!/dna/DnaQ.java:21-30)
+    tr = {"N": "A", "n": "A", ".": "A"}
+    return ["".join(tr.get(c, c.upper()) for c in d) for d in dnas], comments
+
+
+def lib_targets(path):
+    lib = _ffi.load_library()
+    h = C.c_void_p()
+    rc = lib.mc_targets_load(str(path).encode(), C.byref(h))
+    assert rc == 0, lib.mc_last_error()
+    try:
+        n = lib.mc_targets_count(h)
+        seqs = [lib.mc_targets_seq(h, i).decode() for i in range(n)]
+        names = []
+        i = 0
+        while True:
+            name = lib.mc_targets_name(h, i)
+            if name is None:
+                break
+            names.append(name.decode())
+            i += 1
+        return seqs, names
+    finally:
+        lib.mc_targets_free(h)
+
+
+TARGET_FILES = {
+    "plain": ">gene one\nACGTACGT\nTTGA\n>two\nGGGCCC\n",
+    "headerless (the Hi-C example's seq.fasta)": "ACGTTGCAACGT\n",
+    "multi-line header": ">part1\n;part2\nACGT\nAC\n",
+    "crlf, lower case, N and dot": ">g\r\nacgtNn.\r\nTT\r\n",
+    "header only at the end": ">a\nACGT\n>dangling\n",
+    "empty header": ">\nACGT\n",
+    "no final newline": ">x\nACGT",
+    "semicolon header": ";old style\nACGTAC\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(TARGET_FILES))
+def test_target_loading_matches_rich_fasta_reader(tmp_path, name):
+    p = tmp_path / "t.fasta"
+    p.write_text(TARGET_FILES[name], newline="")
+    seqs, names = lib_targets(p)
+    want_seqs, want_names = rich_fasta_reader(TARGET_FILES[name])
+    assert seqs == want_seqs
+    assert names == want_names
+
+
+def test_target_loading_errors(tmp_path):
+    lib = _ffi.load_library()
+    h = C.c_void_p()
+    assert lib.mc_targets_load(str(tmp_path / "missing.fasta").encode(), C.byref(h)) != 0
+    assert b"Could not load sequences from" in (lib.mc_last_error() or b"")
+    p = tmp_path / "bad.fasta"
+    p.write_text(">g\nACGTXACGT\n")
+    assert lib.mc_targets_load(str(p).encode(), C.byref(h)) != 0
+    assert b"Incorrect nucleotide char" in (lib.mc_last_error() or b"")
