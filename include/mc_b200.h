@@ -216,6 +216,11 @@ int mc_table_expect_keys(mc_table* t, uint64_t n);
  * out[2] = sum of digest(key) * count mod 2^64 with digest(x) = (x ^ (x >> 29)) * 0xBF58476D1CE4E5B9 + 1, out[3] = largest
  * count.  The sum of shard digests of a sharded table equals the digest of the whole table. */
 int mc_table_checksum(const mc_table* t, int min_count, uint64_t out[4]);
+/* Host only: the reader set-up of ReadersUtils -- format by file suffix (ITMO!/io/ReadersUtils.java:27-54; returns MC_FMT_FASTA or
+ * MC_FMT_FASTQ, *gz = 1 for a ".gz" name, or a negative mc_status with the reference's message) and the FASTQ quality offset
+ * sniffed on the first 1000 records (:63-77; returns 33 or 64). */
+int mc_detect_file_format(const char* path, int* gz);
+int mc_sniff_quality_offset(const void* buf, size_t len);
 /* Host only (no device needed; test surface of the environment stage's host logic): iteration order of a
  * java.util.HashMap<String,Integer> whose keys are the k-mers `codes` (2-bit, A0 G1 C2 T3, first base most significant), put in
  * this order -- the order of graph.txt / env.txt lines and of node ids (src/algo/OneSequenceCalculator.java:297-310,387-405).

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "mc_table_expect_keys": (i32, [vp, u64]),
     "mc_table_checksum": (i32, [vp, i32, C.POINTER(u64)]),
     "mc_kmer_hashmap_order": (i32, [vp, sz, i32, sz, vp, C.POINTER(sz)]),
+    "mc_detect_file_format": (i32, [cp, C.POINTER(i32)]),
+    "mc_sniff_quality_offset": (i32, [vp, sz]),
 }
 
 

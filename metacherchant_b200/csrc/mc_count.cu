@@ -605,6 +605,26 @@ static int detect_file_format(const std::string& path, bool* gz) {
     mc_throw(MC_ERR_IO, "Failed to read from file %s", path.c_str());   // "Can't detect file format" wrapped by IOUtils.java:292
 }
 
+extern "C" int mc_detect_file_format(const char* path, int* gz) {
+    try {
+        if (!path) mc_throw(MC_ERR_ARG, "null argument");
+        bool z = false;
+        const int fmt = detect_file_format(path, &z);
+        if (gz) *gz = z ? 1 : 0;
+        return fmt;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+extern "C" int mc_sniff_quality_offset(const void* buf, size_t len) {
+    if (len && !buf) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    return resolve_qoff_host((const uint8_t*)buf, len, MC_FMT_FASTQ);
+}
+
 extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
     try {
         if (!ctx || !path || !t) mc_throw(MC_ERR_ARG, "null argument");

@@ -151,3 +151,36 @@ def test_target_loading_errors(tmp_path):
     p.write_text(">g\nACGTXACGT\n")
     assert lib.mc_targets_load(str(p).encode(), C.byref(h)) != 0
     assert b"Incorrect nucleotide char" in (lib.mc_last_error() or b"")
+
+
+# ---- reader set-up: format by suffix and quality-offset sniffing (ITMO!/io/ReadersUtils.java:27-54,63-77) ---------------------
+@pytest.mark.parametrize("name", ["a.fastq", "A.FQ", "x/y.fasta", "b.fa", "c.fn", "d.fna", "r1.fastq.gz", "R.FA.GZ", "reads.txt", "a.fastq.bz2",
+                                  "b.binq", "noext", "a.fastq.gz.gz"])
+def test_format_detection_matches_the_oracle(oracle, name):
+    import oracle_ffi
+    lib = _ffi.load_library()
+    gz = C.c_int(-1)
+    got = lib.mc_detect_file_format(name.encode(), C.byref(gz))
+    plain = name[:-3] if name.lower().endswith(".gz") else name
+    try:
+        want = oracle.detect_format(plain)           # the oracle's suffix rules on the name without ".gz"
+    except oracle_ffi.OracleError:
+        want = None
+    if want is None:
+        assert got < 0 and b"Failed to read from file" in (lib.mc_last_error() or b"")
+    else:
+        assert got == want and gz.value == int(name.lower().endswith(".gz"))
+
+
+def test_quality_offset_sniffing_matches_pyref():
+    from helpers import make_fastq
+    lib = _ffi.load_library()
+    rng = random.Random(21)
+    cases = [make_fastq(rng, 50, offset=64), make_fastq(rng, 50, offset=33), make_fastq(rng, 1500, offset=64, max_len=30),
+             make_fastq(rng, 3, offset=64, crlf=True), b"", b"@r\nACGT\n+\nIIII\n", b"@r\nACGT\n+\nhhhh\n"]
+    # a low quality character only after the first 1000 records does not change the verdict (and crashes the Java reader later)
+    late = make_fastq(rng, 1001, offset=64, p_n=0, max_len=20, min_len=5, final_newline=True) + b"@late\nACGT\n+\n!!!!\n"
+    cases.append(late)
+    for data in cases:
+        got = lib.mc_sniff_quality_offset(data, len(data))
+        assert got == pyref.sniff_offset(data), data[:60]
