@@ -217,7 +217,7 @@ int mc_table_expect_keys(mc_table* t, uint64_t n);
  * count.  The sum of shard digests of a sharded table equals the digest of the whole table. */
 int mc_table_checksum(const mc_table* t, int min_count, uint64_t out[4]);
 /* Host only: the reader set-up of ReadersUtils -- format by file suffix (ITMO!/io/ReadersUtils.java:27-54; returns MC_FMT_FASTA or
- * MC_FMT_FASTQ, *gz = 1 for a ".gz" name, or a negative mc_status with the reference's message) and the FASTQ quality offset
+ * MC_FMT_FASTQ, *gz = 1 for a ".gz" name and 2 for a ".bz2" name, or a negative mc_status with the reference's message) and the FASTQ quality offset
  * sniffed on the first 1000 records (:63-77; returns 33 or 64). */
 int mc_detect_file_format(const char* path, int* gz);
 int mc_sniff_quality_offset(const void* buf, size_t len);

@@ -4,6 +4,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -588,17 +589,71 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
 // --------------------------------------------------------------------------------------------
 // files: format by suffix (ITMO!/io/ReadersUtils.java:27-54), one file after the other (src/io/IOUtils.java:283-316)
 // --------------------------------------------------------------------------------------------
-static int detect_file_format(const std::string& path, bool* gz) {
+// libbz2 through dlopen: the image ships libbz2.so.1.0 but no bzlib.h; the structure and the three entry points used are the
+// library's stable public ABI (bzlib.h 1.0.x).  Concatenated streams are read one after the other, like
+// org.apache.hadoop.io.compress.BZip2Codec (ITMO!/io/readers/FastqBZ2Reader.java:26-34, FastaBZ2Reader.java).
+struct McBzStream {
+    char* next_in;
+    unsigned int avail_in, total_in_lo32, total_in_hi32;
+    char* next_out;
+    unsigned int avail_out, total_out_lo32, total_out_hi32;
+    void* state;
+    void* (*bzalloc)(void*, int, int);
+    void (*bzfree)(void*, void*);
+    void* opaque;
+};
+static void inflate_bz2(const char* path, const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+    typedef int (*init_t)(McBzStream*, int, int);
+    typedef int (*step_t)(McBzStream*);
+    static void* lib = nullptr;
+    if (!lib) lib = dlopen("libbz2.so.1.0", RTLD_NOW);
+    if (!lib) lib = dlopen("libbz2.so.1", RTLD_NOW);
+    if (!lib) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (libbz2 is not installed)", path);
+    const init_t init = (init_t)dlsym(lib, "BZ2_bzDecompressInit");
+    const step_t step = (step_t)dlsym(lib, "BZ2_bzDecompress"), end = (step_t)dlsym(lib, "BZ2_bzDecompressEnd");
+    if (!init || !step || !end) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (libbz2 lacks the decompression entry points)", path);
+    std::vector<uint8_t> piece(16 << 20);
+    size_t pos = 0;
+    while (pos < n) {
+        McBzStream z{};
+        if (init(&z, 0, 0) != 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
+        z.next_in = (char*)in + pos;
+        z.avail_in = (unsigned)std::min<size_t>(n - pos, 1u << 30);
+        int rc = 0;
+        while (rc != 4) {   // BZ_STREAM_END
+            z.next_out = (char*)piece.data();
+            z.avail_out = (unsigned)piece.size();
+            const unsigned in_before = z.avail_in;
+            rc = step(&z);
+            if (rc != 0 && rc != 4) { end(&z); mc_throw(MC_ERR_IO, "Failed to read from file %s (corrupt bzip2 stream)", path); }
+            out.insert(out.end(), piece.begin(), piece.begin() + (piece.size() - z.avail_out));
+            pos += in_before - z.avail_in;
+            if (rc == 0 && z.avail_in == 0) {
+                if (pos >= n) { end(&z); mc_throw(MC_ERR_IO, "Failed to read from file %s (truncated bzip2 stream)", path); }
+                z.next_in = (char*)in + pos;
+                z.avail_in = (unsigned)std::min<size_t>(n - pos, 1u << 30);
+            }
+        }
+        end(&z);
+    }
+}
+
+// *gz: 0 plain, 1 ".gz", 2 ".bz2" (ReadersUtils strips ".gz", then ".bz2": ITMO!/io/ReadersUtils.java:36-43)
+static int detect_file_format(const std::string& path, int* gz) {
     size_t slash = path.find_last_of('/');
     std::string name = slash == std::string::npos ? path : path.substr(slash + 1);
     for (auto& c : name) c = (char)tolower((unsigned char)c);
     auto ends = [&](const char* suf) { size_t m = strlen(suf); return name.size() >= m && name.compare(name.size() - m, m, suf) == 0; };
-    *gz = false;
+    *gz = 0;
     if (ends(".gz")) {   // "fastq.gz" / "fasta.gz": the same readers over a GZIPInputStream (ReadersUtils.java:36-39, FastqGZReader.java:26-34)
-        *gz = true;
+        *gz = 1;
         name.resize(name.size() - 3);
     }
-    if (ends(".gz") || ends(".bz2")) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (bz2 input is not supported by the GPU path)", path.c_str());
+    if (ends(".bz2")) {  // "fastq.bz2" / "fasta.bz2": the same readers over Hadoop's BZip2Codec stream
+        *gz = 2;
+        name.resize(name.size() - 4);
+    }
+    if (ends(".gz") || ends(".bz2")) mc_throw(MC_ERR_IO, "Failed to read from file %s", path.c_str());   // "Can't detect file format"
     if (ends(".binq")) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (binq input is not supported by the GPU path)", path.c_str());
     if (ends(".fastq") || ends(".fq")) return MC_FMT_FASTQ;
     if (ends(".fasta") || ends(".fa") || ends(".fn") || ends(".fna")) return MC_FMT_FASTA;
@@ -608,9 +663,9 @@ static int detect_file_format(const std::string& path, bool* gz) {
 extern "C" int mc_detect_file_format(const char* path, int* gz) {
     try {
         if (!path) mc_throw(MC_ERR_ARG, "null argument");
-        bool z = false;
+        int z = 0;
         const int fmt = detect_file_format(path, &z);
-        if (gz) *gz = z ? 1 : 0;
+        if (gz) *gz = z;
         return fmt;
     } catch (const McError& e) {
         mc_set_error(e.what());
@@ -628,9 +683,29 @@ extern "C" int mc_sniff_quality_offset(const void* buf, size_t len) {
 extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
     try {
         if (!ctx || !path || !t) mc_throw(MC_ERR_ARG, "null argument");
-        bool gz = false;
+        int gz = 0;
         int fmt = detect_file_format(path, &gz);
-        if (gz) {
+        if (gz == 2) {   // whole file through libbz2 on the host, then the usual chunked upload
+            int fd = open(path, O_RDONLY);
+            if (fd < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
+            struct stat sb;
+            if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
+            const size_t len = (size_t)sb.st_size;
+            void* map = len ? mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+            if (len && map == MAP_FAILED) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
+            std::vector<uint8_t> data;
+            try {
+                inflate_bz2(path, (const uint8_t*)map, len, data);
+            } catch (...) {
+                if (len) munmap(map, len);
+                close(fd);
+                throw;
+            }
+            if (len) munmap(map, len);
+            close(fd);
+            return mc_count_bytes(ctx, data.data(), data.size(), fmt, t);
+        }
+        if (gz == 1) {
             // host-side inflate (zlib; concatenated members like java.util.zip.GZIPInputStream), then the usual chunked upload.
             // The whole file is inflated first: the decompressor, not the GPU, bounds a .gz input either way.
             gzFile g = gzopen(path, "rb");

@@ -27,6 +27,7 @@
 #include <unordered_set>
 #include <vector>
 #include <zlib.h>
+#include <dlfcn.h>
 
 namespace {
 
@@ -563,16 +564,71 @@ std::vector<uint8_t> read_gz_file(const std::string& path) {
     return b;
 }
 
-// ITMO!/io/ReadersUtils.java:27-54; *gz = the ".gz" suffix was stripped first (:36-39)
-int detect_format(const std::string& path, bool* gz = nullptr) {
+
+// libbz2 through dlopen: the image ships libbz2.so.1.0 but no bzlib.h; the structure and the three entry points below are
+// the library's stable public ABI (bzlib.h 1.0.x).  Concatenated streams are read one after the other, like
+// org.apache.hadoop.io.compress.BZip2Codec (ITMO!/io/readers/FastqBZ2Reader.java:26-34, FastaBZ2Reader.java).
+struct OrcBzStream {
+    char* next_in;
+    unsigned int avail_in, total_in_lo32, total_in_hi32;
+    char* next_out;
+    unsigned int avail_out, total_out_lo32, total_out_hi32;
+    void* state;
+    void* (*bzalloc)(void*, int, int);
+    void (*bzfree)(void*, void*);
+    void* opaque;
+};
+std::vector<uint8_t> read_bz2_file(const std::string& path) {
+    typedef int (*init_t)(OrcBzStream*, int, int);
+    typedef int (*step_t)(OrcBzStream*);
+    void* lib = dlopen("libbz2.so.1.0", RTLD_NOW);
+    if (!lib) lib = dlopen("libbz2.so.1", RTLD_NOW);
+    if (!lib) fail("Failed to read from file %s (libbz2 is not installed)", path.c_str());
+    init_t init = (init_t)dlsym(lib, "BZ2_bzDecompressInit");
+    step_t step = (step_t)dlsym(lib, "BZ2_bzDecompress"), end = (step_t)dlsym(lib, "BZ2_bzDecompressEnd");
+    if (!init || !step || !end) fail("Failed to read from file %s (libbz2 lacks the decompression entry points)", path.c_str());
+    std::vector<uint8_t> in = read_file(path), out;
+    std::vector<uint8_t> piece(8 << 20);
+    size_t pos = 0;
+    while (pos < in.size()) {
+        OrcBzStream z{};
+        if (init(&z, 0, 0) != 0) fail("Failed to read from file %s", path.c_str());
+        z.next_in = (char*)in.data() + pos;
+        z.avail_in = (unsigned)std::min<size_t>(in.size() - pos, 1u << 30);
+        int rc = 0;
+        while (rc != 4) {   // BZ_STREAM_END
+            z.next_out = (char*)piece.data();
+            z.avail_out = (unsigned)piece.size();
+            const unsigned in_before = z.avail_in;
+            rc = step(&z);
+            if (rc != 0 && rc != 4) { end(&z); fail("Failed to read from file %s (corrupt bzip2 stream)", path.c_str()); }
+            out.insert(out.end(), piece.begin(), piece.begin() + (piece.size() - z.avail_out));
+            pos += in_before - z.avail_in;
+            if (rc == 0 && z.avail_in == 0) {
+                if (pos >= in.size()) { end(&z); fail("Failed to read from file %s (truncated bzip2 stream)", path.c_str()); }
+                z.next_in = (char*)in.data() + pos;
+                z.avail_in = (unsigned)std::min<size_t>(in.size() - pos, 1u << 30);
+            }
+        }
+        end(&z);
+    }
+    return out;
+}
+
+// ITMO!/io/ReadersUtils.java:27-54; *gz = 1 / 2: the ".gz" / ".bz2" suffix was stripped first (:36-43)
+int detect_format(const std::string& path, int* gz = nullptr) {
     size_t slash = path.find_last_of('/');
     std::string name = slash == std::string::npos ? path : path.substr(slash + 1);
     for (auto& c : name) c = (char)tolower((unsigned char)c);
     auto ends = [&](const char* s) { size_t n = strlen(s); return name.size() >= n && name.compare(name.size() - n, n, s) == 0; };
-    if (gz) *gz = false;
+    if (gz) *gz = 0;
     if (gz && ends(".gz")) {
-        *gz = true;
+        *gz = 1;
         name.resize(name.size() - 3);
+    }
+    if (gz && ends(".bz2")) {   // ReadersUtils strips ".gz" and then ".bz2" (a ".bz2.gz" name reads as bz2: kept)
+        *gz = 2;
+        name.resize(name.size() - 4);
     }
     if (ends(".gz") || ends(".bz2")) fail("compressed input is out of scope for the hot path: '%s'", name.c_str());
     if (ends(".binq")) fail("binq input is out of scope for the hot path: '%s'", name.c_str());
@@ -1217,9 +1273,9 @@ int orc_count_bytes(orc_table* t, const uint8_t* buf, size_t len, int fmt) {
 }
 int orc_count_file(orc_table* t, const char* path) {
     return guarded([&] {
-        bool gz = false;
+        int gz = 0;
         int fmt = detect_format(path, &gz);
-        std::vector<uint8_t> b = gz ? read_gz_file(path) : read_file(path);
+        std::vector<uint8_t> b = gz == 1 ? read_gz_file(path) : gz == 2 ? read_bz2_file(path) : read_file(path);
         count_source(t, b.data(), b.size(), fmt);
         return 0;
     });

@@ -266,14 +266,17 @@ def test_binned_growth_from_an_empty_hint(oracle, agg):
 
 
 def test_gz_files_through_the_file_api(ctx, oracle, tmp_path):
-    """mc_count_files on `.fastq.gz` + `.fa.gz` (host-side inflate) == the oracle on the same files."""
+    """mc_count_files on `.fastq.gz` / `.fa.gz` / `.fq.bz2` / `.fasta.bz2` (host-side inflate) == the oracle on the same files."""
     import gzip
     rng = random.Random(12)
     fq, fa = make_fastq(rng, 3000, max_len=120), make_fasta(rng, 1500)
-    paths = [str(tmp_path / "r1.fastq.gz"), str(tmp_path / "r2.fa.gz"), str(tmp_path / "r3.fq")]
+    import bz2
+    paths = [str(tmp_path / "r1.fastq.gz"), str(tmp_path / "r2.fa.gz"), str(tmp_path / "r3.fq"), str(tmp_path / "r4.fq.bz2"), str(tmp_path / "r5.fasta.bz2")]
     open(paths[0], "wb").write(gzip.compress(fq[:50_000]) + gzip.compress(fq[50_000:]))
     open(paths[1], "wb").write(gzip.compress(fa))
     open(paths[2], "wb").write(fq)
+    open(paths[3], "wb").write(bz2.compress(fq[:70_000]) + bz2.compress(fq[70_000:]))
+    open(paths[4], "wb").write(bz2.compress(fa))
     g = ctx.load_reads(paths, 17)
     o = oracle.table(17, threads=4)
     for p in paths:
@@ -281,6 +284,6 @@ def test_gz_files_through_the_file_api(ctx, oracle, tmp_path):
     assert_same_table(g, o)
     assert g.stats() == o.stats()
     from metacherchant_b200._ffi import McError
-    open(tmp_path / "x.fastq.bz2", "wb").write(b"BZh9")
+    open(tmp_path / "x.fastq.bz2", "wb").write(b"BZh9" + b"garbage" * 10)
     with pytest.raises(McError):
         ctx.load_reads([str(tmp_path / "x.fastq.bz2")], 17)

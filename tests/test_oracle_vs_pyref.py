@@ -300,7 +300,7 @@ def test_level_synchronous_rule_equals_fifo_rule():
 
 def test_gz_input_equals_plain_input(oracle, tmp_path):
     """`.fastq.gz` / `.fa.gz` are the plain readers over a GZIPInputStream (ReadersUtils.java:36-39,
-    FastqGZReader.java:26-34), concatenated members included; `.bz2` stays outside the path and fails loudly."""
+    FastqGZReader.java:26-34), concatenated members included; `.bz2` likewise (FastqBZ2Reader.java:26-34)."""
     import gzip
     import random
     from helpers import make_fasta, make_fastq
@@ -319,7 +319,18 @@ def test_gz_input_equals_plain_input(oracle, tmp_path):
         pk, pc = p.dump()
         gk, gc = g.dump()
         assert (pk == gk).all() and (pc == gc).all()
-    (tmp_path / "c.fastq.bz2").write_bytes(b"BZh9")
+    # .bz2: the same readers over Hadoop's BZip2Codec stream, which also reads concatenated streams
+    import bz2
     import oracle_ffi
+    (tmp_path / "a.fq.bz2").write_bytes(bz2.compress(fq[:9000]) + bz2.compress(fq[9000:]))
+    (tmp_path / "b.fasta.bz2").write_bytes(bz2.compress(fa))
+    for plain, packed, k in (("a.fastq", "a.fq.bz2", 13), ("b.fa", "b.fasta.bz2", 9)):
+        p = oracle.table(k)
+        p.count_file(str(tmp_path / plain))
+        g = oracle.table(k)
+        g.count_file(str(tmp_path / packed))
+        assert p.stats() == g.stats()
+        assert all((a == b).all() for a, b in zip(p.dump(), g.dump()))
+    (tmp_path / "c.fastq.bz2").write_bytes(b"BZh9" + b"garbage" * 10)
     with pytest.raises(oracle_ffi.OracleError):
         oracle.table(13).count_file(str(tmp_path / "c.fastq.bz2"))
