@@ -13,6 +13,16 @@ from metacherchant_b200 import _ffi
 from oracle import pyref
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hic_example1")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built_library():
+    """The product library is built in-tree (nvcc cross-compiles without a GPU); the host-only entry points need no device."""
+    import subprocess
+    if not os.path.exists(_ffi.lib_path()):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "metacherchant_b200", "csrc"), "-j", "8"], check=True)
+    return _ffi.load_library()
 
 
 def lib_order(codes, k, peak=0):
