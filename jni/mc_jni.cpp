@@ -96,6 +96,27 @@ JNIEXPORT void JNICALL Java_io_NativeCounter_findEnvironments(JNIEnv* env, jclas
     if (rc != MC_OK) throw_execution_failed(env);
 }
 
+// void io.NativeCounter.findEnvironmentsEx(long ctx, long table, String[] seqs, String[] names, String[] hicSeqs, int k, int minCov,
+//        long maxKmers, long maxRadius, boolean bothDirs, int chunkLength, boolean merge, boolean trim, String outDir)
+//   ~ the same loop with --merge (one OneSequenceCalculator over every target and Hi-C sequence, output <out>/merged/),
+//     --hicseq and --trim (src/tools/EnvironmentFinderMain.java:146-150,218-233, src/algo/OneSequenceCalculator.java:168-192,208-216,241-262)
+JNIEXPORT void JNICALL Java_io_NativeCounter_findEnvironmentsEx(JNIEnv* env, jclass, jlong ctx, jlong table, jobjectArray seqs, jobjectArray names,
+                                                                jobjectArray hicSeqs, jint k, jint minCov, jlong maxKmers, jlong maxRadius,
+                                                                jboolean bothDirs, jint chunkLength, jboolean merge, jboolean trim, jstring outDir) {
+    std::vector<std::string> s = to_strings(env, seqs), nm = to_strings(env, names), hic = to_strings(env, hicSeqs);
+    std::vector<const char*> sp = c_strs(s), np = c_strs(nm), hp = c_strs(hic);
+    const char* od = env->GetStringUTFChars(outDir, nullptr);
+    mc_table* solid = nullptr;
+    int rc = mc_table_filter((mc_ctx*)ctx, (mc_table*)table, minCov, &solid);
+    if (rc == MC_OK) {
+        rc = mc_env_find_ex((mc_ctx*)ctx, solid, sp.data(), np.data(), (int)sp.size(), hp.data(), (int)hp.size(), k, minCov, maxKmers, maxRadius,
+                            bothDirs ? 1 : 0, chunkLength, merge ? 1 : 0, trim ? 1 : 0, od, nullptr);
+        mc_table_free(solid);
+    }
+    env->ReleaseStringUTFChars(outDir, od);
+    if (rc != MC_OK) throw_execution_failed(env);
+}
+
 // void io.NativeCounter.multiEnvironment(long ctx, String[] envFiles, String seqFasta, int geneId, String outDir)
 //   ~ MultiSequenceCalculator(...).run() + printGene + printProbability (src/tools/EnvironmentFinderMultiMain.java:81-91)
 JNIEXPORT void JNICALL Java_io_NativeCounter_multiEnvironment(JNIEnv* env, jclass, jlong ctx, jobjectArray envFiles, jstring seqFasta, jint geneId,
