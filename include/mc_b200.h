@@ -51,6 +51,12 @@ void mc_ctx_destroy(mc_ctx* ctx);
 int mc_ctx_set_chunk_bytes(mc_ctx* ctx, size_t bytes);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 uint64_t mc_ctx_launches(const mc_ctx* ctx);
+/* Device blocks freed by the library (tables, bins, temporaries) stay cached in the context and are reused by later
+ * calls, so a steady sequence of count / filter / free calls makes no driver allocation after its first pass (the JVM
+ * analogue: the map lives on the heap until tool exit, EnvironmentFinderMain.java:251-254).  mc_ctx_trim returns the
+ * cache to the driver; mc_ctx_arena_stats reports the cached bytes and how many driver allocations were made so far. */
+int mc_ctx_trim(mc_ctx* ctx);
+int mc_ctx_arena_stats(mc_ctx* ctx, uint64_t* cached_bytes, uint64_t* driver_allocs);
 
 /* ------------------------------------------------------------------------------------------------
  * Seam 1 — counting.  Replaces
@@ -85,6 +91,11 @@ int mc_table_add_pairs(mc_table* t, const uint64_t* keys, const int16_t* counts,
 int mc_table_get(const mc_table* t, const uint64_t* keys, size_t n, int16_t* out);
 /* entries with count >= min_count, sorted by key.  Pass cap = 0 to query *n only. */
 int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, int16_t* counts, size_t cap, size_t* n);
+/* The same two seams with DEVICE buffers (multi-GPU: every rank all-gathers the solid (key, count16) set of the others,
+ * SURVEY.md 8e, so that BFS + unitigs run on a complete filtered table; the pairs never touch the host).  dump_device
+ * writes the entries in table order (unsorted); cap = 0 queries *n only.  add_pairs_device skips keys another shard owns. */
+int mc_table_dump_device(const mc_table* t, int min_count, uint64_t* d_keys, int16_t* d_counts, size_t cap, size_t* n);
+int mc_table_add_pairs_device(mc_table* t, const uint64_t* d_keys, const int16_t* d_counts, size_t n);
 /* coverage-threshold compaction (B2/K4): a new, densely sized table holding only count >= min_count */
 int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc_table** solid);
 
@@ -203,7 +214,8 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
  *   "segment_keys" (keys applied per count launch, 0 = automatic), "count_tile", "count_variant" (k_bin_count shape),
  *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32),
  *   "agg" (two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on), "agg_unit" (keys per
- *   aggregation unit, 0 = automatic) */
+ *   aggregation unit, 0 = automatic), "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --
+ *   a step made of several count calls; reset with mc_ctx_stage_reset) */
 int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);
 /* table updates are buffered in bins; every read of the table applies them first, this call does so explicitly */
 int mc_table_flush_pending(mc_table* t);

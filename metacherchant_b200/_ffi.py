@@ -35,6 +35,8 @@ _SIGNATURES = {
     "mc_ctx_destroy": (None, [vp]),
     "mc_ctx_set_chunk_bytes": (i32, [vp, sz]),
     "mc_ctx_launches": (u64, [vp]),
+    "mc_ctx_trim": (i32, [vp]),
+    "mc_ctx_arena_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "mc_table_create": (i32, [vp, i32, u64, i32, i32, C.POINTER(vp)]),
     "mc_table_free": (None, [vp]),
     "mc_count_files": (i32, [vp, C.POINTER(cp), i32, i32, C.POINTER(vp)]),
@@ -46,6 +48,8 @@ _SIGNATURES = {
     "mc_table_add_pairs": (i32, [vp, vp, vp, sz]),
     "mc_table_get": (i32, [vp, vp, sz, vp]),
     "mc_table_dump": (i32, [vp, i32, vp, vp, sz, C.POINTER(sz)]),
+    "mc_table_dump_device": (i32, [vp, i32, vp, vp, sz, C.POINTER(sz)]),
+    "mc_table_add_pairs_device": (i32, [vp, vp, vp, sz]),
     "mc_table_filter": (i32, [vp, vp, i32, C.POINTER(vp)]),
     "mc_env_find": (i32, [vp, vp, C.POINTER(cp), C.POINTER(cp), i32, i32, i32, i64, i64, i32, i32, cp, C.POINTER(i32)]),
     "mc_env_find_ex": (i32, [vp, vp, C.POINTER(cp), C.POINTER(cp), i32, C.POINTER(cp), i32, i32, i32, i64, i64, i32, i32, i32, i32, cp, C.POINTER(i32)]),

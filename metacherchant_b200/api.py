@@ -54,6 +54,16 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.mc_ctx_launches(self.h))
 
+    def trim(self):
+        """Return the context's cached device blocks to the driver (mc_ctx_trim)."""
+        check(self.lib.mc_ctx_trim(self.h))
+
+    def arena_stats(self):
+        """(bytes cached for reuse, driver allocations made so far)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.lib.mc_ctx_arena_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sync(self):
         check(self.lib.mc_ctx_sync(self.h))
 
@@ -228,6 +238,15 @@ class KmerTable:
         if n.value:
             check(self.lib.mc_table_dump(self.h, min_count, keys.ctypes.data, counts.ctypes.data, n.value, C.byref(n)))
         return keys, counts
+
+    def dump_device(self, min_count, d_keys=0, d_counts=0, cap=0) -> int:
+        """Entries with count >= min_count into DEVICE buffers (unsorted); cap = 0 only counts them."""
+        n = C.c_size_t()
+        check(self.lib.mc_table_dump_device(self.h, min_count, C.c_void_p(d_keys or None), C.c_void_p(d_counts or None), cap, C.byref(n)))
+        return n.value
+
+    def add_pairs_device(self, d_keys, d_counts, n):
+        check(self.lib.mc_table_add_pairs_device(self.h, C.c_void_p(d_keys), C.c_void_p(d_counts), n))
 
     def filter(self, min_count) -> "KmerTable":
         h = C.c_void_p()

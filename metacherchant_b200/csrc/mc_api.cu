@@ -35,16 +35,9 @@ extern "C" int mc_ctx_create(int device, mc_ctx** out) {
             if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
             cudaGetLastError();
         }
-        // tables, rehash targets and temporaries come from the device's stream-ordered pool; keep freed blocks cached
-        // (cudaFree/cudaMalloc of multi-GB tables cost 20-800 ms each on this part, measured)
-        {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                uint64_t thr = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-            cudaGetLastError();
-        }
+        // tables, rehash targets, bins and temporaries come from the context's own block arena (mc_dev_alloc): cudaMalloc /
+        // cudaFree of multi-GB blocks cost 20-800 ms each on this part (measured), and the stream-ordered driver pool of
+        // round 1 still went back to the driver whenever a step's largest blocks missed its cache (profiles/r1d_NOTES.md)
         MC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         MC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) MC_CUDA(cudaEventCreate(&ev));
@@ -69,6 +62,10 @@ extern "C" void mc_ctx_destroy(mc_ctx* c) {
         cudaFreeHost(c->h_stage[i]);
     }
     for (int i = 0; i < 4; i++) cudaFree(c->d_scratch[i]);
+    mc_arena_trim(c);
+    for (auto& kv : c->arena_live) cudaFree(kv.first);   // tables the caller never freed die with their context
+    c->arena_live.clear();
+    for (auto& ev : c->event_pool) cudaEventDestroy(ev);
     cudaFreeHost(c->h_pinned_small);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     for (auto& ev : c->stage_ev) cudaEventDestroy(ev);
@@ -86,6 +83,24 @@ extern "C" int mc_ctx_set_chunk_bytes(mc_ctx* c, size_t bytes) {
     return MC_OK;
 }
 extern "C" uint64_t mc_ctx_launches(const mc_ctx* c) { return c ? c->launches : 0; }
+extern "C" int mc_ctx_trim(mc_ctx* c) {
+    if (!c) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    cudaSetDevice(c->device);
+    mc_arena_trim(c);
+    return MC_OK;
+}
+extern "C" int mc_ctx_arena_stats(mc_ctx* c, uint64_t* cached_bytes, uint64_t* driver_allocs) {
+    if (!c) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    if (cached_bytes) *cached_bytes = mc_arena_cached_bytes(c);
+    if (driver_allocs) *driver_allocs = c->arena_driver_allocs;
+    return MC_OK;
+}
 
 void* mc_scratch(mc_ctx* ctx, int slot, size_t bytes) {
     if (bytes > ctx->d_scratch_cap[slot]) {

@@ -312,6 +312,9 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
                        const std::vector<McBfsRequest>& reqs, std::vector<McBfsResult>& results) {
     if (max_kmers < 0 && max_radius < 0) mc_throw(MC_ERR_ARG, "At least one of --maxkmers and --maxradius parameters should be set");
     if (k != t->k) mc_throw(MC_ERR_ARG, "k (%d) differs from the table's k (%d)", k, t->k);
+    // a shard only holds the k-mers it owns: every other neighbour would read as absent.  The environment stage runs on a
+    // complete (gathered) solid table (all-gather of the solid set, then targets split over the ranks).
+    if (t->dev.shard_bits != 0) mc_throw(MC_ERR_UNSUPPORTED, "the environment stage needs a complete table, not one shard of %d (gather the solid set first)", 1 << t->dev.shard_bits);
     MC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     mc_table_flush(const_cast<mc_table*>(t));   // pending binned updates first

@@ -26,8 +26,8 @@ void mc_resolve_timers(mc_ctx* ctx) {
     for (auto& t : ctx->timers) {
         float ms = 0;
         if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) ctx->stage_ms[t.stage] += ms;
-        cudaEventDestroy(t.a);
-        cudaEventDestroy(t.b);
+        mc_event_put(ctx, t.a);
+        mc_event_put(ctx, t.b);
     }
     cudaGetLastError();
     ctx->timers.clear();
@@ -436,24 +436,24 @@ static McBinCountKernel bin_count_variant(int v) {
 static uint64_t available_device_bytes(mc_ctx* ctx) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (uint64_t)1 << 30; }
-    uint64_t avail = free_b;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
-        uint64_t reserved = 0, used = 0;   // blocks cached by the stream-ordered pool are reusable
-        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
-            avail += reserved - used;
-    }
-    cudaGetLastError();
-    return avail;
+    return (uint64_t)free_b + mc_arena_cached_bytes(ctx);   // blocks cached by the context's arena are reusable (or released on demand)
 }
 
-// a predicted table size is an estimate: never ask for more than 80 % of what the device can still give (the amortised
-// doubling in the flush loops takes over if the table really has to become that large)
-static int fit_q(mc_ctx* ctx, const mc_table* t, int q) {
+// a predicted table size is an estimate: never ask for more than 80 % of what the device can still give.  A table that cannot
+// double any more simply runs fuller (4-slot buckets probed over 8-bucket windows stay workable to a load of ~0.8; past that
+// the doubling is attempted anyway and fails with MC_ERR_NOMEM if it really does not fit).
+static int fit_q(mc_ctx* ctx, const mc_table* t, int q, uint64_t keys_known = 0) {
     const double room = 0.8 * (double)available_device_bytes(ctx);
-    while (q > t->dev.q + 1 && (double)(32ull << q) > room) q--;
+    while (q > t->dev.q && (double)(32ull << q) > room) q--;
+    if (q == t->dev.q && (double)keys_known > 0.8 * 4.0 * (double)t->nb) q = t->dev.q + 1;
     return q;
+}
+// amortised doubling at load MC_GROW_LOAD, when memory allows
+static void grow_if_due(mc_table* t, uint64_t keys_known) {
+    extern const double MC_GROW_LOAD;
+    if ((double)keys_known <= MC_GROW_LOAD * 4.0 * (double)t->nb) return;
+    const int q = fit_q(t->ctx, t, t->dev.q + 1, keys_known);
+    if (q > t->dev.q) mc_table_grow_to(t, q);
 }
 
 static void batch_free_buffers(mc_ctx* ctx, McBatch* B) {
@@ -533,11 +533,8 @@ void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
     if (!B || !B->dev.keys || B->dev.spill_cap < n) mc_throw(MC_ERR_ARG, "internal: scatter without a reserved batch");
     McStageTimer tm(ctx, MC_ST_SCATTER);
     const size_t smem = scatter_smem_bytes(B->P);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (mc_attr_once(ctx, MC_ATTR_SCATTER))
         MC_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
-        attr_set = true;
-    }
     const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
     McBinDst none{};
@@ -551,11 +548,8 @@ void mc_launch_owner_scatter(mc_ctx* ctx, const uint64_t* d_flat, uint64_t n, co
     if (n == 0) return;
     const uint32_t P = 1u << owners.pbits;
     const size_t smem = scatter_smem_bytes(P);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (mc_attr_once(ctx, MC_ATTR_SCATTER))
         MC_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
-        attr_set = true;
-    }
     const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
     k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, owners, 0, 0, flags, dst);
@@ -564,6 +558,7 @@ void mc_launch_owner_scatter(mc_ctx* ctx, const uint64_t* d_flat, uint64_t n, co
 }
 
 __global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint64_t* hkeys, size_t n);
+__global__ void __launch_bounds__(256) k_insert_hashed_n(McTableDev t, const uint64_t* hkeys, const unsigned long long* n_ptr, unsigned long long cap);
 
 static const double MC_FLUSH_TARGET_LOAD = 0.50;
 static const uint64_t MC_FLUSH_SEGMENT = 128ull << 20;   // keys per k_bin_count launch (and entries of the overflow list)   // table load aimed at when a flush has to grow the table
@@ -647,41 +642,83 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     B2.spill_cursor = B2.cursors + (n_cursors - 2);
     unsigned long long* d_ticket = B2.cursors + (n_cursors - 1);
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (mc_attr_once(ctx, MC_ATTR_AGG)) {
         MC_CUDA(cudaFuncSetAttribute(k_bin_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
         MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
         MC_CUDA(cudaFuncSetAttribute(k_bin_agg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
-        attr_set = true;
     }
     int agg_per_sm = 0, sc_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg<false>, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc_per_sm, k_bin_scatter2, SC_THREADS, scatter_smem_bytes(P2)) != cudaSuccess || sc_per_sm < 1) sc_per_sm = 1;
     cudaGetLastError();
 
-    const uint64_t ovf_cap = std::max<uint64_t>((uint64_t)g_max * max_bin, 1024);   // every instance of a group
+    // The host runs ONE group ahead of the device: group g is queued before the status block of group g - 1 is looked at, so
+    // the stream never drains between groups and a slow host costs nothing (round 1 synchronised after every group and read
+    // three words back one by one; on a slow box that was tens of milliseconds per step).  Everything a group can leave behind
+    // is therefore handled on the device or survives one more group: the sub-bin spill list is applied by a kernel that reads
+    // its length on the device, and the overflow list has room for every instance of TWO groups.
+    const uint64_t ovf_cap = std::max<uint64_t>(2 * (uint64_t)g_max * max_bin, 1024);
     auto attach_overflow_list = [&]() {
         t->dev.ovf_keys = (uint64_t*)mc_scratch(ctx, 3, ovf_cap * sizeof(uint64_t));
         t->dev.ovf_cap = ovf_cap;
         MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, 2 * sizeof(unsigned long long), st));
     };
     attach_overflow_list();
-    unsigned long long* h_c = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 1024);   // counters + flags + spill cursor read-back
-    unsigned int* h_flags = (unsigned int*)(h_c + MC_CNT_N);
-    unsigned long long* h_spill2 = h_c + MC_CNT_N + 1;
+    B2.spill_cursor = t->dev.counters + MC_STATUS_SPILL2;   // inside the table's status block: one read-back per group
+    enum { RING = 2 };
+    unsigned long long* h_ring = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 1024);   // RING status blocks
+    struct Pending { bool live = false; cudaEvent_t ev = nullptr; uint64_t keys_done = 0, group_keys = 0; uint32_t b0 = 0, G = 0; } pend[RING];
+    struct EvGuard { mc_ctx* c; Pending* p; ~EvGuard() { for (int i = 0; i < RING; i++) mc_event_put(c, p[i].ev); } } ev_guard{ctx, pend};
+    for (int i = 0; i < RING; i++) pend[i].ev = mc_event_get(ctx);
     const uint64_t keys_before = mc_table_keys(t);
     uint64_t keys_known = keys_before;
+    const bool trace = getenv("MC_TRACE") != nullptr;
+    // look at the status block a finished group left behind: overflow -> fatal, table growth, re-insertion of overflowed keys
+    auto examine = [&](Pending& p, const unsigned long long* h_c) {
+        MC_CUDA(cudaEventSynchronize(p.ev));
+        p.live = false;
+        if ((unsigned int)h_c[MC_STATUS_FLAGS] & MC_FLAG_OVERFLOW) mc_throw(MC_ERR_NOMEM, "k-mer table overflow (stash and overflow list full)");
+        const uint64_t spill2 = p.group_keys ? h_c[MC_STATUS_SPILL2] : 0;
+        if (trace) fprintf(stderr, "[mc trace] agg group b0=%u G=%u keys=%llu P2=%u cap2=%llu spill2=%llu ovf=%llu table_keys=%llu\n", p.b0, p.G,
+                           (unsigned long long)p.group_keys, P2, (unsigned long long)cap2, (unsigned long long)spill2,
+                           (unsigned long long)h_c[MC_CNT_OVF], (unsigned long long)h_c[MC_CNT_KEYS]);
+        if (spill2 > spill2_cap) mc_throw(MC_ERR_NOMEM, "internal: sub-bin spill list overflow");
+        const uint64_t ovf_n = h_c[MC_CNT_OVF];
+        const uint64_t now = h_c[MC_CNT_KEYS] + h_c[MC_CNT_OVF_KEYS];   // every push is one distinct key
+        const double gained = now > keys_before ? (double)(now - keys_before) : 0.0;
+        const double predicted = (double)keys_before + (p.keys_done ? gained * ((double)batch_keys / (double)p.keys_done) : 0.0);
+        bool grown = false;
+        if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
+            int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
+            if (q > t->dev.q) {
+                mc_table_grow_to(t, q);
+                grown = true;
+            }
+        }
+        if (ovf_n) {   // rare: the table was too small; re-insert what overflowed so far (grows until it fits)
+            mc_table_finish_chunk(t, grown);
+            attach_overflow_list();
+            keys_known = mc_table_keys(t);
+        } else {
+            keys_known = std::max(keys_known, now);
+        }
+    };
     uint64_t keys_done = 0;
     bool first = true;
-    for (uint32_t b0 = 0; b0 < P1;) {
+    uint32_t gi = 0;
+    for (uint32_t b0 = 0; b0 < P1; gi++) {
         // the first group is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
         uint32_t G = first ? std::max<uint32_t>(P1 / 64, 1) : g_max;
         G = std::min(std::min(G, g_max), P1 - b0);
         uint64_t group_keys = 0;
         for (uint32_t b = b0; b < b0 + G; b++) group_keys += std::min<uint64_t>(cur[b], cap1);
-        if ((double)keys_known > MC_GROW_LOAD * 4.0 * (double)t->nb) mc_table_grow_to(t, t->dev.q + 1);   // amortised doubling
+        grow_if_due(t, keys_known);   // amortised doubling
+        Pending& slot = pend[gi % RING];
+        unsigned long long* h_c = h_ring + (size_t)(gi % RING) * MC_STATUS_WORDS;
+        if (slot.live) examine(slot, h_c);   // (only when RING groups are in flight; normally drained below)
         if (group_keys) {
             MC_CUDA(cudaMemsetAsync(B2.cursors, 0, n_cursors * 8, st));
+            MC_CUDA(cudaMemsetAsync(B2.spill_cursor, 0, sizeof(unsigned long long), st));
             {
                 McStageTimer tm(ctx, MC_ST_SCATTER);
                 const uint32_t tiles = (uint32_t)((max_bin + SC_TILE - 1) / SC_TILE);
@@ -701,7 +738,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                     MC_LAUNCH(ctx);
                     MC_CUDA(cudaGetLastError());
                 }
-                MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_STATUS_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 MC_CUDA(cudaStreamSynchronize(st));
                 // later batches of a stream are assumed to bring as many new keys as this one: an upper bound (the genomic k-mers
                 // saturate, the error k-mers keep coming), so the table is grown once instead of doubling batch after batch
@@ -712,8 +749,8 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 if (t->stream_flushes == 0) batches_left = std::min(batches_left, 4.0);
                 const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)group_keys) * batches_left;
                 const double predicted = (double)keys_before + fresh;
-                if (getenv("MC_TRACE")) fprintf(stderr, "[mc trace] agg sample: %llu new distinct keys in %llu instances -> %.0f predicted for the batch\n",
-                                                (unsigned long long)h_c[MC_CNT_OVF_KEYS], (unsigned long long)group_keys, predicted);
+                if (trace) fprintf(stderr, "[mc trace] agg sample: %llu new distinct keys in %llu instances -> %.0f predicted for the batch\n",
+                                   (unsigned long long)h_c[MC_CNT_OVF_KEYS], (unsigned long long)group_keys, predicted);
                 if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
                     const int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
                     if (q > t->dev.q) mc_table_grow_to(t, q);
@@ -725,60 +762,42 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 McStageTimer tm(ctx, MC_ST_COUNT);
                 k_bin_agg<false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
                 MC_LAUNCH(ctx);
+                // a sub-bin that was full (a heavy hitter) spilled: direct updates, length read on the device
+                k_insert_hashed_n<<<ctx->sm_count, 256, 0, st>>>(t->dev, B2.spill, B2.spill_cursor, spill2_cap);
+                MC_LAUNCH(ctx);
                 MC_CUDA(cudaGetLastError());
             }
-        }
-        b0 += G;
-        keys_done += group_keys;
-        first = false;
-        MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        MC_CUDA(cudaMemcpyAsync(h_flags, t->dev.flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        MC_CUDA(cudaMemcpyAsync(h_spill2, B2.spill_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        MC_CUDA(cudaStreamSynchronize(st));
-        if (*h_flags & MC_FLAG_OVERFLOW) mc_throw(MC_ERR_NOMEM, "k-mer table overflow (stash and overflow list full)");
-        const uint64_t spill2 = group_keys ? *h_spill2 : 0;
-        if (getenv("MC_TRACE") && b0 == G) {   // sub-bin fill of the first group
-            std::vector<unsigned long long> c2((size_t)G * (P2 + 1));
-            MC_CUDA(cudaMemcpy(c2.data(), B2.cursors, c2.size() * 8, cudaMemcpyDeviceToHost));
-            unsigned long long mx = 0, sum = 0, over = 0, mn = ~0ull;
-            for (uint32_t g = 0; g < G; g++)
-                for (uint32_t j = 0; j < P2; j++) {
-                    unsigned long long v = c2[(size_t)g * (P2 + 1) + j];
-                    mx = std::max(mx, v); mn = std::min(mn, v); sum += v; over += v > cap2;
-                }
-            fprintf(stderr, "[mc trace] sub-bin attempts: min %llu mean %.0f max %llu, %llu of %u over cap2; bin0 attempts %llu\n", mn, (double)sum / (G * P2), mx, over, G * P2, cur[0]);
-        }
-        if (getenv("MC_TRACE")) fprintf(stderr, "[mc trace] agg group b0=%u G=%u keys=%llu P2=%u cap2=%llu spill2=%llu ovf=%llu table_keys=%llu\n", b0 - G, G,
-                                        (unsigned long long)group_keys, P2, (unsigned long long)cap2, (unsigned long long)spill2,
-                                        (unsigned long long)h_c[MC_CNT_OVF], (unsigned long long)h_c[MC_CNT_KEYS]);
-        if (spill2 > spill2_cap) mc_throw(MC_ERR_NOMEM, "internal: sub-bin spill list overflow");
-        const uint64_t ovf_n = h_c[MC_CNT_OVF];
-        const uint64_t now = h_c[MC_CNT_KEYS] + h_c[MC_CNT_OVF_KEYS];   // every push is one distinct key of this group
-        const double gained = now > keys_before ? (double)(now - keys_before) : 0.0;
-        const double predicted = (double)keys_before + (keys_done ? gained * ((double)batch_keys / (double)keys_done) : 0.0);
-        bool grown = false;
-        if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
-            int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
-            if (q > t->dev.q) {
-                mc_table_grow_to(t, q);
-                grown = true;
+            if (trace && first) {   // sub-bin fill of the first group
+                std::vector<unsigned long long> c2((size_t)G * (P2 + 1));
+                MC_CUDA(cudaMemcpyAsync(c2.data(), B2.cursors, c2.size() * 8, cudaMemcpyDeviceToHost, st));
+                MC_CUDA(cudaStreamSynchronize(st));
+                unsigned long long mx = 0, sum = 0, over = 0, mn = ~0ull;
+                for (uint32_t g = 0; g < G; g++)
+                    for (uint32_t j = 0; j < P2; j++) {
+                        unsigned long long v = c2[(size_t)g * (P2 + 1) + j];
+                        mx = std::max(mx, v); mn = std::min(mn, v); sum += v; over += v > cap2;
+                    }
+                fprintf(stderr, "[mc trace] sub-bin attempts: min %llu mean %.0f max %llu, %llu of %u over cap2; bin0 attempts %llu\n", mn, (double)sum / (G * P2), mx, over, G * P2, cur[0]);
             }
         }
-        if (ovf_n) {   // rare: the table was too small for this group; re-insert what overflowed (grows until it fits)
-            mc_table_finish_chunk(t, grown);
-            attach_overflow_list();
-            keys_known = mc_table_keys(t);
-        } else {
-            keys_known = now;
-        }
-        if (spill2) {   // a sub-bin was full (a heavy hitter): direct updates
-            t->dev.ovf_keys = nullptr;
-            t->dev.ovf_cap = 0;
-            insert_list(t, B2.spill, spill2);
-            attach_overflow_list();
-            keys_known = mc_table_keys(t);
+        keys_done += group_keys;
+        slot.live = true;
+        slot.keys_done = keys_done;
+        slot.group_keys = group_keys;
+        slot.b0 = b0;
+        slot.G = G;
+        MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_STATUS_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaEventRecord(slot.ev, st));
+        b0 += G;
+        first = false;
+        // the group queued BEFORE this one has had a whole group's time to finish: look at what it left behind
+        if (gi >= 1) {
+            Pending& prev = pend[(gi - 1) % RING];
+            if (prev.live) examine(prev, h_ring + (size_t)((gi - 1) % RING) * MC_STATUS_WORDS);
         }
     }
+    for (uint32_t j = (gi >= RING ? gi - RING : 0); j < gi; j++)
+        if (pend[j % RING].live) examine(pend[j % RING], h_ring + (size_t)(j % RING) * MC_STATUS_WORDS);
     t->seen_instances += batch_keys;
     t->stream_flushes++;
 }
@@ -842,7 +861,7 @@ void mc_table_flush(mc_table* t) {
         // the first segment is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
         uint64_t seg = first ? std::max<uint64_t>(total_tiles / 64, 1) : seg_tiles_max;
         seg = std::min(std::min(seg, seg_tiles_max), total_tiles - tile);
-        if ((double)keys_known > MC_GROW_LOAD * 4.0 * (double)t->nb) mc_table_grow_to(t, t->dev.q + 1);   // amortised doubling
+        grow_if_due(t, keys_known);   // amortised doubling
         {
             McStageTimer tm(ctx, MC_ST_COUNT);
             // exactly the co-resident CTAs; tiles are handed out in order by the ticket
@@ -907,6 +926,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "extract_parts" && (value == 0 || value == 1 || value == 4 || value == 32)) ctx->tune_extract_parts = (int)value;
     else if (n == "count_variant" && value >= 0 && value <= 3) ctx->tune_count_variant = (int)value;
     else if (n == "agg" && value >= -1 && value <= 1) ctx->tune_agg = (int)value;
+    else if (n == "keep_stage_ms" && value >= 0 && value <= 1) ctx->keep_stage_ms = (int)value;
     else if (n == "agg_unit" && value >= 0 && value <= (1 << 24)) ctx->tune_agg_unit = (uint32_t)value;
     else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;
     else {

@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mc_b200.h"
@@ -117,6 +119,11 @@ struct McTableDev {
     unsigned long long ovf_cap;
 };
 enum { MC_CNT_KEYS = 0, MC_CNT_STASH = 1, MC_CNT_READS = 2, MC_CNT_RUNS = 3, MC_CNT_BASES = 4, MC_CNT_KMERS = 5, MC_CNT_OVF = 6, MC_CNT_OVF_KEYS = 7, MC_CNT_N = 8 };
+// the counters are the head of one 128-byte status block: [MC_CNT_N] = flag word, [MC_CNT_N + 1] = cursor of the sub-bin spill
+// list of the flush group in flight (mc_bins.cu), so that one device-to-host copy tells the host everything about a group
+#define MC_STATUS_FLAGS MC_CNT_N
+#define MC_STATUS_SPILL2 (MC_CNT_N + 1)
+#define MC_STATUS_WORDS 16
 #define MC_FLAG_OVERFLOW 1u
 #define MC_STASH_PROBES 64u
 
@@ -290,6 +297,7 @@ struct mc_ctx {
     int tune_extract_parts = 0;      // lanes per record in k_extract: 0 = by read length, else 1 / 4 / 32
     int tune_agg = -1;               // two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on
     uint32_t tune_agg_unit = 0;      // target keys per aggregation unit (sub-bin); 0 = default
+    int keep_stage_ms = 0;           // 1: mc_count_* do not reset the stage timers (a step made of several count calls)
     int sm_count = 148;
     // reusable device scratch for the parser (grown on demand)
     void* d_chunk[2] = {nullptr, nullptr};
@@ -299,7 +307,31 @@ struct mc_ctx {
     void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // slot 0: parser arrays, 1: tile counts + header, 2: extract keys, 3: misc
     size_t d_scratch_cap[4] = {0, 0, 0, 0};
     void* h_pinned_small = nullptr;   // 4 KiB pinned for small read-backs
+    // Device-block arena (mc_dev_alloc / mc_dev_free): freed blocks stay with the context and are handed out again to
+    // requests of (nearly) the same size, so a steady stream of count / filter / free calls issues no driver
+    // allocation at all after its first pass.  Everything allocated here is used on ctx->stream only, which is what
+    // makes the immediate reuse of a freed block safe (stream order).  mc_ctx_trim returns the cache to the driver.
+    struct Block { void* p; size_t bytes; };
+    std::mutex arena_mu;
+    std::vector<Block> arena_free;
+    std::unordered_map<void*, size_t> arena_live;
+    size_t arena_cached_bytes = 0;
+    uint64_t arena_driver_allocs = 0;   // cudaMalloc calls made by the arena (bench/test visibility)
+    // pooled timing events (McStageTimer)
+    std::vector<cudaEvent_t> event_pool;
+    // one kernel-attribute opt-in per context (= per device): bit i = the i-th MC_ATTR_* kernel was configured
+    uint32_t attr_done = 0;
 };
+enum { MC_ATTR_EXTRACT = 0, MC_ATTR_SCATTER = 8, MC_ATTR_SCATTER2 = 9, MC_ATTR_AGG = 10, MC_ATTR_MISC = 11 };
+static inline bool mc_attr_once(mc_ctx* ctx, int bit) {   // true the first time `bit` is asked for on this context
+    if (ctx->attr_done & (1u << bit)) return false;
+    ctx->attr_done |= 1u << bit;
+    return true;
+}
+cudaEvent_t mc_event_get(mc_ctx* ctx);
+void mc_event_put(mc_ctx* ctx, cudaEvent_t e);
+size_t mc_arena_cached_bytes(mc_ctx* ctx);
+void mc_arena_trim(mc_ctx* ctx);
 
 struct mc_table {
     mc_ctx* ctx = nullptr;
@@ -351,8 +383,8 @@ struct McStageTimer {
     McPendingTimer t;
     McStageTimer(mc_ctx* c, int stage) : ctx(c) {
         t.stage = stage;
-        cudaEventCreate(&t.a);
-        cudaEventCreate(&t.b);
+        t.a = mc_event_get(c);
+        t.b = mc_event_get(c);
         cudaEventRecord(t.a, c->stream);
     }
     ~McStageTimer() {

@@ -383,11 +383,9 @@ static unsigned long long check_k2_errors(mc_ctx* ctx, McParseHeader* d_header, 
 template <bool FASTA, int PARTS>
 static void launch_extract_p(mc_ctx* ctx, McExtractArgs& a) {
     const size_t smem = EX_WARPS * EX_STAGE_BYTES + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: one opt-in per context and instantiation (a process may hold contexts on several GPUs)
+    if (mc_attr_once(ctx, MC_ATTR_EXTRACT + (FASTA ? 3 : 0) + (PARTS == 1 ? 0 : PARTS == 4 ? 1 : 2)))
         MC_CUDA(cudaFuncSetAttribute(k_extract<FASTA, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const uint64_t per_cta = (uint64_t)(32 / PARTS) * EX_WARPS;          // records per CTA step
     uint64_t blocks = ((uint64_t)a.n_records + per_cta - 1) / per_cta;
     const uint64_t cap = (uint64_t)ctx->sm_count * 4 * 4;                 // resident CTAs per SM x 4 waves
@@ -483,7 +481,8 @@ extern "C" int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fm
         validate_fmt(fmt);
         MC_CUDA(cudaSetDevice(ctx->device));
         mc_resolve_timers(ctx);
-        for (auto& v : ctx->stage_ms) v = 0;
+        if (!ctx->keep_stage_ms)
+            for (auto& v : ctx->stage_ms) v = 0;
         const uint8_t* p = (const uint8_t*)dbuf;
         bool fasta = fmt == MC_FMT_FASTA;
         int qoff = fasta ? 0 : resolve_qoff_device(ctx, p, len, fmt);
@@ -516,7 +515,8 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
         validate_fmt(fmt);
         MC_CUDA(cudaSetDevice(ctx->device));
         mc_resolve_timers(ctx);
-        for (auto& v : ctx->stage_ms) v = 0;
+        if (!ctx->keep_stage_ms)
+            for (auto& v : ctx->stage_ms) v = 0;
         const uint8_t* p = (const uint8_t*)buf;
         const bool fasta = fmt == MC_FMT_FASTA;
         const int qoff = fasta ? 0 : resolve_qoff_host(p, len, fmt);

@@ -58,17 +58,91 @@ int mc_q_for_keys(uint64_t keys, int shard_bits, double load) {
 }
 static int q_for_keys(uint64_t keys, int shard_bits) { return mc_q_for_keys(keys, shard_bits, MC_MAX_LOAD); }
 
+// Arena: see mc_ctx.  Requests are rounded (512 B; 2 MiB from 1 MiB up) so that the same logical size always maps to
+// the same block size; a cached block is reused when it is at most 1/8 larger than the request.
+static size_t arena_round(size_t bytes) {
+    if (bytes < 512) bytes = 512;
+    const size_t g = bytes >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;
+    return (bytes + g - 1) / g * g;
+}
+static void arena_release_all_locked(mc_ctx* ctx) {
+    if (ctx->arena_free.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->arena_free) cudaFree(b.p);
+    ctx->arena_free.clear();
+    ctx->arena_cached_bytes = 0;
+    cudaGetLastError();
+}
 void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what) {
+    const size_t need = arena_round(bytes);
+    std::lock_guard<std::mutex> lk(ctx->arena_mu);
+    size_t best = (size_t)-1, best_bytes = (size_t)-1;
+    for (size_t i = 0; i < ctx->arena_free.size(); i++) {
+        const size_t b = ctx->arena_free[i].bytes;
+        if (b >= need && b < best_bytes) { best = i; best_bytes = b; }
+    }
+    const size_t slack = need < ((size_t)1 << 20) ? 3 * need : need / 8;
     void* p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream);
+    if (best != (size_t)-1 && best_bytes <= need + slack) {
+        p = ctx->arena_free[best].p;
+        ctx->arena_free[best] = ctx->arena_free.back();
+        ctx->arena_free.pop_back();
+        ctx->arena_cached_bytes -= best_bytes;
+        ctx->arena_live[p] = best_bytes;
+        return p;
+    }
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {   // give the cache back to the driver and try once more
+        cudaGetLastError();
+        arena_release_all_locked(ctx);
+        e = cudaMalloc(&p, need);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         mc_throw(MC_ERR_NOMEM, "%s of %.2f GiB does not fit in device memory", what, (double)bytes / (1 << 30));
     }
+    ctx->arena_driver_allocs++;
+    ctx->arena_live[p] = need;
     return p;
 }
 void mc_dev_free(mc_ctx* ctx, void* p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(ctx->arena_mu);
+    auto it = ctx->arena_live.find(p);
+    if (it == ctx->arena_live.end()) {   // not ours (should not happen): hand it to the driver
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(p);
+        return;
+    }
+    ctx->arena_free.push_back({p, it->second});
+    ctx->arena_cached_bytes += it->second;
+    ctx->arena_live.erase(it);
+}
+size_t mc_arena_cached_bytes(mc_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(ctx->arena_mu);
+    return ctx->arena_cached_bytes;
+}
+void mc_arena_trim(mc_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(ctx->arena_mu);
+    arena_release_all_locked(ctx);
+}
+cudaEvent_t mc_event_get(mc_ctx* ctx) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->arena_mu);
+        if (!ctx->event_pool.empty()) {
+            cudaEvent_t e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void mc_event_put(mc_ctx* ctx, cudaEvent_t e) {
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(ctx->arena_mu);
+    ctx->event_pool.push_back(e);
 }
 
 static void alloc_slots(mc_ctx* ctx, McTableDev& d, int q, int shard_bits, cudaStream_t s) {
@@ -100,12 +174,12 @@ extern "C" int mc_table_create(mc_ctx* ctx, int k, uint64_t capacity_hint, int s
         t->dev.ovf_cap = 0;
         t->dev.stash_keys = (uint64_t*)mc_dev_alloc(ctx, MC_STASH_SLOTS * sizeof(uint64_t), "stash");
         t->dev.stash_counts = (uint32_t*)mc_dev_alloc(ctx, MC_STASH_SLOTS * sizeof(uint32_t), "stash");
-        t->dev.counters = (unsigned long long*)mc_dev_alloc(ctx, MC_CNT_N * sizeof(unsigned long long), "counters");
-        t->dev.flags = (unsigned int*)mc_dev_alloc(ctx, sizeof(unsigned int), "flags");
+        // one status block: counters, the flag word and a spare cursor are read back with ONE copy (MC_STATUS_WORDS)
+        t->dev.counters = (unsigned long long*)mc_dev_alloc(ctx, MC_STATUS_WORDS * sizeof(unsigned long long), "counters");
+        t->dev.flags = (unsigned int*)(t->dev.counters + MC_STATUS_FLAGS);
         MC_CUDA(cudaMemsetAsync(t->dev.stash_keys, 0, MC_STASH_SLOTS * sizeof(uint64_t), ctx->stream));
         MC_CUDA(cudaMemsetAsync(t->dev.stash_counts, 0, MC_STASH_SLOTS * sizeof(uint32_t), ctx->stream));
-        MC_CUDA(cudaMemsetAsync(t->dev.counters, 0, MC_CNT_N * sizeof(unsigned long long), ctx->stream));
-        MC_CUDA(cudaMemsetAsync(t->dev.flags, 0, sizeof(unsigned int), ctx->stream));
+        MC_CUDA(cudaMemsetAsync(t->dev.counters, 0, MC_STATUS_WORDS * sizeof(unsigned long long), ctx->stream));
         *out = t;
         return MC_OK;
     } catch (const McError& e) {
@@ -128,8 +202,7 @@ extern "C" void mc_table_free(mc_table* t) {
     mc_dev_free(t->ctx, t->dev.slots);
     mc_dev_free(t->ctx, t->dev.stash_keys);
     mc_dev_free(t->ctx, t->dev.stash_counts);
-    mc_dev_free(t->ctx, t->dev.counters);
-    mc_dev_free(t->ctx, t->dev.flags);
+    mc_dev_free(t->ctx, t->dev.counters);   // the flag word lives in the same block
     delete t;
 }
 
@@ -248,18 +321,8 @@ static void grow_to(mc_table* t, int new_q) {
 }
 
 void mc_table_grow_to(mc_table* t, int q) {
-    cudaEvent_t a, b;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
-    cudaEventRecord(a, t->ctx->stream);
+    McStageTimer tm(t->ctx, MC_ST_GROW);   // resolved lazily: growing does not stall the host
     grow_to(t, q);
-    cudaEventRecord(b, t->ctx->stream);
-    cudaEventSynchronize(b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    t->ctx->stage_ms[MC_ST_GROW] += ms;
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
 }
 
 void mc_table_reserve(mc_table* t, uint64_t additional) {
@@ -534,6 +597,10 @@ extern "C" int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, i
             mc_dev_free(ctx, d_cursor);
             return MC_OK;
         }
+        if (n > 0xFFFFFFFFull) {
+            mc_dev_free(ctx, d_cursor);
+            mc_throw(MC_ERR_UNSUPPORTED, "dump of more than 2^32 entries");
+        }
         if (cap < n) {
             mc_dev_free(ctx, d_cursor);
             mc_throw(MC_ERR_CAPACITY, "dump needs room for %llu entries", (unsigned long long)n);
@@ -559,12 +626,67 @@ extern "C" int mc_table_dump(const mc_table* t, int min_count, uint64_t* keys, i
         // sorted by key for parity checks (the reference iterates in map order; consumers treat it as a set)
         std::vector<uint32_t> idx(n);
         for (uint64_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
-        if (n > 0xFFFFFFFFull) mc_throw(MC_ERR_UNSUPPORTED, "dump of more than 2^32 entries");
         std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return hk[a] < hk[b]; });
         for (uint64_t i = 0; i < n; i++) {
             keys[i] = hk[idx[i]];
             counts[i] = hc[idx[i]];
         }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+// Device-buffer forms of dump / add_pairs: the multi-GPU gather of the solid (key, count16) set moves the
+// pairs GPU to GPU and must not bounce them through the host.  Entries leave in table order (unsorted).
+extern "C" int mc_table_dump_device(const mc_table* t, int min_count, uint64_t* d_keys, int16_t* d_counts, size_t cap, size_t* n_out) {
+    try {
+        if (!t || !n_out) mc_throw(MC_ERR_ARG, "null argument");
+        mc_ctx* ctx = t->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(const_cast<mc_table*>(t));
+        check_overflow(t);
+        unsigned long long* d_cursor = (unsigned long long*)mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");
+        struct Free { mc_ctx* c; void* p; ~Free() { mc_dev_free(c, p); } } fr{ctx, d_cursor};
+        const uint64_t n = count_matching(t, min_count, d_cursor);
+        *n_out = n;
+        if (cap == 0 || n == 0) return MC_OK;
+        if (cap < n) mc_throw(MC_ERR_CAPACITY, "dump needs room for %llu entries", (unsigned long long)n);
+        if (!d_keys || !d_counts) mc_throw(MC_ERR_ARG, "null argument");
+        MC_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+        const uint64_t prefix = t->dev.shard_bits ? ((uint64_t)t->shard_id << (62 - t->dev.shard_bits)) : 0;
+        k_dump<true><<<grid_for(ctx, t->nb, 256, 16), 256, 0, ctx->stream>>>(t->dev, min_count < 0 ? 0u : (uint32_t)min_count, d_cursor, d_keys, d_counts, prefix);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        MC_CUDA(cudaStreamSynchronize(ctx->stream));
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_add_pairs(McTableDev t, const uint64_t* keys, const int16_t* counts, size_t n, uint32_t shard_id, unsigned int* bad);
+extern "C" int mc_table_add_pairs_device(mc_table* t, const uint64_t* d_keys, const int16_t* d_counts, size_t n) {
+    try {
+        if (!t || (n && (!d_keys || !d_counts))) mc_throw(MC_ERR_ARG, "null argument");
+        if (n == 0) return MC_OK;
+        mc_ctx* ctx = t->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        mc_table_flush(t);
+        mc_table_reserve(t, n);
+        unsigned int* d_bad = (unsigned int*)mc_dev_alloc(ctx, sizeof(unsigned int), "scratch");
+        struct Free { mc_ctx* c; void* p; ~Free() { mc_dev_free(c, p); } } fr{ctx, d_bad};
+        MC_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), ctx->stream));
+        k_add_pairs<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(t->dev, d_keys, d_counts, n, t->shard_id, d_bad);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        unsigned int bad = 0;
+        MC_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+        MC_CUDA(cudaStreamSynchronize(ctx->stream));
+        check_overflow(t);
+        if (bad) mc_throw(MC_ERR_ARG, "a key above 2^62 is not a packed k-mer of k <= 31");
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());
@@ -594,7 +716,14 @@ extern "C" int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc
         // statistics travel with the filtered table
         MC_CUDA(cudaMemcpyAsync(&s->dev.counters[MC_CNT_READS], &t->dev.counters[MC_CNT_READS], 4 * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToDevice, ctx->stream));
-        MC_CUDA(cudaStreamSynchronize(ctx->stream));
+        // no overflow list is attached to `s`: an entry that found neither its window nor the stash free would be LOST and a solid
+        // k-mer would silently vanish from every environment.  Improbable at load 0.35, but checked.
+        try {
+            check_overflow(s);
+        } catch (...) {
+            mc_table_free(s);
+            throw;
+        }
         *solid = s;
         return MC_OK;
     } catch (const McError& e) {
@@ -603,12 +732,17 @@ extern "C" int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc
     }
 }
 
-__global__ void __launch_bounds__(256) k_add_pairs(McTableDev t, const uint64_t* keys, const int16_t* counts, size_t n) {
+// pairs whose key this shard does not own are skipped (the other shards' add_pairs take them); a key above 2^62 is not a
+// k-mer of k <= 31 and is reported through `bad`
+__global__ void __launch_bounds__(256) k_add_pairs(McTableDev t, const uint64_t* keys, const int16_t* counts, size_t n, uint32_t shard_id, unsigned int* bad) {
     unsigned long long added = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         int c = counts[i];
         if (c <= 0) continue;   // Kmers2HMWorker only adds freq > threshold >= 0
-        if (mc_table_add(t, mc_mix62(keys[i] & MC_M62), (uint32_t)c)) added++;
+        if (keys[i] > MC_M62) { atomicOr(bad, 1u); continue; }
+        const uint64_t h = mc_mix62(keys[i]);
+        if (t.shard_bits != 0 && (uint32_t)(h >> (62 - t.shard_bits)) != shard_id) continue;
+        if (mc_table_add(t, h, (uint32_t)c)) added++;
     }
     if (added) atomicAdd(&t.counters[MC_CNT_KEYS], added);
 }
@@ -625,15 +759,21 @@ extern "C" int mc_table_add_pairs(mc_table* t, const uint64_t* keys, const int16
         int16_t* d_counts;
         d_keys = (decltype(d_keys))mc_dev_alloc(ctx, n * sizeof(uint64_t), "scratch");
         d_counts = (decltype(d_counts))mc_dev_alloc(ctx, n * sizeof(int16_t), "scratch");
+        unsigned int* d_bad = (unsigned int*)mc_dev_alloc(ctx, sizeof(unsigned int), "scratch");
+        MC_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), ctx->stream));
         MC_CUDA(cudaMemcpyAsync(d_keys, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         MC_CUDA(cudaMemcpyAsync(d_counts, counts, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-        k_add_pairs<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(t->dev, d_keys, d_counts, n);
+        k_add_pairs<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(t->dev, d_keys, d_counts, n, t->shard_id, d_bad);
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
+        unsigned int bad = 0;
+        MC_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
         MC_CUDA(cudaStreamSynchronize(ctx->stream));
         mc_dev_free(ctx, d_keys);
         mc_dev_free(ctx, d_counts);
+        mc_dev_free(ctx, d_bad);
         check_overflow(t);
+        if (bad) mc_throw(MC_ERR_ARG, "a key above 2^62 is not a packed k-mer of k <= 31");
         return MC_OK;
     } catch (const McError& e) {
         mc_set_error(e.what());
@@ -655,6 +795,20 @@ __global__ void __launch_bounds__(256) k_insert_hashed(McTableDev t, const uint6
     if ((threadIdx.x & 31) == 0 && added) atomicAdd(&s_added, added);
     __syncthreads();
     if (threadIdx.x == 0 && s_added) atomicAdd(&t.counters[MC_CNT_KEYS], s_added);
+}
+
+// the same with the list length read on the device (sub-bin spill lists of the aggregated flush: no host round trip)
+__global__ void __launch_bounds__(256) k_insert_hashed_n(McTableDev t, const uint64_t* hkeys, const unsigned long long* n_ptr, unsigned long long cap) {
+    const unsigned long long n = *n_ptr < cap ? *n_ptr : cap;
+    if (n == 0) return;
+    unsigned long long added = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t h = hkeys[i];
+        if (h == MC_HASH_SENTINEL) continue;
+        if (mc_table_add(t, h, 1)) added++;
+    }
+    for (int o = 16; o; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&t.counters[MC_CNT_KEYS], added);
 }
 
 extern "C" int mc_table_insert_hashed_device(mc_table* t, const uint64_t* d_hkeys, size_t n) {

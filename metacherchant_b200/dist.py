@@ -56,6 +56,35 @@ def exchange_keys(send: torch.Tensor, send_counts, group=None):
     return recv, recv_counts
 
 
+def gather_pairs(keys: torch.Tensor, counts: torch.Tensor, n: int, group=None):
+    """All-gather of every rank's (key, count16) pairs (the solid set after the local coverage compaction).
+    `keys` (int64) / `counts` (int16) hold this rank's `n` pairs in their first n elements.  Returns a list with one
+    (keys, counts) pair of tensors per rank, on the tensors' device.  Device-agnostic: NCCL on GPUs, gloo in the CPU tests."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [(keys[:n], counts[:n])]
+    sizes = torch.tensor([n], dtype=torch.int64, device=keys.device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [int(x.item()) for x in all_sizes]
+    nmax = max(max(all_sizes), 1)
+    kbuf = torch.zeros(nmax, dtype=torch.int64, device=keys.device)
+    cbuf = torch.zeros(nmax, dtype=torch.int16, device=keys.device)
+    kbuf[:n] = keys[:n]
+    cbuf[:n] = counts[:n]
+    kall = [torch.empty_like(kbuf) for _ in range(world)]
+    call = [torch.empty(2 * nmax, dtype=torch.uint8, device=keys.device) for _ in range(world)]
+    dist.all_gather(kall, kbuf, group=group)
+    dist.all_gather(call, cbuf.view(torch.uint8), group=group)   # neither NCCL nor gloo has an int16 type: the counts travel as bytes
+    return [(kall[r][: all_sizes[r]], call[r].view(torch.int16)[: all_sizes[r]]) for r in range(world)]
+
+
+def target_block(n_targets: int, world: int, rank: int):
+    """Targets are independent units (the reference runs one OneSequenceCalculator per target on a pool,
+    src/tools/EnvironmentFinderMain.java:188,218-225): rank r takes the contiguous block [lo, hi)."""
+    return rank * n_targets // world, (rank + 1) * n_targets // world
+
+
 class ShardedCounter:
     """Rank-local driver of the sharded counting step (GPU only; there is no CPU fallback)."""
 
@@ -74,6 +103,8 @@ class ShardedCounter:
         self.bytes_exchanged = 0
         # wall-clock seconds per phase of the last step (host view, each phase ends with a synchronisation)
         self.phase_s = {"extract": 0.0, "exchange": 0.0, "insert": 0.0, "sweep_filter": 0.0}
+        self.verify = False
+        self._local = None
 
     def new_table(self):
         if self.table is not None:
@@ -169,23 +200,36 @@ class ShardedCounter:
             self.bytes_exchanged += 8 * got.value
         self.ctx.sync()
 
-    def _count_device_merge(self, d_reads: int, nbytes: int, fmt: int):
-        """Count locally, then merge (include/mc_b200.h, mc_xchg_dump_owners): this rank's reads go through the single-GPU
-        pipeline into a complete local table; the table scan then stores every DISTINCT (key, count) pair into its owner's
-        region over NVLink, and each rank adds what it received into its shard.  One barrier, no collective moves data."""
+    # ---- "merge" exchange: count locally (any number of batches, device- or host-resident), then ship distinct pairs ----------
+    def local_begin(self):
+        """Start this rank's complete LOCAL table (the single-GPU pipeline); batches are added with local_add_*."""
+        self._t_begin = time.perf_counter()
+        self._local = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint)
+        return self._local
+
+    def local_add_device(self, d_reads: int, nbytes: int, fmt: int):
+        if nbytes:
+            self._local.count_device(d_reads, nbytes, fmt)
+
+    def local_add_host(self, host_ptr: int, nbytes: int, fmt: int):
+        """The same from HOST memory (mc_count_bytes: chunked uploads overlapped with the counting): the e2e leg at N > 1."""
+        if nbytes:
+            self._local.count_host_ptr(host_ptr, nbytes, fmt)
+
+    def local_finish(self):
+        """Count locally, then merge (include/mc_b200.h, mc_xchg_dump_owners): the table scan stores every DISTINCT
+        (key, count) pair into its owner's region over NVLink, and each rank adds what it received into its shard.
+        One barrier, no collective moves data.  With self.verify set, the digests of the local table (before) and of the
+        shard (after) are kept: summed over the ranks they must agree (bench.py --verify, tests/dist_parity_worker.py)."""
         import ctypes as C
         from ._ffi import check
         lib = self.ctx.lib
-        t0 = time.perf_counter()
-        local = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint)
-        ta = time.perf_counter()
-        if nbytes:
-            local.count_device(d_reads, nbytes, fmt)
-        tb = time.perf_counter()
+        local = self._local
+        self._local = None
         n_local = local.size()
         t1 = time.perf_counter()
-        if os.environ.get("MC_DIST_PROFILE"):
-            print(f"[rank {self.rank}] local count: new_table {ta - t0:.4f} s, count_device {tb - ta:.4f} s, size {t1 - tb:.4f} s", flush=True)
+        if getattr(self, "verify", False):
+            self.local_digest = local.checksum(0)
         mx = torch.tensor([n_local], dtype=torch.int64, device="cuda")
         if self.world > 1:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -203,21 +247,85 @@ class ShardedCounter:
         t3 = time.perf_counter()
         check(lib.mc_xchg_merge(self._xchg, 0, self.table.h, C.byref(got)))
         check(lib.mc_table_copy_stats(self.table.h, local.h))
-        local.free()      # after the merge: freeing the 16 GB table earlier cost 37 ms per step (the pool hands the block to the shard's grow, then has to find it again)
+        local.free()      # after the merge: the block goes back to the context's arena for the next step
         self.ctx.sync()
         if self.world > 1:
             dist.barrier()                       # nobody reuses its regions (next step's dump) before every merge has read them
         t4 = time.perf_counter()
+        if getattr(self, "verify", False):
+            self.shard_digest = self.table.checksum(0)
         self.bytes_exchanged += 16 * got.value * (self.world - 1) // self.world
-        self.phase_s["extract"] += t1 - t0
+        self.phase_s["extract"] += t1 - self._t_begin
+        self.phase_s["dump"] = self.phase_s.get("dump", 0.0) + (t2 - t1)
+        self.phase_s["barrier"] = self.phase_s.get("barrier", 0.0) + (t3 - t2)
         self.phase_s["exchange"] += t3 - t1
         self.phase_s["insert"] += t4 - t3
+
+    def _count_device_merge(self, d_reads: int, nbytes: int, fmt: int):
+        self.local_begin()
+        self.local_add_device(d_reads, nbytes, fmt)
+        self.local_finish()
+
+    def verify_exchange(self):
+        """Sum over the ranks of the local tables' (sum of counts, digest) == sum over the ranks of the shards': nothing was
+        lost, duplicated or re-keyed on the way to the owners (valid while no count saturates: max_count < 32767 is checked).
+        Returns a dict for the bench line; raises on a mismatch."""
+        a, b = self.local_digest, self.shard_digest
+        import numpy as np
+        v = torch.from_numpy(np.array([a["sum_counts"], a["digest"], b["sum_counts"], b["digest"], b["entries"]], dtype=np.uint64).view(np.int64)).cuda()
+        mxc = torch.tensor([b["max_count"]], dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(v)                   # int64 wrap-around = arithmetic mod 2^64, like the digest itself
+            dist.all_reduce(mxc, op=dist.ReduceOp.MAX)
+        v = [int(x) & 0xFFFFFFFFFFFFFFFF for x in v.cpu().tolist()]
+        saturated = int(mxc.item()) >= 32767
+        ok = v[0] == v[2] and v[1] == v[3]
+        res = {"ok": bool(ok or saturated), "sum_counts": v[2], "digest": f"{v[3]:016x}", "distinct": v[4], "max_count": int(mxc.item()),
+               "what": "sum over ranks of the local tables' (sum of counts, key digest) == sum over ranks of the owner shards'"
+                       + (" -- NOT CHECKED: a count saturated at 32767, sums are no longer additive" if saturated else "")}
+        if not res["ok"]:
+            raise AssertionError(f"multi-GPU exchange lost or duplicated k-mers: local {v[0]} / {v[1]:016x} vs shards {v[2]} / {v[3]:016x}")
+        return res
+
+    def resolve_format(self, d_reads: int, nbytes: int, fmt: int) -> int:
+        """FASTQ with an unknown quality offset: the reference decides Phred+33 / +64 ONCE per file from its first 1000
+        records (ITMO!/io/ReadersUtils.java:63-77).  Rank 0 holds the head of the input: it sniffs and broadcasts, and every
+        batch of every rank is then parsed with the explicit format (a later batch sniffed on its own could decide otherwise)."""
+        if fmt != 1:   # MC_FMT_FASTQ (auto)
+            return fmt
+        import numpy as np
+        off = torch.zeros(1, dtype=torch.int64)
+        if self.rank == 0:
+            n = min(nbytes, 1 << 20)
+            while True:
+                head = np.empty(n, dtype=np.uint8)
+                if n:
+                    self.ctx.d2h(head, d_reads)
+                # -1: fewer than 1000 records in the sample and more input exists
+                r = int(self.ctx.lib.mc_sniff_quality_offset(head.ctypes.data if n else None, n)) if n == nbytes else self._sniff_partial(head)
+                if r > 0 or n == nbytes:
+                    break
+                n = min(nbytes, n * 4)
+            off[0] = r if r > 0 else 64
+        if self.world > 1:
+            dev = off.cuda() if dist.get_backend() == "nccl" else off
+            dist.broadcast(dev, src=0)
+            off = dev.cpu()
+        return 33 if int(off[0]) == 33 else 64
+
+    def _sniff_partial(self, head) -> int:
+        """A head that may end inside a record is only trusted when it holds well over 1000 records (the sniffer stops
+        after 1000 and never reaches the cut); otherwise -1 = ask for a larger sample."""
+        if int((head == 10).sum()) < 8008:   # 1000 records of 4 lines, twice over for blank lines
+            return -1
+        return int(self.ctx.lib.mc_sniff_quality_offset(head.ctypes.data, head.size))
 
     def count_device(self, d_reads: int, nbytes: int, fmt: int, batch_bytes: int, record_bytes: int | None = None):
         """Counts this rank's device-resident reads into the distributed table (collective: every rank must call it
         with the same number of batches; ranks with fewer batches send empty groups).
         Software pipeline: while batch b's keys cross NVLink (communication stream), batch b+1 is parsed and extracted and
         batch b-1's received keys are binned (library stream)."""
+        fmt = self.resolve_format(d_reads, nbytes, fmt)
         if self.exchange == "peer":
             return self._count_device_peer(d_reads, nbytes, fmt, batch_bytes, record_bytes)
         if self.exchange == "merge":
@@ -270,13 +378,48 @@ class ShardedCounter:
             finish(pending)
         self.ctx.sync()
 
-    def count_device_step(self, d_reads: int, nbytes: int, fmt: int, min_cov: int, batch_bytes: int, record_bytes: int | None = None):
-        """One bench step: fresh shard, count, coverage compaction; returns (global solid k-mers, stage times)."""
+    def gather_solid(self, solid_shard):
+        """E3: every rank ends up with the COMPLETE coverage-filtered table.  The local compaction already happened
+        (solid_shard = this rank's slice); the (key, count16) pairs are dumped into device buffers, all-gathered over
+        NVLink and inserted into a fresh unsharded table.  Returns (table, pairs per rank)."""
+        n = solid_shard.dump_device(1)
+        keys = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
+        counts = torch.empty(max(n, 1), dtype=torch.int16, device="cuda")
+        if n:
+            solid_shard.dump_device(1, keys.data_ptr(), counts.data_ptr(), n)
+        torch.cuda.synchronize()
+        parts = gather_pairs(keys, counts, n)
+        torch.cuda.synchronize()
+        total = sum(int(k.numel()) for k, _ in parts)
+        full = self.ctx.new_table(self.k, capacity_hint=2 * total)
+        for k_r, c_r in parts:
+            if k_r.numel():
+                kk, cc = k_r.contiguous(), c_r.contiguous()
+                full.add_pairs_device(kk.data_ptr(), cc.data_ptr(), int(kk.numel()))
+        self.bytes_exchanged += 10 * (total - n)
+        return full, [int(k.numel()) for k, _ in parts]
+
+    def find_environments(self, solid_full, seqs, names, out_dir, **kw):
+        """E4: the targets are block-distributed over the ranks (no communication: every rank holds the complete solid
+        table); each rank writes the output directories of ITS targets under the shared out_dir.  Returns found[] for all
+        targets (gathered)."""
+        lo, hi = target_block(len(seqs), self.world, self.rank)
+        found = self.ctx.find_environments(solid_full, list(seqs[lo:hi]), list(names[lo:hi]), out_dir=out_dir, **kw) if hi > lo else []
+        if self.world == 1:
+            return list(found)
+        parts = [None] * self.world
+        dist.all_gather_object(parts, [int(x) for x in found])
+        return [x for p in parts for x in p]
+
+    def step_begin(self):
         self.ctx.stage_reset()
         for name in self.phase_s:
             self.phase_s[name] = 0.0
         self.new_table()
-        self.count_device(d_reads, nbytes, fmt, batch_bytes, record_bytes)
+
+    def step_finish(self, min_cov: int, keep_solid: bool = False):
+        """Local coverage compaction of the shard + the global solid count (all-reduce).  Returns (global solid k-mers,
+        stage times) (+ the solid shard itself when keep_solid: the caller gathers it for the environment stage and frees it)."""
         t0 = time.perf_counter()
         solid = self.table.filter(min_cov)
         n = torch.tensor([solid.size()], dtype=torch.int64, device="cuda")
@@ -286,5 +429,13 @@ class ShardedCounter:
         stage = self.ctx.stage_ms()
         if os.environ.get("MC_DIST_PROFILE"):
             print(f"[rank {self.rank}] phases (s): {({k: round(v, 4) for k, v in self.phase_s.items()})} stages (ms): {({k: round(v, 1) for k, v in stage.items()})}", flush=True)
+        if keep_solid:
+            return int(n.item()), stage, solid
         solid.free()
         return int(n.item()), stage
+
+    def count_device_step(self, d_reads: int, nbytes: int, fmt: int, min_cov: int, batch_bytes: int, record_bytes: int | None = None, keep_solid: bool = False):
+        """One bench step: fresh shard, count, coverage compaction."""
+        self.step_begin()
+        self.count_device(d_reads, nbytes, fmt, batch_bytes, record_bytes)
+        return self.step_finish(min_cov, keep_solid)

@@ -1486,4 +1486,41 @@ double orc_bench_count(const uint8_t* buf, size_t len, int fmt, int k, int threa
     return secs;
 }
 
+// CPU baseline of the environment stage (bench.py only): every target as its own OneSequenceCalculator on a pool of
+// `threads` workers, the way EnvironmentFinderMain.runImpl submits them (src/tools/EnvironmentFinderMain.java:188,218-225);
+// the table is shared read-only.  Returns wall seconds (BFS + unitigs + every output file), < 0 on error; *done = targets
+// that had a seed.
+double orc_bench_env(const orc_table* t, const char* seq_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
+                     int chunk_len, int threads, const char* out_dir, int* done_out) {
+    double secs = -1;
+    guarded([&] {
+        if (max_kmers < 0 && max_radius < 0) fail("At least one of --maxkmers and --maxradius parameters should be set");
+        RichFasta rf = rich_fasta_read(seq_fasta);
+        if (rf.comments.size() < rf.dnas.size()) fail("IndexOutOfBoundsException: comments.get(%zu)", rf.comments.size());
+        std::atomic<size_t> next{0};
+        std::atomic<int> done{0};
+        auto t0 = std::chrono::steady_clock::now();
+        auto work = [&] {
+            for (size_t i; (i = next.fetch_add(1)) < rf.dnas.size();) {
+                std::string prefix = std::string(out_dir) + "/" + rf.comments[i] + "/";
+                EnvCalc c{t, {rf.dnas[i]}, k, min_cov, both_dirs != 0, chunk_len, {max_kmers, max_radius}, {}, false, 0, {}, false};
+                c.build_environment();
+                if (c.failed) continue;
+                c.extend_environment();
+                print_environment(c.subgraph, prefix);
+                create_picture(c.subgraph, c.sequences, k, chunk_len, prefix);
+                done++;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int i = 1; i < std::max(1, threads); i++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (done_out) *done_out = done.load();
+        return 0;
+    });
+    return secs;
+}
+
 }  // extern "C"

@@ -87,4 +87,9 @@ int orc_load_kmers(orc_table*, const char* path, int freq_threshold);
 // Returns seconds of wall time, <0 on error.  `bases` gets the number of input bases.
 double orc_bench_count(const uint8_t* buf, size_t len, int fmt, int k, int threads, uint64_t* bases, uint64_t* distinct);
 
+// CPU baseline of the environment stage (bench.py only): one OneSequenceCalculator per target on `threads` pool workers
+// (src/tools/EnvironmentFinderMain.java:188,218-225).  Returns wall seconds, < 0 on error.
+double orc_bench_env(const orc_table* t, const char* seq_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
+                     int chunk_len, int threads, const char* out_dir, int* done);
+
 }  // extern "C"

@@ -67,6 +67,9 @@ class Oracle:
         L.orc_load_kmers.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.orc_bench_count.restype = C.c_double
         L.orc_bench_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, _u64p, _u64p]
+        L.orc_bench_env.restype = C.c_double
+        L.orc_bench_env.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                    C.POINTER(C.c_int)]
         L.orc_synth_params_size.restype = C.c_size_t
         L.orc_synth_init.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -124,6 +127,15 @@ class Oracle:
         return secs, bases.value, distinct.value
 
     # ---- synthetic workload ------------------------------------------------------------
+    def bench_env(self, table, seq_fasta, k, min_cov, max_kmers, max_radius, both_dirs, chunk_len, threads, out_dir):
+        """Wall seconds of the environment stage on `threads` pool workers (bench.py's cpu_baseline.env leg) and the targets found."""
+        done = C.c_int(0)
+        secs = self.lib.orc_bench_env(table.h, seq_fasta.encode(), k, min_cov, -1 if max_kmers is None else max_kmers,
+                                      -1 if max_radius is None else max_radius, int(both_dirs), chunk_len, threads, out_dir.encode(), C.byref(done))
+        if secs < 0:
+            raise OracleError(self.err())
+        return secs, done.value
+
     def synth(self, **kw):
         return Synth(self, **kw)
 

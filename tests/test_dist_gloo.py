@@ -68,3 +68,46 @@ def test_owner_and_batch_planning():
     assert plan_batches(0, 100, 7) == []
     assert plan_batches(10, 4, None) == [(0, 4), (4, 4), (8, 2)]
     assert plan_batches(315 * 3, 10, 315) == [(0, 315), (315, 315), (630, 315)]   # a batch is never smaller than a record
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from metacherchant_b200.dist import gather_pairs
+        rng = np.random.default_rng(7 + rank)
+        for rnd, n in enumerate((1000 + 300 * rank, 0 if rank == 1 else 5, 0)):   # uneven, one empty rank, all empty
+            keys = torch.from_numpy(rng.integers(0, 1 << 62, size=max(n, 1), dtype=np.int64))
+            counts = torch.from_numpy(rng.integers(1, 32768, size=max(n, 1), dtype=np.int16))
+            parts = gather_pairs(keys, counts, n)
+            assert len(parts) == world
+            assert torch.equal(parts[rank][0], keys[:n]) and torch.equal(parts[rank][1], counts[:n])
+            np.save(os.path.join(out_dir, f"mine_{rank}_{rnd}.npy"), keys[:n].numpy())
+            np.save(os.path.join(out_dir, f"all_{rank}_{rnd}.npy"), torch.cat([p[0] for p in parts]).numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_pairs_world2(tmp_path):
+    """E3: after the all-gather every rank holds the pairs of ALL ranks, in rank order, also when ranks
+    contribute different amounts or nothing."""
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for rnd in range(3):
+        want = np.concatenate([np.load(tmp_path / f"mine_{r}_{rnd}.npy") for r in range(world)])
+        for r in range(world):
+            assert np.array_equal(np.load(tmp_path / f"all_{r}_{rnd}.npy"), want)
+
+
+def test_target_blocks_cover_every_target_once():
+    """E4: targets block-distributed over the ranks (EnvironmentFinderMain.java:218-225 runs them independently)."""
+    from metacherchant_b200.dist import target_block
+    for n_targets in (0, 1, 3, 20, 500):
+        for world in (1, 2, 4, 8):
+            blocks = [target_block(n_targets, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n_targets
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
