@@ -214,7 +214,8 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
  *   "segment_keys" (keys applied per count launch, 0 = automatic), "count_tile", "count_variant" (k_bin_count shape),
  *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32),
  *   "agg" (two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on), "agg_unit" (keys per
- *   aggregation unit, 0 = automatic), "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --
+ *   aggregation unit, 0 = automatic), "scatter_tma" (1 = default: the scatter kernels hand every bin run to the copy engine with cp.async.bulk; 0: per-sector stores),
+ *   "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --
  *   a step made of several count calls; reset with mc_ctx_stage_reset) */
 int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);
 /* table updates are buffered in bins; every read of the table applies them first, this call does so explicitly */
@@ -239,6 +240,10 @@ int mc_sniff_quality_offset(const void* buf, size_t len);
  * `peak` = the largest size the map ever had (a java HashMap never shrinks; 0 = its final size).  order[i] = index into `codes`
  * of the i-th entry; *n_out = number of distinct keys. */
 int mc_kmer_hashmap_order(const uint64_t* codes, size_t n, int k, size_t peak, uint32_t* order, size_t* n_out);
+/* Host only (test surface): the text Java's String.format("%6.2f ", floatValue) produces -- the cells of Jacard_sym.txt /
+ * Jacard_alt.txt (src/tools/EnvironmentFinderMultiMain.java:141-142,163-164): shortest round-trip digits of the widened double,
+ * rounded HALF_UP.  `out` must have room for 48 characters. */
+int mc_java_format_6_2f(float v, char* out);
 
 #ifdef __cplusplus
 }

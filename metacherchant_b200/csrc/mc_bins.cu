@@ -53,9 +53,26 @@ static size_t scatter_smem_bytes(uint32_t P) {
     return keys * 8 + (size_t)P * 8 + (size_t)P * 4 + ((size_t)P + 1) * 4 + (keys / 4) * 2 + 64;
 }
 
+// ---- bulk asynchronous copies (the TMA unit, sm_90+/sm_100a): shared memory -> global memory ----------------------------------
+// A bin's run of the sorted tile is one contiguous, 32-byte aligned piece of shared memory that goes to one contiguous, 32-byte
+// aligned piece of the bin: ONE cp.async.bulk per (tile, non-empty bin) hands the whole run to the copy engine, instead of every
+// lane moving one sector through registers (2 x LDS.128 + three table look-ups + STG.256 per sector in round 1, on the
+// shared-memory pipe that bounds this kernel).  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the copies this thread committed have READ their shared-memory source (it may be overwritten); they need not have landed yet
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory (the sorted tile) become visible to the async proxy (the copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#define SC_MAX_PER ((1u << MC_MAX_PBITS) / SC_THREADS)   // bins owned by one thread in the scan / bulk-store phases
+
 // `D.use` = the bins are the OWNER ranks of the multi-GPU exchange: bin o's run goes to D.base[o], the receive region this rank
 // owns inside rank o's buffer (peer memory mapped through CUDA IPC: the sector stores travel over NVLink), mc_xchg.cu.
-// tiles first_tile, first_tile + tile_stride, ... of `flat` (one CTA)
+// tiles first_tile, first_tile + tile_stride, ... of `flat` (one CTA).  TMA: runs leave through bulk copies (never with D.use:
+// peer-memory destinations keep the per-sector stores).
+template <bool TMA>
 __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat, uint64_t n, const McBinsDev& B, int shard_bits, uint32_t shard_id,
                                               unsigned int* flags, const McBinDst& D, uint32_t first_tile, uint32_t tile_stride) {
     extern __shared__ unsigned long long s_mem[];
@@ -113,6 +130,7 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
             if (j & 1) rk[j >> 1] |= r << 16;
             else rk[j >> 1] = r;
         }
+        if (TMA) bulk_wait_read();   // my bulk stores of the previous tile have read `sorted` (they overlapped the loads + histogram above)
         __syncthreads();
         // exclusive scan of the padded run lengths; reserve the global runs; write pads and the sector -> bin map
         {
@@ -129,12 +147,17 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
             uint32_t wbase = 0;
             for (int w = 0; w < warp; w++) wbase += s_warp_tot[w];
             uint32_t run = wbase + incl - mine;
-            for (uint32_t b = b0; b < b0 + per && b < P; b++) {
+#pragma unroll
+            for (uint32_t i = 0; i < SC_MAX_PER; i++) {
+                const uint32_t b = b0 + i;
+                if (i >= per || b >= P) continue;
                 const uint32_t c = S.hist[b], pc = (c + 3) & ~3u;
                 S.off[b] = run;
-                S.gbase[b] = pc ? atomicAdd(&B.cursors[b], (unsigned long long)pc) : 0ULL;
+                const unsigned long long gpos = pc ? atomicAdd(&B.cursors[b], (unsigned long long)pc) : 0ULL;
+                S.gbase[b] = gpos;
                 for (uint32_t j = c; j < pc; j++) S.sorted[run + j] = MC_HASH_SENTINEL;
-                for (uint32_t j = 0; j < pc; j += 4) S.secbin[(run + j) >> 2] = (uint16_t)b;
+                if (!TMA)
+                    for (uint32_t j = 0; j < pc; j += 4) S.secbin[(run + j) >> 2] = (uint16_t)b;
                 run += pc;
             }
             if (threadIdx.x == SC_THREADS - 1) S.off[P] = run;   // the last thread owns the last bins
@@ -149,18 +172,14 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
             const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
             S.sorted[S.off[bin] + r] = hl;
         }
-        __syncthreads();
-        // pass C: one aligned 32-byte sector per lane
-        const uint32_t n_sec = S.off[P] >> 2;
-        for (uint32_t j = threadIdx.x; j < n_sec; j += SC_THREADS) {
-            const uint32_t bin = S.secbin[j];
-            const unsigned long long pos = S.gbase[bin] + (j * 4 - S.off[bin]);
-            const ulonglong2 lo2 = *(const ulonglong2*)&S.sorted[j * 4], hi2 = *(const ulonglong2*)&S.sorted[j * 4 + 2];
+        // one sector of the sorted tile to its bin, or (bin full: heavy hitter or undersized batch) to the shared spill list
+        auto store_sector = [&](uint32_t bin, unsigned long long pos, uint32_t at) {
+            const ulonglong2 lo2 = *(const ulonglong2*)&S.sorted[at], hi2 = *(const ulonglong2*)&S.sorted[at + 2];
             const uint64_t k0 = lo2.x, k1 = lo2.y, k2 = hi2.x, k3 = hi2.y;
             if (pos + 4 <= B.cap) {
                 uint64_t* dst = (D.use ? D.base[bin] : B.keys + (uint64_t)bin * B.cap) + pos;
                 asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
-            } else {   // bin full (heavy hitter or undersized batch): shared spill list, applied with direct updates
+            } else {   // applied with direct updates
                 const uint64_t kk[4] = {k0, k1, k2, k3};
                 uint32_t real = 0;
 #pragma unroll
@@ -174,20 +193,54 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
                     atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
                 }
             }
+        };
+        if (TMA) {
+            // pass C, bulk form: the thread that reserved a bin's run hands it to the copy engine in one piece
+            fence_async_smem();
+            __syncthreads();
+            const uint32_t b0 = threadIdx.x * per;
+#pragma unroll
+            for (uint32_t i = 0; i < SC_MAX_PER; i++) {
+                const uint32_t b = b0 + i;
+                if (i >= per || b >= P) continue;
+                // (off and gbase stay as the scan left them until the next tile's scan, which is behind a barrier)
+                const uint32_t run = S.off[b], pc = S.off[b + 1] - run;
+                if (pc == 0) continue;
+                const unsigned long long pos = S.gbase[b];
+                if (pos + pc <= B.cap) {
+                    bulk_store_s2g(B.keys + (uint64_t)b * B.cap + pos, &S.sorted[run], pc * 8u);
+                } else {   // the run crosses the end of its bin: sector by sector (what fits goes to the bin, the rest spills)
+                    for (uint32_t j = 0; j < pc; j += 4) store_sector(b, pos + j, run + j);
+                }
+            }
+            bulk_commit();
+            // no barrier here: the next tile's loads and histogram touch neither `sorted` nor my registers' runs; the wait + barrier
+            // in front of the next scan phase orders the overwrite of `sorted` after these copies have read it
+        } else {
+            __syncthreads();
+            // pass C: one aligned 32-byte sector per lane
+            const uint32_t n_sec = S.off[P] >> 2;
+            for (uint32_t j = threadIdx.x; j < n_sec; j += SC_THREADS) {
+                const uint32_t bin = S.secbin[j];
+                store_sector(bin, S.gbase[bin] + (j * 4 - S.off[bin]), j * 4);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
                                                             unsigned int* flags, McBinDst D) {
-    scatter_tiles(flat, n, B, shard_bits, shard_id, flags, D, blockIdx.x, gridDim.x);
+    scatter_tiles<TMA>(flat, n, B, shard_bits, shard_id, flags, D, blockIdx.x, gridDim.x);
+    if (TMA) bulk_wait_read();   // shared memory must outlive the copy engine's reads
 }
 
 // Second level: first-level bins b0 .. b0 + G - 1, each split into 2^B2.pbits sub-bins by the hash bits below the
 // first-level prefix.  Group slot g owns the sub-bin region and cursor block g of B2; the run lengths of the first level
 // are read on the device (no host round trip); the spill list is shared by the whole group.  The (bin, tile) pairs are
 // one flat index space walked by a persistent grid, so the CTAs work on the same one or two bins at any time.
+template <bool TMA>
 __global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter2(McBinsDev B1, uint32_t b0, uint32_t G, uint32_t tiles_per_bin, McBinsDev B2, unsigned int* flags) {
     const uint32_t P2 = 1u << B2.pbits;
     McBinDst none;
@@ -200,8 +253,9 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter2(McBinsDev B1, ui
         McBinsDev S = B2;
         S.keys = B2.keys + (uint64_t)g * P2 * B2.cap;
         S.cursors = B2.cursors + (uint64_t)g * (P2 + 1);
-        scatter_tiles(B1.keys + (uint64_t)(b0 + g) * B1.cap, n, S, 0, 0, flags, none, tile, 0x40000000u);
+        scatter_tiles<TMA>(B1.keys + (uint64_t)(b0 + g) * B1.cap, n, S, 0, 0, flags, none, tile, 0x40000000u);
     }
+    if (TMA) bulk_wait_read();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -526,6 +580,15 @@ void mc_batch_reserve(mc_table* t, uint64_t ub, uint64_t total_hint) {
     batch_create(t, ub, total_hint);
 }
 
+static void scatter_attrs(mc_ctx* ctx) {   // per context (= per device): opt in to > 48 KB of dynamic shared memory
+    if (!mc_attr_once(ctx, MC_ATTR_SCATTER)) return;
+    const int smem = (int)scatter_smem_bytes(1u << MC_MAX_PBITS);
+    MC_CUDA(cudaFuncSetAttribute(k_bin_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MC_CUDA(cudaFuncSetAttribute(k_bin_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MC_CUDA(cudaFuncSetAttribute(k_bin_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MC_CUDA(cudaFuncSetAttribute(k_bin_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+}
+
 void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
     if (n == 0) return;
     mc_ctx* ctx = t->ctx;
@@ -533,12 +596,12 @@ void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
     if (!B || !B->dev.keys || B->dev.spill_cap < n) mc_throw(MC_ERR_ARG, "internal: scatter without a reserved batch");
     McStageTimer tm(ctx, MC_ST_SCATTER);
     const size_t smem = scatter_smem_bytes(B->P);
-    if (mc_attr_once(ctx, MC_ATTR_SCATTER))
-        MC_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
+    scatter_attrs(ctx);
     const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
     McBinDst none{};
-    k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, B->dev, t->dev.shard_bits, t->shard_id, t->dev.flags, none);
+    if (ctx->tune_scatter_tma) k_bin_scatter<true><<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, B->dev, t->dev.shard_bits, t->shard_id, t->dev.flags, none);
+    else k_bin_scatter<false><<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, B->dev, t->dev.shard_bits, t->shard_id, t->dev.flags, none);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
     B->used += n;
@@ -548,11 +611,10 @@ void mc_launch_owner_scatter(mc_ctx* ctx, const uint64_t* d_flat, uint64_t n, co
     if (n == 0) return;
     const uint32_t P = 1u << owners.pbits;
     const size_t smem = scatter_smem_bytes(P);
-    if (mc_attr_once(ctx, MC_ATTR_SCATTER))
-        MC_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
+    scatter_attrs(ctx);
     const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
-    k_bin_scatter<<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, owners, 0, 0, flags, dst);
+    k_bin_scatter<false><<<grid, SC_THREADS, smem, ctx->stream>>>(d_flat, n, owners, 0, 0, flags, dst);   // peer-memory destinations: per-sector stores
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
 }
@@ -642,14 +704,14 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     B2.spill_cursor = B2.cursors + (n_cursors - 2);
     unsigned long long* d_ticket = B2.cursors + (n_cursors - 1);
 
+    scatter_attrs(ctx);
     if (mc_attr_once(ctx, MC_ATTR_AGG)) {
-        MC_CUDA(cudaFuncSetAttribute(k_bin_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1u << MC_MAX_PBITS)));
         MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
         MC_CUDA(cudaFuncSetAttribute(k_bin_agg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
     }
     int agg_per_sm = 0, sc_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg<false>, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc_per_sm, k_bin_scatter2, SC_THREADS, scatter_smem_bytes(P2)) != cudaSuccess || sc_per_sm < 1) sc_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc_per_sm, k_bin_scatter2<true>, SC_THREADS, scatter_smem_bytes(P2)) != cudaSuccess || sc_per_sm < 1) sc_per_sm = 1;
     cudaGetLastError();
 
     // The host runs ONE group ahead of the device: group g is queued before the status block of group g - 1 is looked at, so
@@ -723,7 +785,8 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 McStageTimer tm(ctx, MC_ST_SCATTER);
                 const uint32_t tiles = (uint32_t)((max_bin + SC_TILE - 1) / SC_TILE);
                 const uint32_t x = (uint32_t)std::min<uint64_t>((uint64_t)tiles * G, (uint64_t)ctx->sm_count * sc_per_sm);
-                k_bin_scatter2<<<x, SC_THREADS, scatter_smem_bytes(P2), st>>>(B->dev, b0, G, tiles, B2, t->dev.flags);
+                if (ctx->tune_scatter_tma) k_bin_scatter2<true><<<x, SC_THREADS, scatter_smem_bytes(P2), st>>>(B->dev, b0, G, tiles, B2, t->dev.flags);
+                else k_bin_scatter2<false><<<x, SC_THREADS, scatter_smem_bytes(P2), st>>>(B->dev, b0, G, tiles, B2, t->dev.flags);
                 MC_LAUNCH(ctx);
                 MC_CUDA(cudaGetLastError());
             }
@@ -927,6 +990,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "count_variant" && value >= 0 && value <= 3) ctx->tune_count_variant = (int)value;
     else if (n == "agg" && value >= -1 && value <= 1) ctx->tune_agg = (int)value;
     else if (n == "keep_stage_ms" && value >= 0 && value <= 1) ctx->keep_stage_ms = (int)value;
+    else if (n == "scatter_tma" && value >= 0 && value <= 1) ctx->tune_scatter_tma = (int)value;
     else if (n == "agg_unit" && value >= 0 && value <= (1 << 24)) ctx->tune_agg_unit = (uint32_t)value;
     else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;
     else {

@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <charconv>
 #include <atomic>
 #include <exception>
 #include <mutex>
@@ -873,43 +874,52 @@ extern "C" int mc_kmer_hashmap_order(const uint64_t* codes, size_t n, int k, siz
 // ------------------------------------------------------------------------------------------------
 // Seam 4: environment-finder-multi
 // ------------------------------------------------------------------------------------------------
-static std::string java_format_6_2f(float v) {   // String.format("%6.2f ", float): shortest digits of the widened double, HALF_UP
+// String.format("%6.2f ", floatValue) (src/tools/EnvironmentFinderMultiMain.java:141-142,163-164).  java.util.Formatter widens
+// the float to double, takes the digits of Double.toString -- the shortest decimal that reads back as the same double -- and
+// rounds THAT digit string HALF_UP to two decimals (sun.misc.FormattedFloatingDecimal.applyPrecision); C's printf rounds the
+// exact binary value half-to-even instead, so 0.125f prints " 0.13" in Java and " 0.12" in C.
+// Written on integers (shortest digits from std::to_chars, then one division) and pinned on hand-derived Java outputs in
+// tests/test_host_logic.py; the oracle's own formatter works on digit strings, so the two do not share an algorithm.
+static std::string java_format_6_2f(float v) {
     if (std::isnan(v)) return "   NaN ";
     if (std::isinf(v)) return v > 0 ? "Infinity " : "-Infinity ";
-    double dv = (double)v;
-    bool neg = std::signbit(dv);
-    dv = std::fabs(dv);
-    char sci[64];
-    for (int prec = 0; prec <= 17; prec++) {
-        snprintf(sci, sizeof sci, "%.*e", prec, dv);
-        if (strtod(sci, nullptr) == dv) break;
+    const double dv = std::fabs((double)v);
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, dv, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest round-trip digits
+    *r.ptr = 0;
+    unsigned long long mant = 0;   // the digits as one integer (<= 17 digits)
+    int n_digits = 0, exp10 = 0;
+    for (const char* p = buf; *p; p++) {
+        if (*p == 'e') { exp10 = atoi(p + 1); break; }
+        if (*p >= '0' && *p <= '9') { mant = mant * 10 + (unsigned)(*p - '0'); n_digits++; }
     }
-    std::string m(sci);
-    size_t epos = m.find('e');
-    int exp10 = atoi(m.c_str() + epos + 1);
+    // dv = mant * 10^(exp10 - n_digits + 1); hundredths = dv * 100, HALF_UP: drop `drop` digits, look at the first dropped one
+    const int scale = exp10 - n_digits + 1 + 2;
+    unsigned __int128 hundredths;
+    if (scale >= 0) {
+        hundredths = mant;
+        for (int i = 0; i < scale && i < 30; i++) hundredths *= 10;   // a float is < 3.5e38: fits 128 bits
+    } else if (-scale > 19) {
+        hundredths = 0;                                                // smaller than 0.5e-2 by far
+    } else {
+        unsigned long long p10 = 1;
+        for (int i = 0; i < -scale - 1; i++) p10 *= 10;
+        hundredths = (mant / p10 + 5) / 10;                            // first dropped digit >= 5 rounds up
+    }
     std::string digits;
-    for (size_t i = 0; i < epos; i++)
-        if (m[i] != '.') digits.push_back(m[i]);
-    int point = exp10 + 1;
-    std::string ip, fp;
-    if (point <= 0) { ip = "0"; fp = std::string((size_t)(-point), '0') + digits; }
-    else if ((size_t)point >= digits.size()) { ip = digits + std::string((size_t)point - digits.size(), '0'); fp = ""; }
-    else { ip = digits.substr(0, (size_t)point); fp = digits.substr((size_t)point); }
-    while (fp.size() < 3) fp.push_back('0');
-    bool up = fp[2] >= '5';
-    std::string all = ip + fp.substr(0, 2);
-    if (up) {
-        int i = (int)all.size() - 1;
-        while (i >= 0) {
-            if (all[(size_t)i] == '9') { all[(size_t)i] = '0'; i--; }
-            else { all[(size_t)i]++; break; }
-        }
-        if (i < 0) all = "1" + all;
-    }
-    std::string r = all.substr(0, all.size() - 2) + "." + all.substr(all.size() - 2);
-    if (neg) r = "-" + r;
-    while (r.size() < 6) r = " " + r;
-    return r + " ";
+    do { digits.insert(digits.begin(), (char)('0' + (int)(hundredths % 10))); hundredths /= 10; } while (hundredths != 0);
+    while (digits.size() < 3) digits.insert(digits.begin(), '0');
+    std::string out = digits.substr(0, digits.size() - 2) + "." + digits.substr(digits.size() - 2);
+    if (std::signbit(v)) out.insert(out.begin(), '-');                 // Java prints -0.00 for a negative value that rounds to zero
+    if (out.size() < 6) out.insert(0, 6 - out.size(), ' ');
+    return out + " ";
+}
+// host-only test surface (tests/test_host_logic.py): out receives the NUL-terminated text, at most 48 characters
+extern "C" int mc_java_format_6_2f(float v, char* out) {
+    if (!out) return MC_ERR_ARG;
+    const std::string s = java_format_6_2f(v);
+    memcpy(out, s.c_str(), s.size() + 1);
+    return MC_OK;
 }
 
 extern "C" int mc_env_multi(mc_ctx* ctx, const char* const* env_paths, int n_envs, const char* seq_fasta, int gene_id, const char* out_dir) {

@@ -34,54 +34,75 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t pat) {
     const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
     return ~t & 0x80808080u;
 }
-__device__ __forceinline__ uint32_t term_mask32(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint32_t base, uint8_t pad) {
+// Three masks over the 32 bytes at `base`: bit j of
+//   term = byte j is a line terminator ('\n', or '\r' not followed by '\n'),
+//   crlf = byte j is the '\n' of a "\r\n" pair (the line's content then ends one byte earlier),
+//   mark = byte j is a character that opens a header / comment line ('@' '+' for FASTQ, '>' ';' for FASTA).
+// Passes 2-4 of the parser work from these masks and never touch the input bytes again (round 1 re-read the whole
+// chunk twice for one byte per line).
+struct McMasks { uint32_t term, crlf, mark; };
+__device__ __forceinline__ uint32_t pack_msb(uint32_t x) { return (((x >> 7) * 0x01020408u) >> 24) & 0xFu; }   // 0x80 flags of 4 bytes -> 4 bits
+template <bool FASTA>
+__device__ __forceinline__ McMasks term_mask32(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint32_t base, uint8_t pad) {
     __align__(16) uint8_t b[48];
     const uint32_t lo = mis, hi = mis + n;   // valid aligned-coordinate range [lo, hi)
-    if (base >= lo && base + 33 <= hi) {
-        // interior: eight 32-bit words, four bytes per step (SWAR); '\n', or '\r' not followed by '\n', ends a line
+    const uint32_t m0 = FASTA ? 0x3E3E3E3Eu : 0x40404040u, m1 = FASTA ? 0x3B3B3B3Bu : 0x2B2B2B2Bu;   // '>' ';'  /  '@' '+'
+    McMasks r{0, 0, 0};
+    if (base >= lo + 1 && base + 33 <= hi) {
+        // interior: eight 32-bit words, four bytes per step (SWAR)
         const uint4* p = reinterpret_cast<const uint4*>(abuf + base);
         const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
         const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        uint32_t nl[9];
+        uint32_t nl[9], cr[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) nl[i] = eq_bytes(w[i], 0x0A0A0A0Au);
+        for (int i = 0; i < 8; i++) { nl[i] = eq_bytes(w[i], 0x0A0A0A0Au); cr[i] = eq_bytes(w[i], 0x0D0D0D0Du); }
         nl[8] = __ldg(abuf + base + 32) == '\n' ? 0x80u : 0u;
-        uint32_t m = 0;
+        uint32_t cr_prev = __ldg(abuf + base - 1) == '\r' ? 0x80000000u : 0u;   // the byte in front of this word
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const uint32_t cr = eq_bytes(w[i], 0x0D0D0D0Du);
             const uint32_t nl_next = (nl[i] >> 8) | (nl[i + 1] << 24);
-            const uint32_t term = nl[i] | (cr & ~nl_next);
-            m |= ((((term >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+            const uint32_t term = nl[i] | (cr[i] & ~nl_next);
+            const uint32_t cr_before = (cr[i] << 8) | (cr_prev >> 24);   // byte j-1 is '\r'
+            cr_prev = cr[i];
+            r.term |= pack_msb(term) << (4 * i);
+            r.crlf |= pack_msb(nl[i] & cr_before) << (4 * i);
+            r.mark |= pack_msb(eq_bytes(w[i], m0) | eq_bytes(w[i], m1)) << (4 * i);
         }
-        return m;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 33; j++) {
-            uint32_t a = base + j;
-            b[j] = (a >= lo && a < hi) ? __ldg(abuf + a) : (a == hi ? pad : (uint8_t)0);
-        }
+        return r;
     }
-    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 34; j++) {   // b[0] = the byte in front of the word, b[1..32] the word, b[33] the byte after it
+        const uint32_t a = base + j - 1;
+        b[j] = (base + j >= 1 && a >= lo && a < hi) ? __ldg(abuf + a) : ((base + j >= 1 && a == hi) ? pad : (uint8_t)0);
+    }
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-        uint8_t c = b[j];
-        bool t = (c == '\n') || (c == '\r' && b[j + 1] != '\n');
-        m |= (uint32_t)t << j;
+        const uint8_t c = b[j + 1];
+        r.term |= (uint32_t)((c == '\n') || (c == '\r' && b[j + 2] != '\n')) << j;
+        r.crlf |= (uint32_t)(c == '\n' && b[j] == '\r') << j;
+        r.mark |= (uint32_t)(FASTA ? (c == '>' || c == ';') : (c == '@' || c == '+')) << j;
     }
     // mask off positions outside the chunk
-    if (base < lo) m &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
-    if (base + 32 > hi) m &= (hi <= base) ? 0u : (0xFFFFFFFFu >> (base + 32 - hi));
-    return m;
+    uint32_t keep = 0xFFFFFFFFu;
+    if (base < lo) keep &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
+    if (base + 32 > hi) keep &= (hi <= base) ? 0u : (0xFFFFFFFFu >> (base + 32 - hi));
+    r.term &= keep; r.crlf &= keep; r.mark &= keep;
+    return r;
 }
 
-// pass 1 of the line index: terminator bit masks (kept: pass 2 reads them instead of the bytes) and their count per tile
+// pass 1 of the line index: the three masks (kept: the later passes read them instead of the bytes) and the number of
+// terminators per tile.  masks[] holds, per 32 input bytes, {term, crlf, mark} in three planes of n_words words.
+template <bool FASTA>
 __global__ void __launch_bounds__(256) k_count_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint8_t pad,
-                                                     uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ masks) {
+                                                     uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ masks, uint32_t n_words) {
     uint32_t base = blockIdx.x * TILE_BYTES + threadIdx.x * 32;
-    const uint32_t mask = base < mis + n ? term_mask32(abuf, mis, n, base, pad) : 0;
-    masks[blockIdx.x * 256u + threadIdx.x] = mask;
-    uint32_t c = __popc(mask);
+    McMasks m{0, 0, 0};
+    if (base < mis + n) m = term_mask32<FASTA>(abuf, mis, n, base, pad);
+    const uint32_t wi = blockIdx.x * 256u + threadIdx.x;
+    masks[wi] = m.term;
+    masks[n_words + wi] = m.crlf;
+    masks[2 * n_words + wi] = m.mark;
+    uint32_t c = __popc(m.term);
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     __shared__ uint32_t s[8];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
@@ -95,7 +116,7 @@ __global__ void __launch_bounds__(256) k_count_terms(const uint8_t* __restrict__
 
 // single CTA: exclusive scan of tile_counts in place, total (+ virtual last line) into the header
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_counts, uint32_t n_tiles, const uint8_t* buf, uint32_t n, McParseHeader* h,
-                                                     int final_chunk) {
+                                                     int final_chunk, int fasta) {
     __shared__ uint32_t s[1024];
     uint32_t per = (n_tiles + 1023) / 1024;
     uint32_t lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
@@ -128,15 +149,23 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_counts, uint
         h->final_state = 0;
         h->total_seq_bytes = 0;
         h->max_seq_len = 0;
+        const uint8_t c0 = n ? buf[0] : 0;
+        h->first_mark = fasta ? (c0 == '>' || c0 == ';') : (c0 == '@' || c0 == '+');
+        h->pad_ = 0;
     }
 }
 
-__global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, const uint32_t* __restrict__ masks,
-                                                     const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ line_end, uint32_t n_lines,
-                                                     int final_chunk) {
+// pass 2: line_end[i] = position of line i's terminator, and one flag byte per line:
+//   bit 0 = the terminator is the '\n' of "\r\n" (content ends one byte earlier),
+//   bit 1 = the first byte of the NEXT line is a header / comment mark (line 0's own mark is McParseHeader.first_mark).
+__global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, const uint32_t* __restrict__ masks, uint32_t n_words,
+                                                     const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ line_end, uint8_t* __restrict__ line_flags,
+                                                     uint32_t n_lines, int final_chunk) {
     const uint8_t* buf = abuf + mis;
     uint32_t base = blockIdx.x * TILE_BYTES + threadIdx.x * 32;
-    uint32_t m = masks[blockIdx.x * 256u + threadIdx.x];
+    const uint32_t wi = blockIdx.x * 256u + threadIdx.x;
+    uint32_t m = masks[wi];
+    const uint32_t crlf = masks[n_words + wi], mark = masks[2 * n_words + wi];
     uint32_t c = __popc(m);
     // block exclusive scan of c
     uint32_t incl = c;
@@ -154,17 +183,27 @@ __global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__
     while (m) {
         int j = __ffs(m) - 1;
         m &= m - 1;
+        const uint32_t next_mark = j < 31 ? (mark >> (j + 1)) & 1u : (wi + 1 < n_words ? masks[2 * n_words + wi + 1] & 1u : 0u);
+        line_flags[pos] = (uint8_t)(((crlf >> j) & 1u) | (next_mark << 1));
         line_end[pos++] = base + j - mis;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && final_chunk && n > 0 && buf[n - 1] != '\n' && buf[n - 1] != '\r') line_end[n_lines - 1] = n;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && final_chunk && n > 0 && buf[n - 1] != '\n' && buf[n - 1] != '\r') {
+        line_end[n_lines - 1] = n;      // the unterminated last line of the input (BufferedReader.readLine)
+        line_flags[n_lines - 1] = 0;
+    }
 }
 
-// content span of line i: [start, end), the '\r' of a "\r\n" pair excluded
-__device__ __forceinline__ void line_span(const uint8_t* __restrict__ buf, uint32_t n, const uint32_t* __restrict__ line_end, uint32_t i,
-                                          uint32_t& start, uint32_t& end) {
-    start = i == 0 ? 0 : line_end[i - 1] + 1;
-    end = line_end[i];
-    if (end > start && end < n && buf[end] == '\n' && buf[end - 1] == '\r') end--;
+// content span of line i: [start, end), the '\r' of a "\r\n" pair excluded; `marked` = its first byte opens a header / comment
+// line.  Everything comes from the line index: no input byte is read.
+struct McLineIdx {
+    const uint32_t* line_end;
+    const uint8_t* line_flags;
+    uint32_t first_mark;     // line 0 starts with a mark character
+};
+__device__ __forceinline__ void line_span(const McLineIdx& L, uint32_t i, uint32_t& start, uint32_t& end, bool& marked) {
+    start = i == 0 ? 0 : L.line_end[i - 1] + 1;
+    end = L.line_end[i] - (L.line_flags[i] & 1u);
+    marked = (i == 0 ? L.first_mark != 0 : (L.line_flags[i - 1] & 2u) != 0) && end > start;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -212,17 +251,16 @@ __device__ __forceinline__ void block_scan_comp(const Comp& mine, Comp& excl, Co
 }
 
 template <bool FASTA>
-__device__ __forceinline__ Comp line_comp(const uint8_t* __restrict__ buf, uint32_t n, const uint32_t* __restrict__ line_end, uint32_t i) {
+__device__ __forceinline__ Comp line_comp(const McLineIdx& L, uint32_t i) {
     uint32_t s, e;
-    line_span(buf, n, line_end, i, s, e);
+    bool marked;
+    line_span(L, i, s, e, marked);
     if (FASTA) {
-        bool comment = e > s && (buf[s] == '>' || buf[s] == ';');
-        if (comment) return comp_identity();
+        if (marked) return comp_identity();   // comment line ('>' or ';')
         bool prev_comment = false;
         if (i > 0) {
             uint32_t ps, pe;
-            line_span(buf, n, line_end, i - 1, ps, pe);
-            prev_comment = pe > ps && (buf[ps] == '>' || buf[ps] == ';');
+            line_span(L, i - 1, ps, pe, prev_comment);
         }
         return Comp{e - s, (i == 0 || prev_comment) ? 1u : 0u, 2};
     } else {
@@ -232,12 +270,11 @@ __device__ __forceinline__ Comp line_comp(const uint8_t* __restrict__ buf, uint3
 }
 
 template <bool FASTA>
-__global__ void __launch_bounds__(256) k_block_summaries(const uint8_t* __restrict__ buf, uint32_t n, const uint32_t* __restrict__ line_end,
-                                                         uint32_t n_lines, Comp* __restrict__ blk) {
+__global__ void __launch_bounds__(256) k_block_summaries(McLineIdx L, uint32_t n_lines, Comp* __restrict__ blk) {
     uint32_t first = blockIdx.x * LINES_PER_BLOCK + threadIdx.x * LINES_PER_THREAD;
     Comp mine = comp_identity();
     for (uint32_t j = 0; j < LINES_PER_THREAD; j++)
-        if (first + j < n_lines) mine = compose(mine, line_comp<FASTA>(buf, n, line_end, first + j));
+        if (first + j < n_lines) mine = compose(mine, line_comp<FASTA>(L, first + j));
     Comp excl, total;
     block_scan_comp(mine, excl, total);
     if (threadIdx.x == 0) blk[blockIdx.x] = total;
@@ -246,8 +283,8 @@ __global__ void __launch_bounds__(256) k_block_summaries(const uint8_t* __restri
 // single CTA: exclusive prefix of the block summaries; fills the header totals
 template <bool FASTA>
 __global__ void __launch_bounds__(1024) k_scan_blocks(const Comp* __restrict__ blk, Comp* __restrict__ blk_prefix, uint32_t n_blk,
-                                                      const uint8_t* __restrict__ buf, uint32_t n, const uint32_t* __restrict__ line_end,
-                                                      McParseHeader* h, int final_chunk) {
+                                                      McLineIdx L, uint32_t n, McParseHeader* h, int final_chunk) {
+    const uint32_t* line_end = L.line_end;
     uint32_t per = (n_blk + 1023) / 1024;
     uint32_t lo = min(threadIdx.x * per, n_blk), hi = min(lo + per, n_blk);
     Comp mine = comp_identity();
@@ -269,8 +306,9 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const Comp* __restrict__ b
             bool last_is_data = false;
             if (n_lines > 0) {
                 uint32_t s, e;
-                line_span(buf, n, line_end, n_lines - 1, s, e);
-                last_is_data = !(e > s && (buf[s] == '>' || buf[s] == ';'));
+                bool marked;
+                line_span(L, n_lines - 1, s, e, marked);
+                last_is_data = !marked;
             }
             h->data_lines = n_rec;
             h->total_seq_bytes = total.c0;
@@ -287,7 +325,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const Comp* __restrict__ b
 }
 
 template <bool FASTA>
-__global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, uint32_t n, const uint32_t* __restrict__ line_end, uint32_t n_lines,
+__global__ void __launch_bounds__(256) k_emit(McLineIdx L, uint32_t n_lines,
                                              const Comp* __restrict__ blk_prefix, McParseHeader* h, McRec* __restrict__ recs,
                                              uint32_t* __restrict__ line_dst, uint32_t* __restrict__ rec_off, int final_chunk) {
     uint32_t first = blockIdx.x * LINES_PER_BLOCK + threadIdx.x * LINES_PER_THREAD;
@@ -295,7 +333,7 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
     Comp mine = comp_identity();
 #pragma unroll
     for (uint32_t j = 0; j < LINES_PER_THREAD; j++) {
-        lc[j] = (first + j < n_lines) ? line_comp<FASTA>(buf, n, line_end, first + j) : comp_identity();
+        lc[j] = (first + j < n_lines) ? line_comp<FASTA>(L, first + j) : comp_identity();
         mine = compose(mine, lc[j]);
     }
     Comp excl, total;
@@ -309,8 +347,8 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
             uint32_t i = first + j;
             if (i >= n_lines) break;
             uint32_t s, e;
-            line_span(buf, n, line_end, i, s, e);
-            bool comment = e > s && (buf[s] == '>' || buf[s] == ';');
+            bool comment;
+            line_span(L, i, s, e, comment);
             if (comment) {
                 line_dst[i] = 0xFFFFFFFFu;
                 continue;
@@ -331,10 +369,11 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
             uint32_t i = first + j;
             if (i >= n_lines) break;
             uint32_t s, e;
-            line_span(buf, n, line_end, i, s, e);
+            bool marked;
+            line_span(L, i, s, e, marked);
             if (st == 0) {
                 if (e == s) continue;   // skipped blank line
-                if (buf[s] != '@' && buf[s] != '+') mc_report_error(h, MC_PE_FQ_HEADER, s);
+                if (!marked) mc_report_error(h, MC_PE_FQ_HEADER, s);
                 st = 1;
                 // a header whose data line is not in this chunk: carry it over
                 if (i == n_lines - 1 && !(D & 1)) h->consumed = s;
@@ -346,7 +385,8 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
                     longest = max(longest, e - s);
                     if ((D & 1) && d == D - 1) {   // sequence line whose quality line is not in this chunk: carry the record
                         uint32_t ps, pe;
-                        line_span(buf, n, line_end, i - 1, ps, pe);
+                        bool pm;
+                        line_span(L, i - 1, ps, pe, pm);
                         h->consumed = ps;
                     }
                 } else {
@@ -365,7 +405,7 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t* __restrict__ buf, u
 }
 
 // FASTA: gather the sequence lines into one contiguous buffer (a warp per line)
-__global__ void __launch_bounds__(256) k_fa_copy(const uint8_t* __restrict__ buf, uint32_t n, const uint32_t* __restrict__ line_end, uint32_t n_lines,
+__global__ void __launch_bounds__(256) k_fa_copy(const uint8_t* __restrict__ buf, McLineIdx L, uint32_t n_lines,
                                                 const uint32_t* __restrict__ line_dst, uint8_t* __restrict__ seqbuf) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -373,7 +413,8 @@ __global__ void __launch_bounds__(256) k_fa_copy(const uint8_t* __restrict__ buf
         uint32_t dst = line_dst[i];
         if (dst == 0xFFFFFFFFu) continue;
         uint32_t s, e;
-        line_span(buf, n, line_end, i, s, e);
+        bool marked;
+        line_span(L, i, s, e, marked);
         for (uint32_t p = s + lane; p < e; p += 32) seqbuf[dst + (p - s)] = buf[p];
     }
 }
@@ -402,16 +443,17 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     const int fin = final_chunk ? 1 : 0;
     uint32_t n_tiles = (mis + n + TILE_BYTES - 1) / TILE_BYTES;
     if (n_tiles == 0) n_tiles = 1;
-    // slot 1: header + tile counts
-    // slot 1: header + tile counts + one terminator mask per 32 input bytes
+    // slot 1: header + tile counts + three masks per 32 input bytes (terminators, "\r\n" pairs, header marks)
+    const uint32_t n_words = n_tiles * 256u;
     const size_t off_masks = (256 + (size_t)n_tiles * 4 + 255) & ~(size_t)255;
-    uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, off_masks + (size_t)n_tiles * 256 * 4);
+    uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, off_masks + (size_t)n_words * 4 * 3);
     McParseHeader* d_h = (McParseHeader*)s1;
     uint32_t* d_tiles = (uint32_t*)(s1 + 256);
     uint32_t* d_masks = (uint32_t*)(s1 + off_masks);
-    k_count_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks);
+    if (fasta) k_count_terms<true><<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks, n_words);
+    else k_count_terms<false><<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks, n_words);
     MC_LAUNCH(ctx);
-    k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_buf, n, d_h, fin);
+    k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_buf, n, d_h, fin, fasta ? 1 : 0);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
     McParseHeader* hp = (McParseHeader*)ctx->h_pinned_small;
@@ -424,7 +466,8 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     size_t max_recs = fasta ? (size_t)n_lines + 1 : (size_t)n_lines / 2 + 1;
     // slot 0 layout
     size_t off_line_end = 0;
-    size_t off_blk = align_up(off_line_end + ((size_t)n_lines + 1) * 4, 16);
+    size_t off_line_flags = off_line_end + ((size_t)n_lines + 1) * 4;
+    size_t off_blk = align_up(off_line_flags + (size_t)n_lines + 1, 16);
     size_t off_blk_prefix = off_blk + (size_t)n_blk * sizeof(Comp);
     size_t off_recs = align_up(off_blk_prefix + (size_t)n_blk * sizeof(Comp), 16);
     size_t off_line_dst = off_recs + max_recs * sizeof(McRec);
@@ -433,6 +476,8 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     size_t total = off_seqbuf + (fasta ? (size_t)n + 16 : 0);
     uint8_t* s0 = (uint8_t*)mc_scratch(ctx, 0, total);
     uint32_t* d_line_end = (uint32_t*)(s0 + off_line_end);
+    uint8_t* d_line_flags = s0 + off_line_flags;
+    const McLineIdx L{d_line_end, d_line_flags, hp->first_mark};
     Comp* d_blk = (Comp*)(s0 + off_blk);
     Comp* d_blk_prefix = (Comp*)(s0 + off_blk_prefix);
     McRec* d_recs = (McRec*)(s0 + off_recs);
@@ -448,19 +493,19 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
         if (!final_chunk) out->h.consumed = 0;   // no complete line yet: everything is carried over
         return;
     }
-    k_write_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, d_masks, d_tiles, d_line_end, n_lines, fin);
+    k_write_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, d_masks, n_words, d_tiles, d_line_end, d_line_flags, n_lines, fin);
     MC_LAUNCH(ctx);
     if (fasta) {
-        k_block_summaries<true><<<n_blk, 256, 0, st>>>(d_buf, n, d_line_end, n_lines, d_blk);
-        k_scan_blocks<true><<<1, 1024, 0, st>>>(d_blk, d_blk_prefix, n_blk, d_buf, n, d_line_end, d_h, final_chunk ? 1 : 0);
-        k_emit<true><<<n_blk, 256, 0, st>>>(d_buf, n, d_line_end, n_lines, d_blk_prefix, d_h, d_recs, d_line_dst, d_rec_off, final_chunk ? 1 : 0);
+        k_block_summaries<true><<<n_blk, 256, 0, st>>>(L, n_lines, d_blk);
+        k_scan_blocks<true><<<1, 1024, 0, st>>>(d_blk, d_blk_prefix, n_blk, L, n, d_h, final_chunk ? 1 : 0);
+        k_emit<true><<<n_blk, 256, 0, st>>>(L, n_lines, d_blk_prefix, d_h, d_recs, d_line_dst, d_rec_off, final_chunk ? 1 : 0);
         int copy_blocks = (int)std::min<uint64_t>(((uint64_t)n_lines * 32 + 255) / 256, (uint64_t)ctx->sm_count * 16);
-        k_fa_copy<<<copy_blocks, 256, 0, st>>>(d_buf, n, d_line_end, n_lines, d_line_dst, d_seqbuf);
+        k_fa_copy<<<copy_blocks, 256, 0, st>>>(d_buf, L, n_lines, d_line_dst, d_seqbuf);
         ctx->launches += 4;
     } else {
-        k_block_summaries<false><<<n_blk, 256, 0, st>>>(d_buf, n, d_line_end, n_lines, d_blk);
-        k_scan_blocks<false><<<1, 1024, 0, st>>>(d_blk, d_blk_prefix, n_blk, d_buf, n, d_line_end, d_h, final_chunk ? 1 : 0);
-        k_emit<false><<<n_blk, 256, 0, st>>>(d_buf, n, d_line_end, n_lines, d_blk_prefix, d_h, d_recs, nullptr, nullptr, final_chunk ? 1 : 0);
+        k_block_summaries<false><<<n_blk, 256, 0, st>>>(L, n_lines, d_blk);
+        k_scan_blocks<false><<<1, 1024, 0, st>>>(d_blk, d_blk_prefix, n_blk, L, n, d_h, final_chunk ? 1 : 0);
+        k_emit<false><<<n_blk, 256, 0, st>>>(L, n_lines, d_blk_prefix, d_h, d_recs, nullptr, nullptr, final_chunk ? 1 : 0);
         ctx->launches += 3;
     }
     MC_CUDA(cudaGetLastError());

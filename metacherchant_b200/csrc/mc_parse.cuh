@@ -30,6 +30,8 @@ struct McParseHeader {
     uint32_t final_state;     // FASTQ reader FSM state after the last line
     uint32_t total_seq_bytes; // FASTA: bytes copied into the compacted sequence buffer
     uint32_t max_seq_len;     // longest sequence of the chunk's records (picks the extractor's lanes-per-record)
+    uint32_t first_mark;      // the chunk's first byte opens a header / comment line ('@' '+' / '>' ';')
+    uint32_t pad_;
 };
 
 struct McParsed {

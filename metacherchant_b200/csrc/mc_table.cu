@@ -250,23 +250,37 @@ extern "C" int mc_table_stats(const mc_table* t, uint64_t* reads, uint64_t* runs
 // --------------------------------------------------------------------------------------------
 // rehash: every live slot of `src` re-inserted into `dst` (bigger, or filtered by min_count)
 // --------------------------------------------------------------------------------------------
+// RH_U buckets per thread and step are loaded before any is re-inserted: an insert is a dependent L2 round trip (bucket probe,
+// CAS) and nearly every warp has a lane that needs one, so with a single bucket in flight per thread the scan ran at the
+// insert latency (27 % of the DRAM peak in round 1) instead of the memory bandwidth.
+#define RH_U 4
 __global__ void __launch_bounds__(256) k_rehash(McTableDev src, McTableDev dst, uint32_t min_count) {
     const uint64_t nb = src.nb_mask + 1;
+    const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long added = 0;
-    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t w4[4];
-        mc_load_bucket(src.slots + b * 4, w4);   // one 32-byte bucket per thread
+    for (uint64_t b0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b0 < nb; b0 += T * RH_U) {
+        uint64_t w4[RH_U][4];
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-            uint64_t w = w4[s];
-            if (w == 0) continue;
-            uint32_t c = (uint32_t)(w & MC_COUNT_MASK);
-            if (c > MC_SAT) c = MC_SAT;
-            if (c < min_count) continue;
-            uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
-            uint64_t home = (b - d) & src.nb_mask;
-            uint64_t hl = (home << src.tag_bits) | (w >> MC_TAG_SHIFT);
-            if (mc_table_add(dst, hl, c)) added++;
+        for (int u = 0; u < RH_U; u++) {
+            const uint64_t b = b0 + (uint64_t)u * T;
+            if (b < nb) mc_load_bucket(src.slots + b * 4, w4[u]);   // one 32-byte bucket per thread and load
+            else w4[u][0] = w4[u][1] = w4[u][2] = w4[u][3] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < RH_U; u++) {
+            const uint64_t b = b0 + (uint64_t)u * T;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                uint64_t w = w4[u][s];
+                if (w == 0) continue;
+                uint32_t c = (uint32_t)(w & MC_COUNT_MASK);
+                if (c > MC_SAT) c = MC_SAT;
+                if (c < min_count) continue;
+                uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
+                uint64_t home = (b - d) & src.nb_mask;
+                uint64_t hl = (home << src.tag_bits) | (w >> MC_TAG_SHIFT);
+                if (mc_table_add(dst, hl, c)) added++;
+            }
         }
     }
     // stash entries
@@ -308,7 +322,7 @@ static void grow_to(mc_table* t, int new_q) {
     MC_CUDA(cudaMemsetAsync(nw.stash_keys, 0, MC_STASH_SLOTS * sizeof(uint64_t), ctx->stream));
     MC_CUDA(cudaMemsetAsync(nw.stash_counts, 0, MC_STASH_SLOTS * sizeof(uint32_t), ctx->stream));
     MC_CUDA(cudaMemsetAsync(&nw.counters[MC_CNT_KEYS], 0, 2 * sizeof(unsigned long long), ctx->stream));
-    k_rehash<<<grid_for(ctx, old.nb_mask + 1, 256, 16), 256, 0, ctx->stream>>>(old, nw, 0);
+    k_rehash<<<grid_for(ctx, (old.nb_mask + 1 + RH_U - 1) / RH_U, 256, 16), 256, 0, ctx->stream>>>(old, nw, 0);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
     mc_dev_free(ctx, old.slots);
@@ -703,16 +717,42 @@ extern "C" int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc
         McStageTimer tm(ctx, MC_ST_FILTER);
         unsigned long long* d_cursor;
         d_cursor = (decltype(d_cursor))mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");
-        uint64_t n = count_matching(t, min_count, d_cursor);
-        mc_dev_free(ctx, d_cursor);
+        struct Free { mc_ctx* c; void* p; ~Free() { mc_dev_free(c, p); } } fr{ctx, d_cursor};
+        // Size of the solid table: a large table is only SAMPLED -- the survivors of its first 1/64 (the hash spreads the keys
+        // evenly over the buckets) scaled up, plus a margin -- so the table is scanned once, by the rehash, instead of twice.
+        // The rehash counts exactly; if the estimate was too low the compaction is simply redone with the exact figure.
+        const bool sampled = t->nb >= ((uint64_t)1 << 22);
+        uint64_t n;
+        if (sampled) {
+            McTableDev sub = t->dev;
+            sub.nb_mask = (t->nb >> 6) - 1;
+            MC_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+            k_dump<false><<<grid_for(ctx, sub.nb_mask + 1, 256, 16), 256, 0, ctx->stream>>>(sub, min_count < 0 ? 0u : (uint32_t)min_count, d_cursor, nullptr, nullptr, 0);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+            unsigned long long v = 0;
+            MC_CUDA(cudaMemcpyAsync(&v, d_cursor, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+            MC_CUDA(cudaStreamSynchronize(ctx->stream));
+            n = v * 64 + v * 64 / 16 + 65536;   // + 6 % and a constant: far outside the sampling spread of >= 64 Ki buckets
+        } else {
+            n = count_matching(t, min_count, d_cursor);
+        }
         mc_table* s = nullptr;
-        // dense but comfortably probe-able: load <= 0.35 keeps almost every lookup inside one sector
-        int rc = mc_table_create(ctx, t->k, n * 2, t->dev.shard_bits, (int)t->shard_id, &s);
-        if (rc != MC_OK) return rc;
         uint32_t mc = min_count < 1 ? 1 : (uint32_t)min_count;
-        k_rehash<<<grid_for(ctx, t->nb, 256, 16), 256, 0, ctx->stream>>>(t->dev, s->dev, mc);
-        MC_LAUNCH(ctx);
-        MC_CUDA(cudaGetLastError());
+        for (int attempt = 0;; attempt++) {
+            // dense but comfortably probe-able: load <= 0.35 keeps almost every lookup inside one sector
+            int rc = mc_table_create(ctx, t->k, n * 2, t->dev.shard_bits, (int)t->shard_id, &s);
+            if (rc != MC_OK) return rc;
+            k_rehash<<<grid_for(ctx, (t->nb + RH_U - 1) / RH_U, 256, 16), 256, 0, ctx->stream>>>(t->dev, s->dev, mc);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+            if (!sampled || attempt > 0) break;
+            const uint64_t exact = mc_table_keys(s);
+            if ((double)exact <= 0.40 * (double)s->capacity_slots()) break;
+            mc_table_free(s);   // the sample under-estimated (cannot happen for hashed keys; kept for safety): redo with the exact count
+            s = nullptr;
+            n = exact;
+        }
         // statistics travel with the filtered table
         MC_CUDA(cudaMemcpyAsync(&s->dev.counters[MC_CNT_READS], &t->dev.counters[MC_CNT_READS], 4 * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToDevice, ctx->stream));

@@ -1298,6 +1298,20 @@ uint64_t orc_table_dump(const orc_table* t, int min_count, uint64_t* keys, int16
     for (uint64_t i = 0; i < n; i++) { keys[i] = v[i].first; counts[i] = v[i].second; }
     return n;
 }
+// Order-independent digest of the entries with count >= min_count -- the formula of the library's mc_table_checksum
+// (include/mc_b200.h): out = {entries, sum of counts, sum of digest(key) * count mod 2^64, largest count},
+// digest(x) = (x ^ (x >> 29)) * 0xBF58476D1CE4E5B9 + 1.  Lets a test compare tables far too large to dump and sort.
+void orc_table_checksum(const orc_table* t, int min_count, uint64_t out[4]) {
+    uint64_t n = 0, sum = 0, dig = 0, mx = 0;
+    t->for_each([&](uint64_t k, int16_t c) {
+        if (c <= 0 || c < min_count) return;
+        n++;
+        sum += (uint64_t)c;
+        dig += ((k ^ (k >> 29)) * 0xBF58476D1CE4E5B9ULL + 1ULL) * (uint64_t)c;
+        mx = std::max<uint64_t>(mx, (uint64_t)c);
+    });
+    out[0] = n; out[1] = sum; out[2] = dig; out[3] = mx;
+}
 void orc_table_stats(const orc_table* t, uint64_t* reads, uint64_t* runs, uint64_t* bases, uint64_t* kmers) {
     if (reads) *reads = t->n_reads;
     if (runs) *runs = t->n_runs;
@@ -1484,6 +1498,12 @@ double orc_bench_count(const uint8_t* buf, size_t len, int fmt, int k, int threa
         return 0;
     });
     return secs;
+}
+
+// test surface: the Jaccard cell text (tests/test_host_logic.py compares three independent implementations)
+void orc_java_format_6_2f(float v, char* out) {
+    const std::string s = java_format_6_2f(v);
+    memcpy(out, s.c_str(), s.size() + 1);
 }
 
 // CPU baseline of the environment stage (bench.py only): every target as its own OneSequenceCalculator on a pool of

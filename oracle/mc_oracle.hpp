@@ -46,6 +46,9 @@ int16_t orc_table_get(const orc_table*, uint64_t canonical_key);        // -1 ab
 void orc_table_get_many(const orc_table*, const uint64_t* keys, size_t n, int16_t* out);
 // sorted by key; entries with count >= min_count; returns number written (<= cap); *total = matching entries
 uint64_t orc_table_dump(const orc_table*, int min_count, uint64_t* keys, int16_t* counts, uint64_t cap, uint64_t* total);
+// {entries, sum of counts, sum of digest(key) * count mod 2^64, largest count} over entries with count >= min_count
+// (the digest of the library's mc_table_checksum)
+void orc_table_checksum(const orc_table*, int min_count, uint64_t out[4]);
 // reader statistics of everything counted so far
 void orc_table_stats(const orc_table*, uint64_t* reads, uint64_t* runs, uint64_t* bases, uint64_t* kmers);
 
@@ -86,6 +89,8 @@ int orc_load_kmers(orc_table*, const char* path, int freq_threshold);
 // one serialized parser (ReadsDispatcher monitor) feeding P workers over lock-striped maps.
 // Returns seconds of wall time, <0 on error.  `bases` gets the number of input bases.
 double orc_bench_count(const uint8_t* buf, size_t len, int fmt, int k, int threads, uint64_t* bases, uint64_t* distinct);
+
+void orc_java_format_6_2f(float v, char* out);   // String.format("%6.2f ", v); out: room for 48 characters
 
 // CPU baseline of the environment stage (bench.py only): one OneSequenceCalculator per target on `threads` pool workers
 // (src/tools/EnvironmentFinderMain.java:188,218-225).  Returns wall seconds, < 0 on error.

@@ -30,11 +30,43 @@ def main():
     ctx.synth_generate_device(s.params_bytes(), rank * per, per, d)
     # both exchanges must give the same shards: NCCL all-to-all and the peer-memory scatter (MC_DIST_EXCHANGE picks one to dump)
     tables = {}
+    env_ok, verify = True, None
+    import tempfile
+    shared = [tempfile.mkdtemp(prefix="mc_dist_env_") if rank == 0 else None]
+    dist.broadcast_object_list(shared, src=0)
+    shared = shared[0]
     for mode in ("nccl", "peer", "merge"):
         counter = ShardedCounter(ctx, k, world, rank, exchange=mode)
+        counter.verify = mode == "merge"
         counter.new_table()
         counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)   # several batches
         tables[mode] = counter.table.dump()
+        if mode == "merge":
+            # bench.py --verify's check: the digests of the local tables and of the owner shards add up to the same totals
+            verify = counter.verify_exchange()
+            # E3 + E4: local compaction, all-gather of the solid set, targets split over the ranks
+            cov = 3
+            solid = counter.table.filter(cov)
+            full, per_rank = counter.gather_solid(solid)
+            solid.free()
+            fa = os.path.join(shared, f"genes_{rank}.fasta")
+            open(fa, "w").write(s.targets_fasta())
+            targets = ctx.load_targets(fa)
+            found = counter.find_environments(full, [t[1] for t in targets], [t[0] for t in targets], os.path.join(shared, "gpu"),
+                                              min_cov=cov, max_kmers=3000, both_dirs=False)
+            full.free()
+            dist.barrier()
+            if rank == 0:
+                ref_t = o.table(k, threads=8).count_bytes(s.generate(0, per * world), oracle_ffi.FMT_FASTQ)
+                n_ref = ref_t.env_find(fa, cov, 3000, None, False, 1, os.path.join(shared, "orc"))
+                env_ok = n_ref == sum(found) == len(targets)
+                for name, _ in targets:
+                    for f in ("env.txt", "graph.txt", "graph.gfa", "seqs.fasta", "tsvs/nodes.tsv", "tsvs/edges.tsv"):
+                        a = open(os.path.join(shared, "gpu", name, f), "rb").read()
+                        b = open(os.path.join(shared, "orc", name, f), "rb").read()
+                        env_ok = env_ok and a == b
+                print(f"DIST_ENV_PARITY world={world} targets={len(targets)} found={sum(found)} solid_pairs_per_rank={per_rank} "
+                      f"verify={verify['ok']} digest={verify['digest']} {'OK' if env_ok else 'MISMATCH'}", flush=True)
         stats = counter.table.stats()
         tot = torch.tensor([stats["reads"], stats["kmers"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(tot)
@@ -63,7 +95,7 @@ def main():
         allk, allc = allk[order], allc[order]
         ref = o.table(k, threads=8).count_bytes(s.generate(0, per * world), oracle_ffi.FMT_FASTQ)
         rk, rc = ref.dump()
-        ok = np.array_equal(allk, rk) and np.array_equal(allc, rc) and len(np.unique(allk)) == allk.size and same
+        ok = np.array_equal(allk, rk) and np.array_equal(allc, rc) and len(np.unique(allk)) == allk.size and same and env_ok
         print(f"DIST_PARITY world={world} distinct={allk.size} oracle={rk.size} exchanged_bytes_rank0={counter.bytes_exchanged} {'OK' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -46,6 +46,7 @@ class Oracle:
         L.orc_table_get_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_table_dump.restype = C.c_uint64
         L.orc_table_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
+        L.orc_table_checksum.argtypes = [C.c_void_p, C.c_int, _u64p]
         L.orc_table_stats.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p]
         L.orc_revcomp.restype = C.c_uint64
         L.orc_revcomp.argtypes = [C.c_uint64, C.c_int]
@@ -185,6 +186,12 @@ class OracleTable:
         total = C.c_uint64()
         m = self.o.lib.orc_table_dump(self.h, min_count, keys.ctypes.data, counts.ctypes.data, n, C.byref(total))
         return keys[:m].copy(), counts[:m].copy()
+
+    def checksum(self, min_count=0):
+        """dict(entries, sum_counts, digest, max_count): the digest of the library's mc_table_checksum, computed by the oracle."""
+        out = (C.c_uint64 * 4)()
+        self.o.lib.orc_table_checksum(self.h, min_count, out)
+        return dict(zip(("entries", "sum_counts", "digest", "max_count"), [int(x) for x in out]))
 
     def stats(self):
         v = [C.c_uint64() for _ in range(4)]

@@ -18,7 +18,8 @@ def test_sharded_counting_matches_oracle():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", os.path.join(ROOT, "tests", "dist_parity_worker.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "DIST_PARITY" in r.stdout and "OK" in r.stdout
+    assert "DIST_PARITY" in r.stdout and "DIST_ENV_PARITY" in r.stdout and "MISMATCH" not in r.stdout
+    assert r.stdout.count(" OK") >= 2, r.stdout[-2000:]
 
 
 def test_single_rank_sharded_path_matches_direct_path(oracle):

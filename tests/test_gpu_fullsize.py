@@ -122,10 +122,11 @@ ENV_FILES = ("env.txt", "graph.txt", "graph.gfa", "seqs.fasta", "tsvs/nodes.tsv"
 
 
 def test_config4_shape_deep_frontier(oracle, tmp_path):
-    """BASELINE configs[3] at 1/1000 scale: k = 23, --bothdirs, many targets next to planted 3 kb repeats, --maxkmers hit."""
+    """BASELINE configs[3] at 1/100 scale (2 M reads over a 1.1 Mbp community: ~270x, the depth of the full configuration):
+    k = 23, --bothdirs, many targets next to planted 3 kb repeats, --maxkmers hit."""
     from metacherchant_b200 import Context
     s = oracle.synth(genome_unit=20_000, n_targets=12, repeat_len=3000)
-    data = s.generate(0, 200_000)          # ~27x over 1.1 Mbp
+    data = s.generate(0, 2_000_000, threads=os.cpu_count() or 8)
     fa = tmp_path / "genes.fasta"
     fa.write_text(s.targets_fasta())
     c = Context(0)
@@ -174,5 +175,65 @@ def test_config3_shape_two_time_points(oracle, tmp_path):
         same_tree(str(tmp_path / "gpu_multi"), str(tmp_path / "orc_multi"), ("seqs.fasta", "graph.gfa", "gene.fasta", "Jacard_sym.txt", "Jacard_alt.txt"))
         gfa = open(tmp_path / "gpu_multi" / "graph.gfa").read()
         assert "CL:Z:#0000ff" in gfa, "k-mers shared by both time points are coloured blue"
+    finally:
+        c.close()
+
+
+def test_cfg1_in_full_against_the_oracle(oracle, tmp_path):
+    """BASELINE configs[0] at its real size (1 M reads, k = 31, coverage 5, one target): the sorted (k-mer, count) table, the
+    reader statistics, the digest and every environment file of the target are bit-identical to the oracle's."""
+    from metacherchant_b200 import Context
+    s = oracle.synth(genome_unit=100_000, n_targets=1)
+    reads = 1_000_000
+    c = Context(0)
+    try:
+        d, nbytes = device_reads(c, s, 0, reads)
+        host = np.empty(nbytes, dtype=np.uint8)
+        c.d2h(host, d)
+        g = c.new_table(31).count_device(d, nbytes, FMT_FASTQ)
+        o = oracle.table(31, threads=os.cpu_count() or 8).count_bytes(host, FMT_FASTQ)
+        assert g.stats() == o.stats()
+        assert g.checksum() == o.checksum() and g.checksum(5) == o.checksum(5)
+        gk, gc = g.dump()
+        ok, oc = o.dump()
+        assert np.array_equal(gk, ok) and np.array_equal(gc, oc)
+        fa = tmp_path / "gene.fasta"
+        fa.write_text(s.targets_fasta())
+        targets = c.load_targets(fa)
+        solid = g.filter(5)
+        found = c.find_environments(solid, [t[1] for t in targets], [t[0] for t in targets], min_cov=5, max_kmers=100000, both_dirs=False,
+                                    out_dir=tmp_path / "gpu")
+        assert o.env_find(str(fa), 5, 100000, None, False, 1, str(tmp_path / "orc")) == sum(found) == 1
+        same_tree(str(tmp_path / "gpu" / targets[0][0]), str(tmp_path / "orc" / targets[0][0]), ENV_FILES)
+        c.device_free(d)
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(not os.environ.get("MC_RUN_SLOW"), reason="~3 minutes of host time: the oracle counts all 50 M reads (run once per round, log kept under profiles/)")
+def test_cfg2_in_full_against_the_oracle_digest(oracle):
+    """BASELINE configs[1] at its real size (50 M reads): the GPU table's digest (entries, sum of counts, key digest, largest
+    count), at coverage 0 and 5, and the reader statistics equal the oracle's over the very same bytes."""
+    import time
+    from metacherchant_b200 import Context
+    s = oracle.synth(genome_unit=1_000_000, n_targets=20)
+    reads = 50_000_000
+    c = Context(0, chunk_bytes=1 << 30)
+    try:
+        d, nbytes = device_reads(c, s, 0, reads)
+        host = np.empty(nbytes, dtype=np.uint8)
+        c.d2h(host, d)
+        g = c.new_table(31).count_device(d, nbytes, FMT_FASTQ)
+        gs, g0, g5 = g.stats(), g.checksum(), g.checksum(5)
+        g.free()
+        c.device_free(d)
+        t0 = time.time()
+        o = oracle.table(31, threads=os.cpu_count() or 8).count_bytes(host, FMT_FASTQ)
+        secs = time.time() - t0
+        o0, o5 = o.checksum(), o.checksum(5)
+        print(f"CFG2_FULL_PARITY reads={reads} gpu={g0} oracle={o0} cov5_gpu={g5} cov5_oracle={o5} oracle_count_s={secs:.1f} "
+              f"{'OK' if (g0 == o0 and g5 == o5 and gs == o.stats()) else 'MISMATCH'}", flush=True)
+        assert gs == o.stats()
+        assert g0 == o0 and g5 == o5
     finally:
         c.close()

@@ -199,3 +199,58 @@ def test_quality_offset_sniffing_matches_pyref():
     for data in cases:
         got = lib.mc_sniff_quality_offset(data, len(data))
         assert got == pyref.sniff_offset(data), data[:60]
+
+
+# ---- String.format("%6.2f ", float): the cells of Jacard_sym.txt / Jacard_alt.txt -------------------------------------------
+def lib_fmt(v):
+    lib = _ffi.load_library()
+    buf = C.create_string_buffer(64)
+    assert lib.mc_java_format_6_2f(C.c_float(v), buf) == 0
+    return buf.value.decode()
+
+
+# Hand-derived from java.util.Formatter's rules (EnvironmentFinderMultiMain.java:141-142,163-164): the float is widened to
+# double, Double.toString's digits are rounded HALF_UP to two decimals, the result is right-aligned in 6 columns.
+#   0.125f = 0.125 exactly            -> tie, HALF_UP -> 0.13   (C's printf gives 0.12: half-to-even on the binary value)
+#   0.625f = 0.625 exactly            -> 0.63               (C: 0.62)
+#   0.005f = 0.004999999888241291     -> 0.00
+#   2.675f = 2.674999952316284        -> 2.67
+#   1e-3f  = 0.0010000000474974513    -> 0.00
+#   0.995f = 0.9950000047683716       -> 1.00
+#   0.015f = 0.014999999664723873     -> 0.01,   0.025f = 0.02500000037252903 -> 0.03
+JAVA_FORMAT_VECTORS = [
+    (0.125, "  0.13 "), (0.375, "  0.38 "), (0.625, "  0.63 "), (0.875, "  0.88 "), (0.005, "  0.00 "), (2.675, "  2.67 "), (1e-3, "  0.00 "),
+    (0.995, "  1.00 "), (0.015, "  0.01 "), (0.025, "  0.03 "), (0.0, "  0.00 "), (1.0, "  1.00 "), (0.5, "  0.50 "), (-0.5, " -0.50 "),
+    (12.345, " 12.35 "), (100.0, "100.00 "), (1234.5, "1234.50 "), (float("nan"), "   NaN "), (float("inf"), "Infinity "), (float("-inf"), "-Infinity "),
+    (-0.001, " -0.00 "), (3.0e9, "3000000000.00 "), (0.33333334, "  0.33 "), (0.6666667, "  0.67 "),
+]
+
+
+@pytest.mark.parametrize("v,want", JAVA_FORMAT_VECTORS)
+def test_java_format_on_hand_derived_vectors(v, want):
+    assert lib_fmt(v) == want
+
+
+def test_java_format_matches_an_independent_model(oracle):
+    """Python model of the same rule (repr = shortest round-trip digits, decimal HALF_UP) and the oracle's own formatter over
+    random float32 values, Jaccard-like ratios and every exact tie k/8: three implementations, three algorithms."""
+    from decimal import ROUND_HALF_UP, Decimal
+    olib = oracle.lib
+    has_oracle_fmt = hasattr(olib, "orc_java_format_6_2f")
+    if has_oracle_fmt:
+        olib.orc_java_format_6_2f.argtypes = [C.c_float, C.c_char_p]
+    rng = np.random.default_rng(5)
+    vals = list(rng.random(3000, dtype=np.float32)) + [np.float32(a) / np.float32(b) for a, b in rng.integers(1, 5000, size=(2000, 2))]
+    vals += [np.float32(i / 8) for i in range(0, 80)] + [np.float32(x) for x in rng.normal(0, 1e4, 500)] + [np.float32(i / 200) for i in range(400)]
+    for v in vals:
+        d = Decimal(repr(float(v))).quantize(Decimal("0.01"), rounding=ROUND_HALF_UP)
+        txt = f"{d:.2f}"
+        if float(v) < 0 and not txt.startswith("-"):
+            txt = "-" + txt
+        want = txt.rjust(6) + " "
+        got = lib_fmt(float(v))
+        assert got == want, (float(v), got, want)
+        if has_oracle_fmt:
+            buf = C.create_string_buffer(64)
+            olib.orc_java_format_6_2f(C.c_float(float(v)), buf)
+            assert buf.value.decode() == want, (float(v), buf.value, want)
