@@ -81,6 +81,13 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
                                                     const McBfsJobDev* __restrict__ jobs) {
     const McBfsJobDev j = jobs[blockIdx.x];
     const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    // MC_TRACE: SM cycles and wall nanoseconds of this pass (their ratio is the clock the SM really ran at)
+    long long t_clk = 0;
+    unsigned long long t_ns = 0;
+    if (threadIdx.x == 0) {
+        t_clk = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns));
+    }
     __shared__ uint32_t s_head, s_tail, s_stop;
     if (threadIdx.x == 0) { s_head = 0; s_tail = 0; s_stop = 0; }
     __syncthreads();
@@ -283,6 +290,10 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
     if (threadIdx.x == 0) {
         j.n_out[0] = s_tail;
         j.n_out[1] = steps;
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        *(unsigned long long*)(j.n_out + 2) = (unsigned long long)(clock64() - t_clk);
+        *(unsigned long long*)(j.n_out + 4) = ns1 - t_ns;
     }
 }
 
@@ -341,12 +352,11 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
             uint32_t cap = caps[i];
             uint32_t vis_cap = pow2_at_least((uint64_t)cap * 2);
             offs[w] = Off{take(reqs[i].codes.size() + 1), take((size_t)cap * 8), take((size_t)cap * 4), take((size_t)cap * 2),
-                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(8), take(reqs[i].trim ? (size_t)cap : 1), vis_cap};
+                          take((size_t)vis_cap * 8), take((size_t)vis_cap * 4), take(32), take(reqs[i].trim ? (size_t)cap : 1), vis_cap};
         }
         size_t jobs_off = take(jobs.size() * sizeof(McBfsJobDev));
-        uint8_t* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, bytes);
-        if (e != cudaSuccess) { cudaGetLastError(); mc_throw(MC_ERR_NOMEM, "cannot allocate %.1f MiB of BFS work memory", (double)bytes / (1 << 20)); }
+        uint8_t* d = (uint8_t*)mc_dev_alloc(ctx, bytes, "BFS work memory");   // from the context's arena: reused call after call
+        struct Free { mc_ctx* c; void* p; ~Free() { mc_dev_free(c, p); } } free_d{ctx, d};
         for (size_t w = 0; w < todo.size(); w++) {
             size_t i = todo[w];
             const Off& o = offs[w];
@@ -354,7 +364,7 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
                 MC_CUDA(cudaMemcpyAsync(d + o.seq, reqs[i].codes.data(), reqs[i].codes.size(), cudaMemcpyHostToDevice, st));
             MC_CUDA(cudaMemsetAsync(d + o.vk, 0, (size_t)o.vis_cap * 8, st));
             MC_CUDA(cudaMemsetAsync(d + o.vv, 0xFF, (size_t)o.vis_cap * 4, st));
-            MC_CUDA(cudaMemsetAsync(d + o.nout, 0, 8, st));   // [0] visited count, [1] steps of the queue loop (MC_TRACE)
+            MC_CUDA(cudaMemsetAsync(d + o.nout, 0, 32, st));   // [0] visited count, [1] steps of the queue loop, [2..3] cycles, [4..5] ns (MC_TRACE)
             if (reqs[i].trim) MC_CUDA(cudaMemsetAsync(d + o.last, 0, caps[i], st));
             jobs[w] = McBfsJobDev{d + o.seq, (uint32_t)reqs[i].codes.size(), reqs[i].dir, (uint64_t*)(d + o.queue), (int32_t*)(d + o.dist),
                                   (int16_t*)(d + o.count), (uint64_t*)(d + o.vk), (uint32_t*)(d + o.vv), caps[i], o.vis_cap - 1,
@@ -377,17 +387,24 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
             cudaEventSynchronize(ev_b);
             float ms = 0;
             cudaEventElapsedTime(&ms, ev_a, ev_b);
-            uint64_t steps = 0, visited = 0;
+            uint64_t steps = 0, visited = 0, cyc_most = 0, ns_most = 0;
             uint32_t most = 0;
             for (size_t w = 0; w < todo.size(); w++) {
-                uint32_t v[2] = {0, 0};
-                cudaMemcpy(v, d + offs[w].nout, 8, cudaMemcpyDeviceToHost);
+                uint32_t v[8] = {0};
+                MC_CUDA(cudaMemcpyAsync(v, d + offs[w].nout, 32, cudaMemcpyDeviceToHost, st));
+                MC_CUDA(cudaStreamSynchronize(st));
                 if (v[0] != BFS_OVERFLOW) visited += v[0];
                 steps += v[1];
-                most = std::max(most, v[1]);
+                if (v[1] > most) {
+                    most = v[1];
+                    cyc_most = (uint64_t)v[2] | ((uint64_t)v[3] << 32);
+                    ns_most = (uint64_t)v[4] | ((uint64_t)v[5] << 32);
+                }
             }
-            fprintf(stderr, "[mc trace] k_bfs: %zu passes, %.1f ms on the device, %.1f MiB of work memory; %llu k-mers visited in %llu steps (longest pass %u steps: %.2f us per step)\n",
-                    jobs.size(), ms, (double)bytes / (1 << 20), (unsigned long long)visited, (unsigned long long)steps, most, most ? 1e3 * ms / most : 0.0);
+            fprintf(stderr, "[mc trace] k_bfs: %zu passes, %.1f ms on the device, %.1f MiB of work memory; %llu k-mers visited in %llu steps (longest pass %u steps: %.2f us "
+                            "= %.0f SM cycles per step, SM clock during the pass %.0f MHz)\n",
+                    jobs.size(), ms, (double)bytes / (1 << 20), (unsigned long long)visited, (unsigned long long)steps, most, most ? 1e3 * ms / most : 0.0,
+                    most ? (double)cyc_most / most : 0.0, ns_most ? 1e3 * (double)cyc_most / (double)ns_most : 0.0);
             cudaEventDestroy(ev_a);
             cudaEventDestroy(ev_b);
         }
@@ -399,7 +416,7 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
         for (size_t w = 0; w < todo.size(); w++) {
             size_t i = todo[w];
             if (n_out[w] == BFS_OVERFLOW) {
-                if (caps[i] > 0x1FFFFFFFu) { cudaFree(d); mc_throw(MC_ERR_NOMEM, "environment larger than 2^29 k-mers"); }
+                if (caps[i] > 0x1FFFFFFFu) mc_throw(MC_ERR_NOMEM, "environment larger than 2^29 k-mers");
                 caps[i] *= 4;
                 again.push_back(i);
                 continue;
@@ -419,7 +436,6 @@ void mc_run_bfs_passes(mc_ctx* ctx, const mc_table* t, int k, int min_cov, int64
             }
         }
         MC_CUDA(cudaStreamSynchronize(st));
-        cudaFree(d);
         todo.swap(again);
     }
 }

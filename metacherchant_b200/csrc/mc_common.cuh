@@ -297,6 +297,7 @@ struct mc_ctx {
     int tune_extract_parts = 0;      // lanes per record in k_extract: 0 = by read length, else 1 / 4 / 32
     int tune_agg = -1;               // two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on
     uint32_t tune_agg_unit = 0;      // target keys per aggregation unit (sub-bin); 0 = default
+    size_t tune_device_chunk_bytes = 0;   // device-resident input: bytes per parse/extract pass (0 = as large as 32-bit offsets allow)
     int tune_scatter_tma = 1;        // bin runs leave the sorted tile through bulk copies (cp.async.bulk) instead of per-sector stores
     int keep_stage_ms = 0;           // 1: mc_count_* do not reset the stage timers (a step made of several count calls)
     int sm_count = 148;

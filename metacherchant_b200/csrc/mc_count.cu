@@ -486,13 +486,17 @@ extern "C" int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fm
         const uint8_t* p = (const uint8_t*)dbuf;
         bool fasta = fmt == MC_FMT_FASTA;
         int qoff = fasta ? 0 : resolve_qoff_device(ctx, p, len, fmt);
+        // Device-resident input needs no upload pipelining, so it is cut into the largest pieces the 32-bit record offsets allow
+        // (3 GiB) rather than into upload-sized chunks: every chunk costs four host round trips (line count, record count, key
+        // count, spill cursor), and on a slow host those gaps, not the kernels, were a tenth of the step.
+        const size_t dev_chunk = ctx->tune_device_chunk_bytes ? ctx->tune_device_chunk_bytes : std::max(ctx->chunk_bytes, ((size_t)3 << 30) - ((size_t)1 << 20));
         size_t pos = 0;
         while (pos < len) {
-            size_t n = std::min(len - pos, ctx->chunk_bytes);
+            size_t n = std::min(len - pos, dev_chunk);
             bool final_chunk = pos + n == len;
             uint32_t consumed = count_chunk(ctx, t, p + pos, (uint32_t)n, fasta, qoff, final_chunk, mc_max_kmers(len, fmt, t->k));
             if (final_chunk) break;
-            if (consumed == 0) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", ctx->chunk_bytes);
+            if (consumed == 0) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", dev_chunk);
             pos += consumed;
         }
         finish_table(t);

@@ -336,6 +336,32 @@ struct Graph {
     std::vector<int32_t> seq_id;
     std::vector<std::string> seq;             // materialised for alive nodes and for the rc partners of alive nodes
     std::vector<uint64_t> node_code;          // oriented k-mer of every original node
+    std::vector<long> kc_pre;                 // from_device: KC of every alive node (GFAWriter.java:90-95), else empty
+
+    // The unitigs as the device assembled them (mc_unitig.cu: chains of mergeable links ranked by pointer jumping, sequences and
+    // KC sums gathered along the chains): the host only sets up what the writers read -- which nodes are alive, their partners,
+    // their sequences, the neighbour lists of the alive nodes.  Used when the environment is `regular` (McUnitigNodes).
+    void from_device(const McUnitigInput& in, const McUnitigNodes& nodes) {
+        k = in.k;
+        n2 = (uint32_t)in.kmers.size() * 2;
+        nbrs.assign(n2, NbrList());
+        gene = nodes.gene;
+        deleted.assign(n2, 1);
+        rc.assign(n2, -1);
+        seq.assign(n2, std::string());
+        kc_pre.assign(n2, 0);
+        for (size_t i = 0; i < nodes.u_node.size(); i++) {
+            const uint32_t v = (uint32_t)nodes.u_node[i];
+            deleted[v] = 0;
+            rc[v] = nodes.u_rc[i];
+            seq[v].assign(nodes.u_chars, nodes.u_off[i], nodes.u_len[i]);
+            kc_pre[v] = (long)nodes.u_kc[i];
+            for (int s4 = 0; s4 < 4; s4++) {
+                const int32_t x = nodes.nbr[4 * (size_t)v + s4];
+                if (x >= 0) nbrs[v].push_back(x);   // (a regular environment has no palindromic neighbour)
+            }
+        }
+    }
 
     void build(const McUnitigInput& in, const McUnitigNodes& nodes) {
         k = in.k;
@@ -447,13 +473,21 @@ void write_environment(const KmerMap& subgraph, const std::vector<uint32_t>& ord
     mkdirs(prefix);
     const int k = subgraph.k;
     std::string body;
-    body.resize(ord.size() * (size_t)(k + 8));
+    body.resize(ord.size() * (size_t)(k + 14));   // k-mer, space, up to 10 digits (+ sign), newline
     char* out = &body[0];
     for (uint32_t p : ord) {
         kmer_chars(subgraph.keys[p], k, out);
         out += k;
         *out++ = ' ';
-        out += snprintf(out, 8, "%d", subgraph.vals[p]);   // counts are <= 32767
+        {   // Integer.toString of a count (<= 32767; negative values cannot occur: digits by hand, snprintf was a third of this stage)
+            int32_t sv = subgraph.vals[p];
+            if (sv < 0) *out++ = '-';   // (only through a hand-made graph.txt)
+            uint32_t v = sv < 0 ? 0u - (uint32_t)sv : (uint32_t)sv;
+            char tmp[12];
+            int nd = 0;
+            do { tmp[nd++] = (char)('0' + v % 10); v /= 10; } while (v);
+            while (nd) *out++ = tmp[--nd];
+        }
         *out++ = '\n';
     }
     body.resize((size_t)(out - &body[0]));
@@ -497,7 +531,7 @@ void write_single_outputs(const Graph& g, const KmerMap& subgraph, int chunk_len
         for (uint32_t v = 0; v < g.n2; v++)
             if (!g.deleted[v] && fwd((int32_t)v)) {
                 const std::string& s = g.seq[v];
-                const long coverage = kc(s);
+                const long coverage = g.kc_pre.empty() ? kc(s) : g.kc_pre[v];
                 out << "S\t" << node_id((int32_t)v) << "\t" << s << "\tLN:i:" << s.size() << "\tKC:i:" << coverage << (g.gene[v] ? "\tCL:Z:GREEN" : "") << "\n";
             }
         for (uint32_t i = 0; i < g.n2; i++)
@@ -736,9 +770,14 @@ static void write_environments(mc_ctx* ctx, const std::vector<KmerMap>& subs, co
             mc_unitig_nodes(ctx, in, nodes);
         }
         Graph g;
-        { EnvTrace tr("graph build"); g.build(in, nodes); }
-        { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
-        { EnvTrace tr("assemble"); g.assemble(); }
+        if (nodes.regular && !getenv("MC_HOST_UNITIGS")) {
+            EnvTrace tr("unitigs from the device");
+            g.from_device(in, nodes);
+        } else {   // palindromes, hairpins, cyclic chains: the literal sweep (its outcome depends on the reference's sweep order)
+            { EnvTrace tr("graph build"); g.build(in, nodes); }
+            { EnvTrace tr("merge sweep"); g.sweep(nullptr); }
+            { EnvTrace tr("assemble"); g.assemble(); }
+        }
         { EnvTrace tr("write gfa/fasta/tsv"); write_single_outputs(g, sub, chunk_len, prefixes[job]); }
     });
 }
@@ -836,9 +875,13 @@ extern "C" int mc_env_from_graph_txt(mc_ctx* ctx, const char* graph_txt, const c
         McUnitigNodes nodes;
         mc_unitig_nodes(ctx, in, nodes);
         Graph g;
-        g.build(in, nodes);
-        g.sweep(nullptr);
-        g.assemble();
+        if (nodes.regular && !getenv("MC_HOST_UNITIGS")) {
+            g.from_device(in, nodes);
+        } else {
+            g.build(in, nodes);
+            g.sweep(nullptr);
+            g.assemble();
+        }
         write_single_outputs(g, sub, chunk_len, prefix);
         return MC_OK;
     } catch (const McError& e) {

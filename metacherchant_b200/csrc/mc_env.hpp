@@ -43,5 +43,15 @@ struct McUnitigNodes {
     std::vector<uint8_t> gene;              // isGeneNode
     std::vector<int32_t> head;              // head of my merged path (myself when unmerged); -1 when the path is a cycle (deleted)
     std::vector<int32_t> rank;              // my position inside that path
+    // Unitigs assembled on the device (doMerge / mergeNodes / mergeLabels, OneSequenceCalculator.java:434-462,312-324): one per
+    // alive node = head of a chain, in node-id order.  `regular` = the environment has no palindromic k-mer, no start-to-own-
+    // start link and no cyclic chain; only then are these arrays authoritative (the corner cases keep the literal host sweep,
+    // whose outcome depends on the reference's sweep order).
+    bool regular = false;
+    std::vector<int32_t> u_node;            // alive node id (the chain's head)
+    std::vector<int32_t> u_rc;              // its reverse-complement partner after all merges (tail of the chain ^ 1)
+    std::vector<uint32_t> u_off, u_len;     // sequence = u_chars[u_off .. u_off + u_len)
+    std::vector<int64_t> u_kc;              // sum of the chain's k-mer coverages + coverage of the last one * (k - 1) (GFAWriter.java:90-95)
+    std::string u_chars;
 };
 void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out);

@@ -16,7 +16,10 @@
 
 #include "mc_parse.cuh"
 
-#define TILE_BYTES 8192u          // one CTA pass: 256 threads x 32 bytes
+#define TILE_WPT 4u               // 32-byte words per thread and tile
+#define TILE_WORDS (256u * TILE_WPT)
+#define TILE_BYTES (32u * TILE_WORDS)   // one CTA pass: 256 threads x 4 words of 32 bytes = 32 KiB (131 K tiles per GiB made the
+                                  // single-CTA scan of the tile counts 3 ms per step)
 #define LINES_PER_THREAD 4
 #define LINES_PER_BLOCK (256 * LINES_PER_THREAD)
 
@@ -37,26 +40,57 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t pat) {
 // Three masks over the 32 bytes at `base`: bit j of
 //   term = byte j is a line terminator ('\n', or '\r' not followed by '\n'),
 //   crlf = byte j is the '\n' of a "\r\n" pair (the line's content then ends one byte earlier),
-//   mark = byte j is a character that opens a header / comment line ('@' '+' for FASTQ, '>' ';' for FASTA).
+//   mark = byte j is a terminator AND byte j + 1 -- the first byte of the next line -- opens a header / comment line
+//          ('@' '+' for FASTQ, '>' ';' for FASTA).
 // Passes 2-4 of the parser work from these masks and never touch the input bytes again (round 1 re-read the whole
-// chunk twice for one byte per line).
+// chunk twice for one byte per line).  The marks are looked up per terminator (one per ~80 bytes) in the registers that
+// hold the word; comparing every byte against the two mark characters made the pass ALU-bound.
+// The masks are STORED TRANSPOSED: byte 4i + b of the word (b-th byte of its i-th 32-bit piece) is bit 8b + i.  The SWAR
+// compare leaves one flag per byte at bit 7 of that byte; shifting piece i's flags right by 7 - i and OR-ing the eight pieces
+// builds the transposed mask with two instructions per piece, where packing every piece's four flags into adjacent bits cost
+// six.  Pass 2 turns a non-empty mask back into byte order (transposed_to_mask); popc is the same either way.
 struct McMasks { uint32_t term, crlf, mark; };
-__device__ __forceinline__ uint32_t pack_msb(uint32_t x) { return (((x >> 7) * 0x01020408u) >> 24) & 0xFu; }   // 0x80 flags of 4 bytes -> 4 bits
+__device__ __forceinline__ uint32_t mask_to_transposed(uint32_t m) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        uint32_t x = (m >> b) & 0x11111111u;        // bytes 4i + b, i = 0..7, at bits 4i
+        x = (x | (x >> 3)) & 0x03030303u;
+        x = (x | (x >> 6)) & 0x000F000Fu;
+        x = (x | (x >> 12)) & 0xFFu;
+        r |= x << (8 * b);
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t transposed_to_mask(uint32_t t) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        uint32_t x = (t >> (8 * b)) & 0xFFu;
+        x = (x | (x << 12)) & 0x000F000Fu;
+        x = (x | (x << 6)) & 0x03030303u;
+        x = (x | (x << 3)) & 0x11111111u;
+        r |= x << b;
+    }
+    return r;
+}
+template <bool FASTA>
+__device__ __forceinline__ bool is_mark(uint32_t c) { return FASTA ? (c == '>' || c == ';') : (c == '@' || c == '+'); }
 template <bool FASTA>
 __device__ __forceinline__ McMasks term_mask32(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint32_t base, uint8_t pad) {
     __align__(16) uint8_t b[48];
     const uint32_t lo = mis, hi = mis + n;   // valid aligned-coordinate range [lo, hi)
-    const uint32_t m0 = FASTA ? 0x3E3E3E3Eu : 0x40404040u, m1 = FASTA ? 0x3B3B3B3Bu : 0x2B2B2B2Bu;   // '>' ';'  /  '@' '+'
     McMasks r{0, 0, 0};
     if (base >= lo + 1 && base + 33 <= hi) {
         // interior: eight 32-bit words, four bytes per step (SWAR)
         const uint4* p = reinterpret_cast<const uint4*>(abuf + base);
         const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
         const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const uint32_t after = __ldg(abuf + base + 32);                          // the byte after this word
         uint32_t nl[9], cr[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) { nl[i] = eq_bytes(w[i], 0x0A0A0A0Au); cr[i] = eq_bytes(w[i], 0x0D0D0D0Du); }
-        nl[8] = __ldg(abuf + base + 32) == '\n' ? 0x80u : 0u;
+        nl[8] = after == '\n' ? 0x80u : 0u;
         uint32_t cr_prev = __ldg(abuf + base - 1) == '\r' ? 0x80000000u : 0u;   // the byte in front of this word
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -64,9 +98,19 @@ __device__ __forceinline__ McMasks term_mask32(const uint8_t* __restrict__ abuf,
             const uint32_t term = nl[i] | (cr[i] & ~nl_next);
             const uint32_t cr_before = (cr[i] << 8) | (cr_prev >> 24);   // byte j-1 is '\r'
             cr_prev = cr[i];
-            r.term |= pack_msb(term) << (4 * i);
-            r.crlf |= pack_msb(nl[i] & cr_before) << (4 * i);
-            r.mark |= pack_msb(eq_bytes(w[i], m0) | eq_bytes(w[i], m1)) << (4 * i);
+            r.term |= term >> (7 - i);                    // flags at bits 7, 15, 23, 31 -> bits i, 8 + i, 16 + i, 24 + i
+            r.crlf |= (nl[i] & cr_before) >> (7 - i);
+        }
+        for (uint32_t tm = r.term; tm;) {   // the byte after every terminator, out of the registers
+            const uint32_t jt = (uint32_t)__ffs(tm) - 1u;   // transposed position
+            tm &= tm - 1;
+            const uint32_t j = 4u * (jt & 7u) + (jt >> 3);  // byte position
+            const uint32_t idx = j + 1, ws = idx >> 2;
+            const uint32_t lo4 = ws & 2 ? (ws & 1 ? w[3] : w[2]) : (ws & 1 ? w[1] : w[0]);
+            const uint32_t hi4 = ws & 2 ? (ws & 1 ? w[7] : w[6]) : (ws & 1 ? w[5] : w[4]);
+            const uint32_t word = ws >= 8 ? after : (ws & 4 ? hi4 : lo4);
+            const uint32_t c = ws >= 8 ? (word & 0xFFu) : ((word >> ((idx & 3) * 8)) & 0xFFu);
+            if (is_mark<FASTA>(c)) r.mark |= 1u << jt;
         }
         return r;
     }
@@ -78,15 +122,18 @@ __device__ __forceinline__ McMasks term_mask32(const uint8_t* __restrict__ abuf,
 #pragma unroll
     for (int j = 0; j < 32; j++) {
         const uint8_t c = b[j + 1];
-        r.term |= (uint32_t)((c == '\n') || (c == '\r' && b[j + 2] != '\n')) << j;
+        const bool t = (c == '\n') || (c == '\r' && b[j + 2] != '\n');
+        r.term |= (uint32_t)t << j;
         r.crlf |= (uint32_t)(c == '\n' && b[j] == '\r') << j;
-        r.mark |= (uint32_t)(FASTA ? (c == '>' || c == ';') : (c == '@' || c == '+')) << j;
+        r.mark |= (uint32_t)(t && base + j + 1 < hi && is_mark<FASTA>(b[j + 2])) << j;
     }
     // mask off positions outside the chunk
     uint32_t keep = 0xFFFFFFFFu;
     if (base < lo) keep &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
     if (base + 32 > hi) keep &= (hi <= base) ? 0u : (0xFFFFFFFFu >> (base + 32 - hi));
-    r.term &= keep; r.crlf &= keep; r.mark &= keep;
+    r.term = mask_to_transposed(r.term & keep);
+    r.crlf = mask_to_transposed(r.crlf & keep);
+    r.mark = mask_to_transposed(r.mark & keep);
     return r;
 }
 
@@ -95,14 +142,18 @@ __device__ __forceinline__ McMasks term_mask32(const uint8_t* __restrict__ abuf,
 template <bool FASTA>
 __global__ void __launch_bounds__(256) k_count_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint8_t pad,
                                                      uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ masks, uint32_t n_words) {
-    uint32_t base = blockIdx.x * TILE_BYTES + threadIdx.x * 32;
-    McMasks m{0, 0, 0};
-    if (base < mis + n) m = term_mask32<FASTA>(abuf, mis, n, base, pad);
-    const uint32_t wi = blockIdx.x * 256u + threadIdx.x;
-    masks[wi] = m.term;
-    masks[n_words + wi] = m.crlf;
-    masks[2 * n_words + wi] = m.mark;
-    uint32_t c = __popc(m.term);
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < TILE_WPT; j++) {
+        const uint32_t wi = blockIdx.x * TILE_WORDS + j * 256u + threadIdx.x;
+        const uint32_t base = wi * 32u;
+        McMasks m{0, 0, 0};
+        if (base < mis + n) m = term_mask32<FASTA>(abuf, mis, n, base, pad);
+        masks[wi] = m.term;
+        masks[n_words + wi] = m.crlf;
+        masks[2 * n_words + wi] = m.mark;
+        c += __popc(m.term);
+    }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     __shared__ uint32_t s[8];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
@@ -162,30 +213,41 @@ __global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__
                                                      const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ line_end, uint8_t* __restrict__ line_flags,
                                                      uint32_t n_lines, int final_chunk) {
     const uint8_t* buf = abuf + mis;
-    uint32_t base = blockIdx.x * TILE_BYTES + threadIdx.x * 32;
-    const uint32_t wi = blockIdx.x * 256u + threadIdx.x;
-    uint32_t m = masks[wi];
-    const uint32_t crlf = masks[n_words + wi], mark = masks[2 * n_words + wi];
-    uint32_t c = __popc(m);
-    // block exclusive scan of c
-    uint32_t incl = c;
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ uint32_t s[8];
-    if (lane == 31) s[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int i = 0; i < warp; i++) woff += s[i];
-    uint32_t pos = tile_offsets[blockIdx.x] + woff + incl - c;
-    while (m) {
-        int j = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t next_mark = j < 31 ? (mark >> (j + 1)) & 1u : (wi + 1 < n_words ? masks[2 * n_words + wi + 1] & 1u : 0u);
-        line_flags[pos] = (uint8_t)(((crlf >> j) & 1u) | (next_mark << 1));
-        line_end[pos++] = base + j - mis;
+    uint32_t tile_pos = tile_offsets[blockIdx.x];
+    for (uint32_t j = 0; j < TILE_WPT; j++) {   // the tile's words in position order: row j = words j * 256 .. j * 256 + 255
+        const uint32_t wi = blockIdx.x * TILE_WORDS + j * 256u + threadIdx.x;
+        const uint32_t base = wi * 32u;
+        uint32_t m = masks[wi];
+        uint32_t crlf = 0, mark = 0;
+        const uint32_t c = __popc(m);
+        if (m) {   // back to byte order (one word in three has a terminator)
+            m = transposed_to_mask(m);
+            crlf = transposed_to_mask(masks[n_words + wi]);
+            mark = transposed_to_mask(masks[2 * n_words + wi]);
+        }
+        uint32_t incl = c;   // block exclusive scan of c
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();     // the previous row's readers are done with s[]
+        if (lane == 31) s[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, row_total = 0;
+        for (int i = 0; i < 8; i++) {
+            if (i < warp) woff += s[i];
+            row_total += s[i];
+        }
+        uint32_t pos = tile_pos + woff + incl - c;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            line_flags[pos] = (uint8_t)(((crlf >> b) & 1u) | (((mark >> b) & 1u) << 1));
+            line_end[pos++] = base + b - mis;
+        }
+        tile_pos += row_total;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && final_chunk && n > 0 && buf[n - 1] != '\n' && buf[n - 1] != '\r') {
         line_end[n_lines - 1] = n;      // the unterminated last line of the input (BufferedReader.readLine)
@@ -444,7 +506,7 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     uint32_t n_tiles = (mis + n + TILE_BYTES - 1) / TILE_BYTES;
     if (n_tiles == 0) n_tiles = 1;
     // slot 1: header + tile counts + three masks per 32 input bytes (terminators, "\r\n" pairs, header marks)
-    const uint32_t n_words = n_tiles * 256u;
+    const uint32_t n_words = n_tiles * TILE_WORDS;
     const size_t off_masks = (256 + (size_t)n_tiles * 4 + 255) & ~(size_t)255;
     uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, off_masks + (size_t)n_words * 4 * 3);
     McParseHeader* d_h = (McParseHeader*)s1;

@@ -250,15 +250,26 @@ extern "C" int mc_table_stats(const mc_table* t, uint64_t* reads, uint64_t* runs
 // --------------------------------------------------------------------------------------------
 // rehash: every live slot of `src` re-inserted into `dst` (bigger, or filtered by min_count)
 // --------------------------------------------------------------------------------------------
-// RH_U buckets per thread and step are loaded before any is re-inserted: an insert is a dependent L2 round trip (bucket probe,
-// CAS) and nearly every warp has a lane that needs one, so with a single bucket in flight per thread the scan ran at the
-// insert latency (27 % of the DRAM peak in round 1) instead of the memory bandwidth.
+// Re-insertion is a chain of dependent L2 round trips (bucket probe, CAS).  Done lane by lane and slot by slot -- round 1 --
+// almost every (bucket, slot) position of a warp has SOME lane with a survivor, so a warp ran ~2.5 serial insert phases per
+// 1 KB scanned and the scan crawled at the insert latency (2 TB/s).  Now a warp first scans RH_U x 32 buckets, queues the
+// survivors in shared memory, and then inserts them one per lane: one insert phase per 4 KB scanned in the coverage filter.
 #define RH_U 4
+#define RH_Q 256      // queue entries per warp (what does not fit is inserted on the spot)
 __global__ void __launch_bounds__(256) k_rehash(McTableDev src, McTableDev dst, uint32_t min_count) {
+    __shared__ uint64_t q_h[8][RH_Q];
+    __shared__ uint32_t q_c[8][RH_Q];
+    __shared__ uint32_t q_n[8];
     const uint64_t nb = src.nb_mask + 1;
     const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long added = 0;
-    for (uint64_t b0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b0 < nb; b0 += T * RH_U) {
+    if (lane == 0) q_n[warp] = 0;
+    __syncwarp();
+    // every lane of a warp runs the same number of steps (the warp-level queue needs the whole warp)
+    const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u);
+    for (uint64_t w0 = first; w0 < nb; w0 += T * RH_U) {
+        const uint64_t b0 = w0 + lane;
         uint64_t w4[RH_U][4];
 #pragma unroll
         for (int u = 0; u < RH_U; u++) {
@@ -279,9 +290,22 @@ __global__ void __launch_bounds__(256) k_rehash(McTableDev src, McTableDev dst, 
                 uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
                 uint64_t home = (b - d) & src.nb_mask;
                 uint64_t hl = (home << src.tag_bits) | (w >> MC_TAG_SHIFT);
-                if (mc_table_add(dst, hl, c)) added++;
+                const uint32_t at = atomicAdd(&q_n[warp], 1u);
+                if (at < RH_Q) {
+                    q_h[warp][at] = hl;
+                    q_c[warp][at] = c;
+                } else if (mc_table_add(dst, hl, c)) {
+                    added++;
+                }
             }
         }
+        __syncwarp();
+        const uint32_t n = min(q_n[warp], (uint32_t)RH_Q);
+        for (uint32_t i = lane; i < n; i += 32)
+            if (mc_table_add(dst, q_h[warp][i], q_c[warp][i])) added++;
+        __syncwarp();
+        if (lane == 0) q_n[warp] = 0;
+        __syncwarp();
     }
     // stash entries
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= src.stash_mask; i += (uint64_t)gridDim.x * blockDim.x) {

@@ -137,6 +137,86 @@ __global__ void __launch_bounds__(256) k_finish(uint32_t n2, const int32_t* __re
     out_rank[v] = cycle ? 0 : (int32_t)rank[v];
 }
 
+// ---- unitig assembly on the device --------------------------------------------------------------------------------------
+// Every chain (head h, members ranked 0 .. len-1 along the merge links) is one unitig: its sequence is the head's k-mer
+// followed by the last base of every later member (mergeLabels: a + b[k-1:]), its KC the sum of the members' coverages plus
+// the last member's coverage * (k - 1), its reverse-complement partner the tail's partner.
+// flags: bit 0 palindromic k-mer among the neighbours, bit 1 start-to-own-start link, bit 2 cyclic chain.
+__global__ void __launch_bounds__(256) k_chain_stats(uint32_t n2, const int32_t* __restrict__ head, const int32_t* __restrict__ rank,
+                                                    const uint8_t* __restrict__ deg, const int32_t* __restrict__ nbr, const uint8_t* __restrict__ nbr_pal,
+                                                    const int32_t* __restrict__ counts, uint32_t* __restrict__ len, unsigned long long* __restrict__ kcsum,
+                                                    unsigned int* __restrict__ flags) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n2) return;
+    if (nbr_pal[v]) atomicOr(flags, 1u);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {   // a link to myself or to my own reverse complement (hairpin): the reference's outcome depends on its sweep order
+        const int32_t o = nbr[4 * v + s];
+        if (o == (int32_t)v || o == (int32_t)(v ^ 1u)) atomicOr(flags, 2u);
+    }
+    const int32_t h = head[v];
+    if (h < 0) { atomicOr(flags, 4u); return; }
+    atomicMax(&len[h], (uint32_t)rank[v] + 1u);
+    atomicAdd(&kcsum[h], (unsigned long long)(uint32_t)counts[v >> 1]);
+}
+// single CTA: exclusive prefix of the unitig lengths (k + len - 1 for heads, 0 otherwise) -> off[], total -> *total, heads -> *n_heads
+__global__ void __launch_bounds__(1024) k_unitig_offsets(uint32_t n2, int k, const int32_t* __restrict__ head, const uint32_t* __restrict__ len,
+                                                        uint32_t* __restrict__ off, uint32_t* __restrict__ hidx, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_a[1024], s_b[1024];
+    const uint32_t per = (n2 + 1023) / 1024;
+    const uint32_t lo = min(threadIdx.x * per, n2), hi = min(lo + per, n2);
+    uint32_t sum = 0, cnt = 0;
+    for (uint32_t v = lo; v < hi; v++)
+        if (head[v] == (int32_t)v) { sum += (uint32_t)k + len[v] - 1; cnt++; }
+    s_a[threadIdx.x] = sum;
+    s_b[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const uint32_t va = threadIdx.x >= (uint32_t)o ? s_a[threadIdx.x - o] : 0, vb = threadIdx.x >= (uint32_t)o ? s_b[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_a[threadIdx.x] += va;
+        s_b[threadIdx.x] += vb;
+        __syncthreads();
+    }
+    uint32_t run = s_a[threadIdx.x] - sum, idx = s_b[threadIdx.x] - cnt;
+    for (uint32_t v = lo; v < hi; v++) {
+        if (head[v] == (int32_t)v) {
+            off[v] = run;
+            hidx[v] = idx++;
+            run += (uint32_t)k + len[v] - 1;
+        }
+    }
+    if (threadIdx.x == 1023) { totals[0] = s_a[1023]; totals[1] = s_b[1023]; }
+}
+struct McUnitigRec { int32_t node, rc; uint32_t off, len; long long kc; };
+__global__ void __launch_bounds__(256) k_unitig_fill(uint32_t n2, int k, const uint64_t* __restrict__ kmers, const int32_t* __restrict__ counts,
+                                                    const int32_t* __restrict__ head, const int32_t* __restrict__ rank, const uint32_t* __restrict__ len,
+                                                    const uint32_t* __restrict__ off, const uint32_t* __restrict__ hidx,
+                                                    const unsigned long long* __restrict__ kcsum, char* __restrict__ chars, McUnitigRec* __restrict__ recs) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n2) return;
+    const int32_t h = head[v];
+    if (h < 0) return;
+    uint64_t code = kmers[v >> 1];
+    if (v & 1) code = mc_revcomp(code, k);
+    const uint32_t r = (uint32_t)rank[v], o = off[h], L = len[h];
+    const char NUCS[4] = {'A', 'G', 'C', 'T'};
+    if (r == 0) {
+        for (int i = 0; i < k; i++) chars[o + i] = NUCS[(code >> (2 * (k - 1 - i))) & 3];
+    } else {
+        chars[o + (uint32_t)k - 1 + r] = NUCS[code & 3];
+    }
+    if (r == L - 1) {   // the tail: closes the record of its chain
+        McUnitigRec rec;
+        rec.node = h;
+        rec.rc = (int32_t)(v ^ 1u);
+        rec.off = o;
+        rec.len = (uint32_t)k + L - 1;
+        rec.kc = (long long)kcsum[h] + (long long)counts[v >> 1] * (k - 1);
+        recs[hidx[h]] = rec;
+    }
+}
+
 void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out) {
     MC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -157,11 +237,12 @@ void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out) {
     size_t o_kmers = take((size_t)n * 8), o_hk = take((size_t)hcap * 8), o_hv = take((size_t)hcap * 4), o_win = take((size_t)nw * 8 + 8),
            o_col = take(multi ? (size_t)n * 8 : 8), o_deg = take(n2), o_nbr = take((size_t)n2 * 16), o_pal = take(n2 + 4), o_gene = take(n2),
            o_pred = take((size_t)n2 * 4), o_j0 = take((size_t)n2 * 4), o_j1 = take((size_t)n2 * 4), o_r0 = take((size_t)n2 * 4),
-           o_r1 = take((size_t)n2 * 4), o_head = take((size_t)n2 * 4), o_rank = take((size_t)n2 * 4);
-    uint8_t* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, bytes);
-    if (e != cudaSuccess) { cudaGetLastError(); mc_throw(MC_ERR_NOMEM, "cannot allocate %.1f MiB for the unitig stage", (double)bytes / (1 << 20)); }
-    try {
+           o_r1 = take((size_t)n2 * 4), o_head = take((size_t)n2 * 4), o_rank = take((size_t)n2 * 4),
+           o_cnt = take((size_t)n * 4), o_len = take((size_t)n2 * 4), o_kc = take((size_t)n2 * 8), o_off = take((size_t)n2 * 4), o_hidx = take((size_t)n2 * 4),
+           o_flags = take(16), o_chars = take((size_t)n2 * (size_t)(in.k + 1) + 64), o_recs = take((size_t)n2 * sizeof(McUnitigRec));
+    uint8_t* d = (uint8_t*)mc_dev_alloc(ctx, bytes, "unitig work memory");   // the context's arena: no driver call per environment
+    struct Free { mc_ctx* c; void* p; ~Free() { mc_dev_free(c, p); } } free_d{ctx, d};
+    {
         MC_CUDA(cudaMemcpyAsync(d + o_kmers, in.kmers.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
         if (nw) MC_CUDA(cudaMemcpyAsync(d + o_win, in.gene_windows.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, st));
         if (multi) MC_CUDA(cudaMemcpyAsync(d + o_col, in.colors.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -189,6 +270,43 @@ void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out) {
         k_finish<<<g1, 256, 0, st>>>(n2, (const int32_t*)(d + o_pred), j[cur], r[cur], (int32_t*)(d + o_head), (int32_t*)(d + o_rank));
         MC_LAUNCH(ctx);
         MC_CUDA(cudaGetLastError());
+        // ---- unitig assembly (single environments; the multi tool keeps per-colour paths on the host) ----
+        out.regular = false;
+        const bool assemble = !multi && in.counts.size() == (size_t)n;
+        uint32_t h_tot[4] = {0, 0, 0, 0};
+        if (assemble) {
+            MC_CUDA(cudaMemcpyAsync(d + o_cnt, in.counts.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            MC_CUDA(cudaMemsetAsync(d + o_len, 0, (size_t)n2 * 4, st));
+            MC_CUDA(cudaMemsetAsync(d + o_kc, 0, (size_t)n2 * 8, st));
+            MC_CUDA(cudaMemsetAsync(d + o_flags, 0, 16, st));
+            k_chain_stats<<<g1, 256, 0, st>>>(n2, (const int32_t*)(d + o_head), (const int32_t*)(d + o_rank), d + o_deg, (const int32_t*)(d + o_nbr), d + o_pal,
+                                              (const int32_t*)(d + o_cnt), (uint32_t*)(d + o_len), (unsigned long long*)(d + o_kc), (unsigned int*)(d + o_flags));
+            k_unitig_offsets<<<1, 1024, 0, st>>>(n2, in.k, (const int32_t*)(d + o_head), (const uint32_t*)(d + o_len), (uint32_t*)(d + o_off),
+                                                 (uint32_t*)(d + o_hidx), (uint32_t*)(d + o_flags) + 1);
+            k_unitig_fill<<<g1, 256, 0, st>>>(n2, in.k, (const uint64_t*)(d + o_kmers), (const int32_t*)(d + o_cnt), (const int32_t*)(d + o_head),
+                                              (const int32_t*)(d + o_rank), (const uint32_t*)(d + o_len), (const uint32_t*)(d + o_off),
+                                              (const uint32_t*)(d + o_hidx), (const unsigned long long*)(d + o_kc), (char*)(d + o_chars), (McUnitigRec*)(d + o_recs));
+            ctx->launches += 3;
+            MC_CUDA(cudaGetLastError());
+            MC_CUDA(cudaMemcpyAsync(h_tot, d + o_flags, 12, cudaMemcpyDeviceToHost, st));   // flags, total chars, unitigs
+            MC_CUDA(cudaStreamSynchronize(st));
+            out.regular = h_tot[0] == 0;
+        }
+        if (out.regular) {
+            const uint32_t n_chars = h_tot[1], n_u = h_tot[2];
+            std::vector<McUnitigRec> recs(n_u);
+            out.u_chars.resize(n_chars);
+            if (n_u) MC_CUDA(cudaMemcpyAsync(recs.data(), d + o_recs, (size_t)n_u * sizeof(McUnitigRec), cudaMemcpyDeviceToHost, st));
+            if (n_chars) MC_CUDA(cudaMemcpyAsync(&out.u_chars[0], d + o_chars, n_chars, cudaMemcpyDeviceToHost, st));
+            MC_CUDA(cudaMemcpyAsync(out.nbr.data(), d + o_nbr, (size_t)n2 * 16, cudaMemcpyDeviceToHost, st));
+            MC_CUDA(cudaMemcpyAsync(out.gene.data(), d + o_gene, n2, cudaMemcpyDeviceToHost, st));
+            MC_CUDA(cudaStreamSynchronize(st));
+            out.u_node.resize(n_u); out.u_rc.resize(n_u); out.u_off.resize(n_u); out.u_len.resize(n_u); out.u_kc.resize(n_u);
+            for (uint32_t i = 0; i < n_u; i++) {
+                out.u_node[i] = recs[i].node; out.u_rc[i] = recs[i].rc; out.u_off[i] = recs[i].off; out.u_len[i] = recs[i].len; out.u_kc[i] = recs[i].kc;
+            }
+            return;   // (the guard object returns the work memory to the arena)
+        }
         MC_CUDA(cudaMemcpyAsync(out.deg.data(), d + o_deg, n2, cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaMemcpyAsync(out.nbr.data(), d + o_nbr, (size_t)n2 * 16, cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaMemcpyAsync(out.nbr_pal.data(), d + o_pal, n2, cudaMemcpyDeviceToHost, st));
@@ -196,9 +314,5 @@ void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out) {
         MC_CUDA(cudaMemcpyAsync(out.head.data(), d + o_head, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaMemcpyAsync(out.rank.data(), d + o_rank, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaStreamSynchronize(st));
-    } catch (...) {
-        cudaFree(d);
-        throw;
     }
-    cudaFree(d);
 }

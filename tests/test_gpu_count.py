@@ -67,7 +67,8 @@ def test_chunk_boundaries_do_not_matter(oracle, chunk, fmt):
         o = oracle.table(9).count_bytes(data, f)
         assert_same_table(g, o)
         assert g.stats() == o.stats()
-        # device-resident path with the same small chunks
+        # device-resident path with the same small chunks (by default it takes pieces as large as 32-bit offsets allow)
+        c.set_tuning("device_chunk_bytes", chunk)
         d = c.device_alloc(len(data))
         c.h2d(d, np.frombuffer(data, dtype=np.uint8))
         g2 = c.new_table(9).count_device(d, len(data), f)
