@@ -154,6 +154,18 @@ int mc_table_print_kmers(const mc_table* t, int threshold, const char* out_file,
 int mc_table_load_kmers(mc_table* t, const char* path, int freq_threshold);
 
 /* ------------------------------------------------------------------------------------------------
+ * "next" row f-4b -- reads-classifier.  Replaces, for every read of a FASTQ buffer (host memory, whole records),
+ *   ReadsFinderInGraph.findRead(dnaQ) / findReadWithCorrection(dnaQ)            src/algo/ReadsFinderInGraph.java:37-49,89-123
+ * over `graph` = the k-mer count table the tool loads (ReadsClassifier.loadGraph, src/tools/ReadsClassifier.java:86-105):
+ * found[i] = 1 when read i's coverage breadth is at least found_threshold and inside the z-sigma interval around
+ * 1 - exp(-depth).  z = 1, or 1.96 with --interval95; found_threshold = --found-threshold / 100; correction = --correction.
+ * Pass cap = 0 (found may be NULL) to count the reads only.  The pair logic and the six output files of the tool
+ * (PairFinder.run, ReadsClassifier.runImpl :141-224) are host code in the CLI / Python layer.
+ * ---------------------------------------------------------------------------------------------- */
+int mc_classify_bytes(mc_ctx* ctx, const mc_table* graph, const void* buf, size_t len, int fmt, double z, double found_threshold,
+                      int correction, uint8_t* found, size_t cap, size_t* n_reads);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-GPU building blocks: one process per GPU; keys are exchanged by the host
  * layer (torch.distributed all_to_all over NCCL/NVLink) between these two calls.
  * ---------------------------------------------------------------------------------------------- */
@@ -208,6 +220,9 @@ int mc_event_elapsed_ms(mc_ctx* ctx, int slot_a, int slot_b, float* ms);
  * [0]=parse [1]=extract [2]=grow/rehash [3]=bin scatter [4]=bin count [5]=coverage filter [6..7] reserved */
 int mc_ctx_stage_ms(mc_ctx* ctx, float* ms3);          /* first three only (kept for older callers) */
 int mc_ctx_stage_ms_all(mc_ctx* ctx, float* ms8);
+/* host wall time inside the same phases since the last reset (launches and synchronisations included; [2] = reserving the bins,
+ * [4] = the whole flush, [6] = resolving timers + final flag check): tells kernel time from host time when a step is slow */
+int mc_ctx_host_ms(mc_ctx* ctx, double* ms8);
 int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the timers themselves; the multi-GPU building blocks do not */
 /* tuning knobs of the binned update path (NOT reference API; tests and profiles use them):
  *   "part_bits" (-1 = automatic, else P = 2^value bins), "batch_keys" (capacity of one batch, 0 = automatic),
@@ -215,7 +230,8 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
  *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32),
  *   "agg" (two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on), "agg_unit" (keys per
  *   aggregation unit, 0 = automatic), "device_chunk_bytes" (mc_count_device: bytes per parse / extract pass over device-resident input, 0 = as large as the 32-bit record
- *   offsets allow; tests force small values), "scatter_tma" (1 = default: the scatter kernels hand every bin run to the copy engine with cp.async.bulk; 0: per-sector stores),
+ *   offsets allow; tests force small values), "flush_overlap" (1: in the aggregated flush the sub-bin scatter of group g + 1 runs on a second stream beside the
+ *   aggregation of group g; 0 = default: one after the other), "stage_timing" (0: no per-stage CUDA events), "scatter_tma" (1 = default: the scatter kernels hand every bin run to the copy engine with cp.async.bulk; 0: per-sector stores),
  *   "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --
  *   a step made of several count calls; reset with mc_ctx_stage_reset) */
 int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "mc_table_add_pairs": (i32, [vp, vp, vp, sz]),
     "mc_table_get": (i32, [vp, vp, sz, vp]),
     "mc_table_dump": (i32, [vp, i32, vp, vp, sz, C.POINTER(sz)]),
+    "mc_ctx_host_ms": (i32, [vp, vp]),
+    "mc_classify_bytes": (i32, [vp, vp, vp, sz, i32, C.c_double, C.c_double, i32, vp, sz, C.POINTER(sz)]),
     "mc_java_format_6_2f": (i32, [C.c_float, cp]),
     "mc_table_dump_device": (i32, [vp, i32, vp, vp, sz, C.POINTER(sz)]),
     "mc_table_add_pairs_device": (i32, [vp, vp, vp, sz]),

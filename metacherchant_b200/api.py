@@ -75,6 +75,14 @@ class Context:
         check(self.lib.mc_ctx_stage_ms_all(self.h, v))
         return {name: v[i] for i, name in enumerate(self.STAGES)}
 
+    def host_ms(self):
+        """Host wall milliseconds inside the same phases since the last reset (launch + synchronisation time included)."""
+        v = (C.c_double * 8)()
+        check(self.lib.mc_ctx_host_ms(self.h, v))
+        d = {name: v[i] for i, name in enumerate(self.STAGES)}
+        d["finish"] = v[6]
+        return d
+
     def stage_reset(self):
         check(self.lib.mc_ctx_stage_reset(self.h))
 
@@ -144,6 +152,18 @@ class Context:
                                       -1 if max_radius is None else max_radius, int(both_dirs), chunk_len, int(merge), int(trim),
                                       os.fspath(out_dir).encode(), found))
         return [bool(found[i]) for i in range(1 if merge else n)]
+
+    # ---- "next" row f-4b: reads-classifier -------------------------------------------------------------
+    def classify_reads(self, graph: "KmerTable", data, fmt=FMT_FASTQ, z=1.0, found_threshold=0.9, correction=False) -> np.ndarray:
+        """found[i] of every read of a FASTQ buffer (ReadsFinderInGraph.findRead / findReadWithCorrection,
+        src/algo/ReadsFinderInGraph.java:37-123) against the k-mer table `graph`."""
+        a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        n = C.c_size_t()
+        check(self.lib.mc_classify_bytes(self.h, graph.h, _ptr(a), a.size, fmt, z, found_threshold, int(correction), None, 0, C.byref(n)))
+        found = np.zeros(n.value, dtype=np.uint8)
+        if n.value:
+            check(self.lib.mc_classify_bytes(self.h, graph.h, _ptr(a), a.size, fmt, z, found_threshold, int(correction), _ptr(found), found.size, C.byref(n)))
+        return found
 
     def env_from_graph_txt(self, graph_txt, target_seq, k, chunk_len, out_dir):
         check(self.lib.mc_env_from_graph_txt(self.h, os.fspath(graph_txt).encode(), target_seq.encode(), k, chunk_len, os.fspath(out_dir).encode()))

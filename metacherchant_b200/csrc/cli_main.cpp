@@ -6,6 +6,7 @@
 //   EnvironmentFinderMain parameters              src/tools/EnvironmentFinderMain.java:32-105
 //   EnvironmentFinderMultiMain parameters         src/tools/EnvironmentFinderMultiMain.java:21-42
 //   KmersCounter parameters ("next" row f-1)      src/tools/KmersCounter.java
+//   ReadsClassifier parameters ("next" row f-4b)  src/tools/ReadsClassifier.java:40-84
 // Option syntax follows commons-cli PosixParser as the ITMO Tool uses it: "--name value", "--name=value", short
 // options, multi-valued options taking every following non-option token and re-tokenised on "[, ]"
 // (Tool.java:853-855,888-895), booleans with an optional True/False argument (Parameter.java:51-58).
@@ -143,6 +144,16 @@ const Opt MULTI_OPTS[] = {
     {"seq", nullptr, STR, true, ".fasta file with nucleotide sequence[s]"},
     {"output", "o", STR, true, "output directory to write results to"},
     {"geneid", "g", INT, false, "gene id from .fasta file (default 1)"},
+};
+const Opt READS_CLASSIFIER_OPTS[] = {   // src/tools/ReadsClassifier.java:40-84
+    {"k", "k", INT, true, "k-mer size"},
+    {"input-files", "i", FILES, true, "file with paired input reads for De Bruijn graph OR file with k-mers in binary format"},
+    {"read-files", "r", FILES, true, "files with paired reads to classify"},
+    {"output-dir", "o", STR, false, "directory to output found reads (default <work-dir>/reads_classifier)"},
+    {"correction", "corr", BOOL, false, "Do replacement of nucleotide in read with one low quality position"},
+    {"hash", nullptr, STR, false, "hash function to use [k > 31 only: not supported by the GPU path]"},
+    {"interval95", nullptr, BOOL, false, "Set the interval width to probability 0.95"},
+    {"found-threshold", "found", INT, false, "Minimum coverage breadth for class `found` [0 - 100 %] (default 90)"},
 };
 const Opt KMER_COUNTER_OPTS[] = {
     {"k", "k", INT, true, "k-mer size"},
@@ -375,6 +386,158 @@ int run_kmer_counter(const std::vector<std::string>& rest, const Args& launch, c
     return 0;
 }
 
+// ---- reads-classifier ("next" row f-4b) ---------------------------------------------------------------------------------
+// One FASTQ record as FastqReader keeps it (ITMO!/io/readers/FastqReader.java:53-82): bases as nucleotides (N, n, . -> A) and
+// the stored 6-bit phred; the tool writes its classes back through WritersUtils.writeDnaQsToFastqFile, i.e. with numbered
+// headers, the stored nucleotides and Phred+64 qualities.
+struct FqRead { std::string nucs, phred; };
+std::vector<uint8_t> slurp(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) die("Failed to read from file %s", path.c_str());
+    std::vector<uint8_t> data;
+    uint8_t buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + got);
+    fclose(f);
+    return data;
+}
+std::vector<FqRead> parse_fastq(const std::vector<uint8_t>& d, int qoff) {
+    std::vector<std::string> lines;   // BufferedReader.readLine
+    size_t p = 0;
+    while (p < d.size()) {
+        size_t s = p;
+        while (p < d.size() && d[p] != '\n' && d[p] != '\r') p++;
+        lines.emplace_back((const char*)d.data() + s, p - s);
+        if (p < d.size()) p += (d[p] == '\r' && p + 1 < d.size() && d[p + 1] == '\n') ? 2 : 1;
+    }
+    std::vector<FqRead> out;
+    size_t i = 0;
+    auto data_line = [&](std::string& v) -> bool {   // readNextDataLine (:84-110); structural errors were reported by the library already
+        while (i < lines.size() && lines[i].empty()) i++;
+        if (i >= lines.size()) return false;
+        i++;
+        if (i >= lines.size()) return false;
+        v = lines[i++];
+        return true;
+    };
+    std::string seq, qual;
+    while (data_line(seq) && data_line(qual)) {
+        FqRead r;
+        r.nucs.resize(seq.size());
+        r.phred.resize(seq.size());
+        for (size_t j = 0; j < seq.size(); j++) {
+            const char c = seq[j];
+            const bool unknown = c == 'N' || c == 'n' || c == '.';
+            char u = (char)toupper((unsigned char)c);
+            r.nucs[j] = unknown ? 'A' : u;
+            r.phred[j] = (char)(64 + (unknown ? 0 : (((unsigned char)qual[j] - qoff) & 63)));
+        }
+        out.push_back(std::move(r));
+    }
+    return out;
+}
+void write_fastq(const std::vector<const FqRead*>& reads, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) die("cannot write %s", path.c_str());
+    long n = 0;
+    for (const FqRead* r : reads) {
+        if (r->nucs.empty()) { fclose(f); die("Empty DnaQ!"); }   // FastqDedicatedWriter.writeData
+        fprintf(f, "@%ld\n%s\n+\n%s\n", ++n, r->nucs.c_str(), r->phred.c_str());
+    }
+    fclose(f);
+}
+
+int run_reads_classifier(const std::vector<std::string>& rest, const Args& launch, const std::string& work_dir) {
+    std::vector<Opt> opts = as_vec(READS_CLASSIFIER_OPTS);
+    Args a;
+    parse_args(rest, opts, a);
+    check_mandatory(opts, a);
+    long long k = 0, device = 0, found_pct = 90;
+    a.integer("k", k);
+    a.integer("found-threshold", found_pct);
+    launch.integer("device", device);
+    if (k > 31) die("k > 31 selects the reference's lossy hashed mode (LargeKIOUtils), which is not supported by the GPU path");
+    if (k < 1) die("k must be positive");
+    const std::vector<std::string> inputs = a.values.at("input-files"), reads = a.values.at("read-files");
+    if (inputs.empty()) die("Mandatory argument --input-files (-i) not set");
+    if (reads.empty()) die("Mandatory argument --read-files (-r) not set");
+    const std::string out_dir = a.str("output-dir", work_dir + "/reads_classifier");
+    const bool correction = a.boolean("correction", false);
+    const double z = a.boolean("interval95", false) ? 1.96 : 1.0, threshold = (double)found_pct / 100.0;
+    mkdirs(out_dir);
+    mc_ctx* ctx = nullptr;
+    MC(mc_ctx_create((int)device, &ctx));
+    // loadGraph (:86-105): k-mers in binary format, or reads
+    mc_table* graph = nullptr;
+    std::string first = base_name(inputs[0]);
+    for (auto& c : first) c = (char)tolower((unsigned char)c);
+    if (first.size() >= 9 && first.compare(first.size() - 9, 9, "kmers.bin") == 0) {
+        MC(mc_table_create(ctx, (int)k, 0, 0, 0, &graph));
+        for (const std::string& f : inputs) MC(mc_table_load_kmers(graph, f.c_str(), 0));
+    } else {
+        graph = load_reads(ctx, inputs, (int)k);
+    }
+    info("Hashtable size: %llu kmers", (unsigned long long)mc_table_size(graph));
+    info("Loading reads...");
+    std::vector<std::vector<FqRead>> src;
+    std::vector<std::vector<uint8_t>> flags;
+    for (size_t fi = 0; fi < reads.size() && fi < 2; fi++) {
+        int gz = 0;
+        const int fmt = mc_detect_file_format(reads[fi].c_str(), &gz);
+        if (fmt < 0) die("%s", mc_last_error());
+        if (fmt != MC_FMT_FASTQ || gz) die("reads-classifier on the GPU path reads plain FASTQ files (%s)", reads[fi].c_str());
+        const std::vector<uint8_t> bytes = slurp(reads[fi]);
+        const int qoff = mc_sniff_quality_offset(bytes.data(), bytes.size());
+        size_t n = 0;
+        MC(mc_classify_bytes(ctx, graph, bytes.data(), bytes.size(), qoff, z, threshold, correction ? 1 : 0, nullptr, 0, &n));
+        flags.emplace_back(n);
+        if (fi == 0) info(correction ? "Searching for corrected reads in graph..." : "Searching for reads in graph...");
+        if (n) MC(mc_classify_bytes(ctx, graph, bytes.data(), bytes.size(), qoff, z, threshold, correction ? 1 : 0, flags.back().data(), n, &n));
+        src.push_back(parse_fastq(bytes, qoff));
+        if (src.back().size() != n) die("internal: the host reader sees %zu records in %s, the device %zu", src.back().size(), reads[fi].c_str(), n);
+    }
+    // PairFinder.run (src/algo/PairFinder.java:30-55) + the six output files (ReadsClassifier.java:204-217), reads in input order
+    const bool paired = src.size() == 2;
+    const size_t n = paired ? std::min(src[0].size(), src[1].size()) : src[0].size();
+    const FqRead empty;
+    std::vector<const FqRead*> found_1, found_2, not_found_1, not_found_2, found_s, not_found_s, tail_found, tail_not;
+    long both_found = 0, first_found = 0, second_found = 0, both_not = 0;
+    for (size_t i = 0; i < n; i++) {
+        const FqRead& r1 = src[0][i];
+        const FqRead& r2 = paired ? src[1][i] : empty;
+        bool f1 = flags[0][i] != 0, f2 = paired ? flags[1][i] != 0 : false;
+        if (r2.nucs.empty()) f2 = !f1;
+        if (f1 && f2) { both_found++; found_1.push_back(&r1); found_2.push_back(&r2); }
+        else if (f1) { first_found++; if (!r1.nucs.empty()) found_s.push_back(&r1); if (!r2.nucs.empty()) not_found_s.push_back(&r2); }
+        else if (f2) { second_found++; if (!r2.nucs.empty()) tail_found.push_back(&r2); if (!r1.nucs.empty()) tail_not.push_back(&r1); }
+        else { both_not++; not_found_1.push_back(&r1); not_found_2.push_back(&r2); }
+    }
+    found_s.insert(found_s.end(), tail_found.begin(), tail_found.end());
+    not_found_s.insert(not_found_s.end(), tail_not.begin(), tail_not.end());
+    const long total = 2 * (both_not + both_found + first_found + second_found), paired_n = 2 * (both_found + both_not);
+    const long found_n = 2 * both_found + first_found + second_found, not_found_n = 2 * both_not + first_found + second_found;
+    info("|\tTotal: %ld reads", total);
+    info("|\tPaired: %ld reads", paired_n);
+    info("|\tTotal quality: %.2f %%", 100.0 * (double)paired_n / (double)total);
+    info("|\tFound: %ld reads", found_n);
+    info("|\tPercent of found reads: %.2f %%", 100.0 * (double)found_n / (double)total);
+    info("|\tQuality of found bin: %.2f %%", (double)both_found * 2 / (double)(both_found * 2 + first_found + second_found) * 100);
+    info("|\tNot found: %ld reads", not_found_n);
+    info("|\tPercent of not found reads: %.2f %%", 100.0 * (double)not_found_n / (double)total);
+    info("|\tQuality of not found bin: %.2f %%", (double)both_not * 2 / (double)(both_not * 2 + first_found + second_found) * 100);
+    info("Writing classified reads...");
+    write_fastq(found_1, out_dir + "/found_1.fastq");
+    write_fastq(found_2, out_dir + "/found_2.fastq");
+    write_fastq(not_found_1, out_dir + "/not_found_1.fastq");
+    write_fastq(not_found_2, out_dir + "/not_found_2.fastq");
+    write_fastq(found_s, out_dir + "/found_s.fastq");
+    write_fastq(not_found_s, out_dir + "/not_found_s.fastq");
+    info("Reads have been written. Finishing...");
+    mc_table_free(graph);
+    mc_ctx_destroy(ctx);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -412,6 +575,7 @@ int main(int argc, char** argv) {
     if (launch.boolean("help", false) || argc == 1) {
         if (tool == "environment-finder-multi") print_help(tool.c_str(), as_vec(MULTI_OPTS));
         else if (tool == "kmer-counter") print_help(tool.c_str(), as_vec(KMER_COUNTER_OPTS));
+        else if (tool == "reads-classifier") print_help(tool.c_str(), as_vec(READS_CLASSIFIER_OPTS));
         else print_help("environment-finder", as_vec(ENV_FINDER_OPTS));
         printf("\nLaunch options:\n");
         print_help("(all tools)", launch_opts);
@@ -424,7 +588,8 @@ int main(int argc, char** argv) {
     if (tool == "environment-finder") rc = run_environment_finder(rest, launch);
     else if (tool == "environment-finder-multi") rc = run_multi(rest, launch);
     else if (tool == "kmer-counter") rc = run_kmer_counter(rest, launch, work_dir);
-    else die("Unknown tool '%s': the GPU path provides environment-finder, environment-finder-multi and kmer-counter", tool.c_str());
+    else if (tool == "reads-classifier") rc = run_reads_classifier(rest, launch, work_dir);
+    else die("Unknown tool '%s': the GPU path provides environment-finder, environment-finder-multi, kmer-counter and reads-classifier", tool.c_str());
     if (g_log) fclose(g_log);
     return rc;
 }

@@ -16,6 +16,19 @@ extern "C" int mc_ctx_create(int device, mc_ctx** out) {
             mc_throw(MC_ERR_CUDA, "no CUDA device available (%s): libmcgpu has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
         }
         if (device < 0 || device >= n) mc_throw(MC_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+        // Host synchronisation policy: MC_SYNC=spin|block|yield|auto (default: the driver's choice).
+        {
+            unsigned flags = cudaDeviceScheduleAuto;   // (spinning was measured no better on the shared boxes: profiles/r2_NOTES.md)
+            if (const char* e = getenv("MC_SYNC")) {
+                if (!strcmp(e, "spin")) flags = cudaDeviceScheduleSpin;
+                else if (!strcmp(e, "block")) flags = cudaDeviceScheduleBlockingSync;
+                else if (!strcmp(e, "yield")) flags = cudaDeviceScheduleYield;
+                else if (!strcmp(e, "auto")) flags = cudaDeviceScheduleAuto;
+            }
+            cudaSetDevice(device);
+            cudaSetDeviceFlags(flags);
+            cudaGetLastError();
+        }
         MC_CUDA(cudaSetDevice(device));
         mc_ctx* c = new mc_ctx();
         c->device = device;
@@ -40,6 +53,7 @@ extern "C" int mc_ctx_create(int device, mc_ctx** out) {
         // round 1 still went back to the driver whenever a step's largest blocks missed its cache (profiles/r1d_NOTES.md)
         MC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         MC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        MC_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         for (auto& ev : c->ev) MC_CUDA(cudaEventCreate(&ev));
         for (auto& ev : c->stage_ev) MC_CUDA(cudaEventCreate(&ev));
         MC_CUDA(cudaMallocHost(&c->h_pinned_small, 4096));
@@ -56,6 +70,7 @@ extern "C" void mc_ctx_destroy(mc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->aux_stream);
     mc_resolve_timers(c);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_chunk[i]);
@@ -71,6 +86,7 @@ extern "C" void mc_ctx_destroy(mc_ctx* c) {
     for (auto& ev : c->stage_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->aux_stream);
     delete c;
 }
 
@@ -115,6 +131,7 @@ void* mc_scratch(mc_ctx* ctx, int slot, size_t bytes) {
             mc_throw(MC_ERR_NOMEM, "cannot allocate %.1f MiB of device scratch", (double)cap / (1 << 20));
         }
         ctx->d_scratch_cap[slot] = cap;
+        ctx->scratch_allocs++;
     }
     return ctx->d_scratch[slot];
 }
@@ -189,6 +206,13 @@ extern "C" int mc_ctx_stage_reset(mc_ctx* c) {
     if (!c) mc_throw(MC_ERR_ARG, "null argument");
     mc_resolve_timers(c);
     for (auto& v : c->stage_ms) v = 0;
+    for (auto& v : c->host_ms) v = 0;
+    MC_API_END
+}
+extern "C" int mc_ctx_host_ms(mc_ctx* c, double* ms8) {
+    MC_API_TRY
+    if (!c || !ms8) mc_throw(MC_ERR_ARG, "null argument");
+    for (int i = 0; i < MC_N_STAGES; i++) ms8[i] = c->host_ms[i];
     MC_API_END
 }
 extern "C" int mc_ctx_stage_ms_all(mc_ctx* c, float* ms8) {

@@ -487,10 +487,19 @@ static McBinCountKernel bin_count_variant(int v) {
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
+// Free device memory + what the context's arena holds for reuse.  cudaMemGetInfo goes to the kernel-mode driver, where it
+// queues behind whatever else holds the resource-manager lock (an NVML / nvidia-smi poll takes it for milliseconds): measured on the
+// shared boxes as 20 ms "reserve" phases in otherwise identical steps.  The answer only sizes buffers (never more than a fraction
+// of it is asked for, and a failed allocation releases the arena and retries), so it is cached and refreshed only after the
+// library itself went to the driver for memory.
 static uint64_t available_device_bytes(mc_ctx* ctx) {
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (uint64_t)1 << 30; }
-    return (uint64_t)free_b + mc_arena_cached_bytes(ctx);   // blocks cached by the context's arena are reusable (or released on demand)
+    if (ctx->free_bytes_cached == 0 || ctx->free_bytes_epoch != ctx->arena_driver_allocs + ctx->scratch_allocs) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (uint64_t)1 << 30; }
+        ctx->free_bytes_cached = free_b ? free_b : 1;
+        ctx->free_bytes_epoch = ctx->arena_driver_allocs + ctx->scratch_allocs;
+    }
+    return (uint64_t)ctx->free_bytes_cached + mc_arena_cached_bytes(ctx);   // blocks cached by the arena are reusable (or released on demand)
 }
 
 // a predicted table size is an estimate: never ask for more than 80 % of what the device can still give.  A table that cannot
@@ -679,31 +688,42 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     const uint64_t seg_keys = ctx->tune_segment_keys ? std::min<uint64_t>(ctx->tune_segment_keys, MC_FLUSH_SEGMENT) : MC_FLUSH_SEGMENT;
     const uint32_t g_max = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(P1, seg_keys / max_bin));
     const uint64_t spill2_cap = (uint64_t)g_max * max_bin + 1024;
-    McBinsDev B2{};
-    B2.pbits = pb2;
-    B2.hbits = B->dev.hbits;
-    B2.shift = B->dev.shift - pb2;
-    B2.cap = cap2;
-    B2.spill_cap = spill2_cap;
-    struct Staging {   // returned to the pool, and the overflow list detached, also when a step below throws
+    // Two staging slots: while k_bin_agg works on the sub-bins of group g (slot g & 1) on the main stream, k_bin_scatter2 fills the
+    // slot of group g + 1 on the auxiliary stream.  The two kernels lean on different pipes (the scatter on the shared-memory pipe and
+    // its barriers, the aggregation on instruction issue), so run side by side, one CTA per SM each, they finish sooner than one after
+    // the other with two CTAs per SM each.  "flush_overlap" = 0 gives the serial schedule (one slot).
+    const bool overlap = ctx->tune_flush_overlap != 0 && P1 > 64;
+    const int n_slots = overlap ? 2 : 1;
+    McBinsDev B2s[2] = {};
+    const size_t n_cursors = (size_t)g_max * (P2 + 1) + 2;   // + (unused) + the unit ticket
+    struct Staging {   // returned to the arena, and the overflow list detached, also when a step below throws
         mc_ctx* ctx;
         mc_table* t;
         McBinsDev* b;
+        int n;
         ~Staging() {
+            cudaStreamSynchronize(ctx->aux_stream);
             t->dev.ovf_keys = nullptr;
             t->dev.ovf_cap = 0;
-            mc_dev_free(ctx, b->keys);
-            mc_dev_free(ctx, b->spill);
-            mc_dev_free(ctx, b->cursors);
+            for (int i = 0; i < n; i++) {
+                mc_dev_free(ctx, b[i].keys);
+                mc_dev_free(ctx, b[i].spill);
+                mc_dev_free(ctx, b[i].cursors);
+            }
         }
-    } staging{ctx, t, &B2};
-    B2.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)g_max * P2 * cap2 * 8, "k-mer sub-bins");
-    B2.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)spill2_cap * 8, "k-mer sub-bin spill list");
-    const size_t n_cursors = (size_t)g_max * (P2 + 1) + 2;   // + the shared spill cursor + the unit ticket
-    B2.cursors = (unsigned long long*)mc_dev_alloc(ctx, n_cursors * 8, "sub-bin cursors");
-    B2.spill_cursor = B2.cursors + (n_cursors - 2);
-    unsigned long long* d_ticket = B2.cursors + (n_cursors - 1);
-
+    } staging{ctx, t, B2s, n_slots};
+    for (int i = 0; i < n_slots; i++) {
+        McBinsDev& b = B2s[i];
+        b.pbits = pb2;
+        b.hbits = B->dev.hbits;
+        b.shift = B->dev.shift - pb2;
+        b.cap = cap2;
+        b.spill_cap = spill2_cap;
+        b.keys = (uint64_t*)mc_dev_alloc(ctx, (size_t)g_max * P2 * cap2 * 8, "k-mer sub-bins");
+        b.spill = (uint64_t*)mc_dev_alloc(ctx, (size_t)spill2_cap * 8, "k-mer sub-bin spill list");
+        b.cursors = (unsigned long long*)mc_dev_alloc(ctx, n_cursors * 8, "sub-bin cursors");
+        b.spill_cursor = b.cursors + (n_cursors - 2);   // the slot's own spill cursor (copied into the status block after the group)
+    }
     scatter_attrs(ctx);
     if (mc_attr_once(ctx, MC_ATTR_AGG)) {
         MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
@@ -726,12 +746,16 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
         MC_CUDA(cudaMemsetAsync(&t->dev.counters[MC_CNT_OVF], 0, 2 * sizeof(unsigned long long), st));
     };
     attach_overflow_list();
-    B2.spill_cursor = t->dev.counters + MC_STATUS_SPILL2;   // inside the table's status block: one read-back per group
     enum { RING = 2 };
     unsigned long long* h_ring = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 1024);   // RING status blocks
     struct Pending { bool live = false; cudaEvent_t ev = nullptr; uint64_t keys_done = 0, group_keys = 0; uint32_t b0 = 0, G = 0; } pend[RING];
-    struct EvGuard { mc_ctx* c; Pending* p; ~EvGuard() { for (int i = 0; i < RING; i++) mc_event_put(c, p[i].ev); } } ev_guard{ctx, pend};
+    cudaEvent_t sc_done[2] = {nullptr, nullptr}, agg_done[2] = {nullptr, nullptr};
+    struct EvGuard {
+        mc_ctx* c; Pending* p; cudaEvent_t* a; cudaEvent_t* b;
+        ~EvGuard() { for (int i = 0; i < RING; i++) mc_event_put(c, p[i].ev); for (int i = 0; i < 2; i++) { mc_event_put(c, a[i]); mc_event_put(c, b[i]); } }
+    } ev_guard{ctx, pend, sc_done, agg_done};
     for (int i = 0; i < RING; i++) pend[i].ev = mc_event_get(ctx);
+    for (int i = 0; i < 2; i++) { sc_done[i] = mc_event_get(ctx); agg_done[i] = mc_event_get(ctx); }
     const uint64_t keys_before = mc_table_keys(t);
     uint64_t keys_known = keys_before;
     const bool trace = getenv("MC_TRACE") != nullptr;
@@ -765,42 +789,64 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
             keys_known = std::max(keys_known, now);
         }
     };
-    uint64_t keys_done = 0;
-    bool first = true;
-    uint32_t gi = 0;
-    for (uint32_t b0 = 0; b0 < P1; gi++) {
-        // the first group is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
-        uint32_t G = first ? std::max<uint32_t>(P1 / 64, 1) : g_max;
+    // the groups of first-level bins: the first one is a sample (1/64 of the hash space) that sizes the table for the rest of the batch
+    struct Group { uint32_t b0, G; uint64_t keys; };
+    std::vector<Group> groups;
+    for (uint32_t b0 = 0; b0 < P1;) {
+        uint32_t G = groups.empty() ? std::max<uint32_t>(P1 / 64, 1) : g_max;
         G = std::min(std::min(G, g_max), P1 - b0);
-        uint64_t group_keys = 0;
-        for (uint32_t b = b0; b < b0 + G; b++) group_keys += std::min<uint64_t>(cur[b], cap1);
+        uint64_t gk = 0;
+        for (uint32_t b = b0; b < b0 + G; b++) gk += std::min<uint64_t>(cur[b], cap1);
+        groups.push_back(Group{b0, G, gk});
+        b0 += G;
+    }
+    const uint32_t tiles = (uint32_t)((max_bin + SC_TILE - 1) / SC_TILE);
+    cudaStream_t s2 = overlap ? ctx->aux_stream : st;
+    auto launch_scatter2 = [&](uint32_t gi) {   // sub-bin scatter of group gi into its staging slot, on s2
+        const Group& g = groups[gi];
+        McBinsDev& S = B2s[gi % n_slots];
+        if (overlap && gi >= 2) MC_CUDA(cudaStreamWaitEvent(s2, agg_done[gi & 1], 0));   // agg(gi - 2) has read this slot
+        if (g.keys) {
+            MC_CUDA(cudaMemsetAsync(S.cursors, 0, n_cursors * 8, s2));
+            McStageTimer tm(ctx, MC_ST_SCATTER, s2);
+            const uint32_t x = (uint32_t)std::min<uint64_t>((uint64_t)tiles * g.G, (uint64_t)ctx->sm_count * (overlap ? 1 : sc_per_sm));
+            if (ctx->tune_scatter_tma) k_bin_scatter2<true><<<x, SC_THREADS, scatter_smem_bytes(P2), s2>>>(B->dev, g.b0, g.G, tiles, S, t->dev.flags);
+            else k_bin_scatter2<false><<<x, SC_THREADS, scatter_smem_bytes(P2), s2>>>(B->dev, g.b0, g.G, tiles, S, t->dev.flags);
+            MC_LAUNCH(ctx);
+            MC_CUDA(cudaGetLastError());
+        }
+        if (overlap) MC_CUDA(cudaEventRecord(sc_done[gi & 1], s2));
+    };
+    if (overlap) {   // the first-level bins are complete on the main stream before the auxiliary stream reads them
+        MC_CUDA(cudaEventRecord(agg_done[0], st));
+        MC_CUDA(cudaStreamWaitEvent(s2, agg_done[0], 0));
+        launch_scatter2(0);
+    }
+    uint64_t keys_done = 0;
+    for (uint32_t gi = 0; gi < (uint32_t)groups.size(); gi++) {
+        const Group& g = groups[gi];
+        const bool first = gi == 0;
+        McBinsDev& B2 = B2s[gi % n_slots];
+        unsigned long long* d_ticket = B2.cursors + (n_cursors - 1);
         grow_if_due(t, keys_known);   // amortised doubling
         Pending& slot = pend[gi % RING];
         unsigned long long* h_c = h_ring + (size_t)(gi % RING) * MC_STATUS_WORDS;
         if (slot.live) examine(slot, h_c);   // (only when RING groups are in flight; normally drained below)
-        if (group_keys) {
-            MC_CUDA(cudaMemsetAsync(B2.cursors, 0, n_cursors * 8, st));
-            MC_CUDA(cudaMemsetAsync(B2.spill_cursor, 0, sizeof(unsigned long long), st));
-            {
-                McStageTimer tm(ctx, MC_ST_SCATTER);
-                const uint32_t tiles = (uint32_t)((max_bin + SC_TILE - 1) / SC_TILE);
-                const uint32_t x = (uint32_t)std::min<uint64_t>((uint64_t)tiles * G, (uint64_t)ctx->sm_count * sc_per_sm);
-                if (ctx->tune_scatter_tma) k_bin_scatter2<true><<<x, SC_THREADS, scatter_smem_bytes(P2), st>>>(B->dev, b0, G, tiles, B2, t->dev.flags);
-                else k_bin_scatter2<false><<<x, SC_THREADS, scatter_smem_bytes(P2), st>>>(B->dev, b0, G, tiles, B2, t->dev.flags);
-                MC_LAUNCH(ctx);
-                MC_CUDA(cudaGetLastError());
-            }
-            const uint32_t n_units = G * P2;
-            const int grid = (int)std::min<uint64_t>(n_units, (uint64_t)ctx->sm_count * agg_per_sm);
+        if (!overlap) launch_scatter2(gi);
+        else MC_CUDA(cudaStreamWaitEvent(st, sc_done[gi & 1], 0));
+        if (g.keys) {
+            const uint32_t n_units = g.G * P2;
+            const int grid = (int)std::min<uint64_t>(n_units, (uint64_t)ctx->sm_count * (overlap ? 1 : agg_per_sm));
             if (first) {
                 // the sample is only COUNTED first: its distinct keys that the table does not hold yet, scaled to the whole batch,
                 // size the table before anything is inserted (no overflow churn, no rehash of a half-filled table)
                 {
                     McStageTimer tm(ctx, MC_ST_COUNT);
-                    k_bin_agg<true><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
+                    k_bin_agg<true><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
                     MC_LAUNCH(ctx);
                     MC_CUDA(cudaGetLastError());
                 }
+                if (overlap && groups.size() > 1) launch_scatter2(1);   // the next group's scatter runs under the sample and its read-back
                 MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_STATUS_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 MC_CUDA(cudaStreamSynchronize(st));
                 // later batches of a stream are assumed to bring as many new keys as this one: an upper bound (the genomic k-mers
@@ -810,10 +856,10 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 double batches_left = 1.0;
                 if (t->expect_instances > t->seen_instances + batch_keys) batches_left = (double)(t->expect_instances - t->seen_instances) / (double)batch_keys;
                 if (t->stream_flushes == 0) batches_left = std::min(batches_left, 4.0);
-                const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)group_keys) * batches_left;
+                const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)g.keys) * batches_left;
                 const double predicted = (double)keys_before + fresh;
                 if (trace) fprintf(stderr, "[mc trace] agg sample: %llu new distinct keys in %llu instances -> %.0f predicted for the batch\n",
-                                   (unsigned long long)h_c[MC_CNT_OVF_KEYS], (unsigned long long)group_keys, predicted);
+                                   (unsigned long long)h_c[MC_CNT_OVF_KEYS], (unsigned long long)g.keys, predicted);
                 if (predicted > MC_GROW_LOAD * 4.0 * (double)t->nb) {
                     const int q = fit_q(ctx, t, mc_q_for_keys((uint64_t)predicted, t->dev.shard_bits, MC_FLUSH_TARGET_LOAD));
                     if (q > t->dev.q) mc_table_grow_to(t, q);
@@ -823,7 +869,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
             }
             {
                 McStageTimer tm(ctx, MC_ST_COUNT);
-                k_bin_agg<false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, b0, n_units, d_ticket);
+                k_bin_agg<false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
                 MC_LAUNCH(ctx);
                 // a sub-bin that was full (a heavy hitter) spilled: direct updates, length read on the device
                 k_insert_hashed_n<<<ctx->sm_count, 256, 0, st>>>(t->dev, B2.spill, B2.spill_cursor, spill2_cap);
@@ -831,36 +877,40 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 MC_CUDA(cudaGetLastError());
             }
             if (trace && first) {   // sub-bin fill of the first group
-                std::vector<unsigned long long> c2((size_t)G * (P2 + 1));
+                std::vector<unsigned long long> c2((size_t)g.G * (P2 + 1));
                 MC_CUDA(cudaMemcpyAsync(c2.data(), B2.cursors, c2.size() * 8, cudaMemcpyDeviceToHost, st));
                 MC_CUDA(cudaStreamSynchronize(st));
                 unsigned long long mx = 0, sum = 0, over = 0, mn = ~0ull;
-                for (uint32_t g = 0; g < G; g++)
+                for (uint32_t gg = 0; gg < g.G; gg++)
                     for (uint32_t j = 0; j < P2; j++) {
-                        unsigned long long v = c2[(size_t)g * (P2 + 1) + j];
+                        unsigned long long v = c2[(size_t)gg * (P2 + 1) + j];
                         mx = std::max(mx, v); mn = std::min(mn, v); sum += v; over += v > cap2;
                     }
-                fprintf(stderr, "[mc trace] sub-bin attempts: min %llu mean %.0f max %llu, %llu of %u over cap2; bin0 attempts %llu\n", mn, (double)sum / (G * P2), mx, over, G * P2, cur[0]);
+                fprintf(stderr, "[mc trace] sub-bin attempts: min %llu mean %.0f max %llu, %llu of %u over cap2; bin0 attempts %llu\n", mn, (double)sum / (g.G * P2), mx, over, g.G * P2, cur[0]);
             }
         }
-        keys_done += group_keys;
+        keys_done += g.keys;
         slot.live = true;
         slot.keys_done = keys_done;
-        slot.group_keys = group_keys;
-        slot.b0 = b0;
-        slot.G = G;
+        slot.group_keys = g.keys;
+        slot.b0 = g.b0;
+        slot.G = g.G;
         MC_CUDA(cudaMemcpyAsync(h_c, t->dev.counters, MC_STATUS_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (g.keys) MC_CUDA(cudaMemcpyAsync(h_c + MC_STATUS_SPILL2, B2.spill_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaEventRecord(slot.ev, st));
-        b0 += G;
-        first = false;
+        if (overlap) {
+            MC_CUDA(cudaEventRecord(agg_done[gi & 1], st));                      // this slot may be refilled (by the scatter of group gi + 2)
+            if (gi >= 1 && gi + 1 < (uint32_t)groups.size()) launch_scatter2(gi + 1);   // (group 1 was queued under the sample)
+        }
         // the group queued BEFORE this one has had a whole group's time to finish: look at what it left behind
         if (gi >= 1) {
             Pending& prev = pend[(gi - 1) % RING];
             if (prev.live) examine(prev, h_ring + (size_t)((gi - 1) % RING) * MC_STATUS_WORDS);
         }
     }
-    for (uint32_t j = (gi >= RING ? gi - RING : 0); j < gi; j++)
-        if (pend[j % RING].live) examine(pend[j % RING], h_ring + (size_t)(j % RING) * MC_STATUS_WORDS);
+    for (int j = 0; j < RING; j++)
+        if (pend[j].live) examine(pend[j], h_ring + (size_t)j * MC_STATUS_WORDS);
+    if (overlap) MC_CUDA(cudaStreamSynchronize(s2));
     t->seen_instances += batch_keys;
     t->stream_flushes++;
 }
@@ -991,6 +1041,8 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "agg" && value >= -1 && value <= 1) ctx->tune_agg = (int)value;
     else if (n == "keep_stage_ms" && value >= 0 && value <= 1) ctx->keep_stage_ms = (int)value;
     else if (n == "scatter_tma" && value >= 0 && value <= 1) ctx->tune_scatter_tma = (int)value;
+    else if (n == "flush_overlap" && value >= 0 && value <= 1) ctx->tune_flush_overlap = (int)value;
+    else if (n == "stage_timing" && value >= 0 && value <= 1) ctx->tune_stage_timing = (int)value;
     else if (n == "device_chunk_bytes" && (value == 0 || (value >= 4096 && value <= ((long long)3 << 30)))) ctx->tune_device_chunk_bytes = (size_t)value;
     else if (n == "agg_unit" && value >= 0 && value <= (1 << 24)) ctx->tune_agg_unit = (uint32_t)value;
     else if (n == "count_tile" && value >= 0 && value <= (1 << 20) && value % 256 == 0) ctx->tune_count_tile = (uint32_t)value;

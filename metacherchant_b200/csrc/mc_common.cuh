@@ -281,11 +281,14 @@ struct McPendingTimer { int stage; cudaEvent_t a, b; };
 struct mc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second compute stream: the sub-bin scatter of flush group g + 1 runs beside the aggregation of group g
     cudaEvent_t ev[16] = {};
     cudaEvent_t stage_ev[8] = {};
     size_t chunk_bytes = (size_t)256 << 20;
     uint64_t launches = 0;
     float stage_ms[MC_N_STAGES] = {};
+    double host_ms[MC_N_STAGES] = {};     // host wall time spent inside the same phases (launch + synchronisation included): where a step's
+                                          // time goes when it is NOT in the kernels (McHostTimer)
     std::vector<McPendingTimer> timers;   // recorded, not yet resolved (mc_resolve_timers)
     // tuning knobs (mc_ctx_set_tuning); 0 = automatic
     long tune_part_bits = -1;        // P = 2^bits bins
@@ -298,6 +301,9 @@ struct mc_ctx {
     int tune_agg = -1;               // two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on
     uint32_t tune_agg_unit = 0;      // target keys per aggregation unit (sub-bin); 0 = default
     size_t tune_device_chunk_bytes = 0;   // device-resident input: bytes per parse/extract pass (0 = as large as 32-bit offsets allow)
+    int tune_flush_overlap = 0;      // aggregated flush: scatter2(g + 1) on aux_stream concurrent with agg(g), one CTA per SM each
+                                     // (measured: each kernel slows down 1.5x at half occupancy, nothing is gained: profiles/r2_NOTES.md)
+    int tune_stage_timing = 1;       // 0: McStageTimer records nothing (four CUDA API calls less per kernel launch)
     int tune_scatter_tma = 1;        // bin runs leave the sorted tile through bulk copies (cp.async.bulk) instead of per-sector stores
     int keep_stage_ms = 0;           // 1: mc_count_* do not reset the stage timers (a step made of several count calls)
     int sm_count = 148;
@@ -318,7 +324,10 @@ struct mc_ctx {
     std::vector<Block> arena_free;
     std::unordered_map<void*, size_t> arena_live;
     size_t arena_cached_bytes = 0;
-    uint64_t arena_driver_allocs = 0;   // cudaMalloc calls made by the arena (bench/test visibility)
+    uint64_t arena_driver_allocs = 0;   // cudaMalloc / cudaFree calls made by the arena (bench/test visibility)
+    uint64_t scratch_allocs = 0;        // (re)allocations of the scratch slots and chunk buffers
+    size_t free_bytes_cached = 0;       // cudaMemGetInfo's answer, valid while free_bytes_epoch == arena_driver_allocs + scratch_allocs
+    uint64_t free_bytes_epoch = 0;
     // pooled timing events (McStageTimer)
     std::vector<cudaEvent_t> event_pool;
     // one kernel-attribute opt-in per context (= per device): bit i = the i-th MC_ATTR_* kernel was configured
@@ -382,16 +391,28 @@ int mc_q_for_keys(uint64_t keys, int shard_bits, double load);
 // accumulate the device time between two points of ctx->stream into ctx->stage_ms[stage] (resolved lazily)
 struct McStageTimer {
     mc_ctx* ctx;
+    cudaStream_t on;
     McPendingTimer t;
-    McStageTimer(mc_ctx* c, int stage) : ctx(c) {
+    McStageTimer(mc_ctx* c, int stage, cudaStream_t s = nullptr) : ctx(c), on(s ? s : c->stream) {
         t.stage = stage;
+        t.a = t.b = nullptr;
+        if (!c->tune_stage_timing) return;
         t.a = mc_event_get(c);
         t.b = mc_event_get(c);
-        cudaEventRecord(t.a, c->stream);
+        cudaEventRecord(t.a, on);
     }
     ~McStageTimer() {
-        cudaEventRecord(t.b, ctx->stream);
+        if (!t.a) return;
+        cudaEventRecord(t.b, on);
         ctx->timers.push_back(t);
     }
 };
-void mc_resolve_timers(mc_ctx* ctx);   // synchronises with the recorded events and folds them into ctx->stage_ms
+void mc_resolve_timers(mc_ctx* ctx);
+#include <chrono>
+struct McHostTimer {   // wall time of a host-side phase, accumulated into ctx->host_ms[stage]
+    mc_ctx* ctx;
+    int stage;
+    std::chrono::steady_clock::time_point t0;
+    McHostTimer(mc_ctx* c, int s) : ctx(c), stage(s), t0(std::chrono::steady_clock::now()) {}
+    ~McHostTimer() { ctx->host_ms[stage] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};   // synchronises with the recorded events and folds them into ctx->stage_ms

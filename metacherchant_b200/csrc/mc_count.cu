@@ -428,6 +428,7 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
                             uint64_t stream_bytes = 0) {
     McParsed P;
     {
+        McHostTimer ht(ctx, MC_ST_PARSE);
         McStageTimer tm(ctx, MC_ST_PARSE);
         mc_parse_chunk(ctx, d_buf, n, fasta, final_chunk, &P);
     }
@@ -446,14 +447,22 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
         a.shard_id = t->shard_id;
         {
             // extract -> flat hashed keys -> bins; the table itself is touched only when the batch is flushed
-            mc_batch_reserve(t, ub + 1, total_hint);
+            {
+                McHostTimer ht(ctx, MC_ST_GROW);   // (host view: reserving / creating the batch of bins)
+                mc_batch_reserve(t, ub + 1, total_hint);
+            }
             a.table = t->dev;   // a flush may have grown the table (the extractor only uses its statistics counters)
             uint64_t n_flat = 0;
-            uint64_t* d_flat = extract_flat(ctx, a, fasta, P.h.max_seq_len, ub + 1, d_buf, n, &n_flat);
+            uint64_t* d_flat;
+            {
+                McHostTimer ht(ctx, MC_ST_EXTRACT);
+                d_flat = extract_flat(ctx, a, fasta, P.h.max_seq_len, ub + 1, d_buf, n, &n_flat);
+            }
             // a stream of chunks (host input): the first chunk's k-mers per byte, scaled to the whole input, tells the flush how
             // many more instances to expect
             if (stream_bytes && t->expect_instances == 0 && P.h.consumed)
                 mc_table_expect_keys(t, (uint64_t)((double)n_flat * ((double)stream_bytes / (double)P.h.consumed)));
+            McHostTimer ht(ctx, MC_ST_SCATTER);
             mc_batch_scatter(t, d_flat, n_flat);
         }
     }
@@ -463,7 +472,11 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
 }
 
 static void finish_table(mc_table* t) {
-    mc_table_flush(t);
+    {
+        McHostTimer ht(t->ctx, MC_ST_COUNT);   // host view of the whole flush
+        mc_table_flush(t);
+    }
+    McHostTimer ht2(t->ctx, 6);
     mc_resolve_timers(t->ctx);
     unsigned int f = 0;
     MC_CUDA(cudaMemcpyAsync(&f, t->dev.flags, sizeof f, cudaMemcpyDeviceToHost, t->ctx->stream));
@@ -535,6 +548,7 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
                 cudaError_t e = cudaMalloc(&ctx->d_chunk[i], cap);
                 if (e != cudaSuccess) { cudaGetLastError(); mc_throw(MC_ERR_NOMEM, "cannot allocate the %zu-byte device chunk buffers", cap); }
                 ctx->d_chunk_cap[i] = cap;
+                ctx->scratch_allocs++;
             }
         for (int i = 0; i < 2; i++) MC_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
         MC_CUDA(cudaEventCreateWithFlags(&consumed_ev, cudaEventDisableTiming));

@@ -69,6 +69,7 @@ static void arena_release_all_locked(mc_ctx* ctx) {
     if (ctx->arena_free.empty()) return;
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->arena_free) cudaFree(b.p);
+    ctx->arena_driver_allocs++;   // (invalidates the cached free-memory figure)
     ctx->arena_free.clear();
     ctx->arena_cached_bytes = 0;
     cudaGetLastError();
@@ -738,6 +739,7 @@ extern "C" int mc_table_filter(mc_ctx* ctx, const mc_table* t, int min_count, mc
         MC_CUDA(cudaSetDevice(ctx->device));
         mc_table_flush(const_cast<mc_table*>(t));
         check_overflow(t);
+        McHostTimer ht(ctx, MC_ST_FILTER);
         McStageTimer tm(ctx, MC_ST_FILTER);
         unsigned long long* d_cursor;
         d_cursor = (decltype(d_cursor))mc_dev_alloc(ctx, sizeof(unsigned long long), "scratch");

@@ -1239,6 +1239,110 @@ void env_multi(const std::vector<std::string>& env_paths, const std::string& seq
     }
 }
 
+// =====================================================================================
+// f-4b: reads-classifier (src/tools/ReadsClassifier.java, src/algo/ReadsFinderInGraph.java, src/algo/PairFinder.java)
+// =====================================================================================
+// A read as LazyDnaQReaderTool yields it (ReadersUtils.readDnaQLazy -> FastqReader, NO truncation): value[i] = nuc | phred << 2
+// (N, n, . = nuc 0 with phred 0); nucAt = value & 3, phredAt = (value >> 2) & 63 (ITMO!/dna/DnaQ.java:147-150).
+struct ClassifyParams {
+    int k;
+    double z;                 // 1, or 1.96 with --interval95 (ReadsClassifier.java:171-172)
+    double found_threshold;   // --found-threshold / 100 (:173)
+    bool correction;          // --correction
+};
+// getCoverage (ReadsFinderInGraph.java:51-74), k <= 31: graph.getWithZero(min(fw, rc)) for every k-mer of the read
+static void get_coverage(const orc_table* g, const std::vector<uint8_t>& value, int k, std::vector<int>& cov) {
+    cov.clear();
+    const size_t n = value.size();
+    uint64_t mask = (1ULL << (2 * k)) - 1, fw = 0, rc = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t nuc = value[i] & 3;
+        fw = ((fw << 2) | nuc) & mask;
+        rc = (rc >> 2) | ((3ULL - nuc) << (2 * k - 2));
+        if (i + 1 >= (size_t)k) {
+            int16_t c = g->get(std::min(fw, rc));
+            cov.push_back(c < 0 ? 0 : c);   // getWithZero: 0 for an absent key
+        }
+    }
+}
+// the test shared by findRead (:37-49, threshold = found_threshold) and findReadWithCorrection (:113-119, threshold 0.9);
+// *margin (optional) = distance of the decisive comparison from its boundary (tests skip reads that sit on it)
+static bool width_test(const std::vector<int>& cov, int k, size_t length, double z, double threshold, double* margin) {
+    int sum = 0, nonzero = 0;
+    for (int c : cov) { sum += c; nonzero += c > 0 ? 1 : 0; }
+    const int last = cov.back();
+    const double cov_mean = (double)(sum + last * (k - 1)) / (double)length;
+    const double width = (double)(nonzero + (last > 0 ? 1 : 0) * (k - 1)) / (double)length;
+    const double theory_width = 1.0 - std::exp(-cov_mean);                                    // getTheoryWidth (:76-78)
+    const double sd = z * std::sqrt(std::exp(-cov_mean) * (1 - std::exp(-cov_mean)) / (double)length);   // delta (:81-87)
+    const double d = width - theory_width;
+    // only exp / sqrt differ between math libraries (division and comparisons are exact IEEE): the comparison with sd is the one
+    // that can flip, and only when it decides the outcome
+    if (margin) *margin = (width == 1 || width == 0 || width < threshold) ? 1.0 : std::fabs(std::fabs(d) - sd);
+    const bool delta = width == 1 || (width != 0 && -sd <= d && d <= sd);
+    return !(width < threshold) && delta;
+}
+static bool find_read(const orc_table* g, const std::vector<uint8_t>& value, const ClassifyParams& p, double* margin) {
+    if (margin) *margin = 1.0;
+    if (value.size() < (size_t)p.k) return false;
+    std::vector<int> cov;
+    get_coverage(g, value, p.k, cov);
+    return width_test(cov, p.k, value.size(), p.z, p.found_threshold, margin);
+}
+// findReadWithCorrection (:89-123): exactly one base with phred < 10 -> try the four nucleotides there (threshold 0.9, as coded)
+static bool find_read_with_correction(const orc_table* g, const std::vector<uint8_t>& value, const ClassifyParams& p, double* margin) {
+    if (margin) *margin = 1.0;
+    if (value.size() < (size_t)p.k) return false;
+    std::vector<size_t> bad;
+    for (size_t i = 0; i < value.size(); i++)
+        if (((value[i] >> 2) & 63) < 10) bad.push_back(i);
+    if (bad.size() != 1) return find_read(g, value, p, margin);
+    std::vector<int> cov;
+    double worst = 1.0;
+    for (int nuc = 0; nuc < 4; nuc++) {
+        std::vector<uint8_t> corrected = value;
+        corrected[bad[0]] = (uint8_t)((corrected[bad[0]] & ~3u) | (unsigned)nuc);   // DnaQ.setNuc
+        get_coverage(g, corrected, p.k, cov);
+        double m = 1.0;
+        const bool ok = width_test(cov, p.k, corrected.size(), p.z, 0.9, &m);
+        worst = std::min(worst, m);
+        if (ok) { if (margin) *margin = worst; return true; }
+    }
+    if (margin) *margin = worst;
+    return false;
+}
+static bool classify_one(const orc_table* g, const std::vector<uint8_t>& value, const ClassifyParams& p, double* margin) {
+    return p.correction ? find_read_with_correction(g, value, p, margin) : find_read(g, value, p, margin);
+}
+static std::vector<std::vector<uint8_t>> read_dnaqs(const uint8_t* buf, size_t len, int fmt) {
+    if (fmt == 0) fail("reads-classifier restatement: FASTQ input only");
+    const int off = fmt == 33 || fmt == 64 ? fmt : determine_quality_offset(buf, len);
+    FastqIterator it(buf, len, off);
+    std::vector<std::vector<uint8_t>> out;
+    std::vector<uint8_t> v;
+    while (it.read_next(v)) out.push_back(v);
+    return out;
+}
+// WritersUtils.writeDnaQsToFastqFile(data, file) (ITMO!/io/writers/WritersUtils.java + FastqDedicatedWriter.writeData): comments
+// 1, 2, 3, ... (DataCounter), bases by nucleotide (N was stored as A), qualities re-encoded Phred+64 (Illumina.instance)
+static void write_dnaqs(const std::vector<const std::vector<uint8_t>*>& data, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) fail("cannot write %s", path.c_str());
+    const char NUCS[4] = {'A', 'G', 'C', 'T'};
+    long n = 0;
+    std::string line;
+    for (const std::vector<uint8_t>* d : data) {
+        if (d->empty()) { fclose(f); fail("Empty DnaQ!"); }
+        fprintf(f, "@%ld\n", ++n);
+        line.assign(d->size(), 'A');
+        for (size_t i = 0; i < d->size(); i++) line[i] = NUCS[(*d)[i] & 3];
+        fprintf(f, "%s\n+\n", line.c_str());
+        for (size_t i = 0; i < d->size(); i++) line[i] = (char)(64 + (((*d)[i] >> 2) & 63));
+        fprintf(f, "%s\n", line.c_str());
+    }
+    fclose(f);
+}
+
 template <class F>
 int guarded(F f) {
     try {
@@ -1498,6 +1602,68 @@ double orc_bench_count(const uint8_t* buf, size_t len, int fmt, int k, int threa
         return 0;
     });
     return secs;
+}
+
+// f-4b: found[i] = findRead / findReadWithCorrection of read i of a FASTQ buffer; margins[i] (optional) = how far the decisive
+// floating-point comparison was from its boundary.  Returns the number of reads, < 0 on error.
+long orc_classify_bytes(const orc_table* g, const uint8_t* buf, size_t len, int fmt, double z, double found_threshold, int correction,
+                        uint8_t* found, double* margins, size_t cap) {
+    long n = -1;
+    guarded([&] {
+        const ClassifyParams p{g->k, z, found_threshold, correction != 0};
+        std::vector<std::vector<uint8_t>> reads = read_dnaqs(buf, len, fmt);
+        if (reads.size() > cap) fail("room for %zu reads, the input holds %zu", cap, reads.size());
+        for (size_t i = 0; i < reads.size(); i++) {
+            double m = 1.0;
+            found[i] = classify_one(g, reads[i], p, &m) ? 1 : 0;
+            if (margins) margins[i] = m;
+        }
+        n = (long)reads.size();
+        return 0;
+    });
+    return n;
+}
+// The tool's run (ReadsClassifier.runImpl :141-224 + PairFinder.run :30-55): one or two read files, the four classes, six
+// output files.  The reference appends to its class queues from pool threads, i.e. in no fixed order; here every file lists
+// its reads in INPUT order.  counts[4] = {both found, first only, second only, none}.
+int orc_reads_classifier(const orc_table* g, const char* reads1, const char* reads2, double z, double found_threshold, int correction,
+                         const char* out_dir, long counts[4]) {
+    return guarded([&] {
+        const ClassifyParams p{g->k, z, found_threshold, correction != 0};
+        std::vector<uint8_t> b1 = read_file(reads1), b2;
+        std::vector<std::vector<uint8_t>> r1 = read_dnaqs(b1.data(), b1.size(), 1), r2;
+        const bool paired = reads2 && *reads2;
+        if (paired) {
+            b2 = read_file(reads2);
+            r2 = read_dnaqs(b2.data(), b2.size(), 1);
+        }
+        const std::vector<uint8_t> empty;
+        const size_t n = paired ? std::min(r1.size(), r2.size()) : r1.size();   // PairSource stops at the shorter file
+        std::vector<const std::vector<uint8_t>*> found_1, found_2, not_found_1, not_found_2, found_s, not_found_s, tail_found, tail_not;
+        for (int i = 0; i < 4; i++) counts[i] = 0;
+        for (size_t i = 0; i < n; i++) {
+            const std::vector<uint8_t>& a = r1[i];
+            const std::vector<uint8_t>& b = paired ? r2[i] : empty;
+            bool f1 = classify_one(g, a, p, nullptr), f2 = classify_one(g, b, p, nullptr);
+            if (b.empty()) f2 = !f1;                                              // PairFinder.java:42-44
+            if (f1 && f2) { counts[0]++; found_1.push_back(&a); found_2.push_back(&b); }
+            else if (f1) { counts[1]++; if (!a.empty()) found_s.push_back(&a); if (!b.empty()) not_found_s.push_back(&b); }
+            else if (f2) { counts[2]++; if (!b.empty()) tail_found.push_back(&b); if (!a.empty()) tail_not.push_back(&a); }
+            else { counts[3]++; not_found_1.push_back(&a); not_found_2.push_back(&b); }
+        }
+        // found_s = first_found.first ++ second_found.second; not_found_s = first_found.second ++ second_found.first (:212-217)
+        found_s.insert(found_s.end(), tail_found.begin(), tail_found.end());
+        not_found_s.insert(not_found_s.end(), tail_not.begin(), tail_not.end());
+        mkdirs(out_dir);
+        const std::string o(out_dir);
+        write_dnaqs(found_1, o + "/found_1.fastq");
+        write_dnaqs(found_2, o + "/found_2.fastq");
+        write_dnaqs(not_found_1, o + "/not_found_1.fastq");
+        write_dnaqs(not_found_2, o + "/not_found_2.fastq");
+        write_dnaqs(found_s, o + "/found_s.fastq");
+        write_dnaqs(not_found_s, o + "/not_found_s.fastq");
+        return 0;
+    });
 }
 
 // test surface: the Jaccard cell text (tests/test_host_logic.py compares three independent implementations)

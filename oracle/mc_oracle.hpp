@@ -90,6 +90,15 @@ int orc_load_kmers(orc_table*, const char* path, int freq_threshold);
 // Returns seconds of wall time, <0 on error.  `bases` gets the number of input bases.
 double orc_bench_count(const uint8_t* buf, size_t len, int fmt, int k, int threads, uint64_t* bases, uint64_t* distinct);
 
+// ---- f-4b: reads-classifier (src/algo/ReadsFinderInGraph.java:37-123, src/algo/PairFinder.java:30-55) -------------------------
+// found[i] = 1 when read i of the FASTQ buffer is "found" in the graph; margins (optional) = distance of the decisive f64
+// comparison from its boundary.  z = 1 (or 1.96 with --interval95), found_threshold = --found-threshold / 100.
+long orc_classify_bytes(const orc_table* graph, const uint8_t* buf, size_t len, int fmt, double z, double found_threshold, int correction,
+                        uint8_t* found, double* margins, size_t cap);
+// the tool (src/tools/ReadsClassifier.java:141-224): reads2 may be NULL/"" (single-end); writes the six FASTQ files, input order
+int orc_reads_classifier(const orc_table* graph, const char* reads1, const char* reads2, double z, double found_threshold, int correction,
+                         const char* out_dir, long counts[4]);
+
 void orc_java_format_6_2f(float v, char* out);   // String.format("%6.2f ", v); out: room for 48 characters
 
 // CPU baseline of the environment stage (bench.py only): one OneSequenceCalculator per target on `threads` pool workers

@@ -68,6 +68,9 @@ class Oracle:
         L.orc_load_kmers.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.orc_bench_count.restype = C.c_double
         L.orc_bench_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, _u64p, _u64p]
+        L.orc_classify_bytes.restype = C.c_long
+        L.orc_classify_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_reads_classifier.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_char_p, C.POINTER(C.c_long)]
         L.orc_bench_env.restype = C.c_double
         L.orc_bench_env.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_char_p,
                                     C.POINTER(C.c_int)]
@@ -221,6 +224,25 @@ class OracleTable:
         return self.o.check(self.o.lib.orc_env_find_ex(self.h, seq_fasta.encode(), hic_fasta.encode() if hic_fasta else None, self.k, min_cov,
                                                        -1 if max_kmers is None else max_kmers, -1 if max_radius is None else max_radius,
                                                        int(both_dirs), chunk_len, int(merge), int(trim), out_dir.encode()))
+
+    def classify(self, data, fmt=1, z=1.0, found_threshold=0.9, correction=False):
+        """(found, margins) of every read of a FASTQ buffer: the oracle's findRead / findReadWithCorrection; margins[i] = distance of
+        the decisive f64 comparison from its boundary (a class is only comparable across math libraries when it is not ~0)."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        cap = int((buf == 10).sum()) // 2 + 2
+        found = np.zeros(cap, dtype=np.uint8)
+        margins = np.zeros(cap, dtype=np.float64)
+        n = self.o.lib.orc_classify_bytes(self.h, buf.ctypes.data if buf.size else None, buf.size, fmt, z, found_threshold, int(correction),
+                                          found.ctypes.data, margins.ctypes.data, cap)
+        if n < 0:
+            raise OracleError(self.o.err())
+        return found[:n], margins[:n]
+
+    def reads_classifier(self, reads1, reads2, out_dir, z=1.0, found_threshold=0.9, correction=False):
+        counts = (C.c_long * 4)()
+        self.o.check(self.o.lib.orc_reads_classifier(self.h, reads1.encode(), reads2.encode() if reads2 else None, z, found_threshold, int(correction),
+                                                     out_dir.encode(), counts))
+        return list(counts)
 
     def print_kmers(self, threshold, out_file, stat_file=None):
         return self.o.check(self.o.lib.orc_print_kmers(self.h, threshold, out_file.encode(), stat_file.encode() if stat_file else None))

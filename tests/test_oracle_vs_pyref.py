@@ -334,3 +334,67 @@ def test_gz_input_equals_plain_input(oracle, tmp_path):
     (tmp_path / "c.fastq.bz2").write_bytes(b"BZh9" + b"garbage" * 10)
     with pytest.raises(oracle_ffi.OracleError):
         oracle.table(13).count_file(str(tmp_path / "c.fastq.bz2"))
+
+
+# ---- f-4b: the reads-classifier restatement against a literal Python transcription ------------------------------------------
+def py_find_read(get, nuc, k, z, thr):
+    """ReadsFinderInGraph.findRead (src/algo/ReadsFinderInGraph.java:37-49) + getCoverage (:51-74) + delta (:81-87), line by line."""
+    import math
+    if len(nuc) < k:
+        return False
+    cov = []
+    for i in range(len(nuc) - k + 1):
+        fw = 0
+        for b in nuc[i:i + k]:
+            fw = (fw << 2) | b
+        rc = 0
+        for b in reversed(nuc[i:i + k]):
+            rc = (rc << 2) | (3 - b)
+        cov.append(max(get(min(fw, rc)), 0))
+    cov_mean = (sum(cov) + cov[-1] * (k - 1)) / len(nuc)
+    width = (sum(1 for c in cov if c > 0) + (1 if cov[-1] > 0 else 0) * (k - 1)) / len(nuc)
+    theory = 1.0 - math.exp(-cov_mean)
+    std = z * math.sqrt(math.exp(-cov_mean) * (1 - math.exp(-cov_mean)) / len(nuc))
+    return (not (width < thr)) and (width == 1 or (width != 0 and -std <= width - theory <= std))
+
+
+def test_classifier_restatement_matches_a_literal_transcription(oracle):
+    import random
+    from helpers import rand_seq
+    rng = random.Random(11)
+    k = 7
+    genome = rand_seq(rng, 300)
+    fq = "".join(f"@g{i}\n{genome[s:s + 50]}\n+\n{'I' * len(genome[s:s + 50])}\n" for i, s in enumerate(range(0, 260, 3))).encode()
+    t = oracle.table(k, threads=2).count_bytes(fq, 33)
+    code = {"A": 0, "G": 1, "C": 2, "T": 3}
+    reads, lines = [], []
+    for i in range(400):
+        L = rng.randint(0, 40)
+        st = rng.randrange(0, 250)
+        seq = list(genome[st:st + L])
+        for _ in range(rng.randint(0, 2)):
+            if seq:
+                seq[rng.randrange(len(seq))] = rng.choice("ACGTN")
+        qual = [chr(33 + rng.randint(0, 40)) for _ in seq]
+        reads.append((seq, qual))
+        lines += [f"@r{i}", "".join(seq), "+", "".join(qual)]
+    buf = ("\n".join(lines) + "\n").encode()
+    for z, thr in ((1.0, 0.9), (1.96, 0.4)):
+        found, margins = t.classify(buf, 33, z, thr, False)
+        for i, (seq, qual) in enumerate(reads):
+            nuc = [code.get(ch, 0) for ch in seq]
+            if margins[i] > 1e-9:
+                assert bool(found[i]) == py_find_read(lambda key: int(t.get(key)), nuc, k, z, thr), (i, "".join(seq))
+        # correction: a read with exactly one phred < 10 base is found iff one of the four substitutions passes at threshold 0.9
+        found_c, margins_c = t.classify(buf, 33, z, thr, True)
+        for i, (seq, qual) in enumerate(reads):
+            nuc = [code.get(ch, 0) for ch in seq]
+            phred = [0 if ch == "N" else (ord(q) - 33) & 63 for ch, q in zip(seq, qual)]
+            bad = [j for j, p in enumerate(phred) if p < 10]
+            if len(nuc) < k or margins_c[i] <= 1e-9:
+                continue
+            if len(bad) == 1:
+                want = any(py_find_read(lambda key: int(t.get(key)), nuc[:bad[0]] + [x] + nuc[bad[0] + 1:], k, z, 0.9) for x in range(4))
+            else:
+                want = py_find_read(lambda key: int(t.get(key)), nuc, k, z, thr)
+            assert bool(found_c[i]) == want, (i, "".join(seq), bad)
