@@ -84,6 +84,10 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
     S.off = S.hist + P;
     S.secbin = (uint16_t*)(S.off + P + 1 + ((P + 1) & 1));
     __shared__ uint32_t s_warp_tot[SC_THREADS / 32];
+    // A run is padded with sentinels to the granule its stores need: whole 32-byte sectors (4 keys) for the per-sector stores,
+    // 16 bytes (2 keys) for the bulk copies -- a third of the pads, i.e. ~6 % fewer bytes through both bin levels and the
+    // aggregation that reads them.
+    constexpr uint32_t PADM = TMA ? 1u : 3u;
     const int bshift = B.shift;                  // <= 62
     const uint64_t lmask = (1ULL << B.hbits) - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -136,7 +140,7 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
         {
             const uint32_t b0 = threadIdx.x * per;
             uint32_t mine = 0;
-            for (uint32_t b = b0; b < b0 + per && b < P; b++) mine += (S.hist[b] + 3) & ~3u;
+            for (uint32_t b = b0; b < b0 + per && b < P; b++) mine += (S.hist[b] + PADM) & ~PADM;
             uint32_t incl = mine;
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -151,7 +155,7 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
             for (uint32_t i = 0; i < SC_MAX_PER; i++) {
                 const uint32_t b = b0 + i;
                 if (i >= per || b >= P) continue;
-                const uint32_t c = S.hist[b], pc = (c + 3) & ~3u;
+                const uint32_t c = S.hist[b], pc = (c + PADM) & ~PADM;
                 S.off[b] = run;
                 const unsigned long long gpos = pc ? atomicAdd(&B.cursors[b], (unsigned long long)pc) : 0ULL;
                 S.gbase[b] = gpos;
@@ -209,8 +213,17 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
                 const unsigned long long pos = S.gbase[b];
                 if (pos + pc <= B.cap) {
                     bulk_store_s2g(B.keys + (uint64_t)b * B.cap + pos, &S.sorted[run], pc * 8u);
-                } else {   // the run crosses the end of its bin: sector by sector (what fits goes to the bin, the rest spills)
-                    for (uint32_t j = 0; j < pc; j += 4) store_sector(b, pos + j, run + j);
+                } else {   // the run crosses the end of its bin (heavy hitter or undersized batch): key by key, what fits goes to the bin, the rest spills
+                    for (uint32_t j = 0; j < pc; j++) {
+                        const uint64_t key = S.sorted[run + j];
+                        if (pos + j < B.cap) {
+                            B.keys[(uint64_t)b * B.cap + pos + j] = key;
+                        } else if (key != MC_HASH_SENTINEL) {
+                            const unsigned long long sp = atomicAdd(B.spill_cursor, 1ULL);
+                            if (sp < B.spill_cap) B.spill[sp] = key;
+                            else atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
+                        }
+                    }
                 }
             }
             bulk_commit();

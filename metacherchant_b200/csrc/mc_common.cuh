@@ -358,7 +358,7 @@ struct mc_table {
 };
 
 // kernels / host helpers shared across translation units
-void mc_table_reserve(mc_table* t, uint64_t additional_keys_upper_bound);   // grow (rehash) until it fits at load <= 0.7
+void mc_table_reserve(mc_table* t, uint64_t additional_keys_upper_bound);   // grow (rehash) until it fits at load <= 0.55
 void mc_table_prepare_chunk(mc_table* t, uint64_t chunk_kmers_upper_bound);  // amortised growth + attach the overflow list
 void mc_table_finish_chunk(mc_table* t, bool grown_already = false);         // re-insert overflowed keys (growing), detach the list
 void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what);            // stream-ordered pool allocation on ctx->stream

@@ -37,19 +37,16 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t pat) {
     const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
     return ~t & 0x80808080u;
 }
-// Three masks over the 32 bytes at `base`: bit j of
-//   term = byte j is a line terminator ('\n', or '\r' not followed by '\n'),
-//   crlf = byte j is the '\n' of a "\r\n" pair (the line's content then ends one byte earlier),
-//   mark = byte j is a terminator AND byte j + 1 -- the first byte of the next line -- opens a header / comment line
-//          ('@' '+' for FASTQ, '>' ';' for FASTA).
-// Passes 2-4 of the parser work from these masks and never touch the input bytes again (round 1 re-read the whole
-// chunk twice for one byte per line).  The marks are looked up per terminator (one per ~80 bytes) in the registers that
-// hold the word; comparing every byte against the two mark characters made the pass ALU-bound.
-// The masks are STORED TRANSPOSED: byte 4i + b of the word (b-th byte of its i-th 32-bit piece) is bit 8b + i.  The SWAR
-// compare leaves one flag per byte at bit 7 of that byte; shifting piece i's flags right by 7 - i and OR-ing the eight pieces
-// builds the transposed mask with two instructions per piece, where packing every piece's four flags into adjacent bits cost
-// six.  Pass 2 turns a non-empty mask back into byte order (transposed_to_mask); popc is the same either way.
-struct McMasks { uint32_t term, crlf, mark; };
+// Terminator mask of the 32 bytes at `base`: a byte is a line terminator when it is '\n', or '\r' not followed by '\n'.
+// The mask is STORED TRANSPOSED: byte 4i + b of the word (b-th byte of its i-th 32-bit piece) is bit 8b + i.  The SWAR compare
+// leaves one flag per byte at bit 7 of that byte; shifting piece i's flags right by 7 - i and OR-ing the eight pieces builds the
+// transposed mask with two instructions per piece, where packing every piece's four flags into adjacent bits cost six.  Pass 2
+// turns a non-empty mask back into byte order (transposed_to_mask); popc is the same either way.
+// What else the later passes need to know about a line -- does its terminator belong to a "\r\n" pair, does the NEXT line open
+// with a header / comment mark -- is read by pass 2 from the two bytes around every terminator (one sector per line), and kept
+// as a flag byte per line: passes 3 and 4 never touch the input (round 1 re-read the whole chunk twice for one byte per line).
+// (Measured alternatives, profiles/r2_NOTES.md: three SWAR mask planes from pass 1, 8.0 ms; marks / CR-LF looked up per terminator
+// inside pass 1, 9.2 ms -- the divergent look-up loop costs more than it saves; this form: pass 1 at its round-1 cost.)
 __device__ __forceinline__ uint32_t mask_to_transposed(uint32_t m) {
     uint32_t r = 0;
 #pragma unroll
@@ -74,85 +71,56 @@ __device__ __forceinline__ uint32_t transposed_to_mask(uint32_t t) {
     }
     return r;
 }
-template <bool FASTA>
-__device__ __forceinline__ bool is_mark(uint32_t c) { return FASTA ? (c == '>' || c == ';') : (c == '@' || c == '+'); }
-template <bool FASTA>
-__device__ __forceinline__ McMasks term_mask32(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint32_t base, uint8_t pad) {
-    __align__(16) uint8_t b[48];
+__device__ __forceinline__ uint32_t term_mask32(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint32_t base, uint8_t pad) {
     const uint32_t lo = mis, hi = mis + n;   // valid aligned-coordinate range [lo, hi)
-    McMasks r{0, 0, 0};
-    if (base >= lo + 1 && base + 33 <= hi) {
+    if (base >= lo && base + 33 <= hi) {
         // interior: eight 32-bit words, four bytes per step (SWAR)
         const uint4* p = reinterpret_cast<const uint4*>(abuf + base);
         const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
         const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        const uint32_t after = __ldg(abuf + base + 32);                          // the byte after this word
-        uint32_t nl[9], cr[8];
+        uint32_t nl[9];
 #pragma unroll
-        for (int i = 0; i < 8; i++) { nl[i] = eq_bytes(w[i], 0x0A0A0A0Au); cr[i] = eq_bytes(w[i], 0x0D0D0D0Du); }
-        nl[8] = after == '\n' ? 0x80u : 0u;
-        uint32_t cr_prev = __ldg(abuf + base - 1) == '\r' ? 0x80000000u : 0u;   // the byte in front of this word
+        for (int i = 0; i < 8; i++) nl[i] = eq_bytes(w[i], 0x0A0A0A0Au);
+        nl[8] = __ldg(abuf + base + 32) == '\n' ? 0x80u : 0u;
+        uint32_t m = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+            const uint32_t cr = eq_bytes(w[i], 0x0D0D0D0Du);
             const uint32_t nl_next = (nl[i] >> 8) | (nl[i + 1] << 24);
-            const uint32_t term = nl[i] | (cr[i] & ~nl_next);
-            const uint32_t cr_before = (cr[i] << 8) | (cr_prev >> 24);   // byte j-1 is '\r'
-            cr_prev = cr[i];
-            r.term |= term >> (7 - i);                    // flags at bits 7, 15, 23, 31 -> bits i, 8 + i, 16 + i, 24 + i
-            r.crlf |= (nl[i] & cr_before) >> (7 - i);
+            m |= (nl[i] | (cr & ~nl_next)) >> (7 - i);   // flags at bits 7, 15, 23, 31 -> bits i, 8 + i, 16 + i, 24 + i
         }
-        for (uint32_t tm = r.term; tm;) {   // the byte after every terminator, out of the registers
-            const uint32_t jt = (uint32_t)__ffs(tm) - 1u;   // transposed position
-            tm &= tm - 1;
-            const uint32_t j = 4u * (jt & 7u) + (jt >> 3);  // byte position
-            const uint32_t idx = j + 1, ws = idx >> 2;
-            const uint32_t lo4 = ws & 2 ? (ws & 1 ? w[3] : w[2]) : (ws & 1 ? w[1] : w[0]);
-            const uint32_t hi4 = ws & 2 ? (ws & 1 ? w[7] : w[6]) : (ws & 1 ? w[5] : w[4]);
-            const uint32_t word = ws >= 8 ? after : (ws & 4 ? hi4 : lo4);
-            const uint32_t c = ws >= 8 ? (word & 0xFFu) : ((word >> ((idx & 3) * 8)) & 0xFFu);
-            if (is_mark<FASTA>(c)) r.mark |= 1u << jt;
-        }
-        return r;
+        return m;
     }
+    uint8_t b[34];
 #pragma unroll
-    for (int j = 0; j < 34; j++) {   // b[0] = the byte in front of the word, b[1..32] the word, b[33] the byte after it
-        const uint32_t a = base + j - 1;
-        b[j] = (base + j >= 1 && a >= lo && a < hi) ? __ldg(abuf + a) : ((base + j >= 1 && a == hi) ? pad : (uint8_t)0);
+    for (int j = 0; j < 33; j++) {
+        const uint32_t a = base + j;
+        b[j] = (a >= lo && a < hi) ? __ldg(abuf + a) : (a == hi ? pad : (uint8_t)0);
     }
+    uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-        const uint8_t c = b[j + 1];
-        const bool t = (c == '\n') || (c == '\r' && b[j + 2] != '\n');
-        r.term |= (uint32_t)t << j;
-        r.crlf |= (uint32_t)(c == '\n' && b[j] == '\r') << j;
-        r.mark |= (uint32_t)(t && base + j + 1 < hi && is_mark<FASTA>(b[j + 2])) << j;
+        const uint8_t c = b[j];
+        m |= (uint32_t)((c == '\n') || (c == '\r' && b[j + 1] != '\n')) << j;
     }
     // mask off positions outside the chunk
-    uint32_t keep = 0xFFFFFFFFu;
-    if (base < lo) keep &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
-    if (base + 32 > hi) keep &= (hi <= base) ? 0u : (0xFFFFFFFFu >> (base + 32 - hi));
-    r.term = mask_to_transposed(r.term & keep);
-    r.crlf = mask_to_transposed(r.crlf & keep);
-    r.mark = mask_to_transposed(r.mark & keep);
-    return r;
+    if (base < lo) m &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
+    if (base + 32 > hi) m &= (hi <= base) ? 0u : (0xFFFFFFFFu >> (base + 32 - hi));
+    return mask_to_transposed(m);
 }
 
-// pass 1 of the line index: the three masks (kept: the later passes read them instead of the bytes) and the number of
-// terminators per tile.  masks[] holds, per 32 input bytes, {term, crlf, mark} in three planes of n_words words.
-template <bool FASTA>
+// pass 1 of the line index: the terminator masks (kept: pass 2 reads them instead of scanning the bytes again) and the number of
+// terminators per tile
 __global__ void __launch_bounds__(256) k_count_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, uint8_t pad,
-                                                     uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ masks, uint32_t n_words) {
+                                                     uint32_t* __restrict__ tile_counts, uint32_t* __restrict__ masks) {
     uint32_t c = 0;
 #pragma unroll
     for (uint32_t j = 0; j < TILE_WPT; j++) {
         const uint32_t wi = blockIdx.x * TILE_WORDS + j * 256u + threadIdx.x;
         const uint32_t base = wi * 32u;
-        McMasks m{0, 0, 0};
-        if (base < mis + n) m = term_mask32<FASTA>(abuf, mis, n, base, pad);
-        masks[wi] = m.term;
-        masks[n_words + wi] = m.crlf;
-        masks[2 * n_words + wi] = m.mark;
-        c += __popc(m.term);
+        const uint32_t m = base < mis + n ? term_mask32(abuf, mis, n, base, pad) : 0u;
+        masks[wi] = m;
+        c += __popc(m);
     }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     __shared__ uint32_t s[8];
@@ -208,8 +176,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_counts, uint
 
 // pass 2: line_end[i] = position of line i's terminator, and one flag byte per line:
 //   bit 0 = the terminator is the '\n' of "\r\n" (content ends one byte earlier),
-//   bit 1 = the first byte of the NEXT line is a header / comment mark (line 0's own mark is McParseHeader.first_mark).
-__global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, const uint32_t* __restrict__ masks, uint32_t n_words,
+//   bit 1 = the first byte of the NEXT line is a header / comment mark ('@' '+' for FASTQ, '>' ';' for FASTA; line 0's own mark is
+//           McParseHeader.first_mark).
+template <bool FASTA>
+__global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__ abuf, uint32_t mis, uint32_t n, const uint32_t* __restrict__ masks,
                                                      const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ line_end, uint8_t* __restrict__ line_flags,
                                                      uint32_t n_lines, int final_chunk) {
     const uint8_t* buf = abuf + mis;
@@ -220,13 +190,8 @@ __global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__
         const uint32_t wi = blockIdx.x * TILE_WORDS + j * 256u + threadIdx.x;
         const uint32_t base = wi * 32u;
         uint32_t m = masks[wi];
-        uint32_t crlf = 0, mark = 0;
         const uint32_t c = __popc(m);
-        if (m) {   // back to byte order (one word in three has a terminator)
-            m = transposed_to_mask(m);
-            crlf = transposed_to_mask(masks[n_words + wi]);
-            mark = transposed_to_mask(masks[2 * n_words + wi]);
-        }
+        if (m) m = transposed_to_mask(m);   // back to byte order (one word in three has a terminator)
         uint32_t incl = c;   // block exclusive scan of c
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -244,8 +209,15 @@ __global__ void __launch_bounds__(256) k_write_terms(const uint8_t* __restrict__
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            line_flags[pos] = (uint8_t)(((crlf >> b) & 1u) | (((mark >> b) & 1u) << 1));
-            line_end[pos++] = base + b - mis;
+            const uint32_t p = base + b - mis;   // chunk coordinate of the terminator
+            const bool crlf = p > 0 && __ldg(buf + p) == '\n' && __ldg(buf + p - 1) == '\r';
+            bool mark = false;
+            if (p + 1 < n) {
+                const uint8_t nx = __ldg(buf + p + 1);
+                mark = FASTA ? (nx == '>' || nx == ';') : (nx == '@' || nx == '+');
+            }
+            line_flags[pos] = (uint8_t)((crlf ? 1u : 0u) | (mark ? 2u : 0u));
+            line_end[pos++] = p;
         }
         tile_pos += row_total;
     }
@@ -505,15 +477,14 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
     const int fin = final_chunk ? 1 : 0;
     uint32_t n_tiles = (mis + n + TILE_BYTES - 1) / TILE_BYTES;
     if (n_tiles == 0) n_tiles = 1;
-    // slot 1: header + tile counts + three masks per 32 input bytes (terminators, "\r\n" pairs, header marks)
+    // slot 1: header + tile counts + one terminator mask per 32 input bytes
     const uint32_t n_words = n_tiles * TILE_WORDS;
     const size_t off_masks = (256 + (size_t)n_tiles * 4 + 255) & ~(size_t)255;
-    uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, off_masks + (size_t)n_words * 4 * 3);
+    uint8_t* s1 = (uint8_t*)mc_scratch(ctx, 1, off_masks + (size_t)n_words * 4);
     McParseHeader* d_h = (McParseHeader*)s1;
     uint32_t* d_tiles = (uint32_t*)(s1 + 256);
     uint32_t* d_masks = (uint32_t*)(s1 + off_masks);
-    if (fasta) k_count_terms<true><<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks, n_words);
-    else k_count_terms<false><<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks, n_words);
+    k_count_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, pad, d_tiles, d_masks);
     MC_LAUNCH(ctx);
     k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_buf, n, d_h, fin, fasta ? 1 : 0);
     MC_LAUNCH(ctx);
@@ -555,7 +526,8 @@ void mc_parse_chunk(mc_ctx* ctx, const uint8_t* d_buf, uint32_t n, bool fasta, b
         if (!final_chunk) out->h.consumed = 0;   // no complete line yet: everything is carried over
         return;
     }
-    k_write_terms<<<n_tiles, 256, 0, st>>>(abuf, mis, n, d_masks, n_words, d_tiles, d_line_end, d_line_flags, n_lines, fin);
+    if (fasta) k_write_terms<true><<<n_tiles, 256, 0, st>>>(abuf, mis, n, d_masks, d_tiles, d_line_end, d_line_flags, n_lines, fin);
+    else k_write_terms<false><<<n_tiles, 256, 0, st>>>(abuf, mis, n, d_masks, d_tiles, d_line_end, d_line_flags, n_lines, fin);
     MC_LAUNCH(ctx);
     if (fasta) {
         k_block_summaries<true><<<n_blk, 256, 0, st>>>(L, n_lines, d_blk);

@@ -365,8 +365,9 @@ void mc_table_grow_to(mc_table* t, int q) {
 }
 
 void mc_table_reserve(mc_table* t, uint64_t additional) {
+    // callers insert without an overflow list: room at load <= 0.55, where the 8-bucket windows practically never fill
     uint64_t keys = mc_table_keys(t);
-    int q = q_for_keys(keys + additional, t->dev.shard_bits);
+    int q = mc_q_for_keys(keys + additional, t->dev.shard_bits, 0.55);
     if (q > t->dev.q) mc_table_grow_to(t, q);
 }
 

@@ -287,14 +287,30 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
     }
 }
 
-// Adds (hashed key, count) pairs to the table; count-0 pairs are padding.  The pairs arrive in hash order, so neighbouring
-// lanes update the same few buckets at the same time: the bucket is read right before its CAS (a version that kept four
-// prefetched buckets per thread lost more to stale copies and failed CAS retries than it gained: 70 ms against 47 ms).
+// Adds (hashed key, count) pairs to the table; count-0 pairs are padding.  The pairs of one source arrive in hash order, i.e. in
+// the order of the buckets they update.  Round 1 gave consecutive pairs to consecutive lanes: neighbouring lanes then hit the
+// SAME bucket at the same moment (two pairs per bucket at load 0.5), lost their CAS to each other and went round again, and a
+// thread had one dependent chain (pair -> bucket -> CAS) in flight: 47 ms for 0.72 G pairs.  Now every thread owns MP_RUN
+// CONSECUTIVE pairs: it loads them with full-sector 16-byte loads, has all their home buckets in flight at once, and the lanes of
+// a warp work MP_RUN pairs (~4 buckets) apart, so they do not collide.
+#define MP_RUN 8
 __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, const ulonglong2* __restrict__ pairs, uint64_t n) {
     unsigned long long added = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const ulonglong2 p = __ldcs(pairs + i);
-        if (p.y && mc_table_add(t, p.x, (uint32_t)p.y)) added++;
+    const uint64_t n_runs = (n + MP_RUN - 1) / MP_RUN;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_runs; r += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 p[MP_RUN];
+        uint64_t w[MP_RUN][4];
+#pragma unroll
+        for (int i = 0; i < MP_RUN; i++) {
+            const uint64_t at = r * MP_RUN + i;
+            p[i] = at < n ? __ldcs(pairs + at) : make_ulonglong2(0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < MP_RUN; i++)
+            if (p[i].y) mc_load_bucket(t.slots + (((p[i].x & ((1ULL << (62 - t.shard_bits)) - 1)) >> t.tag_bits) & t.nb_mask) * 4, w[i]);
+#pragma unroll
+        for (int i = 0; i < MP_RUN; i++)
+            if (p[i].y && mc_table_add_impl<true>(t, p[i].x & ((1ULL << (62 - t.shard_bits)) - 1), (uint32_t)p[i].y, w[i])) added++;
     }
     __shared__ unsigned long long s_added;
     if (threadIdx.x == 0) s_added = 0;
@@ -365,11 +381,17 @@ extern "C" int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_
             if (counts[src] > x->region_keys / 2) mc_throw(MC_ERR_CUDA, "exchange: mailbox of rank %d is corrupt", src);
             total += counts[src];
         }
-        mc_table_reserve(shard, total);   // every pair may be a new key: no overflow list needed
+        // every pair may be a new key and no overflow list is attached here: room for all of them at load <= 0.55 (at 0.7 -- one rank
+        // merging 0.72 G pairs into 2^28 buckets -- the 8-bucket windows fill up and the stash overflows)
+        {
+            const uint64_t have = mc_table_keys(shard);
+            const int q = mc_q_for_keys(have + total, shard->dev.shard_bits, 0.55);
+            if (q > shard->dev.q) mc_table_grow_to(shard, q);
+        }
         for (int src = 0; src < x->world; src++) {
             if (counts[src] == 0) continue;
             McStageTimer tm(ctx, MC_ST_COUNT);
-            const int grid = (int)std::min<uint64_t>((counts[src] + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            const int grid = (int)std::min<uint64_t>((counts[src] / MP_RUN + 256) / 256, (uint64_t)ctx->sm_count * 8);
             k_merge_pairs<<<grid, 256, 0, st>>>(shard->dev, (const ulonglong2*)x->region(x->local, slot, src), counts[src]);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
