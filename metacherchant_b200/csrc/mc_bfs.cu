@@ -45,9 +45,13 @@ struct McBfsJobDev {
 };
 #define BFS_SEPARATOR 4    // code between the sequences of a merged seed list: no seed window may span it
 
+// home slot of an oriented k-mer in the pass's visited set (Fibonacci hashing: one multiply on the step's critical path)
+__device__ __forceinline__ uint32_t vis_home(const McBfsJobDev& j, uint64_t kmer) {
+    return (uint32_t)((kmer * 0x9E3779B97F4A7C15ULL) >> 32) & j.vis_mask;
+}
 __device__ __forceinline__ uint32_t vis_find_or_claim(const McBfsJobDev& j, uint64_t kmer, uint32_t code) {
     const uint64_t want = kmer + 1;
-    uint32_t pos = (uint32_t)(mc_mix62(kmer) >> 20) & j.vis_mask;
+    uint32_t pos = vis_home(j, kmer);
     while (true) {
         uint64_t cur = atomicCAS((unsigned long long*)&j.vis_keys[pos], 0ULL, (unsigned long long)want);
         if (cur == 0 || cur == want) {
@@ -163,28 +167,48 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
                     bool cand = false;
                     uint64_t nb = 0xFFFFFFFFFFFFFF00ULL | lane;   // distinct per lane: never matches a k-mer or another lane
                     int c = -1;
+                    uint32_t vpos = 0;
+                    uint64_t vk = 0;
                     if (lane < (uint32_t)NB && within) {
                         const uint64_t nuc = (NB == 8) ? (lane >> 1) : lane;
                         const bool left = (j.dir == -1) || (j.dir == 0 && (lane & 1) == 0);
                         const uint64_t x = left ? ((nuc << (2 * k - 2)) | (kmer >> 2)) : (((kmer << 2) | nuc) & kmask);
+                        // The visited-set slot of the neighbour is read BEFORE the table answers, so the two global round trips of a
+                        // step overlap instead of following each other (3 700 -> ~2 000 cycles per step of a linear stretch).  A plain
+                        // load is enough: while the walk lasts this warp is the only writer of the pass's visited set, and its own
+                        // earlier stores are ordered before this load by the __syncwarp() that ends every step.
+                        vpos = vis_home(j, x);
+                        vk = __ldcg(&j.vis_keys[vpos]);
                         c = mc_table_lookup(table, mc_mix62(mc_canonical(x, k)));
                         if (c >= min_cov) { cand = true; nb = x; }
                     }
-                    // first occurrence among the neighbours of this parent, then "not visited before" (the same slot protocol as
-                    // vis_find_or_claim; vis_val gets the queue index so that the general step sees the k-mer as visited).
-                    // Claiming all neighbours before the probe answers, to overlap the two round trips, was measured slower
-                    // (2.39 us per step against 1.90: profiles/r1d_NOTES.md).
-                    const unsigned same = __match_any_sync(0xffffffffu, nb);
+                    // (Letting the idle lanes prefetch the home buckets of the neighbours' neighbours into L2 was measured twice, in
+                    // round 1 and again on this loop: 2 971 against 2 777 cycles per step -- the extra divergent path costs more issue
+                    // time on the critical path than the L2 hit saves.)
+                    // first occurrence among the neighbours of this parent (left and right neighbours can only coincide when both
+                    // directions are expanded), then "not visited before"; vis_val gets the queue index so that the general step sees
+                    // the k-mer as visited.
+                    const unsigned same = NB == 8 ? __match_any_sync(0xffffffffu, nb) : (1u << lane);
                     bool win = cand && (uint32_t)(__ffs(same) - 1) == lane;
-                    uint32_t vpos = 0;
+                    const unsigned win_mask = __ballot_sync(0xffffffffu, win);
                     if (win) {
                         const uint64_t want = nb + 1;
-                        vpos = (uint32_t)(mc_mix62(nb) >> 20) & j.vis_mask;
-                        while (true) {
-                            const uint64_t cur = atomicCAS((unsigned long long*)&j.vis_keys[vpos], 0ULL, (unsigned long long)want);
-                            if (cur == 0) break;
-                            if (cur == want) { win = false; break; }
-                            vpos = (vpos + 1) & j.vis_mask;
+                        // two candidates of this step whose home slots coincide cannot both take it blindly: the first one may, the
+                        // others walk on from the NEXT slot (the first one's plain store and their CAS must not meet on one slot)
+                        const unsigned clash = __match_any_sync(win_mask, vpos);
+                        const bool first_here = (uint32_t)(__ffs(clash) - 1) == lane;
+                        if (vk == want) {
+                            win = false;                                   // visited before
+                        } else if (vk == 0 && first_here) {
+                            j.vis_keys[vpos] = want;                       // new: claimed with a plain store (no other writer, see above)
+                        } else {                                           // occupied by another k-mer, or contested: walk on with the CAS protocol
+                            if (vk == 0) vpos = (vpos + 1) & j.vis_mask;   // (contested and free: the first candidate is storing there right now)
+                            while (true) {
+                                const uint64_t cur = atomicCAS((unsigned long long*)&j.vis_keys[vpos], 0ULL, (unsigned long long)want);
+                                if (cur == 0) break;
+                                if (cur == want) { win = false; break; }
+                                vpos = (vpos + 1) & j.vis_mask;
+                            }
                         }
                     }
                     const unsigned winners = __ballot_sync(0xffffffffu, win);
@@ -210,6 +234,7 @@ __global__ void __launch_bounds__(BFS_THREADS) k_bfs(McTableDev table, uint32_t 
                     tl += accept;
                     steps++;
                     if (stop || tl - h != 1) break;
+                    __syncwarp();   // orders this step's visited-set stores before the next step's loads (any lane)
                     // exactly one k-mer was appended and it is the whole frontier: it is the next parent
                     const int src = __ffs(__ballot_sync(0xffffffffu, added)) - 1;
                     kmer = __shfl_sync(0xffffffffu, nb, src);

@@ -579,6 +579,7 @@ static void batch_create(mc_table* t, uint64_t ub, uint64_t total_hint) {
     MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(B->P + 1) * 8, ctx->stream));
     B->used = 0;
     B->spill_used = 0;
+    B->ub_sum = 0;
 }
 
 static uint64_t read_spill_cursor(mc_table* t) {
@@ -593,13 +594,20 @@ void mc_batch_reserve(mc_table* t, uint64_t ub, uint64_t total_hint) {
     McBatch* B = t->batch;
     if (B && B->dev.keys) {
         if (B->used) B->spill_used = read_spill_cursor(t);
-        const bool fits = B->used + ub <= B->capacity && B->spill_used + ub <= B->dev.spill_cap;
+        // Room in the bins is planned with the density seen so far (+ 5 %) rather than with the chunk's worst case (one k-mer per two
+        // input bytes: 30 % above a real FASTQ file's), which ended batches one chunk early and cost a second table sizing + rehash;
+        // a bin that does fill up diverts to the spill list, whose room IS checked against the worst case.
+        uint64_t expect = ub;
+        if (B->ub_sum) expect = std::min<uint64_t>(ub, (uint64_t)((double)ub * ((double)B->used / (double)B->ub_sum) * 1.05) + 1024);
+        const bool fits = B->used + expect <= B->capacity && B->spill_used + ub <= B->dev.spill_cap;
+        B->last_ub = ub;
         if (fits) return;
         mc_table_flush(t);
         if (ub <= B->dev.spill_cap) return;
         batch_free_buffers(t->ctx, B);   // a larger chunk than the buffers were made for
     }
     batch_create(t, ub, total_hint);
+    t->batch->last_ub = ub;
 }
 
 static void scatter_attrs(mc_ctx* ctx) {   // per context (= per device): opt in to > 48 KB of dynamic shared memory
@@ -627,6 +635,7 @@ void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n) {
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
     B->used += n;
+    B->ub_sum += std::max<uint64_t>(B->last_ub, n);
 }
 
 void mc_launch_owner_scatter(mc_ctx* ctx, const uint64_t* d_flat, uint64_t n, const McBinsDev& owners, const McBinDst& dst, unsigned int* flags) {
@@ -673,6 +682,7 @@ static void apply_spill_list(mc_table* t, uint64_t sp) {
     MC_CUDA(cudaMemsetAsync(B->dev.cursors, 0, (size_t)(B->P + 1) * 8, t->ctx->stream));
     B->used = 0;
     B->spill_used = 0;
+    B->ub_sum = 0;
 }
 
 static const uint64_t MC_AGG_MIN_KEYS = 1ull << 25;   // batches below this are swept directly (k_bin_count)

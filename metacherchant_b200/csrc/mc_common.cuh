@@ -374,6 +374,8 @@ struct McBatch {
     uint64_t capacity = 0;      // total keys the batch is meant to hold (P * cap has slack on top)
     uint64_t used = 0;          // keys scattered so far (upper bound: includes sentinels and foreign-shard keys)
     uint64_t spill_used = 0;
+    uint64_t ub_sum = 0, last_ub = 0;   // what the callers RESERVED for those scatters (worst case per chunk): used / ub_sum is the input's
+                                        // real k-mer density, which plans the next chunk better than its worst case
 };
 // make sure the table's batch has room for `ub` more keys (flushing if needed); total_hint = all keys the caller expects to add
 void mc_batch_reserve(mc_table* t, uint64_t ub, uint64_t total_hint);

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -360,6 +361,21 @@ static void grow_to(mc_table* t, int new_q) {
 }
 
 void mc_table_grow_to(mc_table* t, int q) {
+    if (getenv("MC_TRACE")) {   // (synchronising: trace runs only)
+        cudaEvent_t a = mc_event_get(t->ctx), b = mc_event_get(t->ctx);
+        const int q0 = t->dev.q;
+        cudaEventRecord(a, t->ctx->stream);
+        grow_to(t, q);
+        cudaEventRecord(b, t->ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        t->ctx->stage_ms[MC_ST_GROW] += ms;
+        fprintf(stderr, "[mc trace] table grown from 2^%d to 2^%d buckets (%.1f GiB) in %.2f ms\n", q0, q, (double)(32ull << q) / (1 << 30), ms);
+        mc_event_put(t->ctx, a);
+        mc_event_put(t->ctx, b);
+        return;
+    }
     McStageTimer tm(t->ctx, MC_ST_GROW);   // resolved lazily: growing does not stall the host
     grow_to(t, q);
 }

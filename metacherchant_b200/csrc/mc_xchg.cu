@@ -287,30 +287,34 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
     }
 }
 
-// Adds (hashed key, count) pairs to the table; count-0 pairs are padding.  The pairs of one source arrive in hash order, i.e. in
-// the order of the buckets they update.  Round 1 gave consecutive pairs to consecutive lanes: neighbouring lanes then hit the
-// SAME bucket at the same moment (two pairs per bucket at load 0.5), lost their CAS to each other and went round again, and a
-// thread had one dependent chain (pair -> bucket -> CAS) in flight: 47 ms for 0.72 G pairs.  Now every thread owns MP_RUN
-// CONSECUTIVE pairs: it loads them with full-sector 16-byte loads, has all their home buckets in flight at once, and the lanes of
-// a warp work MP_RUN pairs (~4 buckets) apart, so they do not collide.
-#define MP_RUN 8
-__global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, const ulonglong2* __restrict__ pairs, uint64_t n) {
+// Adds the (hashed key, count) pairs every source left in this rank's regions to the shard; count-0 pairs are padding.
+// Each source's pairs arrive in hash order, i.e. in the order of the buckets they update, and every source covers the shard's
+// whole hash range.  Round 1 ran one launch per source, each sweeping the complete shard table (N x 8-16 GB of table traffic).
+// Now ONE launch walks all sources in lockstep: virtual position v of the longest stream maps to position v * n_s / n_max of
+// source s, so at any moment the grid updates the same narrow window of the table for all sources and every table line crosses
+// HBM once.  Neighbouring lanes still update neighbouring buckets (the bucket is read right before its CAS: a version with
+// several prefetched buckets per thread lost more to stale copies and failed CAS retries than it gained, and a version with a
+// run of 8 consecutive pairs per thread was 3.6x slower at N = 4: profiles/r2_NOTES.md).
+struct McMergeSrc {
+    const ulonglong2* pairs[MC_MAX_XCHG_RANKS];
+    unsigned long long n[MC_MAX_XCHG_RANKS];
+    unsigned long long n_max;
+    int world;
+};
+__global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, McMergeSrc src) {
     unsigned long long added = 0;
-    const uint64_t n_runs = (n + MP_RUN - 1) / MP_RUN;
-    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_runs; r += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 p[MP_RUN];
-        uint64_t w[MP_RUN][4];
-#pragma unroll
-        for (int i = 0; i < MP_RUN; i++) {
-            const uint64_t at = r * MP_RUN + i;
-            p[i] = at < n ? __ldcs(pairs + at) : make_ulonglong2(0, 0);
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < src.n_max; v += (uint64_t)gridDim.x * blockDim.x) {
+        for (int s = 0; s < src.world; s++) {
+            const unsigned long long ns = src.n[s];
+            if (ns == 0) continue;
+            // positions [lo, hi) of source s that fall to virtual position v (0 or 1 pair when n_s <= n_max)
+            const unsigned long long lo = (unsigned long long)(((unsigned __int128)v * ns) / src.n_max);
+            const unsigned long long hi = (unsigned long long)(((unsigned __int128)(v + 1) * ns) / src.n_max);
+            for (unsigned long long i = lo; i < hi; i++) {
+                const ulonglong2 p = __ldcs(src.pairs[s] + i);
+                if (p.y && mc_table_add(t, p.x, (uint32_t)p.y)) added++;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < MP_RUN; i++)
-            if (p[i].y) mc_load_bucket(t.slots + (((p[i].x & ((1ULL << (62 - t.shard_bits)) - 1)) >> t.tag_bits) & t.nb_mask) * 4, w[i]);
-#pragma unroll
-        for (int i = 0; i < MP_RUN; i++)
-            if (p[i].y && mc_table_add_impl<true>(t, p[i].x & ((1ULL << (62 - t.shard_bits)) - 1), (uint32_t)p[i].y, w[i])) added++;
     }
     __shared__ unsigned long long s_added;
     if (threadIdx.x == 0) s_added = 0;
@@ -388,11 +392,17 @@ extern "C" int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_
             const int q = mc_q_for_keys(have + total, shard->dev.shard_bits, 0.55);
             if (q > shard->dev.q) mc_table_grow_to(shard, q);
         }
-        for (int src = 0; src < x->world; src++) {
-            if (counts[src] == 0) continue;
+        if (total) {
+            McMergeSrc ms{};
+            ms.world = x->world;
+            for (int src = 0; src < x->world; src++) {
+                ms.pairs[src] = (const ulonglong2*)x->region(x->local, slot, src);
+                ms.n[src] = counts[src];
+                ms.n_max = std::max<unsigned long long>(ms.n_max, counts[src]);
+            }
             McStageTimer tm(ctx, MC_ST_COUNT);
-            const int grid = (int)std::min<uint64_t>((counts[src] / MP_RUN + 256) / 256, (uint64_t)ctx->sm_count * 8);
-            k_merge_pairs<<<grid, 256, 0, st>>>(shard->dev, (const ulonglong2*)x->region(x->local, slot, src), counts[src]);
+            const int grid = (int)std::min<uint64_t>((ms.n_max + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            k_merge_pairs<<<grid, 256, 0, st>>>(shard->dev, ms);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
         }

@@ -78,8 +78,25 @@ def test_cli_flag_surface(tmp_path, lib):
     assert r.returncode == 1 and "k > 31" in r.stderr
     r = run_cli("--tool", "environment-finder-multi", "--seq", "x.fa", "--output", "o", cwd=tmp_path)
     assert r.returncode == 1 and "Mandatory argument --env (-e) not set" in r.stderr
-    r = run_cli("--tool", "reads-classifier", cwd=tmp_path)
+    r = run_cli("--tool", "reads-classifier", "-k", "21", "-i", "g.fastq", cwd=tmp_path)
+    assert r.returncode == 1 and "Mandatory argument --read-files (-r) not set" in r.stderr
+    r = run_cli("--tool", "assembler", cwd=tmp_path)
     assert r.returncode == 1 and "Unknown tool" in r.stderr
     r = run_cli("-k", "31", "--seq", "x.fa", "--output", "o", "--maxkmers", "5", "--bogus", "1", cwd=tmp_path)
     assert r.returncode == 1 and "Unrecognized option: --bogus" in r.stderr
     assert (tmp_path / "workDir" / "log").exists()          # Tool.updateFileLoggers: work-dir/log
+
+
+def test_jni_shim_compiles(tmp_path):
+    """jni/mc_jni.cpp is source-only in this image (no JDK): type-check it against include/mc_b200.h with a stand-in <jni.h> that
+    declares the JNI types and the JNIEnv members it uses (tests/jni_stub/jni.h).  Compile only: nothing is linked or run."""
+    import shutil
+    import subprocess
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-DMC_HAVE_JNI=1", "-I", os.path.join(root, "tests", "jni_stub"),
+                        "-I", os.path.join(root, "include"), os.path.join(root, "jni", "mc_jni.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(root, "jni", "mc_jni.cpp")).read()
+    for fn in ("createContext", "loadReads", "size", "get", "findEnvironments", "findEnvironmentsEx", "multiEnvironment", "freeTable", "destroyContext"):
+        assert f"Java_io_NativeCounter_{fn}" in src
