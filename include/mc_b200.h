@@ -230,7 +230,8 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
  *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32),
  *   "agg" (two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on), "agg_unit" (keys per
  *   aggregation unit, 0 = automatic), "device_chunk_bytes" (mc_count_device: bytes per parse / extract pass over device-resident input, 0 = as large as the 32-bit record
- *   offsets allow; tests force small values), "flush_overlap" (1: in the aggregated flush the sub-bin scatter of group g + 1 runs on a second stream beside the
+ *   offsets allow; tests force small values), "extract_tma" (1 = default: the extractor stages the byte span of a warp's records with one cp.async.bulk + mbarrier; 0: per-lane
+ *   16-byte loads), "flush_overlap" (1: in the aggregated flush the sub-bin scatter of group g + 1 runs on a second stream beside the
  *   aggregation of group g; 0 = default: one after the other), "stage_timing" (0: no per-stage CUDA events), "scatter_tma" (1 = default: the scatter kernels hand every bin run to the copy engine with cp.async.bulk; 0: per-sector stores),
  *   "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --
  *   a step made of several count calls; reset with mc_ctx_stage_reset) */

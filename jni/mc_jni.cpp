@@ -131,5 +131,24 @@ JNIEXPORT void JNICALL Java_io_NativeCounter_multiEnvironment(JNIEnv* env, jclas
     if (rc != MC_OK) throw_execution_failed(env);
 }
 
+// byte[] io.NativeCounter.classifyReads(long ctx, long table, byte[] fastq, double z, double foundThreshold, boolean correction)
+//   ~ ReadsFinderInGraph.findRead / findReadWithCorrection for every read of the buffer (src/algo/ReadsFinderInGraph.java:37-123);
+//     PairFinder.run (src/algo/PairFinder.java:30-55) keeps its bookkeeping on the Java side, fed from the returned flags
+JNIEXPORT jbyteArray JNICALL Java_io_NativeCounter_classifyReads(JNIEnv* env, jclass, jlong ctx, jlong table, jbyteArray fastq, jdouble z,
+                                                                 jdouble foundThreshold, jboolean correction) {
+    const jsize len = env->GetArrayLength(fastq);
+    jbyte* buf = env->GetByteArrayElements(fastq, nullptr);
+    size_t n = 0;
+    int rc = mc_classify_bytes((mc_ctx*)ctx, (const mc_table*)table, buf, (size_t)len, MC_FMT_FASTQ, z, foundThreshold, correction ? 1 : 0, nullptr, 0, &n);
+    std::vector<uint8_t> found(n);
+    if (rc == MC_OK && n)
+        rc = mc_classify_bytes((mc_ctx*)ctx, (const mc_table*)table, buf, (size_t)len, MC_FMT_FASTQ, z, foundThreshold, correction ? 1 : 0, found.data(), n, &n);
+    env->ReleaseByteArrayElements(fastq, buf, JNI_ABORT);
+    if (rc != MC_OK) { throw_execution_failed(env); return nullptr; }
+    jbyteArray res = env->NewByteArray((jsize)n);
+    env->SetByteArrayRegion(res, 0, (jsize)n, (const jbyte*)found.data());
+    return res;
+}
+
 }  // extern "C"
 #endif  // MC_HAVE_JNI

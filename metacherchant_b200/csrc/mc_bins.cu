@@ -1065,6 +1065,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "keep_stage_ms" && value >= 0 && value <= 1) ctx->keep_stage_ms = (int)value;
     else if (n == "scatter_tma" && value >= 0 && value <= 1) ctx->tune_scatter_tma = (int)value;
     else if (n == "flush_overlap" && value >= 0 && value <= 1) ctx->tune_flush_overlap = (int)value;
+    else if (n == "extract_tma" && value >= 0 && value <= 1) ctx->tune_extract_tma = (int)value;
     else if (n == "stage_timing" && value >= 0 && value <= 1) ctx->tune_stage_timing = (int)value;
     else if (n == "device_chunk_bytes" && (value == 0 || (value >= 4096 && value <= ((long long)3 << 30)))) ctx->tune_device_chunk_bytes = (size_t)value;
     else if (n == "agg_unit" && value >= 0 && value <= (1 << 24)) ctx->tune_agg_unit = (uint32_t)value;

@@ -301,6 +301,7 @@ struct mc_ctx {
     int tune_agg = -1;               // two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on
     uint32_t tune_agg_unit = 0;      // target keys per aggregation unit (sub-bin); 0 = default
     size_t tune_device_chunk_bytes = 0;   // device-resident input: bytes per parse/extract pass (0 = as large as 32-bit offsets allow)
+    int tune_extract_tma = 1;        // k_extract stages the warps' record spans with cp.async.bulk + mbarrier
     int tune_flush_overlap = 0;      // aggregated flush: scatter2(g + 1) on aux_stream concurrent with agg(g), one CTA per SM each
                                      // (measured: each kernel slows down 1.5x at half occupancy, nothing is gained: profiles/r2_NOTES.md)
     int tune_stage_timing = 1;       // 0: McStageTimer records nothing (four CUDA API calls less per kernel launch)

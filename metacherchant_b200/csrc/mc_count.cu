@@ -43,6 +43,7 @@ struct McExtractArgs {
     uint32_t shard_id;        // (kept for the statistics sink; keys are filtered by shard when they are binned)
     uint64_t* out_keys;       // flat hashed keys (sentinel-padded)
     unsigned long long* out_cursor;
+    int use_tma;              // stage the warps' record spans with bulk copies + mbarriers (0: per-lane 16-byte loads)
 };
 
 __device__ __forceinline__ bool is_iupac(uint8_t c) {
@@ -89,6 +90,25 @@ __device__ __forceinline__ uint32_t ex_lds_u8(uint32_t saddr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+// ---- bulk asynchronous copy global -> shared with an mbarrier (TMA unit; SASS UBLKCP.S.G + SYNCS) -----------------------------------
+// The byte span of a warp's records is ONE contiguous, 16-byte aligned piece of the chunk: lane 0 arms the warp's mbarrier with the
+// byte count and hands the whole span to the copy engine; the lanes wait on the barrier's phase instead of moving 16 bytes each
+// through registers (LDG.128 -> STS.128).  Spans that touch the edges of the buffer keep the per-lane loop.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_load_g2s(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
 struct McRollOut {
     uint32_t emitted, good, splits, flags;
 };
@@ -143,8 +163,13 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     constexpr int RPW = 32 / PARTS;   // records per warp and step
     uint8_t* const s_cls = s_dyn + EX_WARPS * EX_STAGE_BYTES;
+    __shared__ __align__(8) unsigned long long s_bar[EX_WARPS];   // one mbarrier per warp (its staging window)
     for (int i = threadIdx.x; i < 256; i += EX_THREADS) s_cls[i] = ex_class((uint32_t)i, FASTA);
+    if ((threadIdx.x & 31) == 0) mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[threadIdx.x >> 5]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    const uint32_t my_bar = (uint32_t)__cvta_generic_to_shared(&s_bar[threadIdx.x >> 5]);
+    uint32_t bar_phase = 0;
     const int lane = threadIdx.x & 31;
     const int part = lane & (PARTS - 1);
     const uint32_t group_mask = PARTS == 32 ? 0xffffffffu : (((1u << PARTS) - 1u) << (lane & ~(PARTS - 1)));
@@ -179,6 +204,16 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
                 if (span <= EX_STAGE_BYTES) {
                     const uint8_t* g0 = gp - al;
                     const uint8_t* end = a.base + a.n_bytes;
+                    const uint32_t span16 = (span + 15u) & ~15u;
+                    if (a.use_tma && g0 >= a.base && g0 + span16 <= end && span16 <= EX_STAGE_BYTES) {
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the window's earlier (generic) readers before the engine's writes
+                            mbar_expect_tx(my_bar, span16);
+                            bulk_load_g2s((uint32_t)__cvta_generic_to_shared(sw), g0, span16, my_bar);
+                        }
+                        while (!mbar_try_wait(my_bar, bar_phase)) {}
+                        bar_phase ^= 1u;
+                    } else
                     for (uint32_t off = lane * 16; off < span; off += 512) {
                         const uint8_t* p = g0 + off;
                         if (p >= a.base && p + 16 <= end) {
@@ -414,6 +449,7 @@ static uint64_t* extract_flat(mc_ctx* ctx, McExtractArgs& a, bool fasta, uint32_
     MC_CUDA(cudaMemsetAsync(s2, 0, MC_FLAT_HEAD, st));
     a.out_keys = d_flat;
     a.out_cursor = d_cursor;
+    a.use_tma = ctx->tune_extract_tma;
     {
         McStageTimer tm(ctx, MC_ST_EXTRACT);
         if (fasta) launch_extract<true>(ctx, a, max_seq_len);

@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
                                                              unsigned int* flags) {
     __shared__ uint32_t s_tot[MC_MAX_XCHG_RANKS][DUMP_THREADS / 32];
     __shared__ unsigned long long s_base[MC_MAX_XCHG_RANKS];
+    __shared__ uint32_t s_otot[MC_MAX_XCHG_RANKS];
+    __shared__ ulonglong2 s_pairs[DUMP_THREADS * 4];   // every live entry of the CTA's 512 buckets, grouped by owner (32 KB)
     const uint64_t nb = t.nb_mask + 1;
     const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
     const uint64_t total = nb + stash_units;
@@ -260,30 +262,48 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
                 base = ~0ULL;
             }
             s_base[threadIdx.x] = base;
+            s_otot[threadIdx.x] = tot;
         }
         __syncthreads();
+        // pass 2: the CTA's pairs, grouped by owner, into shared memory ...
+        uint32_t ooff = 0;   // start of owner o's group inside s_pairs
         for (int o = 0; o < world; o++) {
             uint32_t mine = 0;
 #pragma unroll
             for (int s = 0; s < 4; s++) mine += ((own >> (8 * s)) & 0xFFu) == (uint32_t)o;
             const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
-            if (!any) continue;
-            uint32_t incl = mine;
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const unsigned long long base = s_base[o];
-            if (base == ~0ULL || mine == 0) continue;
-            uint32_t before = 0;
-            for (int w = 0; w < warp; w++) before += s_tot[o][w];
-            unsigned long long pos = base + before + incl - mine;
-            ulonglong2* out = (ulonglong2*)dst.base[o];
+            if (any) {
+                uint32_t incl = mine;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (mine) {
+                    uint32_t before = 0;
+                    for (int w = 0; w < warp; w++) before += s_tot[o][w];
+                    uint32_t pos = ooff + before + incl - mine;
 #pragma unroll
-            for (int s = 0; s < 4; s++)
-                if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) out[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
+                    for (int s = 0; s < 4; s++)
+                        if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) s_pairs[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
+                }
+            }
+            ooff += s_otot[o];
         }
-        __syncthreads();   // s_tot / s_base are rewritten by the next step
+        __syncthreads();
+        // ... and out in whole runs: consecutive lanes store consecutive 16-byte pairs of ONE owner's region, i.e. full 512-byte
+        // segments per warp on NVLink (round 1 stored every lane's pairs from registers: 16-byte writes strided by the lanes' own
+        // counts, ~250 GB/s to the peers)
+        ooff = 0;
+        for (int o = 0; o < world; o++) {
+            const uint32_t tot = s_otot[o];
+            const unsigned long long base = s_base[o];
+            if (base != ~0ULL) {
+                ulonglong2* out = (ulonglong2*)dst.base[o] + base;
+                for (uint32_t i = threadIdx.x; i < tot; i += DUMP_THREADS) out[i] = s_pairs[ooff + i];
+            }
+            ooff += tot;
+        }
+        __syncthreads();   // s_tot / s_base / s_pairs are rewritten by the next step
     }
 }
 

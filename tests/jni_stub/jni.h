@@ -12,6 +12,8 @@ typedef int32_t jint;
 typedef int64_t jlong;
 typedef int16_t jshort;
 typedef uint8_t jboolean;
+typedef int8_t jbyte;
+typedef double jdouble;
 typedef jint jsize;
 class _jobject {};
 class _jclass : public _jobject {};
@@ -20,6 +22,7 @@ class _jarray : public _jobject {};
 class _jobjectArray : public _jarray {};
 class _jlongArray : public _jarray {};
 class _jshortArray : public _jarray {};
+class _jbyteArray : public _jarray {};
 typedef _jobject* jobject;
 typedef _jclass* jclass;
 typedef _jstring* jstring;
@@ -27,6 +30,7 @@ typedef _jarray* jarray;
 typedef _jobjectArray* jobjectArray;
 typedef _jlongArray* jlongArray;
 typedef _jshortArray* jshortArray;
+typedef _jbyteArray* jbyteArray;
 struct JNIEnv {
     jclass FindClass(const char*);
     jint ThrowNew(jclass, const char*);
@@ -39,5 +43,9 @@ struct JNIEnv {
     void ReleaseLongArrayElements(jlongArray, jlong*, jint);
     jshortArray NewShortArray(jsize);
     void SetShortArrayRegion(jshortArray, jsize, jsize, const jshort*);
+    jbyte* GetByteArrayElements(jbyteArray, jboolean*);
+    void ReleaseByteArrayElements(jbyteArray, jbyte*, jint);
+    jbyteArray NewByteArray(jsize);
+    void SetByteArrayRegion(jbyteArray, jsize, jsize, const jbyte*);
 };
 #endif

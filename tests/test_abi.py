@@ -98,5 +98,5 @@ def test_jni_shim_compiles(tmp_path):
                         "-I", os.path.join(root, "include"), os.path.join(root, "jni", "mc_jni.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     src = open(os.path.join(root, "jni", "mc_jni.cpp")).read()
-    for fn in ("createContext", "loadReads", "size", "get", "findEnvironments", "findEnvironmentsEx", "multiEnvironment", "freeTable", "destroyContext"):
+    for fn in ("createContext", "loadReads", "size", "get", "findEnvironments", "findEnvironmentsEx", "multiEnvironment", "classifyReads", "freeTable", "destroyContext"):
         assert f"Java_io_NativeCounter_{fn}" in src
