@@ -45,3 +45,26 @@ def test_single_rank_sharded_path_matches_direct_path(oracle):
         assert c.table.stats() == ref.stats()
     finally:
         ctx.close()
+
+
+def test_two_devices_in_one_process(oracle):
+    """One process, two contexts on two GPUs (a JVM that opens two devices): the kernels' shared-memory opt-in is per DEVICE, so the
+    second context must configure its own (round 1 guarded it with a process-wide flag and the second device's launches failed)."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from metacherchant_b200 import Context
+    import oracle_ffi
+    s = oracle.synth(genome_unit=10_000)
+    data = s.generate(0, 40_000)
+    ref = oracle.table(31, threads=4).count_bytes(data, oracle_ffi.FMT_FASTQ).dump()
+    ctxs = [Context(0), Context(1)]
+    try:
+        for c in ctxs:
+            c.set_tuning("agg", 1)          # the full-size path: scatter2 + aggregation kernels with > 48 KB of dynamic shared memory
+            got = c.new_table(31).count_bytes(data, oracle_ffi.FMT_FASTQ).dump()
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    finally:
+        for c in ctxs:
+            c.close()
