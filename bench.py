@@ -588,7 +588,7 @@ def main():
                            "table": (f"pre-sized for bases/{args.hint_div} distinct k-mers, grows by rehash beyond" if args.hint_div > 0 else
                                      "no capacity hint: sized by the library from a counted 1/64 sample of the hash space (load 0.5), grows by rehash beyond"),
                            "solid_kmers": int(n_solid), "wall_s": round(wall, 3), "exchange": args.exchange if sharded else None},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "driver_allocs_in_timed_region": int(driver_allocs),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "fused_dump": (counter.fused_last if sharded else None), "driver_allocs_in_timed_region": int(driver_allocs),
                 "roofline": roofline, "cpu_baseline": cpu, "env": env, "phases_ms_last_step": phases, "verify": verify}
         print(json.dumps(line), flush=True)
     if sharded:

@@ -198,6 +198,12 @@ int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_received);
  *   every rank: mc_xchg_merge(slot, shard)         adds the received pairs (saturating) into this rank's shard table
  * mc_table_copy_stats carries the reader statistics (reads, runs, bases, k-mers) of the local table over to the shard. */
 int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, uint64_t* n_pairs);
+/* The dump fused into the local table's LAST flush: `local` still holds pending binned updates (filled with the "defer_flush" tuning
+ * on); they are applied group by group in hash order, and every hash range of the table is shipped to its owners on a second stream
+ * as soon as the flush has finished it -- the NVLink transfer overlaps the aggregation of the following groups.  *fused = 0 when the
+ * flush could not be followed range by range (spill lists, a small batch) and the whole table was dumped afterwards instead; -1 when a
+ * receive region overflowed (nothing usable was shipped: create larger regions on every rank and call mc_xchg_dump_owners). */
+int mc_xchg_flush_and_dump(mc_xchg* x, mc_table* local, int slot, uint64_t* n_pairs, int* fused);
 int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_pairs);
 int mc_table_copy_stats(mc_table* dst, const mc_table* src);
 void mc_xchg_destroy(mc_xchg* x);
@@ -230,7 +236,8 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
  *   "extract_parts" (lanes per record in k_extract: 0 = by read length, 1, 4 or 32),
  *   "agg" (two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on), "agg_unit" (keys per
  *   aggregation unit, 0 = automatic), "device_chunk_bytes" (mc_count_device: bytes per parse / extract pass over device-resident input, 0 = as large as the 32-bit record
- *   offsets allow; tests force small values), "extract_tma" (1 = default: the extractor stages the byte span of a warp's records with one cp.async.bulk + mbarrier; 0: per-lane
+ *   offsets allow; tests force small values), "defer_flush" (1: mc_count_* leave their last batch of bins pending for mc_xchg_flush_and_dump),
+ *   "extract_tma" (1 = default: the extractor stages the byte span of a warp's records with one cp.async.bulk + mbarrier; 0: per-lane
  *   16-byte loads), "flush_overlap" (1: in the aggregated flush the sub-bin scatter of group g + 1 runs on a second stream beside the
  *   aggregation of group g; 0 = default: one after the other), "stage_timing" (0: no per-stage CUDA events), "scatter_tma" (1 = default: the scatter kernels hand every bin run to the copy engine with cp.async.bulk; 0: per-sector stores),
  *   "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "mc_xchg_scatter_device": (i32, [vp, vp, sz, i32, i32, i32, vp]),
     "mc_xchg_insert": (i32, [vp, i32, vp, C.POINTER(u64)]),
     "mc_xchg_dump_owners": (i32, [vp, vp, i32, C.POINTER(u64)]),
+    "mc_xchg_flush_and_dump": (i32, [vp, vp, i32, C.POINTER(u64), C.POINTER(i32)]),
     "mc_xchg_merge": (i32, [vp, i32, vp, C.POINTER(u64)]),
     "mc_table_copy_stats": (i32, [vp, vp]),
     "mc_xchg_destroy": (None, [vp]),

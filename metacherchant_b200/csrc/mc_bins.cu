@@ -805,6 +805,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
             }
         }
         if (ovf_n) {   // rare: the table was too small; re-insert what overflowed so far (grows until it fits)
+            if (t->hook) t->hook->failed = true;   // keys of ranges already handed on come back into the table
             mc_table_finish_chunk(t, grown);
             attach_overflow_list();
             keys_known = mc_table_keys(t);
@@ -912,6 +913,10 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 fprintf(stderr, "[mc trace] sub-bin attempts: min %llu mean %.0f max %llu, %llu of %u over cap2; bin0 attempts %llu\n", mn, (double)sum / (g.G * P2), mx, over, g.G * P2, cur[0]);
             }
         }
+        if (t->hook && !t->hook->failed) {   // everything whose home bucket lies in this group's hash range is final now
+            t->hook->group_done(t->hook->user, t, g.b0, g.G, P1);
+            t->hook->groups++;
+        }
         keys_done += g.keys;
         slot.live = true;
         slot.keys_done = keys_done;
@@ -955,10 +960,12 @@ void mc_table_flush(mc_table* t) {
     // large batches: second-level bins + shared-memory aggregation (one table update per DISTINCT key of a sub-bin)
     const bool aggregate = ctx->tune_agg < 0 ? batch_keys >= MC_AGG_MIN_KEYS : ctx->tune_agg != 0;
     if (aggregate) {
+        if (t->hook && cur[P] > 0) t->hook->failed = true;   // the first-level spill list is applied at the very end, to any range
         flush_aggregated(t, cur, batch_keys);
         apply_spill_list(t, cur[P]);
         return;
     }
+    if (t->hook) t->hook->failed = true;   // the direct sweep has no per-range completion points
     std::vector<uint64_t> prefix(P + 1);
     prefix[0] = 0;
     for (uint32_t b = 0; b < P; b++) {
@@ -1066,6 +1073,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "scatter_tma" && value >= 0 && value <= 1) ctx->tune_scatter_tma = (int)value;
     else if (n == "flush_overlap" && value >= 0 && value <= 1) ctx->tune_flush_overlap = (int)value;
     else if (n == "extract_tma" && value >= 0 && value <= 1) ctx->tune_extract_tma = (int)value;
+    else if (n == "defer_flush" && value >= 0 && value <= 1) ctx->tune_defer_flush = (int)value;
     else if (n == "stage_timing" && value >= 0 && value <= 1) ctx->tune_stage_timing = (int)value;
     else if (n == "device_chunk_bytes" && (value == 0 || (value >= 4096 && value <= ((long long)3 << 30)))) ctx->tune_device_chunk_bytes = (size_t)value;
     else if (n == "agg_unit" && value >= 0 && value <= (1 << 24)) ctx->tune_agg_unit = (uint32_t)value;

@@ -301,6 +301,8 @@ struct mc_ctx {
     int tune_agg = -1;               // two-level bins + shared-memory aggregation in the flush: -1 = by batch size, 0 = off, 1 = on
     uint32_t tune_agg_unit = 0;      // target keys per aggregation unit (sub-bin); 0 = default
     size_t tune_device_chunk_bytes = 0;   // device-resident input: bytes per parse/extract pass (0 = as large as 32-bit offsets allow)
+    int tune_defer_flush = 0;        // mc_count_* leave their last batch of bins pending (the next reader of the table, or
+                                     // mc_xchg_flush_and_dump, applies it)
     int tune_extract_tma = 1;        // k_extract stages the warps' record spans with cp.async.bulk + mbarrier
     int tune_flush_overlap = 0;      // aggregated flush: scatter2(g + 1) on aux_stream concurrent with agg(g), one CTA per SM each
                                      // (measured: each kernel slows down 1.5x at half occupancy, nothing is gained: profiles/r2_NOTES.md)
@@ -345,8 +347,19 @@ void mc_event_put(mc_ctx* ctx, cudaEvent_t e);
 size_t mc_arena_cached_bytes(mc_ctx* ctx);
 void mc_arena_trim(mc_ctx* ctx);
 
+// Observer of the aggregated flush (mc_bins.cu): called on the host right after the kernels of a group of first-level bins have been
+// queued on ctx->stream, i.e. once everything in the table whose HOME bucket lies in that hash range is final for this flush.  The
+// multi-GPU owner dump uses it to ship a finished range to its owners while the next groups are still being aggregated (mc_xchg.cu).
+struct McFlushHook {
+    void (*group_done)(void* user, struct mc_table* t, uint32_t b0, uint32_t G, uint32_t P1);
+    void (*before_grow)(void* user, struct mc_table* t);   // the table's memory is about to be replaced (rehash)
+    void* user;
+    bool failed;    // the flush did something a per-range consumer cannot follow (first-level spill list, overflow re-insertion, direct sweep)
+    uint32_t groups;
+};
 struct mc_table {
     mc_ctx* ctx = nullptr;
+    McFlushHook* hook = nullptr;
     int k = 0;
     uint32_t shard_id = 0;   // this table owns hashes whose top dev.shard_bits bits equal shard_id
     McTableDev dev{};

@@ -508,7 +508,7 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
 }
 
 static void finish_table(mc_table* t) {
-    {
+    if (!t->ctx->tune_defer_flush) {
         McHostTimer ht(t->ctx, MC_ST_COUNT);   // host view of the whole flush
         mc_table_flush(t);
     }

@@ -361,6 +361,7 @@ static void grow_to(mc_table* t, int new_q) {
 }
 
 void mc_table_grow_to(mc_table* t, int q) {
+    if (t->hook && t->hook->before_grow) t->hook->before_grow(t->hook->user, t);
     if (getenv("MC_TRACE")) {   // (synchronising: trace runs only)
         cudaEvent_t a = mc_event_get(t->ctx), b = mc_event_get(t->ctx);
         const int q0 = t->dev.q;

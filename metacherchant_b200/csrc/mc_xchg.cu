@@ -197,13 +197,18 @@ extern "C" int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_rec
 // to consecutive positions: whole 32-byte sectors on NVLink.  The grid walks the table in bucket order = hash order, so a
 // receiver sees its pairs in nearly ascending order of ITS bucket index and the merge streams through its shard table.
 #define DUMP_THREADS 512
+// Range form: the scan covers buckets [scan_lo, scan_lo + scan_n) (mod nb) and emits the entries whose HOME bucket lies in
+// [home_lo, home_hi) -- an entry sits up to 7 buckets past its home, so a range is scanned 8 buckets beyond its end and entries that
+// were displaced INTO it from the range before are left to that range.  Every entry is thereby emitted exactly once whatever the
+// order of the ranges and whatever the table's geometry at the time (the fused flush + dump below ships a hash range as soon as
+// the flush has finished it).  The whole table is the range [0, nb) scanned once.
 __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, int sb, McBinDst dst, unsigned long long* __restrict__ cursors, uint64_t cap_pairs,
-                                                             unsigned int* flags) {
+                                                             unsigned int* flags, uint64_t scan_lo, uint64_t scan_n, uint64_t home_lo, uint64_t home_hi) {
     __shared__ uint32_t s_tot[MC_MAX_XCHG_RANKS][DUMP_THREADS / 32];
     __shared__ unsigned long long s_base[MC_MAX_XCHG_RANKS];
     __shared__ uint32_t s_otot[MC_MAX_XCHG_RANKS];
     __shared__ ulonglong2 s_pairs[DUMP_THREADS * 4];   // every live entry of the CTA's 512 buckets, grouped by owner (32 KB)
-    const uint64_t nb = t.nb_mask + 1;
+    const uint64_t nb = scan_n;   // buckets scanned by this launch
     const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
     const uint64_t total = nb + stash_units;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -212,17 +217,19 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
     const int world = 1 << sb;
     uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint64_t w4[4] = {0, 0, 0, 0};
-    if (u < nb) mc_load_bucket(t.slots + u * 4, w4);
+    if (u < nb) mc_load_bucket(t.slots + ((scan_lo + u) & t.nb_mask) * 4, w4);
     for (uint64_t it = 0; it < iters; it++, u += stride) {
         uint64_t h[4];
         uint32_t c[4] = {0, 0, 0, 0};
         if (u < nb) {
+            const uint64_t b = (scan_lo + u) & t.nb_mask;
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 const uint64_t w = w4[s];
                 const uint64_t d = (w >> MC_COUNT_BITS) & (MC_MAX_DISP - 1);
-                h[s] = (((u - d) & t.nb_mask) << t.tag_bits) | (w >> MC_TAG_SHIFT);
-                c[s] = w ? (uint32_t)(w & MC_COUNT_MASK) : 0;
+                const uint64_t home = (b - d) & t.nb_mask;
+                h[s] = (home << t.tag_bits) | (w >> MC_TAG_SHIFT);
+                c[s] = (w && home >= home_lo && home < home_hi) ? (uint32_t)(w & MC_COUNT_MASK) : 0;
             }
         } else if (u < total) {
 #pragma unroll
@@ -230,10 +237,11 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
                 const uint64_t i = (u - nb) * 4 + s;
                 const uint64_t kx = i <= t.stash_mask ? t.stash_keys[i] : 0;
                 h[s] = kx - 1;
-                c[s] = kx ? t.stash_counts[i] : 0;
+                const uint64_t home = ((kx - 1) >> t.tag_bits) & t.nb_mask;
+                c[s] = (kx && home >= home_lo && home < home_hi) ? t.stash_counts[i] : 0;
             }
         }
-        if (u + stride < nb) mc_load_bucket(t.slots + (u + stride) * 4, w4);   // the next step's bucket is in flight during this one
+        if (u + stride < nb) mc_load_bucket(t.slots + ((scan_lo + u + stride) & t.nb_mask) * 4, w4);   // the next step's bucket is in flight during this one
         uint32_t own = 0;   // owner of entry s in bits [8s, 8s+8), 0xFF = no entry
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -366,7 +374,7 @@ extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, 
             McStageTimer tm(ctx, MC_ST_SCATTER);
             const uint64_t units = local->nb;
             const int grid = (int)std::min<uint64_t>((units + DUMP_THREADS - 1) / DUMP_THREADS, (uint64_t)ctx->sm_count * 4);
-            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags);
+            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags, 0, local->nb, 0, local->nb);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
         }
@@ -379,6 +387,97 @@ extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, 
         MC_CUDA(cudaMemcpyAsync(cur, x->d_cursors, sizeof cur, cudaMemcpyDeviceToHost, st));
         MC_CUDA(cudaStreamSynchronize(st));
         if (f) mc_throw(MC_ERR_NOMEM, "exchange: a receive region overflowed");
+        if (n_pairs) {
+            *n_pairs = 0;
+            for (int o = 0; o < x->world; o++) *n_pairs += cur[o];
+        }
+        return MC_OK;
+    } catch (const McError& e) {
+        mc_set_error(e.what());
+        return e.code;
+    }
+}
+
+// ---- the dump fused into the local table's last flush -------------------------------------------------------------------------
+// The flush applies the bins group by group in hash order; once a group's kernels are queued, every table entry whose home bucket
+// lies in the group's hash range is final.  The hook below ships that range to its owners on the context's second stream while the
+// main stream goes on with the next group: an NVLink-bound scan beside issue- and shared-memory-bound kernels.  Anything the hook
+// cannot follow (first-level spill list, re-insertion of overflowed keys, a batch small enough for the direct sweep) marks the
+// attempt failed and the whole table is dumped afterwards instead, as in round 1.
+struct McFusedDump {
+    mc_xchg* x;
+    McBinDst dst;
+    cudaEvent_t ready;
+};
+static void fused_group_done(void* user, mc_table* t, uint32_t b0, uint32_t G, uint32_t P1) {
+    McFusedDump* f = (McFusedDump*)user;
+    mc_ctx* ctx = t->ctx;
+    const uint64_t per = t->nb / P1;                       // nb >= 2^10 > P1: whole buckets per first-level bin
+    const uint64_t lo = (uint64_t)b0 * per, hi = (uint64_t)(b0 + G) * per;
+    const uint64_t scan_n = std::min<uint64_t>(t->nb, hi - lo + MC_MAX_DISP);
+    MC_CUDA(cudaEventRecord(f->ready, ctx->stream));
+    MC_CUDA(cudaStreamWaitEvent(ctx->aux_stream, f->ready, 0));
+    const int grid = (int)std::min<uint64_t>((scan_n + DUMP_THREADS - 1) / DUMP_THREADS, (uint64_t)ctx->sm_count);   // one CTA per SM: it shares the SM with the flush
+    k_dump_owners<<<grid, DUMP_THREADS, 0, ctx->aux_stream>>>(t->dev, f->x->shard_bits, f->dst, f->x->d_cursors, f->x->region_keys / 2, f->x->d_flags, lo, scan_n, lo, hi);
+    MC_LAUNCH(ctx);
+    MC_CUDA(cudaGetLastError());
+}
+static void fused_before_grow(void* user, mc_table* t) {   // the range dumps in flight read the memory the rehash is about to give back
+    (void)user;
+    MC_CUDA(cudaStreamSynchronize(t->ctx->aux_stream));
+}
+
+extern "C" int mc_xchg_flush_and_dump(mc_xchg* x, mc_table* local, int slot, uint64_t* n_pairs, int* fused_out) {
+    try {
+        if (!x || !local || slot < 0 || slot > 1) mc_throw(MC_ERR_ARG, "bad argument");
+        if (local->dev.shard_bits != 0) mc_throw(MC_ERR_ARG, "exchange: the local table must be unsharded");
+        mc_ctx* ctx = x->ctx;
+        MC_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        for (int r = 0; r < x->world; r++)
+            if (!x->peer[r]) mc_throw(MC_ERR_ARG, "exchange: rank %d's buffer has not been opened", r);
+        MC_CUDA(cudaMemsetAsync(x->d_cursors, 0, (MC_MAX_XCHG_RANKS + 1) * sizeof(unsigned long long), st));
+        MC_CUDA(cudaMemsetAsync(x->d_flags, 0, sizeof(unsigned int), st));
+        McFusedDump f{};
+        f.x = x;
+        f.dst.use = 1;
+        McBinDst mail{};
+        for (int o = 0; o < x->world; o++) {
+            f.dst.base[o] = x->region(x->peer[o], slot, x->rank);
+            mail.base[o] = (uint64_t*)x->mailbox(x->peer[o], slot);
+        }
+        f.ready = mc_event_get(ctx);
+        McFlushHook hook{fused_group_done, fused_before_grow, &f, false, 0};
+        local->hook = &hook;
+        try {
+            mc_table_flush(local);
+        } catch (...) {
+            local->hook = nullptr;
+            cudaStreamSynchronize(ctx->aux_stream);
+            mc_event_put(ctx, f.ready);
+            throw;
+        }
+        local->hook = nullptr;
+        MC_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+        mc_event_put(ctx, f.ready);
+        mc_batch_release(local);   // returns the bins (tens of GB) to the arena: the shard table needs the room
+        unsigned int fl = 0;
+        MC_CUDA(cudaMemcpyAsync(&fl, x->d_flags, sizeof fl, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+        const bool fused = !hook.failed && hook.groups > 0 && fl == 0;
+        if (fused_out) *fused_out = fused ? 1 : 0;
+        if (fl) {   // a receive region was too small for this table: the caller agrees on larger regions with the other ranks and dumps again
+            if (fused_out) *fused_out = -1;
+            if (n_pairs) *n_pairs = 0;
+            return MC_OK;
+        }
+        if (!fused) return mc_xchg_dump_owners(x, local, slot, n_pairs);
+        k_post_counts<<<1, 32, 0, st>>>(x->d_cursors, mail, x->world, x->rank);
+        MC_LAUNCH(ctx);
+        MC_CUDA(cudaGetLastError());
+        unsigned long long cur[MC_MAX_XCHG_RANKS + 1];
+        MC_CUDA(cudaMemcpyAsync(cur, x->d_cursors, sizeof cur, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
         if (n_pairs) {
             *n_pairs = 0;
             for (int o = 0; o < x->world; o++) *n_pairs += cur[o];

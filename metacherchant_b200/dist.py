@@ -105,6 +105,11 @@ class ShardedCounter:
         self.phase_s = {"extract": 0.0, "exchange": 0.0, "insert": 0.0, "sweep_filter": 0.0}
         self.verify = False
         self._local = None
+        # ship finished hash ranges to their owners DURING the local table's last flush (mc_xchg_flush_and_dump).  Correct (parity
+        # worker) but no faster at N = 2 (203.1 vs 203.3 ms per step: the range dumps take from the flush kernels the SM time they
+        # use), so it is off unless asked for
+        self.fuse_dump = os.environ.get("MC_FUSE_DUMP", "0") != "0"
+        self.fused_last = None
 
     def new_table(self):
         if self.table is not None:
@@ -205,6 +210,8 @@ class ShardedCounter:
         """Start this rank's complete LOCAL table (the single-GPU pipeline); batches are added with local_add_*."""
         self._t_begin = time.perf_counter()
         self._local = self.ctx.new_table(self.k, capacity_hint=self.capacity_hint)
+        if self.fuse_dump and self._xchg is not None:
+            self.ctx.set_tuning("defer_flush", 1)   # the last batch of bins stays pending: local_finish flushes AND dumps it
         return self._local
 
     def local_add_device(self, d_reads: int, nbytes: int, fmt: int):
@@ -226,19 +233,36 @@ class ShardedCounter:
         lib = self.ctx.lib
         local = self._local
         self._local = None
-        n_local = local.size()
-        t1 = time.perf_counter()
-        if getattr(self, "verify", False):
-            self.local_digest = local.checksum(0)
-        mx = torch.tensor([n_local], dtype=torch.int64, device="cuda")
-        if self.world > 1:
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        # an owner's share of a table is binomial around size / world: 25 % + a constant is far outside its spread
-        pairs = int(mx.item()) // self.world
-        pairs = pairs + pairs // 4 + (1 << 16)
-        self._peer_setup(2 * pairs)
         got = C.c_uint64()
-        check(lib.mc_xchg_dump_owners(self._xchg, local.h, 0, C.byref(got)))
+        fused = C.c_int(0)
+        t1 = time.perf_counter()
+        dumped = False
+        if self.fuse_dump and self._xchg is not None:
+            # The dump rides on the local table's last flush (mc_xchg_flush_and_dump): regions keep the size of the previous step;
+            # a rank whose table outgrew them reports -1 and every rank then falls back to the sized, unfused dump below.
+            self.ctx.set_tuning("defer_flush", 0)
+            check(lib.mc_xchg_flush_and_dump(self._xchg, local.h, 0, C.byref(got), C.byref(fused)))
+            bad = torch.tensor([1 if fused.value < 0 else 0], dtype=torch.int32, device="cuda")
+            if self.world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            dumped = int(bad.item()) == 0
+            self.fused_last = fused.value
+            if dumped and getattr(self, "verify", False):
+                self.local_digest = local.checksum(0)   # (the local table is complete once its last flush has run)
+        self.ctx.set_tuning("defer_flush", 0)
+        if not dumped:
+            n_local = local.size()
+            t1 = time.perf_counter()
+            if getattr(self, "verify", False):
+                self.local_digest = local.checksum(0)
+            mx = torch.tensor([n_local], dtype=torch.int64, device="cuda")
+            if self.world > 1:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            # an owner's share of a table is binomial around size / world: 25 % + a constant is far outside its spread
+            pairs = int(mx.item()) // self.world
+            pairs = pairs + pairs // 4 + (1 << 16)
+            self._peer_setup(2 * pairs)
+            check(lib.mc_xchg_dump_owners(self._xchg, local.h, 0, C.byref(got)))
         t2 = time.perf_counter()
         if self.world > 1:
             sync = torch.zeros(1, dtype=torch.int32, device="cuda")

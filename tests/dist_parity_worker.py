@@ -42,6 +42,22 @@ def main():
         counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)   # several batches
         tables[mode] = counter.table.dump()
         if mode == "merge":
+            # once more: the exchange regions exist now, so the owner dump rides on the local table's last flush (mc_xchg_flush_and_dump;
+            # "agg" forces the aggregated flush this small input would not take by itself)
+            ctx.set_tuning("agg", 1)
+            counter.fuse_dump = True
+            counter.new_table()
+            counter.count_device(d, per * rb, oracle_ffi.FMT_FASTQ, batch_bytes=3_000_000, record_bytes=rb)
+            again = counter.table.dump()
+            counter.fuse_dump = False
+            ctx.set_tuning("agg", -1)
+            fused_ok = np.array_equal(again[0], tables[mode][0]) and np.array_equal(again[1], tables[mode][1])
+            fl = torch.tensor([1 if (fused_ok and counter.fused_last == 1) else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(fl, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"DIST_FUSED_DUMP world={world} fused={counter.fused_last} {'OK' if int(fl.item()) == 1 else 'MISMATCH'}", flush=True)
+            env_ok = env_ok and int(fl.item()) == 1
+        if mode == "merge":
             # bench.py --verify's check: the digests of the local tables and of the owner shards add up to the same totals
             verify = counter.verify_exchange()
             # E3 + E4: local compaction, all-gather of the solid set, targets split over the ranks
