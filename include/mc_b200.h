@@ -121,6 +121,10 @@ int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const c
 int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets,
                    const char* const* hic_seqs, int n_hic, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
                    int chunk_len, int merge, int trim, const char* out_dir, int* found);
+/* extendEnvironment (OneSequenceCalculator.java:265-295) does not change an environment (`cont = kmer`, :276); what remains of it is
+ * its log line "Extending endings by N kmers" (:291), N = environment k-mers with exactly one solid neighbour outside the environment.
+ * out[i] = N of target i of the LAST mc_env_find / mc_env_find_ex call on this context (-1: no environment for it); *n = targets. */
+int mc_env_extend_counts(mc_ctx* ctx, long long* out, int cap, int* n);
 /* one BFS pass (runBfs, OneSequenceCalculator.java:154-220): oriented k-mers in discovery order.
  * dir: -1 left, +1 right, 0 both.  Returns in *n the number visited (0 = no seeds). */
 int mc_bfs(mc_ctx* ctx, const mc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int dir,

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "mc_table_filter": (i32, [vp, vp, i32, C.POINTER(vp)]),
     "mc_env_find": (i32, [vp, vp, C.POINTER(cp), C.POINTER(cp), i32, i32, i32, i64, i64, i32, i32, cp, C.POINTER(i32)]),
     "mc_env_find_ex": (i32, [vp, vp, C.POINTER(cp), C.POINTER(cp), i32, C.POINTER(cp), i32, i32, i32, i64, i64, i32, i32, i32, i32, cp, C.POINTER(i32)]),
+    "mc_env_extend_counts": (i32, [vp, vp, i32, C.POINTER(i32)]),
     "mc_bfs": (i32, [vp, vp, cp, i32, i32, i64, i64, i32, vp, vp, vp, sz, C.POINTER(sz)]),
     "mc_env_kmers": (i32, [vp, vp, cp, i32, i32, i64, i64, i32, vp, vp, sz, C.POINTER(sz)]),
     "mc_env_from_graph_txt": (i32, [vp, cp, cp, i32, i32, cp]),

@@ -140,6 +140,14 @@ class Context:
                                    -1 if max_radius is None else max_radius, int(both_dirs), chunk_len, os.fspath(out_dir).encode(), found))
         return [bool(x) for x in found]
 
+    def extend_counts(self):
+        """"Extending endings by N kmers" of every environment of the last find_environments call (-1: none was built)."""
+        n = C.c_int()
+        check(self.lib.mc_env_extend_counts(self.h, None, 0, C.byref(n)))
+        out = (C.c_longlong * max(n.value, 1))()
+        check(self.lib.mc_env_extend_counts(self.h, out, n.value, C.byref(n)))
+        return [int(out[i]) for i in range(n.value)]
+
     def find_environments_ex(self, table: "KmerTable", seqs, names=None, hic_seqs=(), min_cov=1, max_kmers=None, max_radius=None,
                              both_dirs=False, chunk_len=1, merge=False, trim=False, out_dir="."):
         """environment-finder with --merge / --hicseq / --trim (mc_env_find_ex)."""

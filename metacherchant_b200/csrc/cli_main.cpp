@@ -321,8 +321,15 @@ int run_environment_finder(const std::vector<std::string>& rest, const Args& lau
     MC(mc_env_find_ex(ctx, solid, seqs.data(), merge ? nullptr : names.data(), n, hic_seqs.empty() ? nullptr : hic_seqs.data(), (int)hic_seqs.size(),
                       (int)k, (int)coverage, max_kmers, max_radius, both ? 1 : 0, (int)chunk_len, merge ? 1 : 0, trim ? 1 : 0,
                       a.str("output").c_str(), found.data()));
-    for (int i = 0; i < (merge ? 1 : n); i++)
-        if (!found[(size_t)i]) info("Could not find any k-mers of the target gene in the input, halting.");
+    {
+        std::vector<long long> ext((size_t)std::max(n, 1), -1);
+        int n_ext = 0;
+        MC(mc_env_extend_counts(ctx, ext.data(), (int)ext.size(), &n_ext));
+        for (int i = 0; i < (merge ? 1 : n); i++) {
+            if (!found[(size_t)i]) info("Could not find any k-mers of the target gene in the input, halting.");
+            else if (i < n_ext && ext[(size_t)i] >= 0) info("Extending endings by %lld kmers", ext[(size_t)i]);   // OneSequenceCalculator.java:291
+        }
+    }
     info("Finished processing all sequences!");
     mc_targets_free(targets);
     if (hic) mc_targets_free(hic);

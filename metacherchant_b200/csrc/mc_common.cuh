@@ -331,6 +331,7 @@ struct mc_ctx {
     uint64_t scratch_allocs = 0;        // (re)allocations of the scratch slots and chunk buffers
     size_t free_bytes_cached = 0;       // cudaMemGetInfo's answer, valid while free_bytes_epoch == arena_driver_allocs + scratch_allocs
     uint64_t free_bytes_epoch = 0;
+    std::vector<long long> last_extend_counts;   // mc_env_extend_counts: per environment of the last mc_env_find call
     // pooled timing events (McStageTimer)
     std::vector<cudaEvent_t> event_pool;
     // one kernel-attribute opt-in per context (= per device): bit i = the i-th MC_ATTR_* kernel was configured

@@ -750,7 +750,9 @@ static void run_targets(mc_ctx* ctx, const mc_table* t, const std::vector<Target
 // hash, neighbour lists, chain ranks: mc_unitig.cu) is taken in turns (one stream per context), so it overlaps the other
 // workers' host stages.
 static void write_environments(mc_ctx* ctx, const std::vector<KmerMap>& subs, const std::vector<int>& found,
-                               const std::vector<std::vector<std::string>>& gene_seqs, int k, int chunk_len, const std::vector<std::string>& prefixes) {
+                               const std::vector<std::vector<std::string>>& gene_seqs, int k, int chunk_len, const std::vector<std::string>& prefixes,
+                               const mc_table* table = nullptr, int min_cov = 0) {
+    ctx->last_extend_counts.assign(subs.size(), -1);
     std::vector<size_t> todo;
     for (size_t i = 0; i < subs.size(); i++)
         if (found[i]) todo.push_back(i);   // else: "Could not find any k-mers of the target gene in the input, halting."
@@ -764,10 +766,13 @@ static void write_environments(mc_ctx* ctx, const std::vector<KmerMap>& subs, co
         { EnvTrace tr("subgraph order"); ord = sub.order(); }
         { EnvTrace tr("write env.txt/graph.txt"); write_environment(sub, ord, prefixes[job]); }
         { EnvTrace tr("unitig input"); unitig_input_from_subgraph(sub, ord, gene_seqs[job], k, in); }
+        in.table = table;
+        in.min_cov = min_cov;
         {
             std::lock_guard<std::mutex> turn(device_turn);
             EnvTrace tr("unitig nodes (device)");
             mc_unitig_nodes(ctx, in, nodes);
+            ctx->last_extend_counts[job] = nodes.extend_count;
         }
         Graph g;
         if (nodes.regular && !getenv("MC_HOST_UNITIGS")) {
@@ -812,7 +817,7 @@ extern "C" int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const*
             if (found_out) found_out[i] = found[i];
         {
             EnvTrace tr("environments -> files (wall)");
-            write_environments(ctx, subgraphs, found, gene_seqs, k, chunk_len, prefixes);
+            write_environments(ctx, subgraphs, found, gene_seqs, k, chunk_len, prefixes, t, min_cov);
         }
         EnvTrace::report();
         return MC_OK;
@@ -820,6 +825,18 @@ extern "C" int mc_env_find_ex(mc_ctx* ctx, const mc_table* t, const char* const*
         mc_set_error(e.what());
         return e.code;
     }
+}
+
+// "Extending endings by N kmers" (OneSequenceCalculator.java:291) of every environment of the last mc_env_find(_ex) call on this
+// context, in the order of its targets (-1: no environment was built for that target)
+extern "C" int mc_env_extend_counts(mc_ctx* ctx, long long* out, int cap, int* n) {
+    if (!ctx || !n || (cap && !out)) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    *n = (int)ctx->last_extend_counts.size();
+    for (int i = 0; i < *n && i < cap; i++) out[i] = ctx->last_extend_counts[(size_t)i];
+    return MC_OK;
 }
 
 extern "C" int mc_env_find(mc_ctx* ctx, const mc_table* t, const char* const* seqs, const char* const* names, int n_targets, int k, int min_cov,

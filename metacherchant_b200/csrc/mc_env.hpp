@@ -32,6 +32,10 @@ struct McUnitigInput {
     std::vector<int32_t> counts;            // coverage of env k-mer i (summed over environments in multi mode)
     std::vector<uint64_t> gene_windows;     // sorted codes of every k-window of the target(s), forward strand
     std::vector<uint64_t> colors;           // multi mode: bitmask/hash of the set of environments holding k-mer i (else empty)
+    // extendEnvironment's log line (OneSequenceCalculator.java:265-295): with a table, the stage also counts the environment k-mers
+    // that have exactly ONE solid neighbour outside the environment ("Extending endings by N kmers")
+    const mc_table* table = nullptr;
+    int min_cov = 0;
     bool order_by_nucleotide = false;       // neighbour lists in A,G,C,T order of the appended base (MultiSequenceCalculator.java:90-99)
                                             // instead of ascending node id (OneSequenceCalculator.java:406-418)
 };
@@ -47,6 +51,7 @@ struct McUnitigNodes {
     // alive node = head of a chain, in node-id order.  `regular` = the environment has no palindromic k-mer, no start-to-own-
     // start link and no cyclic chain; only then are these arrays authoritative (the corner cases keep the literal host sweep,
     // whose outcome depends on the reference's sweep order).
+    long long extend_count = -1;            // see McUnitigInput.table; -1 = not computed
     bool regular = false;
     std::vector<int32_t> u_node;            // alive node id (the chain's head)
     std::vector<int32_t> u_rc;              // its reverse-complement partner after all merges (tail of the chain ^ 1)

@@ -217,6 +217,25 @@ __global__ void __launch_bounds__(256) k_unitig_fill(uint32_t n2, int k, const u
     }
 }
 
+// extendEnvironment (src/algo/OneSequenceCalculator.java:265-295) changes nothing in the environment (`cont = kmer`, :276) but logs how
+// many of its k-mers have exactly one solid neighbour OUTSIDE the environment: 8 lanes per environment k-mer (allNeighbors: left
+// and right neighbours of the k-mer as printed), membership through the node hash (it holds both strands), coverage through the
+// count table.
+__global__ void __launch_bounds__(256) k_extend_count(NodeHash h, const uint64_t* __restrict__ kmers, uint32_t n, int k, McTableDev table, int min_cov,
+                                                     unsigned long long* __restrict__ out) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = gt >> 3, s = gt & 7;
+    const int lane = threadIdx.x & 31;
+    bool outside_solid = false;
+    if (i < n) {
+        const uint64_t kmask = (1ULL << (2 * k)) - 1, kmer = kmers[i], nuc = s >> 1;
+        const uint64_t x = (s & 1) ? (((kmer << 2) | nuc) & kmask) : ((nuc << (2 * k - 2)) | (kmer >> 2));
+        if (node_lookup(h, x) < 0 && node_lookup(h, mc_revcomp(x, k)) < 0) outside_solid = mc_table_lookup(table, mc_mix62(mc_canonical(x, k))) >= min_cov;
+    }
+    const unsigned m = (__ballot_sync(0xffffffffu, outside_solid) >> (lane & ~7)) & 0xFFu;
+    if (i < n && s == 0 && __popc(m) == 1) atomicAdd(out, 1ULL);
+}
+
 void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out) {
     MC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -257,6 +276,17 @@ void mc_unitig_nodes(mc_ctx* ctx, const McUnitigInput& in, McUnitigNodes& out) {
         k_links<<<g1, 256, 0, st>>>(n2, d + o_deg, (const int32_t*)(d + o_nbr), d + o_gene, multi ? (const uint64_t*)(d + o_col) : nullptr,
                                     (int32_t*)(d + o_pred), (int32_t*)(d + o_j0), (uint32_t*)(d + o_r0));
         ctx->launches += 3;
+        out.extend_count = -1;
+        if (in.table && !multi) {
+            unsigned long long* d_ext = (unsigned long long*)(d + o_flags) + 1;   // (the flag block is zeroed again before the assembly uses it)
+            MC_CUDA(cudaMemsetAsync(d_ext, 0, sizeof(unsigned long long), st));
+            k_extend_count<<<(unsigned)(((uint64_t)n * 8 + 255) / 256), 256, 0, st>>>(h, (const uint64_t*)(d + o_kmers), n, in.k, in.table->dev, in.min_cov, d_ext);
+            MC_LAUNCH(ctx);
+            unsigned long long ext = 0;
+            MC_CUDA(cudaMemcpyAsync(&ext, d_ext, sizeof ext, cudaMemcpyDeviceToHost, st));
+            MC_CUDA(cudaStreamSynchronize(st));
+            out.extend_count = (long long)ext;
+        }
         int rounds = 1;
         while ((1ull << rounds) < (uint64_t)n2 + 1) rounds++;
         rounds += 1;

@@ -1666,6 +1666,25 @@ int orc_reads_classifier(const orc_table* g, const char* reads1, const char* rea
     });
 }
 
+// "Extending endings by N kmers" (OneSequenceCalculator.java:291) for every target of a FASTA, in order (-1: no seed k-mer)
+int orc_env_extend_counts(const orc_table* t, const char* seq_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
+                          long long* out, int cap) {
+    int n = -1;
+    guarded([&] {
+        RichFasta rf = rich_fasta_read(seq_fasta);
+        n = (int)rf.dnas.size();
+        for (size_t i = 0; i < rf.dnas.size() && (int)i < cap; i++) {
+            EnvCalc c{t, {rf.dnas[i]}, k, min_cov, both_dirs != 0, 1, {max_kmers, max_radius}, {}, false, 0, {}, false};
+            c.build_environment();
+            if (c.failed) { out[i] = -1; continue; }
+            c.extend_environment();
+            out[i] = c.extend_additions;
+        }
+        return 0;
+    });
+    return n;
+}
+
 // test surface: the Jaccard cell text (tests/test_host_logic.py compares three independent implementations)
 void orc_java_format_6_2f(float v, char* out) {
     const std::string s = java_format_6_2f(v);

@@ -99,6 +99,9 @@ long orc_classify_bytes(const orc_table* graph, const uint8_t* buf, size_t len, 
 int orc_reads_classifier(const orc_table* graph, const char* reads1, const char* reads2, double z, double found_threshold, int correction,
                          const char* out_dir, long counts[4]);
 
+// N of "Extending endings by N kmers" (src/algo/OneSequenceCalculator.java:265-295) per target; returns the number of targets
+int orc_env_extend_counts(const orc_table* t, const char* seq_fasta, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int both_dirs,
+                          long long* out, int cap);
 void orc_java_format_6_2f(float v, char* out);   // String.format("%6.2f ", v); out: room for 48 characters
 
 // CPU baseline of the environment stage (bench.py only): one OneSequenceCalculator per target on `threads` pool workers

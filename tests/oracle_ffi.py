@@ -71,6 +71,7 @@ class Oracle:
         L.orc_classify_bytes.restype = C.c_long
         L.orc_classify_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_reads_classifier.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_char_p, C.POINTER(C.c_long)]
+        L.orc_env_extend_counts.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int]
         L.orc_bench_env.restype = C.c_double
         L.orc_bench_env.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_char_p,
                                     C.POINTER(C.c_int)]
@@ -243,6 +244,14 @@ class OracleTable:
         self.o.check(self.o.lib.orc_reads_classifier(self.h, reads1.encode(), reads2.encode() if reads2 else None, z, found_threshold, int(correction),
                                                      out_dir.encode(), counts))
         return list(counts)
+
+    def extend_counts(self, seq_fasta, min_cov, max_kmers, max_radius, both_dirs, cap=1024):
+        out = (C.c_longlong * cap)()
+        n = self.o.lib.orc_env_extend_counts(self.h, seq_fasta.encode(), self.k, min_cov, -1 if max_kmers is None else max_kmers,
+                                             -1 if max_radius is None else max_radius, int(both_dirs), out, cap)
+        if n < 0:
+            raise OracleError(self.o.err())
+        return [int(out[i]) for i in range(min(n, cap))]
 
     def print_kmers(self, threshold, out_file, stat_file=None):
         return self.o.check(self.o.lib.orc_print_kmers(self.h, threshold, out_file.encode(), stat_file.encode() if stat_file else None))

@@ -38,6 +38,8 @@ def test_environment_finder_cli(oracle, tmp_path):
     o.count_file(str(tmp_path / "b.fq"))
     assert f"Hashtable size: {o.size()} kmers" in r.stderr
     assert o.env_find(str(tmp_path / "genes.fa"), 2, 300, None, False, 10, str(tmp_path / "orc")) == 2
+    for n_ext in o.extend_counts(str(tmp_path / "genes.fa"), 2, 300, None, False):
+        assert f"Extending endings by {n_ext} kmers" in r.stderr
     for gene in ("geneA", "geneB"):
         for f in FILES:
             assert (tmp_path / "out" / gene / f).read_bytes() == (tmp_path / "orc" / gene / f).read_bytes(), (gene, f)

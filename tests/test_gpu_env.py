@@ -72,6 +72,8 @@ def test_environment_files_identical_to_oracle(ctx, oracle, tmp_path, k, both, l
     found = ctx.find_environments(solid, [t[1] for t in targets], [t[0] for t in targets], min_cov=2, max_kmers=max_kmers, max_radius=max_radius,
                                   both_dirs=both, chunk_len=20, out_dir=tmp_path / "gpu")
     assert sum(found) == n
+    # "Extending endings by N kmers" (OneSequenceCalculator.java:291)
+    assert ctx.extend_counts() == o.extend_counts(str(fa), 2, max_kmers, max_radius, both)
     for name, ok in zip(("gene one", "second", "absent"), found):
         if ok:
             same_files(str(tmp_path / "gpu" / name), str(tmp_path / "orc" / name))
