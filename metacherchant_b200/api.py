@@ -73,7 +73,9 @@ class Context:
         """Device milliseconds per stage since the start of the last count call (CUDA events on the library's stream)."""
         v = (C.c_float * 8)()
         check(self.lib.mc_ctx_stage_ms_all(self.h, v))
-        return {name: v[i] for i, name in enumerate(self.STAGES)}
+        d = {name: v[i] for i, name in enumerate(self.STAGES)}
+        d["expand"] = v[7]   # super-k-mer records -> hashed keys (mc_sk.cu)
+        return d
 
     def host_ms(self):
         """Host wall milliseconds inside the same phases since the last reset (launch + synchronisation time included)."""

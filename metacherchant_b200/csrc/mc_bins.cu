@@ -515,6 +515,8 @@ static uint64_t available_device_bytes(mc_ctx* ctx) {
     return (uint64_t)ctx->free_bytes_cached + mc_arena_cached_bytes(ctx);   // blocks cached by the arena are reusable (or released on demand)
 }
 
+uint64_t mc_available_device_bytes(mc_ctx* ctx) { return available_device_bytes(ctx); }
+
 // a predicted table size is an estimate: never ask for more than 80 % of what the device can still give.  A table that cannot
 // double any more simply runs fuller (4-slot buckets probed over 8-bucket windows stay workable to a load of ~0.8; past that
 // the doubling is attempted anyway and fails with MC_ERR_NOMEM if it really does not fit).
@@ -683,6 +685,7 @@ static void apply_spill_list(mc_table* t, uint64_t sp) {
     B->used = 0;
     B->spill_used = 0;
     B->ub_sum = 0;
+    B->inst_equiv = 0;
 }
 
 static const uint64_t MC_AGG_MIN_KEYS = 1ull << 25;   // batches below this are swept directly (k_bin_count)
@@ -697,6 +700,9 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     cudaStream_t st = ctx->stream;
     const uint32_t P1 = B->P;
     const uint64_t cap1 = B->dev.cap;
+    // the caller's expectation (mc_table_expect_keys) is in k-mer INSTANCES; keys that came out of de-duplicated super-k-mer records
+    // stand for more instances than there are keys
+    const uint64_t batch_inst = std::max<uint64_t>(B->inst_equiv, batch_keys);
     uint64_t max_bin = 0;
     for (uint32_t b = 0; b < P1; b++) max_bin = std::max<uint64_t>(max_bin, std::min<uint64_t>(cur[b], cap1));
     if (max_bin == 0) return;
@@ -878,7 +884,7 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 // The first batch of a stream over-predicts most (everything is new): it is trusted for 4 batches only; the
                 // second batch already shows the marginal rate and the table is then grown to its final size.
                 double batches_left = 1.0;
-                if (t->expect_instances > t->seen_instances + batch_keys) batches_left = (double)(t->expect_instances - t->seen_instances) / (double)batch_keys;
+                if (t->expect_instances > t->seen_instances + batch_inst) batches_left = (double)(t->expect_instances - t->seen_instances) / (double)batch_inst;
                 if (t->stream_flushes == 0) batches_left = std::min(batches_left, 4.0);
                 const double fresh = (double)h_c[MC_CNT_OVF_KEYS] * ((double)batch_keys / (double)g.keys) * batches_left;
                 const double predicted = (double)keys_before + fresh;
@@ -939,12 +945,13 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     for (int j = 0; j < RING; j++)
         if (pend[j].live) examine(pend[j], h_ring + (size_t)j * MC_STATUS_WORDS);
     if (overlap) MC_CUDA(cudaStreamSynchronize(s2));
-    t->seen_instances += batch_keys;
+    t->seen_instances += batch_inst;
     t->stream_flushes++;
 }
 
 void mc_table_flush(mc_table* t) {
     McBatch* B = t->batch;
+    if (B && B->sk_nb && !B->sk_flushing && B->sk_kmers) mc_sk_flush(t);   // pending super-k-mer records -> key bins / table (mc_sk.cu)
     if (!B || !B->dev.keys || B->used == 0) return;
     mc_ctx* ctx = t->ctx;
     MC_CUDA(cudaSetDevice(ctx->device));
@@ -1048,6 +1055,7 @@ void mc_table_flush(mc_table* t) {
 void mc_batch_release(mc_table* t) {
     if (!t->batch) return;
     mc_table_flush(t);
+    mc_sk_release(t);
     batch_free_buffers(t->ctx, t->batch);
     delete t->batch;
     t->batch = nullptr;
@@ -1071,6 +1079,9 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "agg" && value >= -1 && value <= 1) ctx->tune_agg = (int)value;
     else if (n == "keep_stage_ms" && value >= 0 && value <= 1) ctx->keep_stage_ms = (int)value;
     else if (n == "scatter_tma" && value >= 0 && value <= 1) ctx->tune_scatter_tma = (int)value;
+    else if (n == "superkmers" && value >= 0 && value <= 1) ctx->tune_superkmers = (int)value;
+    else if (n == "sk_bits" && value >= -1 && value <= MC_SK_MAX_BITS) ctx->tune_sk_bits = (int)value;
+    else if (n == "sk_cap" && value >= 0 && value <= (1ll << 30)) ctx->tune_sk_cap = (uint64_t)value;
     else if (n == "flush_overlap" && value >= 0 && value <= 1) ctx->tune_flush_overlap = (int)value;
     else if (n == "extract_tma" && value >= 0 && value <= 1) ctx->tune_extract_tma = (int)value;
     else if (n == "defer_flush" && value >= 0 && value <= 1) ctx->tune_defer_flush = (int)value;

@@ -265,6 +265,35 @@ struct McBinsDev {
     unsigned long long* spill_cursor;   // &cursors[P] for the first level; shared by all sub-bin groups of the second level
 };
 
+// --------------------------------------------------------------------------------------------
+// Super-k-mer front end (mc_sk.cu).  For k >= 22 the extractor does not emit one hashed key per k-mer: it cuts every run of valid
+// bases into SUPER-K-MERS -- maximal stretches of consecutive k-mers whose window minimum (the smallest hashed canonical m-mer among
+// the W = k - m + 1 m-mers of the k-mer) falls into the same minimizer bin -- and appends each as one 16-byte record to that bin.
+// A k-mer and its reverse complement hold the same canonical m-mers, so every instance of a canonical k-mer lands in the same bin,
+// and identical stretches of the sequenced genomes give identical records: at flush time a bin is de-duplicated in shared memory
+// (record -> multiplicity) before its records are unpacked into (hashed k-mer, weight) updates.
+//
+//   record (128 bits):  [122,128) n = k-mers in the record (1 .. MC_SK_NMAX)
+//                       [0,122)   bases, 2 bits each, first base highest: base i at bit 2 * (60 - i); unused low bits are zero
+//   k-mer j of a record = (bases >> (122 - 2k - 2j)) & (4^k - 1), the reference's packing (ShortKmer.java:68-71)
+// --------------------------------------------------------------------------------------------
+#define MC_SK_MIN_K 22
+#define MC_SK_MAX_BITS 18
+struct McSkDev {
+    uint4* recs;                    // NB * cap records
+    unsigned long long* cursors;    // [NB]: (k-mers << 32 | records) appended to the bin (attempts: may exceed cap);
+                                    // [NB] spill records, [NB + 1] spill k-mers, [NB + 2] k-mers of the current extractor launch
+    uint4* spill;                   // records of full bins
+    uint64_t cap;                   // records per bin
+    uint64_t spill_cap;
+    uint32_t nb_mask;               // NB - 1
+    uint32_t n_max;                 // k-mers per record: min(62 - k, 33)
+    unsigned int* flags;            // MC_FLAG_OVERFLOW: the spill list is full too (the host redoes the chunk with flat keys)
+};
+__host__ __device__ __forceinline__ int mc_sk_window(int k) { return k >= 30 ? 20 : 12; }   // W; m = k - W + 1
+// the m-mers are rolled in 32-bit registers (m <= 16) and must be long enough to spread over the bins (m >= 11): k in [22,27] or [30,31]
+__host__ __device__ __forceinline__ bool mc_sk_supported(int k) { const int m = k - mc_sk_window(k) + 1; return k >= MC_SK_MIN_K && k <= 31 && m >= 11 && m <= 16; }
+
 #define MC_MAX_XCHG_RANKS 16
 struct McBinDst {   // per-bin destination override of k_bin_scatter (owner groups written straight into peer memory)
     uint64_t* base[MC_MAX_XCHG_RANKS];
@@ -276,7 +305,7 @@ struct McBinDst {   // per-bin destination override of k_bin_scatter (owner grou
 // --------------------------------------------------------------------------------------------
 // host-side objects behind the opaque handles
 // --------------------------------------------------------------------------------------------
-enum { MC_ST_PARSE = 0, MC_ST_EXTRACT = 1, MC_ST_GROW = 2, MC_ST_SCATTER = 3, MC_ST_COUNT = 4, MC_ST_FILTER = 5, MC_N_STAGES = 8 };
+enum { MC_ST_PARSE = 0, MC_ST_EXTRACT = 1, MC_ST_GROW = 2, MC_ST_SCATTER = 3, MC_ST_COUNT = 4, MC_ST_FILTER = 5, MC_ST_EXPAND = 7, MC_N_STAGES = 8 };
 struct McPendingTimer { int stage; cudaEvent_t a, b; };
 struct mc_ctx {
     int device = 0;
@@ -307,6 +336,10 @@ struct mc_ctx {
     int tune_flush_overlap = 0;      // aggregated flush: scatter2(g + 1) on aux_stream concurrent with agg(g), one CTA per SM each
                                      // (measured: each kernel slows down 1.5x at half occupancy, nothing is gained: profiles/r2_NOTES.md)
     int tune_stage_timing = 1;       // 0: McStageTimer records nothing (four CUDA API calls less per kernel launch)
+    int tune_superkmers = 0;         // 1 (and k supported): the extractor emits super-k-mer records into minimizer bins.  OFF: measured 3.3x slower
+                                     // than the flat path at cfg2 (509 vs 153 ms per step, profiles/r2_NOTES.md section 6); kept for the parity tests
+    int tune_sk_bits = -1;           // log2 of the number of minimizer bins (-1: by input size)
+    uint64_t tune_sk_cap = 0;        // records per minimizer bin (0: by input size) -- tests force spills with tiny bins
     int tune_scatter_tma = 1;        // bin runs leave the sorted tile through bulk copies (cp.async.bulk) instead of per-sector stores
     int keep_stage_ms = 0;           // 1: mc_count_* do not reset the stage timers (a step made of several count calls)
     int sm_count = 148;
@@ -337,7 +370,7 @@ struct mc_ctx {
     // one kernel-attribute opt-in per context (= per device): bit i = the i-th MC_ATTR_* kernel was configured
     uint32_t attr_done = 0;
 };
-enum { MC_ATTR_EXTRACT = 0, MC_ATTR_SCATTER = 8, MC_ATTR_SCATTER2 = 9, MC_ATTR_AGG = 10, MC_ATTR_MISC = 11 };
+enum { MC_ATTR_EXTRACT = 0, MC_ATTR_SCATTER = 8, MC_ATTR_SCATTER2 = 9, MC_ATTR_AGG = 10, MC_ATTR_MISC = 11, MC_ATTR_EXTRACT_SK = 12 /* .. 23 */, MC_ATTR_SK_EXPAND = 24 };
 static inline bool mc_attr_once(mc_ctx* ctx, int bit) {   // true the first time `bit` is asked for on this context
     if (ctx->attr_done & (1u << bit)) return false;
     ctx->attr_done |= 1u << bit;
@@ -389,6 +422,14 @@ struct McBatch {
     uint64_t capacity = 0;      // total keys the batch is meant to hold (P * cap has slack on top)
     uint64_t used = 0;          // keys scattered so far (upper bound: includes sentinels and foreign-shard keys)
     uint64_t spill_used = 0;
+    // super-k-mer bins in front of the key bins (mc_sk.cu)
+    McSkDev sk{};
+    uint32_t sk_nb = 0;                 // 0: not allocated
+    uint64_t sk_kmers = 0;              // k-mer instances held by the records (exact)
+    uint64_t sk_records_est = 0;        // records appended so far (estimated from the bytes seen; the exact figure is on the device)
+    uint64_t sk_room = 0;               // records the bins were sized for
+    bool sk_flushing = false;           // mc_sk_flush is feeding the key bins: a nested mc_table_flush leaves the records alone
+    uint64_t inst_equiv = 0;            // k-mer instances the keys in the key bins stand for (de-duplicated records weigh more than one)
     uint64_t ub_sum = 0, last_ub = 0;   // what the callers RESERVED for those scatters (worst case per chunk): used / ub_sum is the input's
                                         // real k-mer density, which plans the next chunk better than its worst case
 };
@@ -398,6 +439,13 @@ void mc_batch_reserve(mc_table* t, uint64_t ub, uint64_t total_hint);
 void mc_batch_scatter(mc_table* t, const uint64_t* d_flat, uint64_t n);
 // apply every pending update to the table (growing it as needed) and keep the buffers for reuse
 void mc_table_flush(mc_table* t);
+// super-k-mer bins (mc_sk.cu): room for a chunk of at most ub_kmers k-mer instances (false: use flat keys for this chunk);
+// roll a failed chunk back; unpack every pending record into the key bins / the table
+bool mc_sk_reserve(mc_table* t, uint64_t ub_kmers, uint64_t total_hint);
+void mc_sk_snapshot(mc_table* t);
+void mc_sk_rollback(mc_table* t);
+void mc_sk_flush(mc_table* t);
+void mc_sk_release(mc_table* t);
 // flush + release the batch buffers
 void mc_batch_release(mc_table* t);
 void mc_table_grow_to(mc_table* t, int new_q);   // timed rehash into 2^new_q buckets

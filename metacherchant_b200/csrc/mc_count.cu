@@ -44,6 +44,7 @@ struct McExtractArgs {
     uint64_t* out_keys;       // flat hashed keys (sentinel-padded)
     unsigned long long* out_cursor;
     int use_tma;              // stage the warps' record spans with bulk copies + mbarriers (0: per-lane 16-byte loads)
+    McSkDev sk;               // super-k-mer mode (k_extract<.., W > 0>): records go to these minimizer bins, out_keys is unused
 };
 
 __device__ __forceinline__ bool is_iupac(uint8_t c) {
@@ -158,7 +159,135 @@ __device__ __forceinline__ McRollOut ex_roll(uint64_t seq, uint64_t qual, uint32
     return o;
 }
 
-template <bool FASTA, int PARTS>
+// ---- super-k-mer mode ------------------------------------------------------------------------------------------------------
+// One finished super-k-mer -> its minimizer bin (or the spill list when the bin is full).  r0 = the first k-mer (forward strand),
+// ext = the n - 1 bases that follow it (first one highest).  Not inlined: lanes finish records at different steps, the call sits
+// behind a divergent branch and should stay out of the rolling loop's instruction footprint.
+struct McSkSink {   // what sk_emit needs of McSkDev, passed by value (registers): a reference would put the struct on the local stack
+    uint4* recs;
+    unsigned long long* cursors;
+    uint4* spill;
+    unsigned int* flags;
+    uint32_t cap, spill_cap, nb_mask;
+};
+__device__ __noinline__ void sk_emit(McSkSink o, uint32_t bin, uint64_t r0, uint64_t ext, uint32_t n, int k) {
+    if (o.cap == 0xFFFFFFF0u) return;   // EXPERIMENT: no emission
+    const int s0 = 122 - 2 * k;                      // 58 .. 78 for k in [22, 32]
+    uint64_t hi = s0 >= 64 ? r0 << (s0 - 64) : r0 >> (64 - s0);
+    uint64_t lo = s0 >= 64 ? 0ULL : r0 << s0;
+    const uint32_t e = n - 1;
+    if (e) {
+        const int s1 = 2 * (61 - k - (int)e);        // >= 0: offset of the last base
+        hi |= s1 >= 64 ? ext << (s1 - 64) : (s1 ? ext >> (64 - s1) : 0ULL);
+        lo |= s1 >= 64 ? 0ULL : ext << s1;
+    }
+    hi |= (uint64_t)n << 58;
+    const uint4 rec = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    const unsigned long long at = atomicAdd(&o.cursors[bin], ((unsigned long long)n << 32) | 1ULL);
+    const uint32_t pos = (uint32_t)at;
+    if (pos < o.cap) {
+        o.recs[(uint64_t)bin * o.cap + pos] = rec;
+    } else {
+        const uint32_t nb = o.nb_mask + 1;
+        const unsigned long long sp = atomicAdd(&o.cursors[nb], 1ULL);
+        atomicAdd(&o.cursors[nb + 1], (unsigned long long)n);
+        if (sp < o.spill_cap) o.spill[sp] = rec;
+        else atomicOr(o.flags, MC_FLAG_OVERFLOW);   // the host withdraws this chunk and redoes it with flat keys
+    }
+}
+// 32-bit order-and-bin hash of a canonical m-mer (m <= 16: the m-mer itself fits 32 bits)
+__device__ __forceinline__ uint32_t sk_mhash(uint32_t cm) {
+    uint32_t x = cm * 0x9E3779B1u;
+    return x ^ (x >> 15);
+}
+__device__ __forceinline__ uint32_t sk_bin_of(uint32_t mn, uint32_t nb_mask) { return ((mn * 0x85EBCA6Bu) >> 13) & nb_mask; }
+
+// The rolling pass of ex_roll with the k-mer hash replaced by the minimizer machinery.  The loop is unrolled W times so that every
+// access to the register ring below has a static index; the iteration count is the same for all lanes of a warp (each starts at its
+// own s_lo), so the unrolled position is warp-uniform.
+//
+// Window minimum in ~3 operations per base (van Herk / Gil-Werman): positions are cut into blocks of W.  While block B is being
+// read, ring[0..u] holds its raw m-mer hashes and ring[u+1..W-1] the SUFFIX minima of block B - 1; the minimum over the last W
+// m-mers is min(prefix minimum of block B up to u, ring[u + 1]).  At the end of a block one backward pass turns its raw values into
+// suffix minima.  An m-mer that is not inside a run enters as 0xFFFFFFFF; a k-mer is complete when the run is >= k = m + W - 1 long,
+// and by then the last W entries all belong to it.
+template <bool FASTA, bool STAGED, int W>
+__device__ __forceinline__ McRollOut ex_roll_sk(uint64_t seq, uint64_t qual, uint32_t cls_saddr, uint32_t s_lo, uint32_t j_end, uint32_t own_hi, uint32_t len,
+                                                int k, uint64_t kmask, uint32_t qoff, uint32_t qspan, const McSkDev& skd) {
+    McRollOut o{0, 0, 0, 0};
+    const McSkSink sk{skd.recs, skd.cursors, skd.spill, skd.flags, (uint32_t)skd.cap, (uint32_t)min(skd.spill_cap, (uint64_t)0xFFFFFFFFu), skd.nb_mask};
+    const uint32_t n_max = skd.n_max;
+    uint64_t fw = 0;
+    uint32_t run = 0;
+    const int m = k - W + 1;                         // 11 .. 16
+    const uint32_t mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    const int mshift = 2 * m - 2;
+    uint32_t mf = 0, mr = 0;
+    uint32_t ring[W];
+#pragma unroll
+    for (int u = 0; u < W; u++) ring[u] = 0xFFFFFFFFu;
+    uint32_t prefix = 0xFFFFFFFFu;
+    uint64_t r0 = 0, ext = 0;
+    uint32_t cur_n = 0, cur_bin = 0;
+    uint32_t j = s_lo;
+    while (j < j_end) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            if (j < j_end) {
+                const uint32_t c = STAGED ? ex_lds_u8((uint32_t)seq + j) : (uint32_t) __ldg((const uint8_t*)seq + j);
+                const uint32_t cls = ex_lds_u8(cls_saddr + c);
+                uint32_t split = cls & EX_CLS_SPLIT;
+                if (!FASTA) {
+                    const uint32_t q = STAGED ? ex_lds_u8((uint32_t)qual + j) : (uint32_t) __ldg((const uint8_t*)qual + j);
+                    const uint32_t qd = q - qoff;
+                    o.flags |= (cls & EX_CLS_BAD) | ((split == 0 && qd > qspan) ? EX_FLAG_QUAL : 0u);
+                    split |= ((qd & 63u) == 0) ? 1u : 0u;
+                    if (j < own_hi) {
+                        o.good += split ? 0u : 1u;
+                        o.splits += (split && j + 1 != len) ? 1u : 0u;
+                    }
+                } else {
+                    o.flags |= cls;
+                }
+                const uint32_t b = cls & 3u;
+                fw = ((fw << 2) | b) & kmask;
+                mf = ((mf << 2) | b) & mmask;
+                mr = (mr >> 2) | ((3u - b) << mshift);
+                run = split ? 0u : run + 1u;
+                const uint32_t mh = run >= (uint32_t)m ? sk_mhash(min(mf, mr)) : 0xFFFFFFFFu;
+                prefix = u == 0 ? mh : min(prefix, mh);
+                const uint32_t mn = u == W - 1 ? prefix : min(prefix, ring[u == W - 1 ? 0 : u + 1]);
+                ring[u] = mh;
+                if (u == W - 1) {
+#pragma unroll
+                    for (int x = W - 2; x >= 0; x--) ring[x] = min(ring[x], ring[x + 1]);
+                }
+                if (run >= (uint32_t)k) {
+                    const uint32_t bin = sk_bin_of(mn, sk.nb_mask);
+                    if (cur_n != 0 && bin == cur_bin && cur_n < n_max) {
+                        ext = (ext << 2) | b;
+                        cur_n++;
+                    } else {
+                        if (cur_n) sk_emit(sk, cur_bin, r0, ext, cur_n, k);
+                        r0 = fw;
+                        ext = 0;
+                        cur_n = 1;
+                        cur_bin = bin;
+                    }
+                    o.emitted++;
+                } else if (cur_n) {   // the run ended
+                    sk_emit(sk, cur_bin, r0, ext, cur_n, k);
+                    cur_n = 0;
+                }
+                j++;
+            }
+        }
+    }
+    if (cur_n) sk_emit(sk, cur_bin, r0, ext, cur_n, k);
+    return o;
+}
+
+template <bool FASTA, int PARTS, int W>
 __global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     constexpr int RPW = 32 / PARTS;   // records per warp and step
@@ -236,39 +365,65 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
             if (part == 0) mc_report_error(a.header, MC_PE_FQ_LEN, rec.seq_off);
             skip = true;
         }
+        const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(s_cls);
+        bool predrop = false;
+        if (W > 0 && FASTA) {
+            // records cannot be withdrawn from their bins afterwards: a FASTA record holding an N (dropped whole, FastaReader.java:58-59)
+            // is recognised before anything is emitted
+            uint32_t f = 0;
+            if (!skip) {
+                const uint32_t S0 = (len + PARTS - 1) / PARTS;
+                const uint32_t lo0 = min(len, part * S0), hi0 = min(len, lo0 + S0);
+                for (uint32_t j = lo0; j < hi0; j++) f |= s_cls[seq[j]];
+            }
+            predrop = (__ballot_sync(0xffffffffu, (f & EX_CLS_N) != 0) & group_mask) != 0;
+        }
         // ---- my share of the record -------------------------------------------------------------
-        const uint32_t nk = (!skip && len >= (uint32_t)k) ? len - k + 1 : 0;
+        const uint32_t nk = (!skip && !predrop && len >= (uint32_t)k) ? len - k + 1 : 0;
         const uint32_t S = (nk + PARTS - 1) / PARTS;
         const uint32_t s_lo = min(nk, part * S), s_hi = min(nk, s_lo + S);
         const uint32_t reserve = s_hi - s_lo;
-        const uint32_t own_hi = skip ? s_lo : (part == PARTS - 1 ? len : s_hi);          // statistics: bases [s_lo, own_hi)
-        const uint32_t j_end = skip ? s_lo : (part == PARTS - 1 ? len : (reserve ? s_hi + k - 1 : s_lo));
-        // warp-aggregated reservation of the warp's flat-key block (sum of `reserve`), laid out as McOutSlots describes
-        McOutSlots out;
-        {
-            const uint32_t act = __ballot_sync(0xffffffffu, reserve > 0);
-            out.stride = __popc(act);
-            out.rows = act ? __reduce_min_sync(0xffffffffu, reserve ? reserve : 0xFFFFFFFFu) : 0u;
-            const uint32_t rest = reserve > out.rows ? reserve - out.rows : 0u;
-            uint32_t incl = rest;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const uint32_t warp_total = out.rows * out.stride + __shfl_sync(0xffffffffu, incl, 31);
-            unsigned long long base = 0;
-            if (lane == 0 && warp_total) base = atomicAdd(a.out_cursor, (unsigned long long)warp_total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            out.row = a.out_keys + base + __popc(act & ((1u << lane) - 1u));
-            out.tail = a.out_keys + base + (uint64_t)out.rows * out.stride + (incl - rest);
-        }
-        const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(s_cls);
+        const bool idle = skip || predrop;
+        const uint32_t own_hi = idle ? s_lo : (part == PARTS - 1 ? len : s_hi);          // statistics: bases [s_lo, own_hi)
+        const uint32_t j_end = idle ? s_lo : (part == PARTS - 1 ? len : (reserve ? s_hi + k - 1 : s_lo));
         McRollOut ro;
-        if (staged)
-            ro = ex_roll<FASTA, true>((uint64_t)__cvta_generic_to_shared(seq), (uint64_t)__cvta_generic_to_shared(qual), cls_saddr, s_lo, j_end, own_hi, len, k,
-                                      kmask, rc_shift, qoff, qspan, out);
-        else
-            ro = ex_roll<FASTA, false>((uint64_t)seq, (uint64_t)qual, cls_saddr, s_lo, j_end, own_hi, len, k, kmask, rc_shift, qoff, qspan, out);
+        if (W == 0) {
+            // warp-aggregated reservation of the warp's flat-key block (sum of `reserve`), laid out as McOutSlots describes
+            McOutSlots out;
+            {
+                const uint32_t act = __ballot_sync(0xffffffffu, reserve > 0);
+                out.stride = __popc(act);
+                out.rows = act ? __reduce_min_sync(0xffffffffu, reserve ? reserve : 0xFFFFFFFFu) : 0u;
+                const uint32_t rest = reserve > out.rows ? reserve - out.rows : 0u;
+                uint32_t incl = rest;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const uint32_t warp_total = out.rows * out.stride + __shfl_sync(0xffffffffu, incl, 31);
+                unsigned long long base = 0;
+                if (lane == 0 && warp_total) base = atomicAdd(a.out_cursor, (unsigned long long)warp_total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                out.row = a.out_keys + base + __popc(act & ((1u << lane) - 1u));
+                out.tail = a.out_keys + base + (uint64_t)out.rows * out.stride + (incl - rest);
+            }
+            if (staged)
+                ro = ex_roll<FASTA, true>((uint64_t)__cvta_generic_to_shared(seq), (uint64_t)__cvta_generic_to_shared(qual), cls_saddr, s_lo, j_end, own_hi, len, k,
+                                          kmask, rc_shift, qoff, qspan, out);
+            else
+                ro = ex_roll<FASTA, false>((uint64_t)seq, (uint64_t)qual, cls_saddr, s_lo, j_end, own_hi, len, k, kmask, rc_shift, qoff, qspan, out);
+            // (a FASTA record with an N: its k-mers are withdrawn below) -- unused slots of the reservation become sentinels
+            const bool dropped = FASTA && (__ballot_sync(0xffffffffu, (ro.flags & EX_CLS_N) != 0) & group_mask) != 0;
+            for (uint32_t e = dropped ? 0u : ro.emitted; e < reserve; e++) *out.at(e) = MC_HASH_SENTINEL;
+        } else {
+            constexpr int WW = W > 0 ? W : 12;
+            if (staged)
+                ro = ex_roll_sk<FASTA, true, WW>((uint64_t)__cvta_generic_to_shared(seq), (uint64_t)__cvta_generic_to_shared(qual), cls_saddr, s_lo, j_end, own_hi, len,
+                                                 k, kmask, qoff, qspan, a.sk);
+            else
+                ro = ex_roll_sk<FASTA, false, WW>((uint64_t)seq, (uint64_t)qual, cls_saddr, s_lo, j_end, own_hi, len, k, kmask, qoff, qspan, a.sk);
+            if (predrop) ro.flags |= EX_CLS_N;
+        }
         uint32_t emitted = ro.emitted;
         const uint32_t good = ro.good, splits = ro.splits, flags = ro.flags;
         // ---- record-level outcome ---------------------------------------------------------------
@@ -302,7 +457,6 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
         }
         if (drop) emitted = 0;   // FASTA record with an N: its k-mers are withdrawn
         st_kmers += emitted;
-        for (uint32_t e = emitted; e < reserve; e++) *out.at(e) = MC_HASH_SENTINEL;
     }
 
     // ---- block-aggregated statistics ---------------------------------------------------------
@@ -322,6 +476,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(McExtractArgs a) {
         if (s_acc[1]) atomicAdd(&a.table.counters[MC_CNT_RUNS], s_acc[1]);
         if (s_acc[2]) atomicAdd(&a.table.counters[MC_CNT_BASES], s_acc[2]);
         if (s_acc[3]) atomicAdd(&a.table.counters[MC_CNT_KMERS], s_acc[3]);
+        if (W > 0 && s_acc[3]) atomicAdd(&a.sk.cursors[a.sk.nb_mask + 3], s_acc[3]);   // k-mers of this launch (the host's chunk accounting)
     }
 }
 
@@ -415,28 +570,51 @@ static unsigned long long check_k2_errors(mc_ctx* ctx, McParseHeader* d_header, 
     return *hc;
 }
 
-template <bool FASTA, int PARTS>
+// super-k-mer mode: the extractor's error word, the k-mers it turned into records and the overflow flag of the bins, one synchronisation
+static unsigned long long sk_finish_chunk(mc_ctx* ctx, mc_table* t, McParseHeader* d_header, const uint8_t* d_buf, uint32_t n, bool* overflow) {
+    const McSkDev& sk = t->batch->sk;
+    const uint32_t nb = sk.nb_mask + 1;
+    McParseHeader* hp = (McParseHeader*)ctx->h_pinned_small;
+    unsigned long long* hc = (unsigned long long*)((uint8_t*)ctx->h_pinned_small + 512);   // [0] k-mers of this launch, [1] flag word
+    hc[0] = hc[1] = 0;
+    MC_CUDA(cudaMemcpyAsync(hp, d_header, sizeof(McParseHeader), cudaMemcpyDeviceToHost, ctx->stream));
+    MC_CUDA(cudaMemcpyAsync(hc, &sk.cursors[nb + 2], 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    MC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hp->err_packed != MC_NO_ERROR) mc_throw_parse_error(hp->err_packed, d_buf, n, ctx);
+    *overflow = ((unsigned int)hc[1] & MC_FLAG_OVERFLOW) != 0;
+    return hc[0];
+}
+
+template <bool FASTA, int PARTS, int W>
 static void launch_extract_p(mc_ctx* ctx, McExtractArgs& a) {
     const size_t smem = EX_WARPS * EX_STAGE_BYTES + 256;
     // function attributes are per device: one opt-in per context and instantiation (a process may hold contexts on several GPUs)
-    if (mc_attr_once(ctx, MC_ATTR_EXTRACT + (FASTA ? 3 : 0) + (PARTS == 1 ? 0 : PARTS == 4 ? 1 : 2)))
-        MC_CUDA(cudaFuncSetAttribute(k_extract<FASTA, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int variant = (FASTA ? 3 : 0) + (PARTS == 1 ? 0 : PARTS == 4 ? 1 : 2);
+    if (mc_attr_once(ctx, W == 0 ? MC_ATTR_EXTRACT + variant : MC_ATTR_EXTRACT_SK + (W == 20 ? 6 : 0) + variant))
+        MC_CUDA(cudaFuncSetAttribute(k_extract<FASTA, PARTS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t per_cta = (uint64_t)(32 / PARTS) * EX_WARPS;          // records per CTA step
     uint64_t blocks = ((uint64_t)a.n_records + per_cta - 1) / per_cta;
     const uint64_t cap = (uint64_t)ctx->sm_count * 4 * 4;                 // resident CTAs per SM x 4 waves
     if (blocks < 1) blocks = 1;
-    k_extract<FASTA, PARTS><<<(unsigned)std::min(blocks, cap), EX_THREADS, smem, ctx->stream>>>(a);
+    k_extract<FASTA, PARTS, W><<<(unsigned)std::min(blocks, cap), EX_THREADS, smem, ctx->stream>>>(a);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
 }
 // lanes per record: one for short reads (no context bases re-read), more when a warp's records would not fit its shared-memory
 // window or a single lane would serialise a long read
-template <bool FASTA>
-static void launch_extract(mc_ctx* ctx, McExtractArgs& a, uint32_t max_seq_len) {
+template <bool FASTA, int W>
+static void launch_extract_w(mc_ctx* ctx, McExtractArgs& a, uint32_t max_seq_len) {
     const uint32_t one = FASTA ? 380u : 170u;
-    if (ctx->tune_extract_parts == 1 || (ctx->tune_extract_parts == 0 && max_seq_len <= one)) launch_extract_p<FASTA, 1>(ctx, a);
-    else if (ctx->tune_extract_parts == 4 || (ctx->tune_extract_parts == 0 && max_seq_len <= 4 * one)) launch_extract_p<FASTA, 4>(ctx, a);
-    else launch_extract_p<FASTA, 32>(ctx, a);
+    if (ctx->tune_extract_parts == 1 || (ctx->tune_extract_parts == 0 && max_seq_len <= one)) launch_extract_p<FASTA, 1, W>(ctx, a);
+    else if (ctx->tune_extract_parts == 4 || (ctx->tune_extract_parts == 0 && max_seq_len <= 4 * one)) launch_extract_p<FASTA, 4, W>(ctx, a);
+    else launch_extract_p<FASTA, 32, W>(ctx, a);
+}
+// sk_w: 0 = flat hashed keys, else the minimizer window of the super-k-mer mode (mc_sk_window(k))
+template <bool FASTA>
+static void launch_extract(mc_ctx* ctx, McExtractArgs& a, uint32_t max_seq_len, int sk_w = 0) {
+    if (sk_w == 20) launch_extract_w<FASTA, 20>(ctx, a, max_seq_len);
+    else if (sk_w == 12) launch_extract_w<FASTA, 12>(ctx, a, max_seq_len);
+    else launch_extract_w<FASTA, 0>(ctx, a, max_seq_len);
 }
 
 #define MC_FLAT_HEAD 8192   // cursor + per-owner counters and cursors in front of the flat keys
@@ -481,7 +659,52 @@ static uint32_t count_chunk(mc_ctx* ctx, mc_table* t, const uint8_t* d_buf, uint
         a.header = P.d_header;
         a.table = t->dev;
         a.shard_id = t->shard_id;
-        {
+        bool done = false;
+        if (ctx->tune_superkmers && mc_sk_supported(t->k)) {
+            // super-k-mer records -> minimizer bins (mc_sk.cu); unpacked into hashed keys when the table is flushed
+            bool room;
+            {
+                McHostTimer ht(ctx, MC_ST_GROW);
+                room = mc_sk_reserve(t, ub + 1, total_hint);
+            }
+            if (room) {
+                McHostTimer ht(ctx, MC_ST_EXTRACT);
+                McBatch* B = t->batch;
+                a.table = t->dev;
+                a.sk = B->sk;
+                a.use_tma = ctx->tune_extract_tma;
+                a.out_keys = nullptr;
+                a.out_cursor = nullptr;
+                mc_sk_snapshot(t);
+                {
+                    McStageTimer tm(ctx, MC_ST_EXTRACT);
+                    if (fasta) launch_extract<true>(ctx, a, P.h.max_seq_len, mc_sk_window(t->k));
+                    else launch_extract<false>(ctx, a, P.h.max_seq_len, mc_sk_window(t->k));
+                }
+                // one synchronisation: the extractor's error word, the k-mers it found (counter delta) and the overflow flag of the bins
+                unsigned long long n_kmers = 0;
+                bool overflow = false;
+                try {
+                    n_kmers = sk_finish_chunk(ctx, t, a.header, d_buf, n, &overflow);
+                } catch (...) {
+                    mc_sk_rollback(t);   // the chunk's records leave the bins again: an input error applies nothing of its chunk
+                    throw;
+                }
+                if (!overflow) {
+                    B->sk_kmers += n_kmers;
+                    B->sk_records_est += (uint64_t)((double)n_kmers * 2.0 / (mc_sk_window(t->k) + 1)) + P.h.n_records;
+                    if (stream_bytes && t->expect_instances == 0 && P.h.consumed)
+                        mc_table_expect_keys(t, (uint64_t)((double)n_kmers * ((double)stream_bytes / (double)P.h.consumed)));
+                    done = true;
+                } else {
+                    // the bins AND their spill list filled up (input far from what the bins were sized for): withdraw the chunk, unpack
+                    // what the bins hold, and take this chunk through the flat-key path
+                    mc_sk_rollback(t);
+                    mc_sk_flush(t);
+                }
+            }
+        }
+        if (!done) {
             // extract -> flat hashed keys -> bins; the table itself is touched only when the batch is flushed
             {
                 McHostTimer ht(ctx, MC_ST_GROW);   // (host view: reserving / creating the batch of bins)
