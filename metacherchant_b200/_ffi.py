@@ -6,7 +6,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "csrc", "libmcgpu.so")
+# MC_B200_LIB: another BUILD of the same library (kernel A/B experiments, profiles/scripts/build_variant.sh); never a fallback
+_LIB = os.environ.get("MC_B200_LIB") or os.path.join(_HERE, "csrc", "libmcgpu.so")
 _HEADER = os.path.join(os.path.dirname(_HERE), "include", "mc_b200.h")
 
 

@@ -18,8 +18,11 @@
 #include "mc_common.cuh"
 
 #define BIN_TILE_DEFAULT 2048u  // keys per k_bin_count work unit (tunable: count_tile)
+#ifndef SC_THREADS
 #define SC_THREADS 512
 #define SC_TILE 8192u           // keys per k_bin_scatter tile (sorted by bin in shared memory)
+#define SC_MINB 2               // resident CTAs per SM the register budget is cut for
+#endif
 #define SC_KPT (SC_TILE / SC_THREADS)   // keys per thread, held in registers between the histogram and the sort
 
 void mc_resolve_timers(mc_ctx* ctx) {
@@ -243,7 +246,7 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
 }
 
 template <bool TMA>
-__global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
+__global__ void __launch_bounds__(SC_THREADS, SC_MINB) k_bin_scatter(const uint64_t* __restrict__ flat, uint64_t n, McBinsDev B, int shard_bits, uint32_t shard_id,
                                                             unsigned int* flags, McBinDst D) {
     scatter_tiles<TMA>(flat, n, B, shard_bits, shard_id, flags, D, blockIdx.x, gridDim.x);
     if (TMA) bulk_wait_read();   // shared memory must outlive the copy engine's reads
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter(const uint64_t* _
 // are read on the device (no host round trip); the spill list is shared by the whole group.  The (bin, tile) pairs are
 // one flat index space walked by a persistent grid, so the CTAs work on the same one or two bins at any time.
 template <bool TMA>
-__global__ void __launch_bounds__(SC_THREADS, 2) k_bin_scatter2(McBinsDev B1, uint32_t b0, uint32_t G, uint32_t tiles_per_bin, McBinsDev B2, unsigned int* flags) {
+__global__ void __launch_bounds__(SC_THREADS, SC_MINB) k_bin_scatter2(McBinsDev B1, uint32_t b0, uint32_t G, uint32_t tiles_per_bin, McBinsDev B2, unsigned int* flags) {
     const uint32_t P2 = 1u << B2.pbits;
     McBinDst none;
     none.use = 0;
@@ -364,7 +367,11 @@ static size_t agg_smem_bytes() { return (size_t)AGG_SLOTS * 14; }
 // COUNT_ONLY: the same aggregation, but the table is only looked up: the kernel reports how many distinct keys of these units are
 // NOT in the table yet (counters[MC_CNT_OVF_KEYS]).  Run on the first group -- 1/64 of the hash space -- it tells the host how
 // large the table must be for the whole batch before anything is inserted.
-template <bool COUNT_ONLY>
+// LANE_LOOP: every lane walks its AGG_U keys of a round in ONE loop (a lane that has placed a key goes on to its next key at once),
+// so a warp iterates max-over-lanes of the SUM of the lanes' probe counts instead of the sum over the keys of the max: at the
+// table's load the probe sequences are short (1.2 probes per key) but their maximum over 32 lanes is 4-5, and the per-key loops
+// ran with 8 of 32 lanes active on average (profiles/r2u_extract_agg.ncu-rep, SASS view).
+template <bool COUNT_ONLY, bool LANE_LOOP>
 __global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBinsDev B2, uint32_t b0, uint32_t n_units, unsigned long long* ticket) {
     extern __shared__ unsigned long long a_mem[];
     unsigned long long* s_key = a_mem;                       // hashed local key + 1, 0 = empty
@@ -414,6 +421,41 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) k_bin_agg(McTableDev t, McBins
                 const uint32_t idx = base + (AGG_U + u) * AGG_THREADS + threadIdx.x;
                 hn[u] = idx < n ? __ldcs(keys + idx) : MC_HASH_SENTINEL;
             }
+            if (LANE_LOOP) {
+                uint32_t u = 0, p = 0;
+                uint64_t key = h[0];
+                uint32_t slot = (uint32_t)key & (AGG_SLOTS - 1);
+#pragma unroll 1
+                while (u < AGG_U) {
+                    bool adv = true;
+                    if (key != MC_HASH_SENTINEL) {
+                        const unsigned long long want = key + 1;
+                        unsigned long long cur = *(volatile unsigned long long*)&s_key[slot];
+                        if (cur == 0) {
+                            cur = atomicCAS(&s_key[slot], 0ULL, want);
+                            if (cur == 0) {
+                                s_list[atomicAdd(&s_used, 1u)] = (uint16_t)slot;
+                                cur = want;
+                            }
+                        }
+                        if (cur == want) {
+                            atomicAdd(&s_cnt[slot], 1u);
+                        } else if (++p < AGG_PROBES) {
+                            slot = (slot + 1) & (AGG_SLOTS - 1);
+                            adv = false;
+                        } else {
+                            if (COUNT_ONLY) added += mc_table_lookup(t, key) < 0;
+                            else if (mc_table_add_impl<false>(t, key, 1, nullptr)) added++;
+                        }
+                    }
+                    if (adv) {
+                        u++;
+                        key = u == 1 ? h[1] : (u == 2 ? h[2] : h[3]);
+                        slot = (uint32_t)key & (AGG_SLOTS - 1);
+                        p = 0;
+                    }
+                }
+            } else
 #pragma unroll
             for (int u = 0; u < AGG_U; u++) {
                 if (h[u] == MC_HASH_SENTINEL) continue;
@@ -755,11 +797,13 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     }
     scatter_attrs(ctx);
     if (mc_attr_once(ctx, MC_ATTR_AGG)) {
-        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
-        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
+        MC_CUDA(cudaFuncSetAttribute(k_bin_agg<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes()));
     }
     int agg_per_sm = 0, sc_per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg<false>, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&agg_per_sm, k_bin_agg<false, true>, AGG_THREADS, agg_smem_bytes()) != cudaSuccess || agg_per_sm < 1) agg_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc_per_sm, k_bin_scatter2<true>, SC_THREADS, scatter_smem_bytes(P2)) != cudaSuccess || sc_per_sm < 1) sc_per_sm = 1;
     cudaGetLastError();
 
@@ -872,7 +916,8 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
                 // size the table before anything is inserted (no overflow churn, no rehash of a half-filled table)
                 {
                     McStageTimer tm(ctx, MC_ST_COUNT);
-                    k_bin_agg<true><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
+                    if (ctx->tune_agg_lane_loop) k_bin_agg<true, true><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
+                    else k_bin_agg<true, false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
                     MC_LAUNCH(ctx);
                     MC_CUDA(cudaGetLastError());
                 }
@@ -899,7 +944,8 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
             }
             {
                 McStageTimer tm(ctx, MC_ST_COUNT);
-                k_bin_agg<false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
+                if (ctx->tune_agg_lane_loop) k_bin_agg<false, true><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
+                else k_bin_agg<false, false><<<grid, AGG_THREADS, agg_smem_bytes(), st>>>(t->dev, B2, g.b0, n_units, d_ticket);
                 MC_LAUNCH(ctx);
                 // a sub-bin that was full (a heavy hitter) spilled: direct updates, length read on the device
                 k_insert_hashed_n<<<ctx->sm_count, 256, 0, st>>>(t->dev, B2.spill, B2.spill_cursor, spill2_cap);
@@ -1079,6 +1125,7 @@ extern "C" int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value)
     else if (n == "agg" && value >= -1 && value <= 1) ctx->tune_agg = (int)value;
     else if (n == "keep_stage_ms" && value >= 0 && value <= 1) ctx->keep_stage_ms = (int)value;
     else if (n == "scatter_tma" && value >= 0 && value <= 1) ctx->tune_scatter_tma = (int)value;
+    else if (n == "agg_lane_loop" && value >= 0 && value <= 1) ctx->tune_agg_lane_loop = (int)value;
     else if (n == "superkmers" && value >= 0 && value <= 1) ctx->tune_superkmers = (int)value;
     else if (n == "sk_bits" && value >= -1 && value <= MC_SK_MAX_BITS) ctx->tune_sk_bits = (int)value;
     else if (n == "sk_cap" && value >= 0 && value <= (1ll << 30)) ctx->tune_sk_cap = (uint64_t)value;

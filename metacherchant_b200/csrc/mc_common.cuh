@@ -340,6 +340,7 @@ struct mc_ctx {
                                      // than the flat path at cfg2 (509 vs 153 ms per step, profiles/r2_NOTES.md section 6); kept for the parity tests
     int tune_sk_bits = -1;           // log2 of the number of minimizer bins (-1: by input size)
     uint64_t tune_sk_cap = 0;        // records per minimizer bin (0: by input size) -- tests force spills with tiny bins
+    int tune_agg_lane_loop = 0;      // k_bin_agg: one probe loop per lane over its keys of a round (0: one loop per key, round 2's first form)
     int tune_scatter_tma = 1;        // bin runs leave the sorted tile through bulk copies (cp.async.bulk) instead of per-sector stores
     int keep_stage_ms = 0;           // 1: mc_count_* do not reset the stage timers (a step made of several count calls)
     int sm_count = 148;
