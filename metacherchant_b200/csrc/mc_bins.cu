@@ -216,15 +216,21 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
                 const unsigned long long pos = S.gbase[b];
                 if (pos + pc <= B.cap) {
                     bulk_store_s2g(B.keys + (uint64_t)b * B.cap + pos, &S.sorted[run], pc * 8u);
-                } else {   // the run crosses the end of its bin (heavy hitter or undersized batch): key by key, what fits goes to the bin, the rest spills
-                    for (uint32_t j = 0; j < pc; j++) {
-                        const uint64_t key = S.sorted[run + j];
-                        if (pos + j < B.cap) {
-                            B.keys[(uint64_t)b * B.cap + pos + j] = key;
-                        } else if (key != MC_HASH_SENTINEL) {
-                            const unsigned long long sp = atomicAdd(B.spill_cursor, 1ULL);
-                            if (sp < B.spill_cap) B.spill[sp] = key;
-                            else atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
+                } else {
+                    // the run crosses the end of its bin (heavy hitter or undersized batch): what fits goes to the bin in one bulk copy
+                    // (pos, cap and pc are even: the piece is a whole number of 16-byte granules), the rest takes the spill list with
+                    // ONE reservation for the whole remainder.  (A reservation per key -- a dependent global atomic each, issued by one
+                    // thread -- made the 3 000 repeat k-mers of cfg4, 8 % of its instances, cost more than everything else together.)
+                    const uint32_t fits = pos < B.cap ? (uint32_t)(B.cap - pos) : 0u;   // < pc
+                    if (fits) bulk_store_s2g(B.keys + (uint64_t)b * B.cap + pos, &S.sorted[run], fits * 8u);
+                    const uint32_t real = pc - (S.sorted[run + pc - 1] == MC_HASH_SENTINEL ? 1u : 0u);   // at most one pad, at the end
+                    if (real > fits) {
+                        const uint32_t rest = real - fits;
+                        const unsigned long long sp = atomicAdd(B.spill_cursor, (unsigned long long)rest);
+                        if (sp + rest <= B.spill_cap) {
+                            for (uint32_t j = 0; j < rest; j++) B.spill[sp + j] = S.sorted[run + fits + j];
+                        } else {
+                            atomicOr(flags, MC_FLAG_OVERFLOW);   // unreachable: the host keeps spill_free >= keys per scatter
                         }
                     }
                 }
@@ -758,7 +764,9 @@ static void flush_aggregated(mc_table* t, const std::vector<unsigned long long>&
     cap2 = (cap2 + 15) & ~15ull;
     const uint64_t seg_keys = ctx->tune_segment_keys ? std::min<uint64_t>(ctx->tune_segment_keys, MC_FLUSH_SEGMENT) : MC_FLUSH_SEGMENT;
     const uint32_t g_max = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(P1, seg_keys / max_bin));
-    const uint64_t spill2_cap = (uint64_t)g_max * max_bin + 1024;
+    // (sized by the segment, not by g_max * max_bin: the product moves by a few MiB from one batch to the next, and a request just above
+    // the cached block of the previous flush would go to the driver -- one cudaMalloc of 1 GiB inside a step)
+    const uint64_t spill2_cap = (g_max == P1 ? (uint64_t)g_max * max_bin : std::max<uint64_t>(seg_keys, max_bin)) + 1024;
     // Two staging slots: while k_bin_agg works on the sub-bins of group g (slot g & 1) on the main stream, k_bin_scatter2 fills the
     // slot of group g + 1 on the auxiliary stream.  The two kernels lean on different pipes (the scatter on the shared-memory pipe and
     // its barriers, the aggregation on instruction issue), so run side by side, one CTA per SM each, they finish sooner than one after

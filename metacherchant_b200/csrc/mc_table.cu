@@ -63,7 +63,14 @@ static int q_for_keys(uint64_t keys, int shard_bits) { return mc_q_for_keys(keys
 // the same block size; a cached block is reused when it is at most 1/8 larger than the request.
 static size_t arena_round(size_t bytes) {
     if (bytes < 512) bytes = 512;
-    const size_t g = bytes >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;
+    size_t g = bytes >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;
+    // large blocks: 1/32 of the size's power of two, so that requests that drift by a few per cent between calls (bins and staging
+    // sized from the data seen so far) keep mapping to the same block size and are served from the cache
+    if (bytes >= ((size_t)64 << 20)) {
+        int lg = 63;
+        while (!(bytes >> lg)) lg--;
+        g = (size_t)1 << (lg - 5);
+    }
     return (bytes + g - 1) / g * g;
 }
 static void arena_release_all_locked(mc_ctx* ctx) {
@@ -105,6 +112,7 @@ void* mc_dev_alloc(mc_ctx* ctx, size_t bytes, const char* what) {
     }
     ctx->arena_driver_allocs++;
     ctx->arena_live[p] = need;
+    if (getenv("MC_TRACE")) fprintf(stderr, "[mc trace] arena: cudaMalloc of %.1f MiB for %s (driver call %llu)\n", (double)need / (1 << 20), what, (unsigned long long)ctx->arena_driver_allocs);
     return p;
 }
 void mc_dev_free(mc_ctx* ctx, void* p) {
