@@ -69,6 +69,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy writes to shared memory (the sorted tile) become visible to the async proxy (the copy engine)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the copy engine pulls a tile this CTA will read one iteration from now into L2 (no destination: the later LDGs hit L2 instead of HBM)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+#ifndef SC_PREFETCH
+#define SC_PREFETCH 1
+#endif
 #define SC_MAX_PER ((1u << MC_MAX_PBITS) / SC_THREADS)   // bins owned by one thread in the scan / bulk-store phases
 
 // `D.use` = the bins are the OWNER ranks of the multi-GPU exchange: bin o's run goes to D.base[o], the receive region this rank
@@ -98,6 +105,13 @@ __device__ __forceinline__ void scatter_tiles(const uint64_t* __restrict__ flat,
     const uint32_t per = (P + SC_THREADS - 1) / SC_THREADS;
     for (uint64_t t0 = (uint64_t)first_tile * SC_TILE; t0 < n; t0 += (uint64_t)tile_stride * SC_TILE) {
         const uint32_t tn = (uint32_t)(n - t0 < SC_TILE ? n - t0 : SC_TILE);
+        if (SC_PREFETCH && TMA && threadIdx.x == 0) {   // my next tile -> L2 while this one is sorted
+            const uint64_t t1 = t0 + (uint64_t)tile_stride * SC_TILE;
+            if (t1 < n && (((uintptr_t)(flat + t1)) & 15) == 0) {
+                const uint64_t nk = n - t1 < SC_TILE ? n - t1 : SC_TILE;
+                if (nk >= 2) bulk_prefetch_l2(flat + t1, (uint32_t)(nk & ~1ull) * 8u);
+            }
+        }
         for (uint32_t i = threadIdx.x; i < P; i += SC_THREADS) S.hist[i] = 0;
         __syncthreads();
         // pass A: the tile is read ONCE, 16 bytes per lane and SC_KPT / 2 loads in flight per thread; every key takes its rank
@@ -272,6 +286,19 @@ __global__ void __launch_bounds__(SC_THREADS, SC_MINB) k_bin_scatter2(McBinsDev 
         const unsigned long long attempts = B1.cursors[b0 + g];
         const uint64_t n = attempts < B1.cap ? attempts : B1.cap;
         if ((uint64_t)tile * SC_TILE >= n) continue;
+        if (SC_PREFETCH && TMA && threadIdx.x == 0) {   // the tile of my next (bin, tile) pair -> L2
+            const uint32_t vn = vt + gridDim.x;
+            if (vn < G * tiles_per_bin) {
+                const uint32_t gn = vn / tiles_per_bin, tl = vn - gn * tiles_per_bin;
+                const unsigned long long an = B1.cursors[b0 + gn];
+                const uint64_t nn = an < B1.cap ? an : B1.cap;
+                const uint64_t at = (uint64_t)tl * SC_TILE;
+                if (at < nn) {
+                    const uint64_t nk = nn - at < SC_TILE ? nn - at : SC_TILE;
+                    if (nk >= 2) bulk_prefetch_l2(B1.keys + (uint64_t)(b0 + gn) * B1.cap + at, (uint32_t)(nk & ~1ull) * 8u);
+                }
+            }
+        }
         McBinsDev S = B2;
         S.keys = B2.keys + (uint64_t)g * P2 * B2.cap;
         S.cursors = B2.cursors + (uint64_t)g * (P2 + 1);
