@@ -248,8 +248,21 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
             if (c[s] > MC_SAT) c[s] = MC_SAT;
             own |= (c[s] ? (uint32_t)(sb ? h[s] >> (62 - sb) : 0) : 0xFFu) << (8 * s);
         }
-        // pass 1: entries per owner and warp (the offsets inside the warp are recomputed in pass 2: cheaper than keeping 16 of them)
-        for (int o = 0; o < world; o++) {
+        // pass 1: entries per owner and warp (the offsets inside the warp are recomputed in pass 2: cheaper than keeping 16 of them).
+        // The table is walked in bucket order = hash order and the owner is the top of the hash: the 128 entries of a warp's 32
+        // buckets belong to ONE owner (two at a shard border, any in the stash), so the warp only visits the owners it holds --
+        // a loop over all `world` owners with a warp scan each made the dump twice as slow at 8 ranks as at 2.
+        uint32_t present = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t o = (own >> (8 * s)) & 0xFFu;
+            if (o != 0xFFu) present |= 1u << o;
+        }
+        present = __reduce_or_sync(0xffffffffu, present);
+        if (lane < world) s_tot[lane][warp] = 0;
+        __syncwarp();
+        for (uint32_t m = present; m; m &= m - 1) {
+            const int o = __ffs(m) - 1;
             uint32_t mine = 0;
 #pragma unroll
             for (int s = 0; s < 4; s++) mine += ((own >> (8 * s)) & 0xFFu) == (uint32_t)o;
@@ -274,38 +287,36 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
         }
         __syncthreads();
         // pass 2: the CTA's pairs, grouped by owner, into shared memory ...
-        uint32_t ooff = 0;   // start of owner o's group inside s_pairs
-        for (int o = 0; o < world; o++) {
+        for (uint32_t m = present; m; m &= m - 1) {
+            const int o = __ffs(m) - 1;
             uint32_t mine = 0;
 #pragma unroll
             for (int s = 0; s < 4; s++) mine += ((own >> (8 * s)) & 0xFFu) == (uint32_t)o;
-            const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
-            if (any) {
-                uint32_t incl = mine;
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                if (mine) {
-                    uint32_t before = 0;
-                    for (int w = 0; w < warp; w++) before += s_tot[o][w];
-                    uint32_t pos = ooff + before + incl - mine;
-#pragma unroll
-                    for (int s = 0; s < 4; s++)
-                        if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) s_pairs[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
-                }
+            uint32_t incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
             }
-            ooff += s_otot[o];
+            if (mine) {
+                uint32_t ooff = 0;   // start of owner o's group inside s_pairs
+                for (int p = 0; p < o; p++) ooff += s_otot[p];
+                uint32_t before = 0;
+                for (int w = 0; w < warp; w++) before += s_tot[o][w];
+                uint32_t pos = ooff + before + incl - mine;
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                    if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) s_pairs[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
+            }
         }
         __syncthreads();
         // ... and out in whole runs: consecutive lanes store consecutive 16-byte pairs of ONE owner's region, i.e. full 512-byte
         // segments per warp on NVLink (round 1 stored every lane's pairs from registers: 16-byte writes strided by the lanes' own
         // counts, ~250 GB/s to the peers)
-        ooff = 0;
+        uint32_t ooff = 0;
         for (int o = 0; o < world; o++) {
             const uint32_t tot = s_otot[o];
             const unsigned long long base = s_base[o];
-            if (base != ~0ULL) {
+            if (tot && base != ~0ULL) {
                 ulonglong2* out = (ulonglong2*)dst.base[o] + base;
                 for (uint32_t i = threadIdx.x; i < tot; i += DUMP_THREADS) out[i] = s_pairs[ooff + i];
             }
@@ -326,6 +337,7 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
 struct McMergeSrc {
     const ulonglong2* pairs[MC_MAX_XCHG_RANKS];
     unsigned long long n[MC_MAX_XCHG_RANKS];
+    unsigned long long ratio[MC_MAX_XCHG_RANKS];   // floor(n[s] * 2^32 / n_max)
     unsigned long long n_max;
     int world;
 };
@@ -335,9 +347,12 @@ __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, McMergeSrc sr
         for (int s = 0; s < src.world; s++) {
             const unsigned long long ns = src.n[s];
             if (ns == 0) continue;
-            // positions [lo, hi) of source s that fall to virtual position v (0 or 1 pair when n_s <= n_max)
-            const unsigned long long lo = (unsigned long long)(((unsigned __int128)v * ns) / src.n_max);
-            const unsigned long long hi = (unsigned long long)(((unsigned __int128)(v + 1) * ns) / src.n_max);
+            // positions [lo, hi) of source s that fall to virtual position v (0 or 1 pair: n_s <= n_max).  f(v) = (v * ratio_s) >> 32
+            // with ratio_s = floor(n_s 2^32 / n_max) <= 2^32 is monotone, f(0) = 0 and f(v) <= n_s; f(n_max) is DEFINED as n_s, so the
+            // ranges [f(v), f(v + 1)) partition [0, n_s) exactly.  (v < 2^31: the product fits 64 bits; the host checks n_max.)
+            // Round 2's first form divided two 128-bit products per source and position: 1.4 G long divisions per step.
+            const unsigned long long lo = (v * src.ratio[s]) >> 32;
+            const unsigned long long hi = v + 1 == src.n_max ? ns : ((v + 1) * src.ratio[s]) >> 32;
             for (unsigned long long i = lo; i < hi; i++) {
                 const ulonglong2 p = __ldcs(src.pairs[s] + i);
                 if (p.y && mc_table_add(t, p.x, (uint32_t)p.y)) added++;
@@ -519,6 +534,8 @@ extern "C" int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_
                 ms.n[src] = counts[src];
                 ms.n_max = std::max<unsigned long long>(ms.n_max, counts[src]);
             }
+            if (ms.n_max >> 32) mc_throw(MC_ERR_UNSUPPORTED, "exchange: more than 2^32 pairs from one rank in one merge");
+            for (int src = 0; src < x->world; src++) ms.ratio[src] = (unsigned long long)(((unsigned __int128)ms.n[src] << 32) / ms.n_max);
             McStageTimer tm(ctx, MC_ST_COUNT);
             const int grid = (int)std::min<uint64_t>((ms.n_max + 255) / 256, (uint64_t)ctx->sm_count * 8);
             k_merge_pairs<<<grid, 256, 0, st>>>(shard->dev, ms);

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import math
 import os
+import sys
 import time
 
 import torch
@@ -110,6 +111,12 @@ class ShardedCounter:
         # use), so it is off unless asked for
         self.fuse_dump = os.environ.get("MC_FUSE_DUMP", "0") != "0"
         self.fused_last = None
+        # NCCL sets a collective's channels up on its first call (0.7 s for the first all_gather at N = 2): done here, at construction,
+        # so that the solid-set gather after the first counting step is the transfer and nothing else
+        if world > 1 and dist.is_initialized() and dist.get_backend() == "nccl":
+            tiny = torch.zeros(8, dtype=torch.uint8, device="cuda")
+            dist.all_gather([torch.empty_like(tiny) for _ in range(world)], tiny)
+            torch.cuda.synchronize()
 
     def new_table(self):
         if self.table is not None:
@@ -407,19 +414,35 @@ class ShardedCounter:
         (solid_shard = this rank's slice); the (key, count16) pairs are dumped into device buffers, all-gathered over
         NVLink and inserted into a fresh unsharded table.  Returns (table, pairs per rank)."""
         n = solid_shard.dump_device(1)
+        # The gather's buffers come from torch's allocator, the counting step's blocks (bins, staging: tens of GB) sit in the
+        # context's arena cache: when the driver has little left, torch's cudaMalloc fails first, empties its own cache and retries
+        # (0.7 s at N = 2).  Counting is over here, so the arena hands its cache back when room is short.
+        prof = os.environ.get("MC_DIST_PROFILE")
+        t0 = time.perf_counter()
+        need = (2 * self.world + 4) * 10 * max(n, 1) * 2
+        free_before = torch.cuda.mem_get_info()[0]
+        if free_before < need:
+            self.ctx.trim()
         keys = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
         counts = torch.empty(max(n, 1), dtype=torch.int16, device="cuda")
         if n:
             solid_shard.dump_device(1, keys.data_ptr(), counts.data_ptr(), n)
         torch.cuda.synchronize()
+        t1 = time.perf_counter()
         parts = gather_pairs(keys, counts, n)
         torch.cuda.synchronize()
+        t2 = time.perf_counter()
         total = sum(int(k.numel()) for k, _ in parts)
         full = self.ctx.new_table(self.k, capacity_hint=2 * total)
         for k_r, c_r in parts:
             if k_r.numel():
                 kk, cc = k_r.contiguous(), c_r.contiguous()
                 full.add_pairs_device(kk.data_ptr(), cc.data_ptr(), int(kk.numel()))
+        if prof:
+            self.ctx.sync()
+            t3 = time.perf_counter()
+            print(f"[dist profile] rank {self.rank} gather_solid: free {free_before / 2**30:.1f} GiB (need {need / 2**30:.1f}), dump {1e3 * (t1 - t0):.1f} ms, "
+                  f"all-gather {1e3 * (t2 - t1):.1f} ms, insert {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
         self.bytes_exchanged += 10 * (total - n)
         return full, [int(k.numel()) for k, _ in parts]
 
