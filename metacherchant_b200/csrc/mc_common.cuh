@@ -175,7 +175,11 @@ __device__ __forceinline__ int mc_stash_get(const McTableDev& t, uint64_t h) {
 // atomicCAS never creates a duplicate.
 // `w0` (optional) = the words of the home bucket, loaded earlier by the caller so that several probes of one
 // thread are in flight at once (k_bin_count); a stale copy is fine for the same reason a stale load is.
-template <bool PREFETCHED>
+// FEW_ADDERS: the caller guarantees that at most 16 updates of ONE key, each <= 32767, can ever be in flight together (the merge of
+// the multi-GPU exchange: one pair per source rank).  The count then goes up with a plain RED even for inc > 1: the 20-bit field
+// cannot overflow (32766 + 16 x 32767 < 2^20), every reader clamps at 32767, and min(sum, 32767) is what sequential saturating adds
+// give.  The general path keeps the saturating CAS loop, which retries when several sources bring the same k-mer at the same time.
+template <bool PREFETCHED, bool FEW_ADDERS = false>
 __device__ __forceinline__ bool mc_table_add_impl(const McTableDev& t, uint64_t hl, uint32_t inc, const uint64_t* w0) {
     const uint64_t tag = hl & t.tag_mask;
     const uint64_t b0 = hl >> t.tag_bits;
@@ -195,8 +199,8 @@ __device__ __forceinline__ bool mc_table_add_impl(const McTableDev& t, uint64_t 
                 if (cur == 0) return true;   // claimed: new key
             }
             if ((cur >> MC_COUNT_BITS) == (want >> MC_COUNT_BITS)) {
-                if (inc == 1) {
-                    if ((cur & MC_COUNT_MASK) < MC_SAT) atomicAdd((unsigned long long*)&bucket[s], 1ULL);
+                if (inc == 1 || FEW_ADDERS) {
+                    if ((cur & MC_COUNT_MASK) < MC_SAT) atomicAdd((unsigned long long*)&bucket[s], (unsigned long long)inc);
                 } else {
                     // rare path (add_pairs, rehash): saturating CAS loop
                     while ((cur & MC_COUNT_MASK) < MC_SAT) {

@@ -343,6 +343,7 @@ struct McMergeSrc {
 };
 __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, McMergeSrc src) {
     unsigned long long added = 0;
+    const uint64_t lmask = (1ULL << (62 - t.shard_bits)) - 1;
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < src.n_max; v += (uint64_t)gridDim.x * blockDim.x) {
         for (int s = 0; s < src.world; s++) {
             const unsigned long long ns = src.n[s];
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, McMergeSrc sr
             const unsigned long long hi = v + 1 == src.n_max ? ns : ((v + 1) * src.ratio[s]) >> 32;
             for (unsigned long long i = lo; i < hi; i++) {
                 const ulonglong2 p = __ldcs(src.pairs[s] + i);
-                if (p.y && mc_table_add(t, p.x, (uint32_t)p.y)) added++;
+                // (one pair per source and key, counts <= 32767: the RED form of the add, mc_common.cuh)
+                if (p.y && mc_table_add_impl<false, true>(t, p.x & lmask, (uint32_t)p.y, nullptr)) added++;
             }
         }
     }
@@ -389,7 +391,12 @@ extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, 
             McStageTimer tm(ctx, MC_ST_SCATTER);
             const uint64_t units = local->nb;
             const int grid = (int)std::min<uint64_t>((units + DUMP_THREADS - 1) / DUMP_THREADS, (uint64_t)ctx->sm_count * 4);
-            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags, 0, local->nb, 0, local->nb);
+            // The scan walks the table in hash order = owner order, and at any moment the whole grid is inside ONE owner's range: started
+            // at bucket 0 on every rank, all ranks would send to owner 0 first, then to owner 1, ... -- one receiver's NVLink ingress
+            // shared by all senders while the other links idle.  Rank r starts at the range of owner r + 1 instead (the ranges are
+            // scanned in the same ascending order inside, so every receiver still sees each source's pairs in its bucket order).
+            const uint64_t scan_lo = (uint64_t)((x->rank + 1) % x->world) * (local->nb / (uint64_t)x->world);
+            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags, scan_lo, local->nb, 0, local->nb);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
         }
