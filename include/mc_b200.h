@@ -29,7 +29,7 @@ typedef enum mc_status {
     MC_ERR_IO = -3,          /* "Failed to read from file <path>" (src/io/IOUtils.java:292) */
     MC_ERR_FORMAT = -4,      /* malformed FASTA/FASTQ: the reference throws from its reader threads */
     MC_ERR_NOMEM = -5,       /* table does not fit in device memory */
-    MC_ERR_UNSUPPORTED = -6, /* reference feature outside the GPU path (gz/bz2/binq input, k > 31, ...) */
+    MC_ERR_UNSUPPORTED = -6, /* reference feature outside the GPU path (binq input, k > 31, ...) */
     MC_ERR_CAPACITY = -7     /* caller-provided output buffer too small */
 } mc_status;
 

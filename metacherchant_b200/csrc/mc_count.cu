@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -779,23 +780,114 @@ extern "C" int mc_count_device(mc_ctx* ctx, const void* dbuf, size_t len, int fm
     }
 }
 
-// Host buffer (pinned memory gives full PCIe speed, pageable works too).  Two device buffers of 2*chunk bytes:
+// --------------------------------------------------------------------------------------------
+// host input as a sequence of slices: a caller's buffer, or a decompressor's output produced slice by slice (a .gz / .bz2 file is
+// never inflated whole: two slices of chunk_bytes are all the host memory it needs)
+// --------------------------------------------------------------------------------------------
+struct McSliceSource {
+    virtual ~McSliceSource() {}
+    // the first (up to) `want` bytes of the input, without consuming them; *complete = that is the whole input
+    virtual size_t peek(size_t want, const uint8_t** p, bool* complete) = 0;
+    // the next slice of at most `max` bytes (0: the input is over); the memory stays valid until the call after the next one
+    virtual size_t next(size_t max, const uint8_t** p) = 0;
+};
+struct McMemSource : McSliceSource {
+    const uint8_t* base;
+    size_t len, pos = 0;
+    McMemSource(const void* b, size_t n) : base((const uint8_t*)b), len(n) {}
+    size_t peek(size_t want, const uint8_t** p, bool* complete) override {
+        *p = base;
+        *complete = want >= len;
+        return std::min(want, len);
+    }
+    size_t next(size_t max, const uint8_t** p) override {
+        const size_t n = std::min(max, len - pos);
+        *p = base + pos;
+        pos += n;
+        return n;
+    }
+};
+// a decompressor: pull() delivers the inflated bytes in order, 0 at the end of the input
+struct McPullSource : McSliceSource {
+    std::vector<uint8_t> head;
+    std::unique_ptr<uint8_t[]> buf[2];   // (not vectors: a resize would zero-fill a GiB per slice buffer)
+    size_t buf_cap[2] = {0, 0};
+    size_t head_pos = 0;
+    int cur = 0;
+    bool eof = false;
+    virtual size_t pull(uint8_t* dst, size_t max) = 0;
+    size_t peek(size_t want, const uint8_t** p, bool* complete) override {
+        while (head.size() < want && !eof) {
+            const size_t old = head.size();
+            head.resize(want);
+            const size_t got = pull(head.data() + old, want - old);
+            head.resize(old + got);
+            if (!got) eof = true;
+        }
+        *p = head.data();
+        *complete = eof;
+        return head.size();
+    }
+    size_t next(size_t max, const uint8_t** p) override {
+        if (buf_cap[cur] < max) {
+            buf[cur].reset(new uint8_t[max]);
+            buf_cap[cur] = max;
+        }
+        uint8_t* const b = buf[cur].get();
+        cur ^= 1;
+        size_t got = 0;
+        while (got < max) {
+            if (head_pos < head.size()) {
+                const size_t n = std::min(max - got, head.size() - head_pos);
+                memcpy(b + got, head.data() + head_pos, n);
+                head_pos += n;
+                got += n;
+                if (head_pos == head.size()) { std::vector<uint8_t>().swap(head); head_pos = 0; }
+            } else if (eof) {
+                break;
+            } else {
+                const size_t n = pull(b + got, max - got);
+                if (!n) eof = true;
+                got += n;
+            }
+        }
+        *p = b;
+        return got;
+    }
+};
+
+// ReadersUtils.determineQualityFormat on the head of the input (ITMO!/io/ReadersUtils.java:63-77): the first 1000 records
+static int resolve_qoff_source(McSliceSource& src, int fmt) {
+    if (fmt == MC_FMT_FASTQ33) return 33;
+    if (fmt == MC_FMT_FASTQ64) return 64;
+    size_t sample = (size_t)1 << 20;
+    while (true) {
+        const uint8_t* p = nullptr;
+        bool complete = false;
+        const size_t n = src.peek(sample, &p, &complete);
+        const int r = sniff_quality_offset(p, n, complete);
+        if (r > 0) return r;
+        if (complete) return 64;
+        sample *= 4;
+    }
+}
+
+// Host input (pinned memory gives full PCIe speed, pageable works too).  Two device buffers of 2*chunk bytes:
 // the slice of chunk i+1 is uploaded on the copy stream to offset `chunk` of the idle buffer while chunk i is parsed
 // and counted on the compute stream; the unconsumed tail of chunk i (an incomplete record, < chunk bytes) is then
 // moved device-to-device right in front of that slice, so every chunk the kernels see starts at a record boundary.
-extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt, mc_table* t) {
+// total_len: the input's size when known (table sizing from the first chunk's k-mer density), 0 for a stream.
+static int count_source(mc_ctx* ctx, McSliceSource& src, size_t total_len, int fmt, mc_table* t) {
     cudaEvent_t copied[2] = {nullptr, nullptr};
     cudaEvent_t consumed_ev = nullptr;   // the compute stream is done reading the buffer the next prefetch overwrites
     try {
-        if (!ctx || !t || (len && !buf)) mc_throw(MC_ERR_ARG, "null argument");
         validate_fmt(fmt);
         MC_CUDA(cudaSetDevice(ctx->device));
         mc_resolve_timers(ctx);
         if (!ctx->keep_stage_ms)
             for (auto& v : ctx->stage_ms) v = 0;
-        const uint8_t* p = (const uint8_t*)buf;
         const bool fasta = fmt == MC_FMT_FASTA;
-        const int qoff = fasta ? 0 : resolve_qoff_host(p, len, fmt);
+        const int qoff = fasta ? 0 : resolve_qoff_source(src, fmt);
         const size_t chunk = ctx->chunk_bytes;
         const size_t cap = 2 * chunk + 256;
         for (int i = 0; i < 2; i++)
@@ -814,37 +906,36 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
         // Host input is PCIe-bound (~20 ms per GiB): the bins are applied after every chunk (measured best: profiles/r1c_NOTES.md), so that the table sweep runs in the
         // shadow of the uploads instead of after the last one (device-resident input is binned whole, one sweep)
         const uint64_t host_chunks = ctx->tune_host_batch_chunks ? ctx->tune_host_batch_chunks : 1;
-        const uint64_t batch_hint = std::min<uint64_t>(mc_max_kmers(len, fmt, t->k), host_chunks * mc_max_kmers(chunk, fmt, t->k));
+        uint64_t batch_hint = host_chunks * mc_max_kmers(chunk, fmt, t->k);
+        if (total_len) batch_hint = std::min<uint64_t>(batch_hint, mc_max_kmers(total_len, fmt, t->k));
         mc_table_expect_keys(t, 0);   // set from the first chunk's k-mers per byte (count_chunk)
-        size_t pos = 0;      // next host byte to upload
         size_t carry = 0;    // bytes of the previous chunk sitting right in front of offset `chunk`
         int cur = 0;
-        size_t n_slice = std::min(len, chunk);
-        if (n_slice) MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[cur] + chunk, p, n_slice, cudaMemcpyHostToDevice, ctx->copy_stream));
+        const uint8_t* ps = nullptr;
+        size_t n_slice = src.next(chunk, &ps);
+        if (n_slice) MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[cur] + chunk, ps, n_slice, cudaMemcpyHostToDevice, ctx->copy_stream));
         MC_CUDA(cudaEventRecord(copied[cur], ctx->copy_stream));
-        pos = n_slice;
         while (true) {
-            const bool final_chunk = pos == len;
             const int nxt = cur ^ 1;
-            size_t n_next = 0;
+            const uint8_t* pn = nullptr;
+            const size_t n_next = n_slice ? src.next(chunk, &pn) : 0;   // (a decompressor produces the slice here, on the host)
+            const bool final_chunk = n_next == 0;
             if (!final_chunk) {   // prefetch the next slice; the idle buffer's kernels finished (count_chunk synchronises)
-                n_next = std::min(len - pos, chunk);
                 // buffer `nxt` held the previous chunk: its kernels and the carry copy out of it must have finished
                 MC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, consumed_ev, 0));
-                MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[nxt] + chunk, p + pos, n_next, cudaMemcpyHostToDevice, ctx->copy_stream));
+                MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[nxt] + chunk, pn, n_next, cudaMemcpyHostToDevice, ctx->copy_stream));
                 MC_CUDA(cudaEventRecord(copied[nxt], ctx->copy_stream));
             }
             MC_CUDA(cudaStreamWaitEvent(ctx->stream, copied[cur], 0));
             const uint8_t* d_start = (const uint8_t*)ctx->d_chunk[cur] + chunk - carry;
             const size_t n = carry + n_slice;
-            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, batch_hint, len);
+            uint32_t consumed = count_chunk(ctx, t, d_start, (uint32_t)n, fasta, qoff, final_chunk, batch_hint, total_len);
             if (final_chunk) break;
             size_t left = n - consumed;
             if (left > chunk) mc_throw(MC_ERR_FORMAT, "a single record is longer than the device chunk (%zu bytes); raise mc_ctx_set_chunk_bytes", chunk);
             if (left) MC_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_chunk[nxt] + chunk - left, d_start + consumed, left, cudaMemcpyDeviceToDevice, ctx->stream));
             MC_CUDA(cudaEventRecord(consumed_ev, ctx->stream));
             carry = left;
-            pos += n_next;
             n_slice = n_next;
             cur = nxt;
         }
@@ -863,6 +954,15 @@ extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt,
     }
 }
 
+extern "C" int mc_count_bytes(mc_ctx* ctx, const void* buf, size_t len, int fmt, mc_table* t) {
+    if (!ctx || !t || (len && !buf)) {
+        mc_set_error("null argument");
+        return MC_ERR_ARG;
+    }
+    McMemSource src(buf, len);
+    return count_source(ctx, src, len, fmt, t);
+}
+
 // --------------------------------------------------------------------------------------------
 // files: format by suffix (ITMO!/io/ReadersUtils.java:27-54), one file after the other (src/io/IOUtils.java:283-316)
 // --------------------------------------------------------------------------------------------
@@ -879,41 +979,79 @@ struct McBzStream {
     void (*bzfree)(void*, void*);
     void* opaque;
 };
-static void inflate_bz2(const char* path, const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+struct McBz2Source : McPullSource {
     typedef int (*init_t)(McBzStream*, int, int);
     typedef int (*step_t)(McBzStream*);
-    static void* lib = nullptr;
-    if (!lib) lib = dlopen("libbz2.so.1.0", RTLD_NOW);
-    if (!lib) lib = dlopen("libbz2.so.1", RTLD_NOW);
-    if (!lib) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (libbz2 is not installed)", path);
-    const init_t init = (init_t)dlsym(lib, "BZ2_bzDecompressInit");
-    const step_t step = (step_t)dlsym(lib, "BZ2_bzDecompress"), end = (step_t)dlsym(lib, "BZ2_bzDecompressEnd");
-    if (!init || !step || !end) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (libbz2 lacks the decompression entry points)", path);
-    std::vector<uint8_t> piece(16 << 20);
-    size_t pos = 0;
-    while (pos < n) {
-        McBzStream z{};
-        if (init(&z, 0, 0) != 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
-        z.next_in = (char*)in + pos;
-        z.avail_in = (unsigned)std::min<size_t>(n - pos, 1u << 30);
-        int rc = 0;
-        while (rc != 4) {   // BZ_STREAM_END
-            z.next_out = (char*)piece.data();
-            z.avail_out = (unsigned)piece.size();
-            const unsigned in_before = z.avail_in;
-            rc = step(&z);
-            if (rc != 0 && rc != 4) { end(&z); mc_throw(MC_ERR_IO, "Failed to read from file %s (corrupt bzip2 stream)", path); }
-            out.insert(out.end(), piece.begin(), piece.begin() + (piece.size() - z.avail_out));
+    std::string path;
+    const uint8_t* in;
+    size_t n, pos = 0;
+    init_t init = nullptr;
+    step_t step = nullptr, end = nullptr;
+    McBzStream z{};
+    bool active = false;
+    McBz2Source(const char* path_, const uint8_t* in_, size_t n_) : path(path_), in(in_), n(n_) {
+        static void* lib = nullptr;
+        if (!lib) lib = dlopen("libbz2.so.1.0", RTLD_NOW);
+        if (!lib) lib = dlopen("libbz2.so.1", RTLD_NOW);
+        if (!lib) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (libbz2 is not installed)", path.c_str());
+        init = (init_t)dlsym(lib, "BZ2_bzDecompressInit");
+        step = (step_t)dlsym(lib, "BZ2_bzDecompress");
+        end = (step_t)dlsym(lib, "BZ2_bzDecompressEnd");
+        if (!init || !step || !end) mc_throw(MC_ERR_UNSUPPORTED, "Failed to read from file %s (libbz2 lacks the decompression entry points)", path.c_str());
+    }
+    ~McBz2Source() override {
+        if (active) end(&z);
+    }
+    size_t pull(uint8_t* dst, size_t max) override {
+        size_t got = 0;
+        while (got < max) {
+            if (!active) {
+                if (pos >= n) break;   // no further stream
+                z = McBzStream{};
+                if (init(&z, 0, 0) != 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path.c_str());
+                active = true;
+                z.next_in = (char*)in + pos;
+                z.avail_in = (unsigned)std::min<size_t>(n - pos, 1u << 30);
+            }
+            z.next_out = (char*)dst + got;
+            z.avail_out = (unsigned)std::min<size_t>(max - got, 1u << 30);
+            const unsigned in_before = z.avail_in, out_before = z.avail_out;
+            const int rc = step(&z);
+            if (rc != 0 && rc != 4) mc_throw(MC_ERR_IO, "Failed to read from file %s (corrupt bzip2 stream)", path.c_str());
+            got += out_before - z.avail_out;
             pos += in_before - z.avail_in;
-            if (rc == 0 && z.avail_in == 0) {
-                if (pos >= n) { end(&z); mc_throw(MC_ERR_IO, "Failed to read from file %s (truncated bzip2 stream)", path); }
+            if (rc == 4) {   // BZ_STREAM_END: a concatenated stream may follow
+                end(&z);
+                active = false;
+            } else if (z.avail_in == 0) {
+                if (pos >= n) mc_throw(MC_ERR_IO, "Failed to read from file %s (truncated bzip2 stream)", path.c_str());
                 z.next_in = (char*)in + pos;
                 z.avail_in = (unsigned)std::min<size_t>(n - pos, 1u << 30);
             }
         }
-        end(&z);
+        return got;
     }
-}
+};
+// zlib's gzread: concatenated members like java.util.zip.GZIPInputStream (ITMO!/io/readers/FastqGZReader.java:26-34)
+struct McGzSource : McPullSource {
+    std::string path;
+    gzFile g;
+    McGzSource(const char* path_) : path(path_), g(gzopen(path_, "rb")) {
+        if (!g) mc_throw(MC_ERR_IO, "Failed to read from file %s", path.c_str());
+        gzbuffer(g, 1 << 20);
+    }
+    ~McGzSource() override { gzclose(g); }
+    size_t pull(uint8_t* dst, size_t max) override {
+        size_t got = 0;
+        while (got < max) {
+            const int r = gzread(g, dst + got, (unsigned)std::min<size_t>(max - got, 1u << 30));
+            if (r < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path.c_str());
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        return got;
+    }
+};
 
 // *gz: 0 plain, 1 ".gz", 2 ".bz2" (ReadersUtils strips ".gz", then ".bz2": ITMO!/io/ReadersUtils.java:36-43)
 static int detect_file_format(const std::string& path, int* gz) {
@@ -962,7 +1100,10 @@ extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
         if (!ctx || !path || !t) mc_throw(MC_ERR_ARG, "null argument");
         int gz = 0;
         int fmt = detect_file_format(path, &gz);
-        if (gz == 2) {   // whole file through libbz2 on the host, then the usual chunked upload
+        // .gz / .bz2: inflated on the host SLICE BY SLICE (zlib; libbz2 through dlopen) into two alternating buffers of chunk_bytes that
+        // feed the usual chunked upload: host memory stays at two slices whatever the file's size, and the GPU counts slice i while the
+        // decompressor -- which bounds such an input either way -- produces slice i + 1
+        if (gz == 2) {
             int fd = open(path, O_RDONLY);
             if (fd < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
             struct stat sb;
@@ -970,9 +1111,10 @@ extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
             const size_t len = (size_t)sb.st_size;
             void* map = len ? mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
             if (len && map == MAP_FAILED) { close(fd); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
-            std::vector<uint8_t> data;
+            int rc;
             try {
-                inflate_bz2(path, (const uint8_t*)map, len, data);
+                McBz2Source src(path, (const uint8_t*)map, len);
+                rc = count_source(ctx, src, 0, fmt, t);
             } catch (...) {
                 if (len) munmap(map, len);
                 close(fd);
@@ -980,24 +1122,11 @@ extern "C" int mc_count_file(mc_ctx* ctx, const char* path, mc_table* t) {
             }
             if (len) munmap(map, len);
             close(fd);
-            return mc_count_bytes(ctx, data.data(), data.size(), fmt, t);
+            return rc;
         }
         if (gz == 1) {
-            // host-side inflate (zlib; concatenated members like java.util.zip.GZIPInputStream), then the usual chunked upload.
-            // The whole file is inflated first: the decompressor, not the GPU, bounds a .gz input either way.
-            gzFile g = gzopen(path, "rb");
-            if (!g) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);
-            gzbuffer(g, 1 << 20);
-            std::vector<uint8_t> data;
-            std::vector<uint8_t> piece(16 << 20);
-            for (;;) {
-                int got = gzread(g, piece.data(), (unsigned)piece.size());
-                if (got < 0) { gzclose(g); mc_throw(MC_ERR_IO, "Failed to read from file %s", path); }
-                if (got == 0) break;
-                data.insert(data.end(), piece.begin(), piece.begin() + got);
-            }
-            gzclose(g);
-            return mc_count_bytes(ctx, data.data(), data.size(), fmt, t);
+            McGzSource src(path);
+            return count_source(ctx, src, 0, fmt, t);
         }
         int fd = open(path, O_RDONLY);
         if (fd < 0) mc_throw(MC_ERR_IO, "Failed to read from file %s", path);

@@ -288,3 +288,32 @@ def test_gz_files_through_the_file_api(ctx, oracle, tmp_path):
     open(tmp_path / "x.fastq.bz2", "wb").write(b"BZh9" + b"garbage" * 10)
     with pytest.raises(McError):
         ctx.load_reads([str(tmp_path / "x.fastq.bz2")], 17)
+
+
+@pytest.mark.parametrize("chunk", [4096, 30000])
+def test_packed_files_are_streamed_slice_by_slice(oracle, tmp_path, chunk):
+    """.gz / .bz2 inputs are inflated slice by slice (two host buffers of chunk_bytes), never whole: with chunks far smaller than the files
+    every slice boundary falls inside a record, the quality sniffer's head spans several slices and concatenated members / streams end
+    in the middle of a slice.  Tables and reader statistics equal the oracle's on the same files."""
+    import bz2
+    import gzip
+    from metacherchant_b200 import Context
+    rng = random.Random(chunk)
+    fq = make_fastq(rng, 4000, max_len=150, offset=64)     # Phred+64: the sniffer must see 1000 records (~300 KB) before deciding
+    fa = make_fasta(rng, 1500, max_len=300)
+    paths = [str(tmp_path / "a.fastq.gz"), str(tmp_path / "b.fq.bz2"), str(tmp_path / "c.fa.gz"), str(tmp_path / "d.fasta.bz2"), str(tmp_path / "e.fq.gz")]
+    open(paths[0], "wb").write(gzip.compress(fq[:123_457]) + gzip.compress(fq[123_457:]))
+    open(paths[1], "wb").write(bz2.compress(fq[:200_001]) + bz2.compress(fq[200_001:]))
+    open(paths[2], "wb").write(gzip.compress(fa))
+    open(paths[3], "wb").write(bz2.compress(fa[:10_000]) + bz2.compress(fa[10_000:]))
+    open(paths[4], "wb").write(gzip.compress(b""))
+    c = Context(0, chunk_bytes=chunk)
+    try:
+        g = c.load_reads(paths, 21)
+        o = oracle.table(21, threads=4)
+        for p in paths:
+            o.count_file(p)
+        assert_same_table(g, o)
+        assert g.stats() == o.stats()
+    finally:
+        c.close()
