@@ -118,8 +118,291 @@ int32_t java_string_hash(const std::string& s) {
     return (int32_t)h;
 }
 
-// Iteration order of a java.util.HashMap<String,V> (bucket index, then insertion order inside a bucket; capacity 16
-// doubling at load 0.75; treeified bins not modelled).  Pinned on the reference's committed graph.txt by the tests.
+// ------------------------------------------------------------------------------------------------
+// java.util.HashMap iteration order (JDK 8+, default constructor), insertions of DISTINCT keys in index order.
+//
+// Bins that never hold 9 nodes are plain lists: the order is "bucket index at the final capacity, insertion order inside a
+// bucket" (resize splits keep the relative order) -- a stable counting sort.  A bin that reaches 9 nodes while the table has >= 64
+// buckets becomes a red-black tree of TreeNodes (HashMap.treeifyBin): iteration still follows the `next` links, but treeify moves
+// the tree's root to the front of the bin, putTreeVal links a new node right after its tree PARENT, and a resize splits the bin
+// into two lists that are re-treeified (root to the front again) or, at <= 6 nodes, turned back into plain nodes in their current
+// order.  With fewer than 64 buckets the table is resized instead.  Either way the final order depends on the history, so such a
+// map is replayed put by put (JavaHashReplay).  `needs_replay` finds out in one counting pass per capacity stage (2n steps).
+// h[i] = the key's SPREAD hash (hashCode ^ hashCode >>> 16); less(a, b) = key a < key b by String.compareTo.
+// ------------------------------------------------------------------------------------------------
+static bool java_hashmap_needs_replay(const std::vector<uint32_t>& h) {
+    std::vector<uint16_t> cnt;
+    size_t cap = 16, lo = 0;
+    while (lo < h.size()) {
+        const size_t hi = std::min(h.size(), cap / 4 * 3 + 1);   // the put that exceeds the threshold still lands in this table
+        cnt.assign(cap, 0);
+        for (size_t i = 0; i < hi; i++) {
+            uint16_t& c = cnt[h[i] & (cap - 1)];
+            if (c < 0xFFFF) c++;
+            if (i >= lo && c >= 9) return true;
+        }
+        lo = hi;
+        cap <<= 1;
+    }
+    return false;
+}
+
+template <class Less>
+struct JavaHashReplay {
+    struct Node {
+        int32_t next = -1, prev = -1, left = -1, right = -1, parent = -1;
+        bool red = false, tree = false;
+    };
+    const std::vector<uint32_t>& h;
+    Less less;
+    std::vector<Node> nd;
+    std::vector<int32_t> tab;
+    size_t threshold = 0, size = 0;
+    JavaHashReplay(const std::vector<uint32_t>& hashes, Less l) : h(hashes), less(l), nd(hashes.size()) {}
+
+    // TreeNode ordering: int compare of the hashes, then compareTo (keys are distinct: never 0)
+    int dir(int32_t x, int32_t p) const {
+        const int32_t hx = (int32_t)h[(size_t)x], hp = (int32_t)h[(size_t)p];
+        if (hp > hx) return -1;
+        if (hp < hx) return 1;
+        return less((uint32_t)x, (uint32_t)p) ? -1 : 1;
+    }
+    int32_t rotate_left(int32_t root, int32_t p) {
+        if (p < 0) return root;
+        const int32_t r = nd[p].right;
+        if (r < 0) return root;
+        const int32_t rl = nd[p].right = nd[r].left;
+        if (rl >= 0) nd[rl].parent = p;
+        const int32_t pp = nd[r].parent = nd[p].parent;
+        if (pp < 0) { root = r; nd[r].red = false; }
+        else if (nd[pp].left == p) nd[pp].left = r;
+        else nd[pp].right = r;
+        nd[r].left = p;
+        nd[p].parent = r;
+        return root;
+    }
+    int32_t rotate_right(int32_t root, int32_t p) {
+        if (p < 0) return root;
+        const int32_t l = nd[p].left;
+        if (l < 0) return root;
+        const int32_t lr = nd[p].left = nd[l].right;
+        if (lr >= 0) nd[lr].parent = p;
+        const int32_t pp = nd[l].parent = nd[p].parent;
+        if (pp < 0) { root = l; nd[l].red = false; }
+        else if (nd[pp].right == p) nd[pp].right = l;
+        else nd[pp].left = l;
+        nd[l].right = p;
+        nd[p].parent = l;
+        return root;
+    }
+    int32_t balance_insertion(int32_t root, int32_t x) {
+        nd[x].red = true;
+        for (;;) {
+            int32_t xp = nd[x].parent;
+            if (xp < 0) { nd[x].red = false; return x; }
+            int32_t xpp = nd[xp].parent;
+            if (!nd[xp].red || xpp < 0) return root;
+            const int32_t xppl = nd[xpp].left;
+            if (xp == xppl) {
+                const int32_t xppr = nd[xpp].right;
+                if (xppr >= 0 && nd[xppr].red) {
+                    nd[xppr].red = false; nd[xp].red = false; nd[xpp].red = true;
+                    x = xpp;
+                } else {
+                    if (x == nd[xp].right) {
+                        root = rotate_left(root, x = xp);
+                        xp = nd[x].parent;
+                        xpp = xp < 0 ? -1 : nd[xp].parent;
+                    }
+                    if (xp >= 0) {
+                        nd[xp].red = false;
+                        if (xpp >= 0) { nd[xpp].red = true; root = rotate_right(root, xpp); }
+                    }
+                }
+            } else {
+                if (xppl >= 0 && nd[xppl].red) {
+                    nd[xppl].red = false; nd[xp].red = false; nd[xpp].red = true;
+                    x = xpp;
+                } else {
+                    if (x == nd[xp].left) {
+                        root = rotate_right(root, x = xp);
+                        xp = nd[x].parent;
+                        xpp = xp < 0 ? -1 : nd[xp].parent;
+                    }
+                    if (xp >= 0) {
+                        nd[xp].red = false;
+                        if (xpp >= 0) { nd[xpp].red = true; root = rotate_left(root, xpp); }
+                    }
+                }
+            }
+        }
+    }
+    void move_root_to_front(int32_t root) {
+        if (root < 0 || tab.empty()) return;
+        const size_t idx = h[(size_t)root] & (tab.size() - 1);
+        const int32_t first = tab[idx];
+        if (root == first) return;
+        tab[idx] = root;
+        const int32_t rp = nd[root].prev, rn = nd[root].next;
+        if (rn >= 0) nd[rn].prev = rp;
+        if (rp >= 0) nd[rp].next = rn;
+        if (first >= 0) nd[first].prev = root;
+        nd[root].next = first;
+        nd[root].prev = -1;
+    }
+    void treeify(int32_t head) {   // TreeNode.treeify: the bin's nodes, in list order, into a fresh tree; root to the front
+        int32_t root = -1;
+        for (int32_t x = head, nx; x >= 0; x = nx) {
+            nx = nd[x].next;
+            nd[x].left = nd[x].right = -1;
+            if (root < 0) {
+                nd[x].parent = -1;
+                nd[x].red = false;
+                root = x;
+                continue;
+            }
+            for (int32_t p = root;;) {
+                const int d = dir(x, p);
+                const int32_t xp = p;
+                p = d <= 0 ? nd[p].left : nd[p].right;
+                if (p < 0) {
+                    nd[x].parent = xp;
+                    (d <= 0 ? nd[xp].left : nd[xp].right) = x;
+                    root = balance_insertion(root, x);
+                    break;
+                }
+            }
+        }
+        move_root_to_front(root);
+    }
+    void split(int32_t b, size_t index, size_t bit) {   // TreeNode.split during a resize
+        int32_t head[2] = {-1, -1}, tail[2] = {-1, -1};
+        size_t count[2] = {0, 0};
+        for (int32_t e = b, nx; e >= 0; e = nx) {
+            nx = nd[e].next;
+            nd[e].next = -1;
+            const int s = (h[(size_t)e] & bit) ? 1 : 0;
+            nd[e].prev = tail[s];
+            if (tail[s] < 0) head[s] = e;
+            else nd[tail[s]].next = e;
+            tail[s] = e;
+            count[s]++;
+        }
+        for (int s = 0; s < 2; s++) {
+            const size_t at = index + (s ? bit : 0);
+            tab[at] = head[s];
+            if (head[s] < 0) continue;
+            if (count[s] <= 6) {   // UNTREEIFY_THRESHOLD: plain nodes again, in the list's current order
+                for (int32_t x = head[s]; x >= 0; x = nd[x].next) {
+                    nd[x].tree = false;
+                    nd[x].left = nd[x].right = nd[x].parent = -1;
+                }
+            } else if (head[1 - s] >= 0) {
+                treeify(head[s]);   // (nothing left the bin otherwise: its tree is intact)
+            }
+        }
+    }
+    void resize() {
+        if (tab.empty()) {
+            tab.assign(16, -1);
+            threshold = 12;
+            return;
+        }
+        const size_t oc = tab.size();
+        std::vector<int32_t> old((size_t)oc * 2, -1);
+        old.swap(tab);   // tab = the new table, old = the previous one
+        threshold *= 2;
+        for (size_t j = 0; j < oc; j++) {
+            int32_t e = old[j];
+            if (e < 0) continue;
+            if (nd[e].tree) { split(e, j, oc); continue; }
+            int32_t head[2] = {-1, -1}, tail[2] = {-1, -1};
+            for (int32_t nx; e >= 0; e = nx) {
+                nx = nd[e].next;
+                nd[e].next = -1;
+                const int s = (h[(size_t)e] & oc) ? 1 : 0;
+                if (tail[s] < 0) head[s] = e;
+                else nd[tail[s]].next = e;
+                tail[s] = e;
+            }
+            tab[j] = head[0];
+            tab[j + oc] = head[1];
+        }
+    }
+    void put(int32_t n) {
+        if (tab.empty()) resize();
+        const size_t i = h[(size_t)n] & (tab.size() - 1);
+        int32_t p = tab[i];
+        if (p < 0) {
+            tab[i] = n;
+        } else if (nd[p].tree) {   // putTreeVal: a leaf of the tree, linked right after its parent
+            int32_t root = p;
+            while (nd[root].parent >= 0) root = nd[root].parent;
+            for (int32_t q = root;;) {
+                const int d = dir(n, q);
+                const int32_t xp = q;
+                q = d <= 0 ? nd[q].left : nd[q].right;
+                if (q < 0) {
+                    const int32_t xpn = nd[xp].next;
+                    nd[n].tree = true;
+                    nd[n].next = xpn;
+                    (d <= 0 ? nd[xp].left : nd[xp].right) = n;
+                    nd[xp].next = n;
+                    nd[n].parent = nd[n].prev = xp;
+                    if (xpn >= 0) nd[xpn].prev = n;
+                    move_root_to_front(balance_insertion(root, n));
+                    break;
+                }
+            }
+        } else {
+            int walked = 0;
+            while (nd[p].next >= 0) { p = nd[p].next; walked++; }
+            nd[p].next = n;
+            if (walked >= 7) {   // TREEIFY_THRESHOLD - 1: the bin now holds 9 nodes
+                if (tab.size() < 64) {
+                    resize();    // MIN_TREEIFY_CAPACITY
+                } else {
+                    int32_t prev = -1;
+                    for (int32_t x = tab[i]; x >= 0; x = nd[x].next) { nd[x].tree = true; nd[x].prev = prev; prev = x; }
+                    treeify(tab[i]);
+                }
+            }
+        }
+        if (++size > threshold) resize();
+    }
+    std::vector<uint32_t> run() {
+        for (size_t i = 0; i < h.size(); i++) put((int32_t)i);
+        std::vector<uint32_t> o;
+        o.reserve(h.size());
+        for (int32_t e : tab)
+            for (; e >= 0; e = nd[e].next) o.push_back((uint32_t)e);
+        return o;
+    }
+};
+
+// positions 0 .. n-1 in iteration order.  peak = the largest size the map ever had (removals never shrink the table).
+template <class Less>
+static std::vector<uint32_t> java_hashmap_order(const std::vector<uint32_t>& h, size_t peak, Less less) {
+    const size_t n = h.size();
+    if (n >= 9 && java_hashmap_needs_replay(h)) {
+        if (peak <= n) return JavaHashReplay<Less>(h, less).run();
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            fprintf(stderr, "WARN: a java.util.HashMap bin of this environment was treeified and keys were removed afterwards (--trim): the order inside "
+                            "that bin is not modelled and may differ from the JVM's\n");
+        }
+    }
+    size_t cap = 16;
+    while ((double)std::max(peak, n) > 0.75 * (double)cap) cap <<= 1;
+    std::vector<uint32_t> start(cap + 1, 0), o(n);
+    for (size_t i = 0; i < n; i++) start[(h[i] & (uint32_t)(cap - 1)) + 1]++;
+    for (size_t b = 0; b < cap; b++) start[b + 1] += start[b];
+    for (size_t i = 0; i < n; i++) o[start[h[i] & (uint32_t)(cap - 1)]++] = (uint32_t)i;
+    return o;
+}
+
+// A java.util.HashMap<String,V> by its iteration order (java_hashmap_order above).  Pinned on the reference's committed graph.txt by the tests.
 template <class V>
 struct JavaMap {
     std::unordered_map<std::string, uint32_t> index;
@@ -150,17 +433,12 @@ struct JavaMap {
         for (size_t i = 0; i < entries.size(); i++) index.emplace(entries[i].first, (uint32_t)i);
     }
     std::vector<uint32_t> order() const {
-        size_t cap = 16;
-        while ((double)std::max(peak, entries.size()) > 0.75 * (double)cap) cap <<= 1;
-        std::vector<std::pair<uint32_t, uint32_t>> v(entries.size());
+        std::vector<uint32_t> h(entries.size());
         for (size_t i = 0; i < entries.size(); i++) {
-            uint32_t h = (uint32_t)java_string_hash(entries[i].first);
-            v[i] = {(h ^ (h >> 16)) & (uint32_t)(cap - 1), (uint32_t)i};
+            const uint32_t x = (uint32_t)java_string_hash(entries[i].first);
+            h[i] = x ^ (x >> 16);
         }
-        std::stable_sort(v.begin(), v.end(), [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; });
-        std::vector<uint32_t> o(v.size());
-        for (size_t i = 0; i < v.size(); i++) o[i] = v[i].second;
-        return o;
+        return java_hashmap_order(h, peak, [this](uint32_t a, uint32_t b) { return entries[a].first < entries[b].first; });
     }
 };
 
@@ -254,19 +532,15 @@ struct KmerMap {
         for (int i = k - 1; i >= 0; i--, code >>= 2) h += hash_tab[i][code & 3];
         return h;
     }
-    std::vector<uint32_t> order() const {             // bucket index, then insertion order inside a bucket: a stable counting sort
-        size_t cap = 16;
-        while ((double)std::max(peak, keys.size()) > 0.75 * (double)cap) cap <<= 1;
-        std::vector<uint32_t> bucket(keys.size()), start(cap + 1, 0);
+    std::vector<uint32_t> order() const {             // java_hashmap_order: a stable counting sort by bucket unless a bin was treeified
+        std::vector<uint32_t> h(keys.size());
         for (size_t i = 0; i < keys.size(); i++) {
-            const uint32_t h = java_hash(keys[i]);
-            bucket[i] = (h ^ (h >> 16)) & (uint32_t)(cap - 1);
-            start[bucket[i] + 1]++;
+            const uint32_t x = java_hash(keys[i]);
+            h[i] = x ^ (x >> 16);
         }
-        for (size_t b = 0; b < cap; b++) start[b + 1] += start[b];
-        std::vector<uint32_t> o(keys.size());
-        for (size_t i = 0; i < keys.size(); i++) o[start[bucket[i]]++] = (uint32_t)i;
-        return o;
+        // String.compareTo on k-mers of one length = numeric order of the codes with G (1) and C (2) exchanged (ASCII A < C < G < T)
+        auto rank = [](uint64_t x) { return ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL); };
+        return java_hashmap_order(h, peak, [this, rank](uint32_t a, uint32_t b) { return rank(keys[a]) < rank(keys[b]); });
     }
 };
 

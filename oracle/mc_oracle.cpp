@@ -125,9 +125,283 @@ int32_t java_string_hash(const std::string& s) {
 // java.util.HashMap<String, V> iteration-order emulation.
 // Buckets are visited in index order; inside a bucket entries keep insertion order (resize
 // splits preserve relative order, java.util.HashMap.resize()).  Capacity: 16, doubled whenever
-// ++size > 0.75*capacity.  Treeified bins (>= 8 entries in one bucket) are NOT emulated.
+// ++size > 0.75*capacity.  A map in which some bin reached 9 nodes (treeifyBin) is replayed put by put
+// through JdkHashMap below, a literal restatement of java.util.HashMap's putVal / resize / treeifyBin /
+// TreeNode.{treeify, putTreeVal, split, untreeify, balanceInsertion, rotate*, moveRootToFront}.
 // Pinned by tests/golden: the reference's committed graph.txt is in exactly this order.
 // =====================================================================================
+// java.util.HashMap<String,?> for keys that are all NEW (the caller de-duplicates), statement by statement after the JDK (8u .. 21:
+// these methods did not change).  Only what decides the iteration order is kept: no values, no removal.
+struct JdkHashMap {
+    struct Node {
+        int hash;                       // spread hash
+        const std::string* key;
+        Node* next = nullptr;
+        // TreeNode part
+        Node *parent = nullptr, *left = nullptr, *right = nullptr, *prev = nullptr;
+        bool red = false, is_tree = false;
+    };
+    static const int TREEIFY_THRESHOLD = 8, UNTREEIFY_THRESHOLD = 6, MIN_TREEIFY_CAPACITY = 64;
+    std::deque<Node> pool;
+    std::vector<Node*> table;
+    size_t threshold = 0, size = 0;
+
+    static int hash_of(const std::string& k) { uint32_t h = (uint32_t)java_string_hash(k); return (int)(h ^ (h >> 16)); }
+    static int compare_keys(const Node* x_new, const Node* p) { return x_new->key->compare(*p->key); }   // String.compareTo (sign only)
+
+    void put(const std::string& key) {   // putVal
+        if (table.empty()) resize();
+        pool.emplace_back();
+        Node* x = &pool.back();
+        x->hash = hash_of(key);
+        x->key = &key;
+        const size_t n = table.size(), i = (n - 1) & (size_t)(uint32_t)x->hash;
+        Node* p = table[i];
+        if (p == nullptr) {
+            table[i] = x;
+        } else if (p->is_tree) {
+            put_tree_val(p, x);
+        } else {
+            for (int binCount = 0;; ++binCount) {
+                Node* e = p->next;
+                if (e == nullptr) {
+                    p->next = x;
+                    if (binCount >= TREEIFY_THRESHOLD - 1) treeify_bin(x->hash);
+                    break;
+                }
+                p = e;
+            }
+        }
+        if (++size > threshold) resize();
+    }
+    void resize() {
+        if (table.empty()) {
+            table.assign(16, nullptr);
+            threshold = 12;
+            return;
+        }
+        const size_t oldCap = table.size(), newCap = oldCap << 1;
+        threshold <<= 1;
+        std::vector<Node*> oldTab(newCap, nullptr);
+        oldTab.swap(table);   // table = newTab
+        for (size_t j = 0; j < oldCap; ++j) {
+            Node* e = oldTab[j];
+            if (e == nullptr) continue;
+            if (e->next == nullptr) {
+                table[(size_t)(uint32_t)e->hash & (newCap - 1)] = e;
+            } else if (e->is_tree) {
+                split(e, j, oldCap);
+            } else {   // preserve order
+                Node *loHead = nullptr, *loTail = nullptr, *hiHead = nullptr, *hiTail = nullptr, *next;
+                do {
+                    next = e->next;
+                    if (((size_t)(uint32_t)e->hash & oldCap) == 0) {
+                        if (loTail == nullptr) loHead = e; else loTail->next = e;
+                        loTail = e;
+                    } else {
+                        if (hiTail == nullptr) hiHead = e; else hiTail->next = e;
+                        hiTail = e;
+                    }
+                } while ((e = next) != nullptr);
+                if (loTail != nullptr) { loTail->next = nullptr; table[j] = loHead; }
+                if (hiTail != nullptr) { hiTail->next = nullptr; table[j + oldCap] = hiHead; }
+            }
+        }
+    }
+    void treeify_bin(int hash) {
+        const size_t n = table.size();
+        if (n < (size_t)MIN_TREEIFY_CAPACITY) { resize(); return; }
+        const size_t index = (n - 1) & (size_t)(uint32_t)hash;
+        Node* e = table[index];
+        if (e == nullptr) return;
+        Node *hd = nullptr, *tl = nullptr;
+        do {   // replacementTreeNode(e, null)
+            e->is_tree = true;
+            e->parent = e->left = e->right = nullptr;
+            if (tl == nullptr) hd = e;
+            else { e->prev = tl; tl->next = e; }
+            tl = e;
+        } while ((e = e->next) != nullptr);
+        hd->prev = nullptr;
+        table[index] = hd;
+        treeify(hd);
+    }
+    static int direction(const Node* x, const Node* p) {   // of x relative to p: hashes as ints, then compareTo
+        if (p->hash > x->hash) return -1;
+        if (p->hash < x->hash) return 1;
+        return compare_keys(x, p) < 0 ? -1 : 1;   // distinct keys: never 0, tieBreakOrder is unreachable
+    }
+    void treeify(Node* self) {
+        Node* root = nullptr;
+        for (Node *x = self, *next; x != nullptr; x = next) {
+            next = x->next;
+            x->left = x->right = nullptr;
+            if (root == nullptr) {
+                x->parent = nullptr;
+                x->red = false;
+                root = x;
+            } else {
+                for (Node* p = root;;) {
+                    const int dir = direction(x, p);
+                    Node* xp = p;
+                    if ((p = (dir <= 0) ? p->left : p->right) == nullptr) {
+                        x->parent = xp;
+                        if (dir <= 0) xp->left = x; else xp->right = x;
+                        root = balance_insertion(root, x);
+                        break;
+                    }
+                }
+            }
+        }
+        move_root_to_front(root);
+    }
+    void put_tree_val(Node* self, Node* x) {
+        Node* root = self;
+        while (root->parent != nullptr) root = root->parent;
+        for (Node* p = root;;) {
+            const int dir = direction(x, p);
+            Node* xp = p;
+            if ((p = (dir <= 0) ? p->left : p->right) == nullptr) {
+                Node* xpn = xp->next;
+                x->is_tree = true;
+                x->next = xpn;
+                if (dir <= 0) xp->left = x; else xp->right = x;
+                xp->next = x;
+                x->parent = x->prev = xp;
+                if (xpn != nullptr) xpn->prev = x;
+                move_root_to_front(balance_insertion(root, x));
+                return;
+            }
+        }
+    }
+    void move_root_to_front(Node* root) {
+        if (root == nullptr || table.empty()) return;
+        const size_t index = (table.size() - 1) & (size_t)(uint32_t)root->hash;
+        Node* first = table[index];
+        if (root != first) {
+            table[index] = root;
+            Node *rp = root->prev, *rn = root->next;
+            if (rn != nullptr) rn->prev = rp;
+            if (rp != nullptr) rp->next = rn;
+            if (first != nullptr) first->prev = root;
+            root->next = first;
+            root->prev = nullptr;
+        }
+    }
+    static Node* untreeify(Node* self) {   // plain nodes, same order
+        for (Node* q = self; q != nullptr; q = q->next) {
+            q->is_tree = false;
+            q->parent = q->left = q->right = q->prev = nullptr;
+        }
+        return self;
+    }
+    void split(Node* b, size_t index, size_t bit) {
+        Node *loHead = nullptr, *loTail = nullptr, *hiHead = nullptr, *hiTail = nullptr;
+        int lc = 0, hc = 0;
+        for (Node *e = b, *next; e != nullptr; e = next) {
+            next = e->next;
+            e->next = nullptr;
+            if (((size_t)(uint32_t)e->hash & bit) == 0) {
+                if ((e->prev = loTail) == nullptr) loHead = e; else loTail->next = e;
+                loTail = e;
+                ++lc;
+            } else {
+                if ((e->prev = hiTail) == nullptr) hiHead = e; else hiTail->next = e;
+                hiTail = e;
+                ++hc;
+            }
+        }
+        if (loHead != nullptr) {
+            if (lc <= UNTREEIFY_THRESHOLD) table[index] = untreeify(loHead);
+            else {
+                table[index] = loHead;
+                if (hiHead != nullptr) treeify(loHead);   // (else is already treeified)
+            }
+        }
+        if (hiHead != nullptr) {
+            if (hc <= UNTREEIFY_THRESHOLD) table[index + bit] = untreeify(hiHead);
+            else {
+                table[index + bit] = hiHead;
+                if (loHead != nullptr) treeify(hiHead);
+            }
+        }
+    }
+    static Node* rotate_left(Node* root, Node* p) {
+        Node *r, *pp, *rl;
+        if (p != nullptr && (r = p->right) != nullptr) {
+            if ((rl = p->right = r->left) != nullptr) rl->parent = p;
+            if ((pp = r->parent = p->parent) == nullptr) (root = r)->red = false;
+            else if (pp->left == p) pp->left = r;
+            else pp->right = r;
+            r->left = p;
+            p->parent = r;
+        }
+        return root;
+    }
+    static Node* rotate_right(Node* root, Node* p) {
+        Node *l, *pp, *lr;
+        if (p != nullptr && (l = p->left) != nullptr) {
+            if ((lr = p->left = l->right) != nullptr) lr->parent = p;
+            if ((pp = l->parent = p->parent) == nullptr) (root = l)->red = false;
+            else if (pp->right == p) pp->right = l;
+            else pp->left = l;
+            l->right = p;
+            p->parent = l;
+        }
+        return root;
+    }
+    static Node* balance_insertion(Node* root, Node* x) {
+        x->red = true;
+        for (Node *xp, *xpp, *xppl, *xppr;;) {
+            if ((xp = x->parent) == nullptr) {
+                x->red = false;
+                return x;
+            } else if (!xp->red || (xpp = xp->parent) == nullptr) {
+                return root;
+            }
+            if (xp == (xppl = xpp->left)) {
+                if ((xppr = xpp->right) != nullptr && xppr->red) {
+                    xppr->red = false;
+                    xp->red = false;
+                    xpp->red = true;
+                    x = xpp;
+                } else {
+                    if (x == xp->right) {
+                        root = rotate_left(root, x = xp);
+                        xpp = (xp = x->parent) == nullptr ? nullptr : xp->parent;
+                    }
+                    if (xp != nullptr) {
+                        xp->red = false;
+                        if (xpp != nullptr) {
+                            xpp->red = true;
+                            root = rotate_right(root, xpp);
+                        }
+                    }
+                }
+            } else {
+                if (xppl != nullptr && xppl->red) {
+                    xppl->red = false;
+                    xp->red = false;
+                    xpp->red = true;
+                    x = xpp;
+                } else {
+                    if (x == xp->left) {
+                        root = rotate_right(root, x = xp);
+                        xpp = (xp = x->parent) == nullptr ? nullptr : xp->parent;
+                    }
+                    if (xp != nullptr) {
+                        xp->red = false;
+                        if (xpp != nullptr) {
+                            xpp->red = true;
+                            root = rotate_left(root, xpp);
+                        }
+                    }
+                }
+            }
+        }
+    }
+};
+
 template <class V>
 struct JHashMap {
     std::unordered_map<std::string, size_t> index;   // key -> position in `entries`
@@ -169,8 +443,34 @@ struct JHashMap {
         while ((double)std::max(peak, entries.size()) > 0.75 * (double)cap) cap <<= 1;
         return cap;
     }
+    // true when, filling a default HashMap with the entries in their order, some bin reaches 9 nodes (the order then depends on the
+    // history: treeified bins, or an early resize of a table under 64 buckets)
+    bool needs_replay() const {
+        size_t cap = 16, lo = 0;
+        std::vector<uint32_t> cnt;
+        while (lo < entries.size()) {
+            const size_t hi = std::min(entries.size(), cap / 4 * 3 + 1);
+            cnt.assign(cap, 0);
+            for (size_t i = 0; i < hi; i++)
+                if (++cnt[spread(java_string_hash(entries[i].first)) & (uint32_t)(cap - 1)] >= 9 && i >= lo) return true;
+            lo = hi;
+            cap <<= 1;
+        }
+        return false;
+    }
     // positions into `entries` in java iteration order
     std::vector<size_t> order() const {
+        if (entries.size() >= 9 && peak <= entries.size() && needs_replay()) {
+            JdkHashMap m;
+            for (auto& e : entries) m.put(e.first);
+            std::unordered_map<const std::string*, size_t> where;
+            for (size_t i = 0; i < entries.size(); i++) where.emplace(&entries[i].first, i);
+            std::vector<size_t> o;
+            o.reserve(entries.size());
+            for (JdkHashMap::Node* e : m.table)
+                for (; e != nullptr; e = e->next) o.push_back(where[e->key]);
+            return o;
+        }
         size_t cap = capacity();
         std::vector<std::pair<uint32_t, size_t>> v(entries.size());
         for (size_t i = 0; i < entries.size(); i++)
@@ -1435,6 +1735,13 @@ void orc_decode(uint64_t kmer, int k, char* out) {
     memcpy(out, s.c_str(), s.size() + 1);
 }
 int32_t orc_java_string_hash(const char* s) { return java_string_hash(s); }
+// iteration order of a java.util.HashMap<String,_> filled with the n distinct keys in their order: order[i] = index of the i-th key visited
+void orc_java_hashmap_order(const char* const* keys, size_t n, uint64_t* order) {
+    JHashMap<int> m;
+    for (size_t i = 0; i < n; i++) m.put(keys[i], (int)i);
+    const std::vector<size_t> o = m.order();
+    for (size_t i = 0; i < o.size(); i++) order[i] = (uint64_t)m.entries[o[i]].second;
+}
 
 int64_t orc_bfs(const orc_table* t, const char* seq, int k, int min_cov, int64_t max_kmers, int64_t max_radius, int dir,
                 char* out_kmers, int32_t* out_dist, uint64_t cap) {

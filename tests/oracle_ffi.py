@@ -57,6 +57,8 @@ class Oracle:
         L.orc_decode.argtypes = [C.c_uint64, C.c_int, C.c_char_p]
         L.orc_java_string_hash.restype = C.c_int32
         L.orc_java_string_hash.argtypes = [C.c_char_p]
+        L.orc_java_hashmap_order.restype = None
+        L.orc_java_hashmap_order.argtypes = [C.POINTER(C.c_char_p), C.c_size_t, C.c_void_p]
         L.orc_bfs.restype = C.c_int64
         L.orc_bfs.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64]
         L.orc_env_find.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char_p]
@@ -113,6 +115,14 @@ class Oracle:
 
     def java_hash(self, s):
         return self.lib.orc_java_string_hash(s.encode())
+
+    def java_hashmap_order(self, keys):
+        """Iteration order (as indices into `keys`, distinct strings) of a java.util.HashMap filled in that order."""
+        import numpy as np
+        arr = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+        out = np.empty(len(keys), dtype=np.uint64)
+        self.lib.orc_java_hashmap_order(arr, len(keys), out.ctypes.data)
+        return [int(x) for x in out]
 
     def detect_format(self, path):
         return self.check(self.lib.orc_detect_format(path.encode()))

@@ -6,7 +6,7 @@ import random
 import numpy as np
 import pytest
 
-from helpers import small_graph
+from helpers import rand_seq, small_graph
 from oracle import pyref
 from oracle_ffi import FMT_FASTA, FMT_FASTQ
 
@@ -119,6 +119,36 @@ def test_stage_d_on_the_reference_golden_environment(ctx, oracle, tmp_path):
     assert (tmp_path / "gpu_plain" / "graph.txt").read_bytes() == p.read_bytes()
     gfa = open(tmp_path / "gpu_gene" / "graph.gfa").read().splitlines()
     assert sum(l.startswith("S\t") for l in gfa) == 18 and sum(l.startswith("L\t") for l in gfa) == 44
+
+
+def test_stage_d_with_treeified_hashmap_bins(ctx, oracle, tmp_path):
+    """A graph.txt whose k-mers crowd a few java.util.HashMap bins (9 .. 40 keys with the same residue of the spread hash): the bins
+    are treeified and the iteration order -- the line order of graph.txt / env.txt and the node ids of the unitig files -- depends on
+    the history of the puts.  The library (JavaHashReplay) and the oracle (a literal JdkHashMap) write the same bytes, and the order
+    really differs from the plain bucket order."""
+    from test_host_logic import crowded_kmers
+    rng = random.Random(77)
+    k = 21
+    genome = rand_seq(rng, 1500)
+    path_kmers = [genome[i:i + k] for i in range(len(genome) - k + 1)]
+    crowd = crowded_kmers(rng, k, 600, 3, 30, 4095)
+    # graph.txt holds every k-mer as written (loadGraph does not normalise): the crowded ones stay as generated, so that their hashes stay crowded
+    kmers = list(dict.fromkeys([pyref.normalize(x) for x in path_kmers] + crowd))
+    rng.shuffle(kmers)
+    p = tmp_path / "graph.txt"
+    p.write_text("".join(f"{x} {rng.randint(1, 300)}\n" for x in kmers))
+    loaded = [l.split(" ")[0] for l in open(p)]
+    assert pyref.java_order_needs_replay(loaded)
+    ctx.env_from_graph_txt(p, genome[100:400], k, 1, tmp_path / "gpu")
+    oracle.env_from_graph_txt(str(p), genome[100:400], k, 1, str(tmp_path / "orc"))
+    same_files(str(tmp_path / "gpu"), str(tmp_path / "orc"))
+    got = [l.split(" ")[0] for l in open(tmp_path / "gpu" / "graph.txt")]
+    assert got == pyref.java_order(loaded)
+    cap = 16
+    while len(loaded) > 0.75 * cap:
+        cap *= 2
+    plain = sorted(loaded, key=lambda x: (lambda h: (h ^ (h >> 16)) & (cap - 1))(pyref.java_hash(x)))
+    assert got != plain and sorted(got) == sorted(plain)
 
 
 def test_multi_tool_matches_oracle(ctx, oracle, tmp_path):

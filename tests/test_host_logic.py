@@ -51,6 +51,50 @@ def test_hashmap_order_matches_pyref(k, n, peak):
     assert [kmers[i] for i in got] == want
 
 
+def crowded_kmers(rng, k, n_total, hot_bins, hot_each, mask):
+    """k-mers of which `hot_each` share each of `hot_bins` residues of the spread String.hashCode modulo mask + 1: those bins are
+    treeified by a real java.util.HashMap once the table has mask + 1 buckets or fewer (and >= 64)."""
+    def spread(s):
+        h = pyref.java_hash(s)
+        return h ^ (h >> 16)
+    hot = {rng.randrange(mask + 1): [] for _ in range(hot_bins)}
+    seen = set()
+    while any(len(v) < hot_each for v in hot.values()):
+        s = "".join(rng.choice("ACGT") for _ in range(k))
+        b = spread(s) & mask
+        if s not in seen and b in hot and len(hot[b]) < hot_each:
+            hot[b].append(s)
+            seen.add(s)
+    kmers = [x for v in hot.values() for x in v]
+    while len(kmers) < n_total:
+        s = "".join(rng.choice("ACGT") for _ in range(k))
+        if s not in seen:
+            seen.add(s)
+            kmers.append(s)
+    rng.shuffle(kmers)
+    return kmers
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_hashmap_order_with_treeified_bins(seed):
+    """Bins of 9 and more nodes (java.util.HashMap.treeifyBin): root moved to the front, new nodes linked after their tree parent,
+    resize splits that re-treeify or untreeify at 6 nodes, tables under 64 buckets resized instead.  The library's replay
+    (JavaHashReplay, C++) against the model in oracle/pyref.py (JavaHashMapModel): two implementations written separately from the
+    JDK's algorithm; the model's own invariants (red-black properties, list/tree consistency) are checked in tests/test_oracle_vs_pyref.py."""
+    rng = random.Random(seed)
+    k = rng.choice([9, 13, 23, 31])
+    n = rng.choice([60, 200, 1500, 3000])                 # final capacities 128 .. 4096: equal residues mod 4096 share a bin throughout
+    kmers = crowded_kmers(rng, k, n, rng.randint(1, 3), rng.randint(9, 40), 4095)
+    assert pyref.java_order_needs_replay(kmers)
+    want = pyref.java_order(kmers)
+    got = lib_order([pyref.encode(s) for s in kmers], k)
+    assert [kmers[i] for i in got] == want
+    # the history matters: the same keys in sorted insertion order give another iteration order, and both sides follow it
+    kmers2 = sorted(kmers)
+    got2 = lib_order([pyref.encode(s) for s in kmers2], k)
+    assert [kmers2[i] for i in got2] == pyref.java_order(kmers2)
+
+
 def test_duplicates_keep_their_first_position():
     kmers = ["ACGTA", "TTTTT", "ACGTA", "GGGCC", "TTTTT", "CATCA"]
     got = lib_order([pyref.encode(s) for s in kmers], 5)

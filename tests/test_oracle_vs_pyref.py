@@ -398,3 +398,102 @@ def test_classifier_restatement_matches_a_literal_transcription(oracle):
             else:
                 want = py_find_read(lambda key: int(t.get(key)), nuc, k, z, thr)
             assert bool(found_c[i]) == want, (i, "".join(seq), bad)
+
+
+# ---- java.util.HashMap with treeified bins (TREEIFY_THRESHOLD): the history decides the iteration order ----------------------------
+def _crowded_keys(rng, k, n_total, hot_bins, hot_each, mask=4095):
+    """strings of which `hot_each` share each of `hot_bins` residues of the spread String.hashCode modulo mask + 1"""
+    def spread(s):
+        h = pyref.java_hash(s)
+        return h ^ (h >> 16)
+    hot = {rng.randrange(mask + 1): [] for _ in range(hot_bins)}
+    seen = set()
+    while any(len(v) < hot_each for v in hot.values()):
+        s = "".join(rng.choice("ACGT") for _ in range(k))
+        b = spread(s) & mask
+        if s not in seen and b in hot and len(hot[b]) < hot_each:
+            hot[b].append(s)
+            seen.add(s)
+    keys = [x for v in hot.values() for x in v]
+    while len(keys) < n_total:
+        s = "".join(rng.choice("ACGT") for _ in range(k))
+        if s not in seen:
+            seen.add(s)
+            keys.append(s)
+    rng.shuffle(keys)
+    return keys
+
+
+def _check_model(m):
+    """Structural invariants of the model after any number of puts: every key once, every node in the bin of its hash, tree bins are
+    valid red-black trees over exactly the nodes of the bin's list, ordered by (hash as int, key), with the root first in the list."""
+    seen = 0
+    for idx, e in enumerate(m.tab):
+        if e == -1:
+            continue
+        lst, x = [], e
+        while x != -1:
+            assert m.h[x] & (len(m.tab) - 1) == idx
+            lst.append(x)
+            x = m.nxt[x]
+        seen += len(lst)
+        if not m.tree[e]:
+            assert not any(m.tree[x] for x in lst) and len(lst) <= 8
+            continue
+        assert all(m.tree[x] for x in lst) and len(lst) >= 7
+        assert all(m.prv[b] == a for a, b in zip(lst, lst[1:]))
+        assert m.prv[e] == -1 and m.par[e] == -1 and not m.red[e]
+        nodes = []
+
+        def walk(x, lo, hi):
+            if x == -1:
+                return 1
+            nodes.append(x)
+            key = (m._sgn(m.h[x]), m.key[x])
+            assert (lo is None or lo < key) and (hi is None or key < hi)
+            for c in (m.left[x], m.right[x]):
+                assert c == -1 or (m.par[c] == x and not (m.red[x] and m.red[c]))
+            lh, rh = walk(m.left[x], lo, key), walk(m.right[x], key, hi)
+            assert lh == rh
+            return lh + (0 if m.red[x] else 1)
+
+        walk(e, None, None)
+        assert sorted(nodes) == sorted(lst)
+    assert seen == len(m.key)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_hashmap_model_with_treeified_bins(oracle, seed):
+    """pyref.JavaHashMapModel keeps its invariants through treeify / putTreeVal / resize splits, equals the plain model when no bin
+    reaches 9 nodes, and the oracle's literal C++ transcription of the JDK methods (JdkHashMap) visits the keys in the same order."""
+    rng = random.Random(100 + seed)
+    k = rng.choice([9, 13, 31])
+    n = rng.choice([40, 200, 1500, 3000])
+    keys = _crowded_keys(rng, k, n, rng.randint(1, 3), rng.randint(7, 40))
+    m = pyref.JavaHashMapModel()
+    for i, key in enumerate(keys):
+        m.put(key)
+        if i % 61 == 0:
+            _check_model(m)
+    _check_model(m)
+    assert sorted(m.keys()) == sorted(keys)
+    want = pyref.java_order(keys)
+    if pyref.java_order_needs_replay(keys):
+        assert want == m.keys()
+    else:
+        assert m.keys() == want            # no bin of 9: the replay and the counting sort are the same thing
+    got = oracle.java_hashmap_order(keys)
+    assert [keys[i] for i in got] == want
+
+
+def test_hashmap_model_equals_plain_order_on_random_keys(oracle):
+    rng = random.Random(3)
+    for n in (1, 12, 13, 97, 5000):
+        keys = list({"".join(rng.choice("ACGT") for _ in range(17)) for _ in range(n)})
+        rng.shuffle(keys)
+        m = pyref.JavaHashMapModel()
+        for key in keys:
+            m.put(key)
+        assert not pyref.java_order_needs_replay(keys)
+        assert m.keys() == pyref.java_order(keys)
+        assert [keys[i] for i in oracle.java_hashmap_order(keys)] == m.keys()
