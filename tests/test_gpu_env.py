@@ -131,8 +131,8 @@ def test_stage_d_with_treeified_hashmap_bins(ctx, oracle, tmp_path):
     k = 21
     genome = rand_seq(rng, 1500)
     path_kmers = [genome[i:i + k] for i in range(len(genome) - k + 1)]
-    crowd = crowded_kmers(rng, k, 600, 3, 30, 4095)
-    # graph.txt holds every k-mer as written (loadGraph does not normalise): the crowded ones stay as generated, so that their hashes stay crowded
+    # graph.txt holds ASCII-canonical k-mers only (a node's k-mer is looked up in its normal form): the crowd is drawn among those
+    crowd = crowded_kmers(rng, k, 600, 3, 30, 4095, accept=lambda x: x == pyref.normalize(x))
     kmers = list(dict.fromkeys([pyref.normalize(x) for x in path_kmers] + crowd))
     rng.shuffle(kmers)
     p = tmp_path / "graph.txt"

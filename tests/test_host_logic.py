@@ -51,7 +51,7 @@ def test_hashmap_order_matches_pyref(k, n, peak):
     assert [kmers[i] for i in got] == want
 
 
-def crowded_kmers(rng, k, n_total, hot_bins, hot_each, mask):
+def crowded_kmers(rng, k, n_total, hot_bins, hot_each, mask, accept=lambda s: True):
     """k-mers of which `hot_each` share each of `hot_bins` residues of the spread String.hashCode modulo mask + 1: those bins are
     treeified by a real java.util.HashMap once the table has mask + 1 buckets or fewer (and >= 64)."""
     def spread(s):
@@ -62,13 +62,13 @@ def crowded_kmers(rng, k, n_total, hot_bins, hot_each, mask):
     while any(len(v) < hot_each for v in hot.values()):
         s = "".join(rng.choice("ACGT") for _ in range(k))
         b = spread(s) & mask
-        if s not in seen and b in hot and len(hot[b]) < hot_each:
+        if s not in seen and accept(s) and b in hot and len(hot[b]) < hot_each:
             hot[b].append(s)
             seen.add(s)
     kmers = [x for v in hot.values() for x in v]
     while len(kmers) < n_total:
         s = "".join(rng.choice("ACGT") for _ in range(k))
-        if s not in seen:
+        if s not in seen and accept(s):
             seen.add(s)
             kmers.append(s)
     rng.shuffle(kmers)
