@@ -121,6 +121,31 @@ def test_stage_d_on_the_reference_golden_environment(ctx, oracle, tmp_path):
     assert sum(l.startswith("S\t") for l in gfa) == 18 and sum(l.startswith("L\t") for l in gfa) == 44
 
 
+def test_bfs_from_the_example_target_reaches_exactly_the_golden_environment(ctx, oracle, tmp_path):
+    """The GPU's BFS + unitigs on the table of the reference's committed environment (see the oracle's test of the same name in
+    tests/test_oracle_golden.py): from the 31 seed k-mers of example/seq.fasta with `--maxradius 100000 --coverage 5 --merge true`
+    the two passes visit exactly the 93 572 golden k-mers; every output file is byte-identical to the oracle's."""
+    from test_oracle_golden import _golden_table_pairs
+    p = tmp_path / "graph.txt"
+    with lzma.open(os.path.join(GOLD, "graph.txt.xz"), "rb") as f:
+        p.write_bytes(f.read())
+    keys, counts, want = _golden_table_pairs(str(p))
+    g = ctx.new_table(31)
+    g.add_pairs(keys, counts)
+    o = oracle.table(31, threads=2)
+    o.add_pairs(keys, counts)
+    fa = os.path.join(GOLD, "seq.fasta")
+    o.env_find_ex(fa, None, 5, None, 100000, False, 10, True, False, str(tmp_path / "orc"))
+    targets = ctx.load_targets(fa)
+    found = ctx.find_environments_ex(g, [x[1] for x in targets], [x[0] for x in targets], min_cov=5, max_radius=100000, both_dirs=False,
+                                     chunk_len=10, merge=True, out_dir=tmp_path / "gpu")
+    assert found == [True]
+    same_files(str(tmp_path / "gpu" / "merged"), str(tmp_path / "orc" / "merged"))
+    got = [l.rstrip("\n") for l in open(tmp_path / "gpu" / "merged" / "graph.txt")]
+    assert len(got) == 93572 and sorted(got) == sorted(want)
+    g.free()
+
+
 def test_stage_d_with_treeified_hashmap_bins(ctx, oracle, tmp_path):
     """A graph.txt whose k-mers crowd a few java.util.HashMap bins (9 .. 40 keys with the same residue of the spread hash): the bins
     are treeified and the iteration order -- the line order of graph.txt / env.txt and the node ids of the unitig files -- depends on

@@ -122,3 +122,42 @@ def test_stage_d_with_current_gene_rule(oracle, graph_txt, tmp_path):
     # seqs.fasta honours --chunklength and the header format
     heads = [l for l in open(out / "seqs.fasta") if l.startswith(">")]
     assert all(h.startswith("> Id") and " Length:" in h and " Neighbors:[" in h for h in heads)
+
+
+def _golden_table_pairs(graph_txt, k=31):
+    """(canonical 2-bit keys, counts) of the k-mers the reference's committed graph.txt lists"""
+    import numpy as np
+    from oracle import pyref
+    lines = [l.split(" ") for l in open(graph_txt) if l.strip()]
+    keys = np.array([min(pyref.encode(a), pyref.revcomp_code(pyref.encode(a), k)) for a, _ in lines], dtype=np.uint64)
+    return keys, np.array([int(b) for _, b in lines], dtype=np.int16), [f"{a} {int(b)}" for a, b in lines]
+
+
+def test_bfs_from_the_example_target_reaches_exactly_the_golden_environment(oracle, graph_txt, tmp_path):
+    """Stage C1 against a reference-produced artefact, at the level of SETS.  The golden graph.txt was written by
+    `--k 31 --coverage 5 --seq example/seq.fasta --maxradius 100000 --bothdirs False --chunklength 10 --merge true`
+    (Hi-C_pipline/HiCEnvironmentFinder.sh:57) from WGS reads that are not in the repository.  A count table holding exactly the
+    golden k-mers with their counts stands in for the reads' table: every k-mer outside the environment was either not solid or not
+    reachable, so the two backward / forward passes from the target's 31 seed k-mers must visit every golden k-mer (each listed
+    k-mer is reachable by a directed walk through listed k-mers) and write the same 93 572 `KMER COUNT` lines.
+    What this does NOT pin: the order of the lines inside a HashMap bucket -- the committed file was written by an older revision
+    (its node ids differ too): 56 % of the multi-entry buckets agree with the insertion order the current code implies,
+    30 % are reversed; no variant of pass order / keySet-vs-queue insertion reproduces it."""
+    keys, counts, want = _golden_table_pairs(graph_txt)
+    assert counts.min() == 5                                   # --coverage 5: nothing below the threshold was ever listed
+    t = oracle.table(31, threads=2)
+    t.add_pairs(keys, counts)
+    out = tmp_path / "out"
+    t.env_find_ex(os.path.join(GOLD, "seq.fasta"), None, 5, None, 100000, False, 10, True, False, str(out))
+    got = [l.rstrip("\n") for l in open(out / "merged" / "graph.txt")]
+    assert len(got) == 93572 and sorted(got) == sorted(want)
+    # the unitigs of the golden GFA (sequences up to reverse complement, with their KC), whatever the node numbering: 15 of the 16
+    # come out unchanged; the current revision's gene flag cuts the 3 715-base one at the borders of the 61-base target into
+    # 95 + 61 (GREEN) + 3 619 bases, overlapping by k - 1 = 30
+    s_mine = _s_lines(out / "merged" / "graph.gfa")
+    mine = set((_canon(s[1]), s[3]) for s in s_mine)
+    gold = set((_canon(s[1]), s[3]) for s in _s_lines(os.path.join(GOLD, "graph.gfa")))
+    assert len(gold) == 16 and len(s_mine) == 18 and len(mine & gold) == 15
+    assert sorted(len(a) for a, _ in gold - mine) == [3715]
+    assert sorted(len(a) for a, _ in mine - gold) == [61, 95, 3619] and 61 + 95 + 3619 - 2 * 30 == 3715
+    assert [s[2] for s in s_mine if s[4] == "GREEN"] == [61]
