@@ -15,10 +15,15 @@
 // PARITY PINNING: stage D (environment -> unitigs/GFA/TSV) and the Java HashMap
 // iteration order are pinned against the reference's committed example outputs
 // (Hi-C_pipline/example_work_dir/output/1/merged/*, fixtures derived by
-// tests/golden/make_golden.py).  Stages A-C (parse, count, BFS) are PARITY
-// UNPINNED by any reference fixture (the JVM, the compiled ITMO jar and the WGS
-// reads are all absent); they are cross-checked against a second, independent
-// pure-Python transcription (oracle/pyref.py).
+// tests/golden/make_golden.py).  Stage C1 (BFS) is pinned on the same example at
+// the level of SETS: from the example target's seeds, over a table holding the
+// golden k-mers, the two passes visit exactly the 93 572 golden k-mers
+// (tests/test_oracle_golden.py); the order of lines inside one HashMap bucket is
+// not reproducible (the committed file comes from an older revision).  Stages A-B
+// (parse, count) and the reads-classifier are PARITY UNPINNED by any reference
+// fixture (the JVM, the compiled ITMO jar and the WGS reads are all absent); they
+// are cross-checked against a second, independent pure-Python transcription
+// (oracle/pyref.py).
 #pragma once
 #include <cstdint>
 #include <cstddef>
