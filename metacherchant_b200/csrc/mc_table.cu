@@ -264,9 +264,14 @@ extern "C" int mc_table_stats(const mc_table* t, uint64_t* reads, uint64_t* runs
 // almost every (bucket, slot) position of a warp has SOME lane with a survivor, so a warp ran ~2.5 serial insert phases per
 // 1 KB scanned and the scan crawled at the insert latency (2 TB/s).  Now a warp first scans RH_U x 32 buckets, queues the
 // survivors in shared memory, and then inserts them one per lane: one insert phase per 4 KB scanned in the coverage filter.
+#ifndef RH_U
 #define RH_U 4
+#endif
+#ifndef RH_MINB
+#define RH_MINB 4     // resident CTAs per SM the register budget is cut for: 64 registers, 1024 threads per SM (filter 5.95 -> 4.8 ms at cfg2)
+#endif
 #define RH_Q 256      // queue entries per warp (what does not fit is inserted on the spot)
-__global__ void __launch_bounds__(256) k_rehash(McTableDev src, McTableDev dst, uint32_t min_count) {
+__global__ void __launch_bounds__(256, RH_MINB) k_rehash(McTableDev src, McTableDev dst, uint32_t min_count) {
     __shared__ uint64_t q_h[8][RH_Q];
     __shared__ uint32_t q_c[8][RH_Q];
     __shared__ uint32_t q_n[8];
