@@ -69,7 +69,9 @@ __device__ __forceinline__ bool is_iupac(uint8_t c) {
 // --------------------------------------------------------------------------------------------
 #define EX_THREADS 128
 #define EX_WARPS (EX_THREADS / 32)
+#ifndef EX_STAGE_BYTES
 #define EX_STAGE_BYTES 12288   // per warp: 32 x 150 bp FASTQ records are ~10 KB
+#endif
 #define EX_CLS_SPLIT 4u        // no k-mer may span this base: N, n, '.' in FASTQ, and every invalid character
 #define EX_CLS_BAD 8u          // not a nucleotide character (an error unless the FASTA record is dropped for an N)
 #define EX_CLS_N 16u           // N or n
@@ -605,7 +607,11 @@ static void launch_extract_p(mc_ctx* ctx, McExtractArgs& a) {
 // window or a single lane would serialise a long read
 template <bool FASTA, int W>
 static void launch_extract_w(mc_ctx* ctx, McExtractArgs& a, uint32_t max_seq_len) {
-    const uint32_t one = FASTA ? 380u : 170u;
+    // one lane per record while the span of a warp's 32 records fits its staging window (FASTQ: 2 L + ~24 bytes per record, FASTA: L + ~10)
+#ifndef EX_ONE_FASTQ
+#define EX_ONE_FASTQ ((EX_STAGE_BYTES / 32 - 44) / 2)
+#endif
+    const uint32_t one = FASTA ? (uint32_t)(EX_STAGE_BYTES / 32 - 4) : (uint32_t)EX_ONE_FASTQ;
     if (ctx->tune_extract_parts == 1 || (ctx->tune_extract_parts == 0 && max_seq_len <= one)) launch_extract_p<FASTA, 1, W>(ctx, a);
     else if (ctx->tune_extract_parts == 4 || (ctx->tune_extract_parts == 0 && max_seq_len <= 4 * one)) launch_extract_p<FASTA, 4, W>(ctx, a);
     else launch_extract_p<FASTA, 32, W>(ctx, a);
