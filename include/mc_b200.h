@@ -196,8 +196,9 @@ int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_received);
 /* "Count locally, then merge": when a rank's own k-mers fit its GPU, every rank first counts ITS reads into a complete local
  * table (the single-GPU pipeline, repeats summed on the spot), and only the DISTINCT (key, count) pairs cross NVLink -- a
  * metagenome's k-mer instances are mostly repeats, so this moves several times fewer bytes than shipping every instance.
- *   every rank: mc_xchg_dump_owners(local, slot)   the table scan itself stores every entry into its owner's region (16 bytes
- *                                                  per pair, peer memory); region_keys of mc_xchg_create must be >= 2 * pairs
+ *   every rank: mc_xchg_dump_owners(local, slot)   the table scan itself stores every entry into its owner's region (peer memory:
+ *                                                  8-byte hashed keys, then 16-bit counts at the same positions = 10 bytes per
+ *                                                  pair); region_keys of mc_xchg_create must be >= 1.25 * pairs + 64
  *   all ranks:  barrier (host layer)
  *   every rank: mc_xchg_merge(slot, shard)         adds the received pairs (saturating) into this rank's shard table
  * mc_table_copy_stats carries the reader statistics (reads, runs, bases, k-mers) of the local table over to the shard. */

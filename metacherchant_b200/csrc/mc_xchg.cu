@@ -24,6 +24,8 @@ struct mc_xchg {
     unsigned long long* d_cursors = nullptr; // [world + 1] local append cursors of the batch being scattered
     unsigned int* d_flags = nullptr;
     uint64_t mailbox_off = 0;
+    // "merge" exchange: a region holds pair_cap() hashed keys (8 bytes each) followed by as many 16-bit counts
+    uint64_t pair_cap() const { return (region_keys * 8 / 10) & ~15ull; }
     uint64_t* region(uint8_t* base, int slot, int src) const { return (uint64_t*)base + ((uint64_t)slot * world + src) * region_keys; }
     unsigned long long* mailbox(uint8_t* base, int slot) const { return (unsigned long long*)(base + mailbox_off) + (uint64_t)slot * MC_MAX_XCHG_RANKS; }
 };
@@ -190,8 +192,9 @@ extern "C" int mc_xchg_insert(mc_xchg* x, int slot, mc_table* t, uint64_t* n_rec
 // --------------------------------------------------------------------------------------------
 // "count locally, then merge" (include/mc_b200.h): distinct (hashed key, count) pairs instead of key instances cross NVLink
 // --------------------------------------------------------------------------------------------
-// One 32-byte bucket per thread and step (plus the stash), like k_dump; every live entry is appended to its owner's region as
-// a 16-byte pair.  Appends are aggregated per CTA: one atomicAdd per owner, CTA and step on a LOCAL cursor (the region
+// One 32-byte bucket per thread and step (plus the stash), like k_dump; every live entry is appended to its owner's region: the
+// hashed key (8 bytes) to the region's key array, the count (16 bits) to its count array at the same position -- 10 bytes per
+// entry on NVLink.  Appends are aggregated per CTA: one atomicAdd per owner, CTA and step on a LOCAL cursor (the region
 // (slot, my rank) of every peer has this rank as its only writer).  Per-warp appends were measured first: tens of millions of
 // atomics on ONE address, which the L2 serialises (20 ms for a 16 GB table, 17 % of DRAM peak).  The threads of a CTA store
 // to consecutive positions: whole 32-byte sectors on NVLink.  The grid walks the table in bucket order = hash order, so a
@@ -206,8 +209,10 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
                                                              unsigned int* flags, uint64_t scan_lo, uint64_t scan_n, uint64_t home_lo, uint64_t home_hi) {
     __shared__ uint32_t s_tot[MC_MAX_XCHG_RANKS][DUMP_THREADS / 32];
     __shared__ unsigned long long s_base[MC_MAX_XCHG_RANKS];
-    __shared__ uint32_t s_otot[MC_MAX_XCHG_RANKS];
-    __shared__ ulonglong2 s_pairs[DUMP_THREADS * 4];   // every live entry of the CTA's 512 buckets, grouped by owner (32 KB)
+    __shared__ uint32_t s_otot[MC_MAX_XCHG_RANKS], s_oreal[MC_MAX_XCHG_RANKS];   // entries per owner in this step: padded, real
+    // every live entry of the CTA's 512 buckets, grouped by owner; every group padded to a multiple of 4 entries (count 0 = padding)
+    __shared__ __align__(16) uint64_t s_keys[DUMP_THREADS * 4 + 4 * MC_MAX_XCHG_RANKS];
+    __shared__ __align__(16) uint16_t s_cnts[DUMP_THREADS * 4 + 4 * MC_MAX_XCHG_RANKS];
     const uint64_t nb = scan_n;   // buckets scanned by this launch
     const uint64_t stash_units = ((uint64_t)t.stash_mask + 1 + 3) / 4;
     const uint64_t total = nb + stash_units;
@@ -277,15 +282,25 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
         if (threadIdx.x < world) {
             uint32_t tot = 0;
             for (int w = 0; w < DUMP_THREADS / 32; w++) tot += s_tot[threadIdx.x][w];
-            unsigned long long base = tot ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)tot) : 0ULL;
-            if (base + tot > cap_pairs) {
+            const uint32_t tot4 = (tot + 3u) & ~3u;   // reservations in units of 4 entries: 32-byte key granules, 8-byte count granules
+            unsigned long long base = tot4 ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)tot4) : 0ULL;
+            if (base + tot4 > cap_pairs) {
                 atomicOr(flags, 1u);
                 base = ~0ULL;
             }
             s_base[threadIdx.x] = base;
-            s_otot[threadIdx.x] = tot;
+            s_otot[threadIdx.x] = tot4;
+            s_oreal[threadIdx.x] = tot;
         }
         __syncthreads();
+        if (threadIdx.x < world) {   // the pads of my owner's group
+            uint32_t ooff = 0;
+            for (int p = 0; p < (int)threadIdx.x; p++) ooff += s_otot[p];
+            for (uint32_t i = s_oreal[threadIdx.x]; i < s_otot[threadIdx.x]; i++) {
+                s_keys[ooff + i] = 0;
+                s_cnts[ooff + i] = 0;
+            }
+        }
         // pass 2: the CTA's pairs, grouped by owner, into shared memory ...
         for (uint32_t m = present; m; m &= m - 1) {
             const int o = __ffs(m) - 1;
@@ -298,31 +313,39 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
                 if (lane >= d) incl += v;
             }
             if (mine) {
-                uint32_t ooff = 0;   // start of owner o's group inside s_pairs
+                uint32_t ooff = 0;   // start of owner o's group inside s_keys / s_cnts
                 for (int p = 0; p < o; p++) ooff += s_otot[p];
                 uint32_t before = 0;
                 for (int w = 0; w < warp; w++) before += s_tot[o][w];
                 uint32_t pos = ooff + before + incl - mine;
 #pragma unroll
                 for (int s = 0; s < 4; s++)
-                    if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) s_pairs[pos++] = make_ulonglong2(h[s], (unsigned long long)c[s]);
+                    if (((own >> (8 * s)) & 0xFFu) == (uint32_t)o) {
+                        s_keys[pos] = h[s];
+                        s_cnts[pos++] = (uint16_t)c[s];   // <= 32767
+                    }
             }
         }
         __syncthreads();
-        // ... and out in whole runs: consecutive lanes store consecutive 16-byte pairs of ONE owner's region, i.e. full 512-byte
-        // segments per warp on NVLink (round 1 stored every lane's pairs from registers: 16-byte writes strided by the lanes' own
-        // counts, ~250 GB/s to the peers)
+        // ... and out in whole runs, keys and counts as two arrays of the owner's region (10 bytes per entry on NVLink instead of the
+        // 16-byte pairs of the first form): consecutive lanes store consecutive 16-byte key granules, then consecutive 8-byte count
+        // granules -- full sectors (round 1 stored every lane's pairs from registers: 16-byte writes strided by the lanes' own counts,
+        // ~250 GB/s to the peers)
         uint32_t ooff = 0;
         for (int o = 0; o < world; o++) {
             const uint32_t tot = s_otot[o];
             const unsigned long long base = s_base[o];
             if (tot && base != ~0ULL) {
-                ulonglong2* out = (ulonglong2*)dst.base[o] + base;
-                for (uint32_t i = threadIdx.x; i < tot; i += DUMP_THREADS) out[i] = s_pairs[ooff + i];
+                ulonglong2* outk = (ulonglong2*)(dst.base[o] + base);
+                const ulonglong2* ink = (const ulonglong2*)(s_keys + ooff);
+                for (uint32_t i = threadIdx.x; i < tot / 2; i += DUMP_THREADS) outk[i] = ink[i];
+                uint64_t* outc = (uint64_t*)((uint16_t*)(dst.base[o] + cap_pairs) + base);
+                const uint64_t* inc = (const uint64_t*)(s_cnts + ooff);
+                for (uint32_t i = threadIdx.x; i < tot / 4; i += DUMP_THREADS) outc[i] = inc[i];
             }
             ooff += tot;
         }
-        __syncthreads();   // s_tot / s_base / s_pairs are rewritten by the next step
+        __syncthreads();   // s_tot / s_base / s_keys / s_cnts are rewritten by the next step
     }
 }
 
@@ -335,7 +358,8 @@ __global__ void __launch_bounds__(DUMP_THREADS, 2) k_dump_owners(McTableDev t, i
 // several prefetched buckets per thread lost more to stale copies and failed CAS retries than it gained, and a version with a
 // run of 8 consecutive pairs per thread was 3.6x slower at N = 4: profiles/r2_NOTES.md).
 struct McMergeSrc {
-    const ulonglong2* pairs[MC_MAX_XCHG_RANKS];
+    const uint64_t* keys[MC_MAX_XCHG_RANKS];    // hashed keys ...
+    const uint16_t* cnts[MC_MAX_XCHG_RANKS];    // ... and their counts (0 = padding), same positions
     unsigned long long n[MC_MAX_XCHG_RANKS];
     unsigned long long ratio[MC_MAX_XCHG_RANKS];   // floor(n[s] * 2^32 / n_max)
     unsigned long long n_max;
@@ -355,9 +379,11 @@ __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, McMergeSrc sr
             const unsigned long long lo = (v * src.ratio[s]) >> 32;
             const unsigned long long hi = v + 1 == src.n_max ? ns : ((v + 1) * src.ratio[s]) >> 32;
             for (unsigned long long i = lo; i < hi; i++) {
-                const ulonglong2 p = __ldcs(src.pairs[s] + i);
+                const uint32_t c = __ldcs(src.cnts[s] + i);
+                if (c == 0) continue;
+                const uint64_t key = __ldcs(src.keys[s] + i);
                 // (one pair per source and key, counts <= 32767: the RED form of the add, mc_common.cuh)
-                if (p.y && mc_table_add_impl<false, true>(t, p.x & lmask, (uint32_t)p.y, nullptr)) added++;
+                if (mc_table_add_impl<false, true>(t, key & lmask, c, nullptr)) added++;
             }
         }
     }
@@ -396,7 +422,7 @@ extern "C" int mc_xchg_dump_owners(mc_xchg* x, const mc_table* local, int slot, 
             // shared by all senders while the other links idle.  Rank r starts at the range of owner r + 1 instead (the ranges are
             // scanned in the same ascending order inside, so every receiver still sees each source's pairs in its bucket order).
             const uint64_t scan_lo = (uint64_t)((x->rank + 1) % x->world) * (local->nb / (uint64_t)x->world);
-            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->region_keys / 2, x->d_flags, scan_lo, local->nb, 0, local->nb);
+            k_dump_owners<<<grid, DUMP_THREADS, 0, st>>>(local->dev, x->shard_bits, dst, x->d_cursors, x->pair_cap(), x->d_flags, scan_lo, local->nb, 0, local->nb);
             MC_LAUNCH(ctx);
             MC_CUDA(cudaGetLastError());
         }
@@ -440,7 +466,7 @@ static void fused_group_done(void* user, mc_table* t, uint32_t b0, uint32_t G, u
     MC_CUDA(cudaEventRecord(f->ready, ctx->stream));
     MC_CUDA(cudaStreamWaitEvent(ctx->aux_stream, f->ready, 0));
     const int grid = (int)std::min<uint64_t>((scan_n + DUMP_THREADS - 1) / DUMP_THREADS, (uint64_t)ctx->sm_count);   // one CTA per SM: it shares the SM with the flush
-    k_dump_owners<<<grid, DUMP_THREADS, 0, ctx->aux_stream>>>(t->dev, f->x->shard_bits, f->dst, f->x->d_cursors, f->x->region_keys / 2, f->x->d_flags, lo, scan_n, lo, hi);
+    k_dump_owners<<<grid, DUMP_THREADS, 0, ctx->aux_stream>>>(t->dev, f->x->shard_bits, f->dst, f->x->d_cursors, f->x->pair_cap(), f->x->d_flags, lo, scan_n, lo, hi);
     MC_LAUNCH(ctx);
     MC_CUDA(cudaGetLastError());
 }
@@ -523,7 +549,7 @@ extern "C" int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_
         MC_CUDA(cudaStreamSynchronize(st));
         uint64_t total = 0;
         for (int src = 0; src < x->world; src++) {
-            if (counts[src] > x->region_keys / 2) mc_throw(MC_ERR_CUDA, "exchange: mailbox of rank %d is corrupt", src);
+            if (counts[src] > x->pair_cap()) mc_throw(MC_ERR_CUDA, "exchange: mailbox of rank %d is corrupt", src);
             total += counts[src];
         }
         // every pair may be a new key and no overflow list is attached here: room for all of them at load <= 0.55 (at 0.7 -- one rank
@@ -537,7 +563,8 @@ extern "C" int mc_xchg_merge(mc_xchg* x, int slot, mc_table* shard, uint64_t* n_
             McMergeSrc ms{};
             ms.world = x->world;
             for (int src = 0; src < x->world; src++) {
-                ms.pairs[src] = (const ulonglong2*)x->region(x->local, slot, src);
+                ms.keys[src] = x->region(x->local, slot, src);
+                ms.cnts[src] = (const uint16_t*)(ms.keys[src] + x->pair_cap());
                 ms.n[src] = counts[src];
                 ms.n_max = std::max<unsigned long long>(ms.n_max, counts[src]);
             }

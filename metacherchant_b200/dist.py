@@ -285,7 +285,7 @@ class ShardedCounter:
         t4 = time.perf_counter()
         if getattr(self, "verify", False):
             self.shard_digest = self.table.checksum(0)
-        self.bytes_exchanged += 16 * got.value * (self.world - 1) // self.world
+        self.bytes_exchanged += 10 * got.value * (self.world - 1) // self.world
         self.phase_s["extract"] += t1 - self._t_begin
         self.phase_s["dump"] = self.phase_s.get("dump", 0.0) + (t2 - t1)
         self.phase_s["barrier"] = self.phase_s.get("barrier", 0.0) + (t3 - t2)
