@@ -246,7 +246,11 @@ int mc_ctx_stage_reset(mc_ctx* ctx);                  /* mc_count_* reset the ti
  *   16-byte loads), "flush_overlap" (1: in the aggregated flush the sub-bin scatter of group g + 1 runs on a second stream beside the
  *   aggregation of group g; 0 = default: one after the other), "stage_timing" (0: no per-stage CUDA events), "scatter_tma" (1 = default: the scatter kernels hand every bin run to the copy engine with cp.async.bulk; 0: per-sector stores),
  *   "keep_stage_ms" (1: mc_count_* accumulate into the stage timers instead of resetting them --
- *   a step made of several count calls; reset with mc_ctx_stage_reset) */
+ *   a step made of several count calls; reset with mc_ctx_stage_reset),
+ *   "superkmers" (0 = default; 1: for k in [22,27] and [30,31] the extractor emits 16-byte super-k-mer records into minimizer bins that
+ *   are de-duplicated and unpacked at flush time, mc_sk.cu: same table, measured slower at cfg2), "sk_bits" / "sk_cap" (log2 of the
+ *   number of minimizer bins / records per bin; tests force spills with tiny bins), "agg_lane_loop" (0 = default; 1: the aggregation
+ *   walks a lane's keys of a round in one probe loop: measured slower) */
 int mc_ctx_set_tuning(mc_ctx* ctx, const char* name, long long value);
 /* table updates are buffered in bins; every read of the table applies them first, this call does so explicitly */
 int mc_table_flush_pending(mc_table* t);
