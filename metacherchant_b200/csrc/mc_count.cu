@@ -174,7 +174,6 @@ struct McSkSink {   // what sk_emit needs of McSkDev, passed by value (registers
     uint32_t cap, spill_cap, nb_mask;
 };
 __device__ __noinline__ void sk_emit(McSkSink o, uint32_t bin, uint64_t r0, uint64_t ext, uint32_t n, int k) {
-    if (o.cap == 0xFFFFFFF0u) return;   // EXPERIMENT: no emission
     const int s0 = 122 - 2 * k;                      // 58 .. 78 for k in [22, 32]
     uint64_t hi = s0 >= 64 ? r0 << (s0 - 64) : r0 >> (64 - s0);
     uint64_t lo = s0 >= 64 ? 0ULL : r0 << s0;

@@ -247,7 +247,7 @@ static void sk_create(mc_table* t, uint64_t ub_kmers, uint64_t total_hint) {
     B->sk.recs = (uint4*)mc_dev_alloc(ctx, (size_t)nb * cap * 16, "super-k-mer bins");
     B->sk.spill = (uint4*)mc_dev_alloc(ctx, (size_t)spill_cap * 16, "super-k-mer spill list");
     B->sk.cursors = (unsigned long long*)mc_dev_alloc(ctx, sk_cursor_words(nb) * 8, "super-k-mer cursors");
-    B->sk.cap = getenv("MC_SK_NOEMIT") ? 0xFFFFFFF0u : cap;
+    B->sk.cap = cap;
     B->sk.spill_cap = spill_cap;
     B->sk.nb_mask = nb - 1;
     B->sk.n_max = (uint32_t)std::min(62 - t->k, 33);

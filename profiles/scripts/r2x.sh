@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_superkmers.py -x -q 2>&1 | tail -5
 B="python bench.py --no-e2e --no-cpu-baseline --no-env"
+# (the MC_SK_NOEMIT experiment hook -- emission compiled out -- was removed from the library after this measurement)
 MC_SK_NOEMIT=1 $B --steps 2 --warmup 1 > gpurun_out/r2x_noemit.log 2> gpurun_out/r2x_noemit.err
 python -c "
 import json
