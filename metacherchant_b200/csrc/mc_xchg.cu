@@ -369,21 +369,40 @@ __global__ void __launch_bounds__(256) k_merge_pairs(McTableDev t, McMergeSrc sr
     unsigned long long added = 0;
     const uint64_t lmask = (1ULL << (62 - t.shard_bits)) - 1;
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < src.n_max; v += (uint64_t)gridDim.x * blockDim.x) {
-        for (int s = 0; s < src.world; s++) {
-            const unsigned long long ns = src.n[s];
-            if (ns == 0) continue;
-            // positions [lo, hi) of source s that fall to virtual position v (0 or 1 pair: n_s <= n_max).  f(v) = (v * ratio_s) >> 32
-            // with ratio_s = floor(n_s 2^32 / n_max) <= 2^32 is monotone, f(0) = 0 and f(v) <= n_s; f(n_max) is DEFINED as n_s, so the
-            // ranges [f(v), f(v + 1)) partition [0, n_s) exactly.  (v < 2^31: the product fits 64 bits; the host checks n_max.)
-            // Round 2's first form divided two 128-bit products per source and position: 1.4 G long divisions per step.
-            const unsigned long long lo = (v * src.ratio[s]) >> 32;
-            const unsigned long long hi = v + 1 == src.n_max ? ns : ((v + 1) * src.ratio[s]) >> 32;
-            for (unsigned long long i = lo; i < hi; i++) {
-                const uint32_t c = __ldcs(src.cnts[s] + i);
-                if (c == 0) continue;
-                const uint64_t key = __ldcs(src.keys[s] + i);
-                // (one pair per source and key, counts <= 32767: the RED form of the add, mc_common.cuh)
-                if (mc_table_add_impl<false, true>(t, key & lmask, c, nullptr)) added++;
+        // positions [lo, hi) of source s that fall to virtual position v (0 or 1 pair: n_s <= n_max).  f(v) = (v * ratio_s) >> 32
+        // with ratio_s = floor(n_s 2^32 / n_max) <= 2^32 is monotone, f(0) = 0 and f(v) <= n_s; f(n_max) is DEFINED as n_s, so the
+        // ranges [f(v), f(v + 1)) partition [0, n_s) exactly.  (v < 2^31: the product fits 64 bits; the host checks n_max.)
+        // Round 2's first form divided two 128-bit products per source and position: 1.4 G long divisions per step.
+        // The sources are taken four at a time: their (key, count) loads are all issued before the first add (one exposed DRAM
+        // round trip per four sources instead of two dependent ones per source).
+        for (int s0 = 0; s0 < src.world; s0 += 4) {
+            unsigned long long lo[4], hi[4];
+            uint64_t key[4];
+            uint32_t c[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int s = s0 + j;
+                lo[j] = hi[j] = 0;
+                c[j] = 0;
+                key[j] = 0;
+                if (s < src.world && src.n[s]) {
+                    lo[j] = (v * src.ratio[s]) >> 32;
+                    hi[j] = v + 1 == src.n_max ? src.n[s] : ((v + 1) * src.ratio[s]) >> 32;
+                    if (hi[j] > lo[j]) {
+                        c[j] = __ldcs(src.cnts[s] + lo[j]);
+                        key[j] = __ldcs(src.keys[s] + lo[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // (one pair per source and key, counts <= 32767: the RED form of the add, mc_common.cuh; count 0 = padding)
+                if (c[j] && mc_table_add_impl<false, true>(t, key[j] & lmask, c[j], nullptr)) added++;
+                for (unsigned long long i = lo[j] + 1; i < hi[j]; i++) {   // (only the last position of a shorter stream holds more than one)
+                    const uint32_t ci = __ldcs(src.cnts[s0 + j] + i);
+                    const uint64_t ki = __ldcs(src.keys[s0 + j] + i);
+                    if (ci && mc_table_add_impl<false, true>(t, ki & lmask, ci, nullptr)) added++;
+                }
             }
         }
     }
