@@ -391,9 +391,13 @@ __global__ void __launch_bounds__(256, MINB) k_bin_count(McTableDev t, McBinsDev
 // --------------------------------------------------------------------------------------------
 #define AGG_THREADS 512
 #define AGG_SLOTS 8192u      // 8 B key + 4 B count + 2 B list entry = 112 KB per CTA: two CTAs per SM
+#ifndef AGG_PROBES
 #define AGG_PROBES 12
+#endif
 #define AGG_U 4       // key loads in flight per thread (double buffered)
-#define AGG_FU 2      // bucket probes in flight per thread in the flush
+#ifndef AGG_FU
+#define AGG_FU 1      // bucket probes in flight per thread in the flush (measured: 1 -> 45.3 ms, 2 -> 46.2, 3 -> 50.5 at cfg2)
+#endif
 #define AGG_PREFETCH_MAX (512u << 10)   // table slices up to this size are pulled into L2 when their unit starts
 static size_t agg_smem_bytes() { return (size_t)AGG_SLOTS * 14; }
 
