@@ -45,3 +45,35 @@ def test_products_fit_64_bits_at_the_largest_supported_stream():
         # the last positions: exact partition at the end of the stream
         lo = ((n_max - 1) * ratio) >> 32
         assert lo <= n_s and n_s - lo <= 2
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8, 16])
+def test_lockstep_walk_in_batches_of_four_visits_every_pair_once(world):
+    """The kernel's loop structure restated: virtual positions x sources taken four at a time, first pair loaded up front, the
+    (rare) further pairs of a position in a tail loop.  Every (source, position) pair must be visited exactly once for any mix of
+    stream lengths, empty sources included."""
+    rng = random.Random(world)
+    for _ in range(30):
+        n = [rng.choice([0, 1, rng.randint(0, 300), rng.randint(200, 300)]) for _ in range(world)]
+        n_max = max(n)
+        if n_max == 0:
+            continue
+        ratio = [(x << 32) // n_max for x in n]
+        seen = [[0] * x for x in n]
+        for v in range(n_max):
+            for s0 in range(0, world, 4):
+                lo, hi = [0] * 4, [0] * 4
+                first = [None] * 4
+                for j in range(4):
+                    s = s0 + j
+                    if s < world and n[s]:
+                        lo[j] = (v * ratio[s]) >> 32
+                        hi[j] = n[s] if v + 1 == n_max else ((v + 1) * ratio[s]) >> 32
+                        if hi[j] > lo[j]:
+                            first[j] = (s, lo[j])
+                for j in range(4):
+                    if first[j] is not None:
+                        seen[first[j][0]][first[j][1]] += 1
+                    for i in range(lo[j] + 1, hi[j]):
+                        seen[s0 + j][i] += 1
+        assert all(c == 1 for row in seen for c in row)
